@@ -1,0 +1,106 @@
+/*
+ * lsthm_b200 — C ABI of the B200-native LSTHM hybrid-recurrence library (liblsthm_b200.so).
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; what a replacement has to bind
+ * is the *operator* each entry point stands in for.  Citations are file:line under the reference
+ * tree (MallVilliers/Multimodal-Framework-for-speaker-emotion-recognition).
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless it says "host".
+ *   - the caller owns all memory (PyTorch's caching allocator in our host mirror); the library
+ *     never allocates or frees device memory and keeps no pointer after a call returns.
+ *   - every launch goes to the cudaStream_t passed as `stream` (void* to keep this header free of
+ *     cuda_runtime.h); calls are asynchronous; there is no device synchronisation inside.
+ *   - return 0 on success; non-zero -> lsthm_last_error() (thread-local, host string).
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails.
+ *   - tensors are contiguous, time-major [T][N][...], fp32.
+ */
+#ifndef LSTHM_B200_H_
+#define LSTHM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSTHM_ABI_VERSION 1
+#define LSTHM_MAX_MOD 3
+
+int lsthm_abi_version(void);
+const char *lsthm_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * AT / ATV: LSTHM cells + multi-attention block (MAB) recurrence.
+ * Replaces the body of the time loop of MARN.forward
+ *     model/HybridRNN_ATV.py:117-143   (AT: model/HybridRNN_AT.py:107-132)
+ * i.e. LSTHM.forward (model/HybridRNN_ATV.py:21-37) for every modality, the 4-head softmax
+ * attention over the concatenated cell states (123-125), the per-modality reduce layers
+ * (126-128) and fc = Linear-ReLU-Dropout-Linear (66, 129).  The input projections W_m x_m and
+ * the per-step head nn_out (68-73,139-141) are time-parallel and stay on the host side.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t T;                 /* padded dialogue length                                   */
+    int32_t N;                 /* dialogues in the batch                                   */
+    int32_t n_mod;             /* 2 (AT: text, audio) or 3 (ATV: + visual)                 */
+    int32_t n_att;             /* attention heads (reference: 4)                           */
+    int32_t map_h;             /* fc hidden width (reference: 64)                          */
+    int32_t dh[LSTHM_MAX_MOD]; /* cell sizes   (ATV 128,16,64)  multiples of 4             */
+    int32_t rd[LSTHM_MAX_MOD]; /* reduce sizes (ATV 16,128,100) multiples of 4             */
+    int32_t rows_per_cta;      /* 0 = auto; else 1..8 dialogues per thread block           */
+} lsthm_mab_desc;
+
+/* Weights in nn.Linear layout [out][in], exactly the module's parameter storage. */
+typedef struct {
+    const float *U[LSTHM_MAX_MOD];    /* lsthm_m.U.weight [4dh_m][dh_m]   HybridRNN_ATV.py:18 */
+    const float *V[LSTHM_MAX_MOD];    /* lsthm_m.V.weight [4dh_m][D]      HybridRNN_ATV.py:19 */
+    const float *Watt, *batt;         /* att.0            [4D][D],[4D]    HybridRNN_ATV.py:60 */
+    const float *Wr[LSTHM_MAX_MOD];   /* reduce_dim_nn_m.0 [rd_m][4dh_m]  HybridRNN_ATV.py:62-64 */
+    const float *br[LSTHM_MAX_MOD];
+    const float *Wf1, *bf1;           /* fc.0 [map_h][R]                  HybridRNN_ATV.py:66 */
+    const float *Wf2, *bf2;           /* fc.3 [D][map_h]                                      */
+} lsthm_mab_weights;
+
+/* Number of floats of the packed (k-major / gate-interleaved) weight image the kernels stream. */
+size_t lsthm_mab_packed_floats(const lsthm_mab_desc *d);
+
+/* Re-layout the weights into `packed` (call after every optimizer step, before fwd/bwd). */
+int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, float *packed, void *stream);
+
+/*
+ * Forward recurrence over all T steps.
+ *   gx        [T][N][4D]   W_m x_m + bW_m + bU_m + bV_m, cell-major, f|i|o|g inside a cell
+ *   drop_mask [T][N][map_h] keep/(1-p) mask of fc's Dropout, or NULL (eval mode)
+ *   hz        [T][N][2D]   out: [h_t | z_t]   (what nn_out consumes, HybridRNN_ATV.py:139)
+ *   stash (all out, may ALL be NULL for inference):
+ *     sC [T][N][D]  cell states      sG [T][N][4D] gates after sigmoid/tanh (layout of gx)
+ *     sA [T][N][4][D] softmax weights   sR [T][N][R] reduce outputs   sU [T][N][map_h] fc hidden
+ */
+int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx, const float *drop_mask,
+                  float *hz, float *sC, float *sG, float *sA, float *sR, float *sU, void *stream);
+
+/*
+ * BPTT.  `w` gives the native-layout weights (the transposed products read them directly),
+ * `packed` the image from lsthm_mab_pack (for the concatenated V).
+ *   dhz  [T][N][2D]  dL/d[h_t|z_t] from the head
+ * out (the adjoints the time-parallel weight-gradient products consume):
+ *   dgx  [T][N][4D]  dL/d(gate pre-activations)  -> dW,dU,dV,db and dx
+ *   de   [T][N][4D]  dL/d(att logits)            -> d att.0
+ *   dr   [T][N][R]   dL/d(reduce outputs)        -> d reduce_dim_nn_*
+ *   dup  [T][N][map_h] dL/d(fc.0 pre-activation) -> d fc.0
+ *   dzt  [T][N][D]   total dL/dz_t               -> d fc.3
+ */
+int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed,
+                  const float *dhz, const float *drop_mask,
+                  const float *sC, const float *sG, const float *sA, const float *sU,
+                  float *dgx, float *de, float *dr, float *dup, float *dzt, void *stream);
+
+/* Launch geometry the library would use (for roofline bookkeeping in bench.py). */
+int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows,
+                          int32_t *smem_fwd, int32_t *smem_bwd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSTHM_B200_H_ */

@@ -1,0 +1,149 @@
+"""ctypes binding of liblsthm_b200.so (the C ABI in include/lsthm_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the
+caller gets a RuntimeError.  PyTorch is used only to own device memory and to name the
+current CUDA stream; no torch type crosses the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_PKG, "liblsthm_b200.so")
+ABI_VERSION = 1
+MAX_MOD = 3
+
+_f32p = C.POINTER(C.c_float)
+
+
+class MabDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("n_mod", C.c_int32), ("n_att", C.c_int32),
+                ("map_h", C.c_int32), ("dh", C.c_int32 * MAX_MOD), ("rd", C.c_int32 * MAX_MOD),
+                ("rows_per_cta", C.c_int32)]
+
+
+class MabWeights(C.Structure):
+    _fields_ = [("U", C.c_void_p * MAX_MOD), ("V", C.c_void_p * MAX_MOD), ("Watt", C.c_void_p),
+                ("batt", C.c_void_p), ("Wr", C.c_void_p * MAX_MOD), ("br", C.c_void_p * MAX_MOD),
+                ("Wf1", C.c_void_p), ("bf1", C.c_void_p), ("Wf2", C.c_void_p), ("bf2", C.c_void_p)]
+
+
+def build(verbose: bool = False, jobs: int = 8) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_PKG, "csrc"), f"-j{jobs}", "all"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode:
+        print(res.stdout)
+    if res.returncode:
+        raise RuntimeError("building liblsthm_b200.so failed (see output above)")
+    return SO_PATH
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            f"{SO_PATH} is missing: the CUDA extension is not built and there is no CPU fallback. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
+    L = C.CDLL(SO_PATH)
+    L.lsthm_abi_version.restype = C.c_int
+    L.lsthm_last_error.restype = C.c_char_p
+    L.lsthm_mab_packed_floats.restype = C.c_size_t
+    L.lsthm_mab_packed_floats.argtypes = [C.POINTER(MabDesc)]
+    L.lsthm_mab_pack.restype = C.c_int
+    L.lsthm_mab_pack.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights), C.c_void_p, C.c_void_p]
+    L.lsthm_mab_fwd.restype = C.c_int
+    L.lsthm_mab_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 10
+    L.lsthm_mab_bwd.restype = C.c_int
+    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 13
+    L.lsthm_mab_launch_info.restype = C.c_int
+    L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 5
+    if L.lsthm_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"liblsthm_b200.so ABI {L.lsthm_abi_version()} != expected {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().lsthm_last_error().decode()}")
+
+
+def _dev_ptr(t: Optional[torch.Tensor], name: str) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+    if t.data_ptr() % 16:
+        raise RuntimeError(f"{name}: storage must be 16-byte aligned")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_desc(T: int, N: int, dh: Sequence[int], rd: Sequence[int], map_h: int = 64, n_att: int = 4,
+              rows_per_cta: int = 0) -> MabDesc:
+    d = MabDesc()
+    d.T, d.N, d.n_mod, d.n_att, d.map_h, d.rows_per_cta = T, N, len(dh), n_att, map_h, rows_per_cta
+    for i, (a, b) in enumerate(zip(dh, rd)):
+        d.dh[i], d.rd[i] = a, b
+    return d
+
+
+def make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2) -> MabWeights:
+    w = MabWeights()
+    for i in range(len(U)):
+        w.U[i], w.V[i] = _dev_ptr(U[i], f"U[{i}]"), _dev_ptr(V[i], f"V[{i}]")
+        w.Wr[i], w.br[i] = _dev_ptr(Wr[i], f"Wr[{i}]"), _dev_ptr(br[i], f"br[{i}]")
+    w.Watt, w.batt = _dev_ptr(Watt, "Watt"), _dev_ptr(batt, "batt")
+    w.Wf1, w.bf1 = _dev_ptr(Wf1, "Wf1"), _dev_ptr(bf1, "bf1")
+    w.Wf2, w.bf2 = _dev_ptr(Wf2, "Wf2"), _dev_ptr(bf2, "bf2")
+    return w
+
+
+def mab_packed_floats(d: MabDesc) -> int:
+    n = lib().lsthm_mab_packed_floats(C.byref(d))
+    if n == 0:
+        raise RuntimeError(f"unsupported recurrence dims: {lib().lsthm_last_error().decode()}")
+    return n
+
+
+def mab_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
+    _check(lib().lsthm_mab_pack(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _stream()), "lsthm_mab_pack")
+
+
+def mab_fwd(d: MabDesc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU) -> None:
+    _check(lib().lsthm_mab_fwd(C.byref(d), _dev_ptr(packed, "packed"), _dev_ptr(gx, "gx"),
+                               _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(hz, "hz"), _dev_ptr(sC, "sC"),
+                               _dev_ptr(sG, "sG"), _dev_ptr(sA, "sA"), _dev_ptr(sR, "sR"), _dev_ptr(sU, "sU"),
+                               _stream()), "lsthm_mab_fwd")
+
+
+def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt) -> None:
+    _check(lib().lsthm_mab_bwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"),
+                               _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"),
+                               _dev_ptr(sA, "sA"), _dev_ptr(sU, "sU"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
+                               _dev_ptr(dr, "dr"), _dev_ptr(dup, "dup"), _dev_ptr(dzt, "dzt"), _stream()),
+           "lsthm_mab_bwd")
+
+
+def mab_launch_info(d: MabDesc) -> dict:
+    v = [C.c_int32() for _ in range(5)]
+    _check(lib().lsthm_mab_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab_launch_info")
+    return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))

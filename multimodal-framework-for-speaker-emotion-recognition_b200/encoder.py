@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference's per-modality utterance encoder (model/encoder.py).
+
+Time-parallel, GEMM-shaped and outside the recurrence, so it stays ordinary PyTorch (cuBLAS);
+a fused kernel for it is the first "next" row of SURVEY.md §8(f).  Parameter names, shapes and
+construction order equal the reference's (encoder.py:10-25, 92-99, 124-127) so that state_dicts
+load both ways and a fixed seed yields identical initial weights.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class ScaledDotProductAttention(nn.Module):
+    """softmax(q k^T / temperature) v with dropout on the weights; never masked in this repo
+    (encoder.py:71-86, call site encoder.py:131 passes mask=None)."""
+
+    def __init__(self, temperature: float, attn_dropout: float = 0.1):
+        super().__init__()
+        self.temperature = temperature
+        self.dropout = nn.Dropout(attn_dropout)
+
+    def forward(self, q, k, v, mask=None):
+        scores = torch.matmul(q / self.temperature, k.transpose(-2, -1))
+        if mask is not None:
+            scores = scores.masked_fill(mask == 0, -1e9)
+        attn = self.dropout(torch.softmax(scores, dim=-1))
+        return torch.matmul(attn, v), attn
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, n_head, d_model, d_model2, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.n_head, self.d_k, self.d_v = n_head, d_k, d_v
+        self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_ks = nn.Linear(d_model2, n_head * d_k, bias=False)
+        self.w_vs = nn.Linear(d_model2, n_head * d_v, bias=False)
+        self.fc = nn.Linear(n_head * d_v, d_model, bias=False)
+        self.attention = ScaledDotProductAttention(temperature=d_k ** 0.5)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+
+    def forward(self, q, k, v, mask=None):
+        B, Lq, Lk = q.size(0), q.size(1), k.size(1)
+        H, dk, dv = self.n_head, self.d_k, self.d_v
+        res = q
+        qh = self.w_qs(q).view(B, Lq, H, dk).transpose(1, 2)
+        kh = self.w_ks(k).view(B, Lk, H, dk).transpose(1, 2)
+        vh = self.w_vs(v).view(B, Lk, H, dv).transpose(1, 2)
+        ctx, attn = self.attention(qh, kh, vh, mask=None if mask is None else mask.unsqueeze(1))
+        ctx = ctx.transpose(1, 2).reshape(B, Lq, H * dv)
+        out = self.layer_norm(self.dropout(self.fc(ctx)) + res)
+        return out, attn
+
+
+class PositionwiseFeedForward(nn.Module):
+    def __init__(self, d_in, d_hid, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Linear(d_in, d_hid)
+        self.w_2 = nn.Linear(d_hid, d_in)
+        self.layer_norm = nn.LayerNorm(d_in, eps=1e-6)
+        self.dropout = nn.Dropout(dropout)
+        self.fc = nn.Linear(d_in, 100)  # registered but never applied (encoder.py:99,111): grad stays None
+
+    def forward(self, x):
+        return self.layer_norm(self.dropout(self.w_2(F.relu(self.w_1(x)))) + x)
+
+
+class EncoderLayer(nn.Module):
+    def __init__(self, d_model, d_inner, n_head, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.slf_attn = MultiHeadAttention(n_head, d_model, d_model, d_k, d_v, dropout=dropout)
+        self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=dropout)
+
+    def forward(self, enc_input, slf_attn_mask=None):
+        y, attn = self.slf_attn(enc_input, enc_input, enc_input, mask=slf_attn_mask)
+        return self.pos_ffn(y), attn

@@ -1,0 +1,100 @@
+"""Shared implementation of the drop-in ``MARN`` modules of HybridRNN_AT / HybridRNN_ATV.
+
+Constructor and ``forward(x)`` signatures, parameter names/shapes/registration order and the
+RNG consumption order of the default initialisation follow the reference
+(model/HybridRNN_ATV.py:40-82, model/HybridRNN_AT.py:40-79); the time loop
+(HybridRNN_ATV.py:117-143) is replaced by one fused CUDA recurrence (``recurrence.py``).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .encoder import EncoderLayer
+from .recurrence import mab_recurrence
+
+_MODS = ("l", "a", "v")
+
+
+class LSTHM(nn.Module):
+    """Parameter container of one LSTHM cell (model/HybridRNN_ATV.py:12-19).  Its arithmetic
+    (lines 21-37) runs inside the fused recurrence kernel; ``forward`` is kept for API parity and
+    evaluates a single step through that same kernel path by delegating to the owner network."""
+
+    def __init__(self, cell_size, in_size, hybrid_in_size):
+        super().__init__()
+        self.cell_size, self.in_size = cell_size, in_size
+        self.W = nn.Linear(in_size, 4 * cell_size)
+        self.U = nn.Linear(cell_size, 4 * cell_size)
+        self.V = nn.Linear(hybrid_in_size, 4 * cell_size)
+
+    def gate_input(self, x: torch.Tensor) -> torch.Tensor:
+        """W x + bW + bU + bV for all steps at once (the hoisted, time-parallel part of line 23-27)."""
+        return F.linear(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias)
+
+
+class MabNet(nn.Module):
+    def __init__(self, d_in: Sequence[int], dh: Sequence[int], reduce: Sequence[int], output_dim: int):
+        super().__init__()
+        self._mods = _MODS[:len(d_in)]
+        self.num_atts = 4
+        self.total_h_dim = sum(dh)
+        self.total_reduce_dim = sum(reduce)
+        self._d_in, self._dh, self._rd = tuple(d_in), tuple(dh), tuple(reduce)
+        h_out, map_h = 32, 64
+        self._map_h = map_h
+        D = self.total_h_dim
+        # --- same construction order as the reference so a fixed seed gives the same weights ---
+        for m, d, h in zip(self._mods, d_in, dh):
+            setattr(self, f"lsthm_{m}", LSTHM(h, d, D))
+        self.att = nn.Sequential(nn.Linear(D, self.num_atts * D))
+        for m, h, r in zip(self._mods, dh, reduce):
+            setattr(self, f"reduce_dim_nn_{m}", nn.Sequential(nn.Linear(self.num_atts * h, r)))
+        self.fc = nn.Sequential(nn.Linear(self.total_reduce_dim, map_h), nn.ReLU(), nn.Dropout(0.3),
+                                nn.Linear(map_h, D))
+        self.nn_out = nn.Sequential(nn.Linear(2 * D, h_out), nn.ReLU(), nn.Dropout(0.0),
+                                    nn.Linear(h_out, output_dim), nn.Softmax(dim=-1))
+        for m, d in zip(self._mods, d_in):
+            setattr(self, f"encoder_{m}", EncoderLayer(d, 50, 8, 40, 40))
+        self.rows_per_cta = 0            # 0 = let the library pick the tile height
+        self.fc_mask_override: Optional[torch.Tensor] = None   # test hook: dropout mask tape [T,N,map_h]
+
+    # -- pieces --------------------------------------------------------------------------------
+    def recurrence_weights(self):
+        cells = [getattr(self, f"lsthm_{m}") for m in self._mods]
+        red = [getattr(self, f"reduce_dim_nn_{m}")[0] for m in self._mods]
+        return ([c.U.weight for c in cells] + [c.V.weight for c in cells] + [self.att[0].weight, self.att[0].bias]
+                + [r.weight for r in red] + [r.bias for r in red]
+                + [self.fc[0].weight, self.fc[0].bias, self.fc[3].weight, self.fc[3].bias])
+
+    def encode(self, x: torch.Tensor):
+        """Per-modality slices through their EncoderLayer (HybridRNN_ATV.py:86-96); returns [T,N,d_m] each."""
+        xs, o = [], 0
+        for m, d in zip(self._mods, self._d_in):
+            y, _ = getattr(self, f"encoder_{m}")(x[:, :, o:o + d].permute(1, 0, 2))
+            xs.append(y.permute(1, 0, 2))
+            o += d
+        return xs
+
+    def gate_inputs(self, xs) -> torch.Tensor:
+        return torch.cat([getattr(self, f"lsthm_{m}").gate_input(xm) for m, xm in zip(self._mods, xs)], dim=-1)
+
+    def _fc_mask(self, T, N, device):
+        if self.fc_mask_override is not None:
+            return self.fc_mask_override.to(device=device, dtype=torch.float32)
+        p = self.fc[2].p
+        if not self.training or p == 0.0:
+            return None
+        keep = torch.empty(T, N, self._map_h, device=device, dtype=torch.float32).bernoulli_(1.0 - p)
+        return keep.mul_(1.0 / (1.0 - p))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        T, N, _ = x.shape
+        gx = self.gate_inputs(self.encode(x))
+        hz = mab_recurrence(gx, self._fc_mask(T, N, x.device), self._dh, self._rd, self._map_h,
+                            self.recurrence_weights(), self.rows_per_cta)
+        self.last_hz = hz
+        return self.nn_out(hz.view(T * N, -1))       # time-major [T*N, C] probabilities (line 153)

@@ -1,0 +1,122 @@
+"""torch.autograd glue around the CUDA recurrence kernels (C ABI: include/lsthm_b200.h).
+
+`mab_recurrence` replaces the time loop of the reference's ``MARN.forward``
+(model/HybridRNN_ATV.py:117-143, model/HybridRNN_AT.py:107-132).  Everything either side of
+it — input projections, encoders, the per-step head — is ordinary PyTorch, so autograd
+composes through ``MabRecurrenceFn.backward``.
+
+Backward contract: the BPTT kernel returns the per-step adjoints; the weight gradients are
+time-parallel products over all T*N rows (``adj^T @ act``) formed here in fp32.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+# Counts launches of OUR kernels (pack/fwd/bwd), for bench.py's `gpu_launches`.
+launch_counter = {"pack": 0, "fwd": 0, "bwd": 0}
+
+
+class MabRecurrenceFn(torch.autograd.Function):
+    """hz[T,N,2D] = recurrence(gx[T,N,4D]; U_m, V_m, att, reduce_m, fc).
+
+    Argument order after (gx, drop_mask, dims): U_0..U_{M-1}, V_0.., Watt, batt, Wr_0.., br_0..,
+    Wf1, bf1, Wf2, bf2  — all in nn.Linear layout, i.e. the modules' own parameter storage.
+    """
+
+    @staticmethod
+    def forward(ctx, gx: torch.Tensor, drop_mask: Optional[torch.Tensor], dims: Tuple, *weights: torch.Tensor):
+        dh, rd, map_h, rows_per_cta = dims
+        M = len(dh)
+        T, N, G = gx.shape
+        D, R = sum(dh), sum(rd)
+        if G != 4 * D:
+            raise RuntimeError(f"gx last dim {G} != 4*sum(dh) = {4 * D}")
+        gx = gx.contiguous()
+        weights = tuple(w.detach().contiguous() for w in weights)
+        U, V = weights[0:M], weights[M:2 * M]
+        Watt, batt = weights[2 * M], weights[2 * M + 1]
+        Wr, br = weights[2 * M + 2:3 * M + 2], weights[3 * M + 2:4 * M + 2]
+        Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
+        desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
+        wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
+        packed = torch.empty(_lib.mab_packed_floats(desc), device=gx.device, dtype=torch.float32)
+        _lib.mab_pack(desc, wstruct, packed)
+        launch_counter["pack"] += 1
+        new = lambda *s: torch.empty(*s, device=gx.device, dtype=torch.float32)
+        hz = new(T, N, 2 * D)
+        need_grad = any(ctx.needs_input_grad)
+        if drop_mask is not None:
+            drop_mask = drop_mask.contiguous()
+        if need_grad:
+            sC, sG, sA, sR, sU = new(T, N, D), new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h)
+        else:
+            sC = sG = sA = sR = sU = None
+        _lib.mab_fwd(desc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU)
+        launch_counter["fwd"] += 1
+        if need_grad:
+            ctx.save_for_backward(packed, hz, sC, sG, sA, sR, sU, *weights)
+            ctx.drop_mask = drop_mask
+            ctx.dims = dims
+        return hz
+
+    @staticmethod
+    def backward(ctx, dhz: torch.Tensor):
+        packed, hz, sC, sG, sA, sR, sU, *weights = ctx.saved_tensors
+        dh, rd, map_h, rows_per_cta = ctx.dims
+        M = len(dh)
+        T, N, _ = hz.shape
+        D, R, G = sum(dh), sum(rd), 4 * sum(dh)
+        U, V = weights[0:M], weights[M:2 * M]
+        Watt, batt = weights[2 * M], weights[2 * M + 1]
+        Wr, br = weights[2 * M + 2:3 * M + 2], weights[3 * M + 2:4 * M + 2]
+        Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
+        desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
+        wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
+        new = lambda *s: torch.empty(*s, device=hz.device, dtype=torch.float32)
+        dgx, de, dr, dup, dzt = new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h), new(T, N, D)
+        _lib.mab_bwd(desc, wstruct, packed, dhz.contiguous(), ctx.drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt)
+        launch_counter["bwd"] += 1
+
+        # ---- time-parallel weight-gradient products (fp32; allow_tf32 stays off) ----
+        TN = T * N
+        gU: List[torch.Tensor] = []
+        gV: List[torch.Tensor] = []
+        if T > 1:
+            # [G, 2D] = dgx[1:]^T @ [h_{t-1} | z_{t-1}]; U_m / V_m grads are blocks of it
+            full = dgx[1:].reshape(-1, G).t() @ hz[:-1].reshape(-1, 2 * D)
+        else:
+            full = dgx.new_zeros(G, 2 * D)
+        o = 0
+        for m in range(M):
+            gU.append(full[4 * o:4 * o + 4 * dh[m], o:o + dh[m]])
+            gV.append(full[4 * o:4 * o + 4 * dh[m], D:])
+            o += dh[m]
+        de2, c2 = de.view(TN, G), sC.view(TN, D)
+        gWatt, gbatt = de2.t() @ c2, de2.sum(0)
+        att = sA.view(TN, 4, D) * c2.unsqueeze(1)           # attended = a * cs (HybridRNN_ATV.py:125)
+        dr2 = dr.view(TN, R)
+        gWr, gbr = [], []
+        o = ro = 0
+        for m in range(M):
+            vec = att[:, :, o:o + dh[m]].reshape(TN, 4 * dh[m])  # head-major regroup (lines 126-128)
+            drm = dr2[:, ro:ro + rd[m]]
+            gWr.append(drm.t() @ vec)
+            gbr.append(drm.sum(0))
+            o += dh[m]
+            ro += rd[m]
+        dup2, dzt2 = dup.view(TN, map_h), dzt.view(TN, D)
+        gWf1, gbf1 = dup2.t() @ sR.view(TN, R), dup2.sum(0)
+        gWf2, gbf2 = dzt2.t() @ sU.view(TN, map_h), dzt2.sum(0)
+        grads = (*gU, *gV, gWatt, gbatt, *gWr, *gbr, gWf1, gbf1, gWf2, gbf2)
+        return (dgx, None, None, *grads)
+
+
+def mab_recurrence(gx: torch.Tensor, drop_mask: Optional[torch.Tensor], dh: Sequence[int], rd: Sequence[int],
+                   map_h: int, weights: Sequence[torch.Tensor], rows_per_cta: int = 0) -> torch.Tensor:
+    if not gx.is_cuda:
+        raise RuntimeError("lsthm_b200: the recurrence runs on a CUDA device only (no CPU fallback)")
+    return MabRecurrenceFn.apply(gx, drop_mask, (tuple(dh), tuple(rd), int(map_h), int(rows_per_cta)), *weights)

@@ -1,0 +1,78 @@
+"""Test-only stand-in for the CUDA library: routes recurrence.py's ABI calls to the fp64 plain-C
+oracle so the HOST logic (autograd plumbing, hoisted weight-gradient products, module wiring) can
+be checked on a machine without a GPU.  Installed by monkeypatching inside a test; the product
+never imports this file (it lives under tests/)."""
+from importlib import import_module
+
+import numpy as np
+import torch
+
+from oracle import cpu as ocpu
+
+MODS = ("l", "a", "v")
+
+
+class OracleBackend:
+    def __init__(self):
+        self.weights = None
+
+    # --- signatures mirror _lib.py ---
+    def make_weights(self, U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2):
+        p = {}
+        for i in range(len(U)):
+            m = MODS[i]
+            p[f"lsthm_{m}.U.weight"], p[f"lsthm_{m}.V.weight"] = U[i], V[i]
+            p[f"reduce_dim_nn_{m}.0.weight"], p[f"reduce_dim_nn_{m}.0.bias"] = Wr[i], br[i]
+        p["att.0.weight"], p["att.0.bias"] = Watt, batt
+        p["fc.0.weight"], p["fc.0.bias"], p["fc.3.weight"], p["fc.3.bias"] = Wf1, bf1, Wf2, bf2
+        self.weights = {k: v.detach().double().numpy() for k, v in p.items()}
+        return self.weights
+
+    def mab_packed_floats(self, d):
+        return 4
+
+    def mab_pack(self, d, w, packed):
+        pass
+
+    @staticmethod
+    def _dims(d):
+        return tuple(d.dh[i] for i in range(d.n_mod)), tuple(d.rd[i] for i in range(d.n_mod))
+
+    def mab_fwd(self, d, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU):
+        dh, rd = self._dims(d)
+        f = ocpu.mab_forward(self.weights, gx.double().numpy(), dh, rd,
+                             None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
+        hz.copy_(torch.from_numpy(f["hz"]))
+        if sC is not None:
+            for t, k in ((sC, "C"), (sG, "G"), (sA, "A"), (sR, "R"), (sU, "UH")):
+                t.copy_(torch.from_numpy(f[k]).reshape(t.shape))
+
+    def mab_bwd(self, d, w, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt):
+        dh, rd = self._dims(d)
+        T, N = d.T, d.N
+        D = sum(dh)
+        # hz / R feed only the oracle's own weight-gradient accumulation, which is not used here
+        f = dict(hz=np.zeros((T, N, 2 * D)), C=sC.double().numpy(), G=sG.double().numpy(),
+                 A=np.ascontiguousarray(sA.double().numpy().reshape(T, N, 4, D)),
+                 R=np.zeros((T, N, sum(rd))), UH=sU.double().numpy())
+        adj, _ = ocpu.mab_backward(self.weights, dhz.double().numpy(), f, dh, rd,
+                                   None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
+        for t, k in ((dgx, "dgx"), (de, "de"), (dr, "dr"), (dup, "dup"), (dzt, "dzt")):
+            t.copy_(torch.from_numpy(adj[k]).reshape(t.shape))
+
+
+def install(monkeypatch):
+    import lsthm_b200
+    lib = import_module(lsthm_b200.__name__ + "._lib")
+    rec = import_module(lsthm_b200.__name__ + ".recurrence")
+    net = import_module(lsthm_b200.__name__ + ".mab_net")
+    be = OracleBackend()
+    for name in ("make_weights", "mab_packed_floats", "mab_pack", "mab_fwd", "mab_bwd"):
+        monkeypatch.setattr(lib, name, getattr(be, name))
+
+    # the public entry point refuses CPU tensors; tests go through the autograd.Function directly
+    def cpu_recurrence(gx, mask, dh, rd, map_h, weights, rows=0):
+        return rec.MabRecurrenceFn.apply(gx, mask, (tuple(dh), tuple(rd), int(map_h), int(rows)), *weights)
+
+    monkeypatch.setattr(net, "mab_recurrence", cpu_recurrence)
+    return be

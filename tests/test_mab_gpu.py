@@ -1,0 +1,179 @@
+"""GPU suite (run with -m gpu on the B200 box): parity of the CUDA recurrence with the oracle.
+
+All calls go through the C ABI (ctypes -> liblsthm_b200.so).  Layers of evidence:
+  1. kernel boundary vs the fp64 plain-C oracle, every stash tensor and every adjoint, ragged
+     tiles (N not a multiple of rows_per_cta), all tile heights, eval and masked (train) mode;
+  2. drop-in module vs the reference-generated fixtures in tests/golden/ (north-star bars:
+     outputs/loss 1e-4, gradients 1e-3 scale-relative, identical argmax);
+  3. drop-in module vs the oracle's torch restatement at the full dialogue length T=110;
+  4. size-independent properties at the benchmark size (T=110, N=1024): dialogue independence
+     (batch permutation equivariance), tile-height invariance, run-to-run determinism,
+     inference path == training path.
+"""
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+
+import lsthm_b200
+from helpers import (SPEC, TOL_GRAD, TOL_OUT, check_against_golden, e_inf, golden_files, load_golden, masked_ce,
+                     run_module, seeded_model)
+from oracle import cpu as ocpu
+from oracle import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+lib = import_module(lsthm_b200.__name__ + "._lib")
+
+
+def _boundary_case(kind, T, N, rows, masked, seed=0):
+    spec = SPEC[kind]
+    dh, rd = spec["dh"], spec["rd"]
+    D, R, MH = sum(dh), sum(rd), 64
+    model = seeded_model(kind, 100 + seed)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():       # make biases / attention non-trivial
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+    gx = torch.randn(T, N, 4 * D, generator=g)
+    mask = (torch.bernoulli(torch.full((T, N, MH), 0.7), generator=g) / 0.7) if masked else None
+    dhz = torch.randn(T, N, 2 * D, generator=g)
+    weights = [w.detach() for w in model.recurrence_weights()]
+    params = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    return dict(dh=dh, rd=rd, D=D, R=R, MH=MH, gx=gx, mask=mask, dhz=dhz, weights=weights, params=params, rows=rows)
+
+
+def _run_kernels(c, T, N):
+    dev = "cuda"
+    dh, rd, D, R, MH = c["dh"], c["rd"], c["D"], c["R"], c["MH"]
+    M = len(dh)
+    w = [t.to(dev).contiguous() for t in c["weights"]]
+    U, V = w[0:M], w[M:2 * M]
+    Watt, batt = w[2 * M], w[2 * M + 1]
+    Wr, br = w[2 * M + 2:3 * M + 2], w[3 * M + 2:4 * M + 2]
+    Wf1, bf1, Wf2, bf2 = w[4 * M + 2:4 * M + 6]
+    d = lib.make_desc(T, N, dh, rd, MH, 4, c["rows"])
+    ws = lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
+    packed = torch.empty(lib.mab_packed_floats(d), device=dev)
+    lib.mab_pack(d, ws, packed)
+    new = lambda *s: torch.full(s, float("nan"), device=dev)
+    out = dict(hz=new(T, N, 2 * D), C=new(T, N, D), G=new(T, N, 4 * D), A=new(T, N, 4 * D), R=new(T, N, R),
+               UH=new(T, N, MH))
+    gx = c["gx"].to(dev)
+    mask = None if c["mask"] is None else c["mask"].to(dev)
+    lib.mab_fwd(d, packed, gx, mask, out["hz"], out["C"], out["G"], out["A"], out["R"], out["UH"])
+    adj = dict(dgx=new(T, N, 4 * D), de=new(T, N, 4 * D), dr=new(T, N, R), dup=new(T, N, MH), dzt=new(T, N, D))
+    lib.mab_bwd(d, ws, packed, c["dhz"].to(dev), mask, out["C"], out["G"], out["A"], out["UH"],
+                adj["dgx"], adj["de"], adj["dr"], adj["dup"], adj["dzt"])
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}, {k: v.cpu().numpy() for k, v in adj.items()}
+
+
+@pytest.mark.parametrize("kind,T,N,rows,masked", [
+    ("ATV", 5, 11, 4, False), ("ATV", 4, 3, 1, True), ("ATV", 3, 13, 8, True), ("ATV", 3, 15, 7, False),
+    ("ATV", 2, 5, 2, False), ("ATV", 2, 7, 3, True), ("ATV", 2, 11, 5, False), ("ATV", 2, 13, 6, True),
+    ("AT", 5, 11, 4, True), ("AT", 3, 17, 8, False), ("AT", 1, 1, 1, False), ("ATV", 1, 9, 8, False),
+])
+def test_kernel_boundary_vs_c_oracle(kind, T, N, rows, masked):
+    c = _boundary_case(kind, T, N, rows, masked, seed=T * 100 + N)
+    out, adj = _run_kernels(c, T, N)
+    mask64 = None if c["mask"] is None else c["mask"].double().numpy()
+    ref = ocpu.mab_forward(c["params"], c["gx"].double().numpy(), c["dh"], c["rd"], mask64)
+    errs = {k: e_inf(out[k].reshape(ref[k].shape), ref[k]) for k in out}
+    assert all(np.isfinite(v) and v < 2e-5 for v in errs.values()), errs
+    # kernel backward consumes the kernel's own stash (as in production); the oracle its own
+    radj, _ = ocpu.mab_backward(c["params"], c["dhz"].double().numpy(), ref, c["dh"], c["rd"], mask64)
+    berrs = {k: e_inf(adj[k].reshape(radj[k].shape), radj[k]) for k in adj}
+    assert all(np.isfinite(v) and v < 1e-4 for v in berrs.values()), (errs, berrs)
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_module_matches_reference_fixture(path):
+    fix = load_golden(path)
+    probs, loss, dx, grads = run_module(fix, device="cuda")
+    errs = check_against_golden(fix, probs, loss, dx, grads, tol_out=TOL_OUT, tol_grad=TOL_GRAD)
+    print(path.split("/")[-1], errs)
+
+
+@pytest.mark.parametrize("kind,N", [("ATV", 6), ("AT", 9)])
+def test_module_vs_oracle_full_length(kind, N):
+    """T = 110 (the IEMOCAP maximum): errors must not grow out of the fp32 bar over a long chain."""
+    T = 110
+    model = seeded_model(kind, 111).eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(T, N, SPEC[kind]["din"], generator=g)
+    labels = torch.randint(0, SPEC[kind]["C"], (T * N,), generator=g)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    pr = tp.mab_forward(params, xr, kind)
+    lr = masked_ce(pr, labels, T, N)
+    lr.backward()
+    cm = model.to("cuda")
+    xc = x.to("cuda").requires_grad_(True)
+    pc = cm(xc)
+    lc = masked_ce(pc, labels.to("cuda"), T, N)
+    lc.backward()
+    assert e_inf(pc.detach().cpu(), pr.detach()) <= TOL_OUT
+    assert abs(lc.item() - lr.item()) / abs(lr.item()) <= TOL_OUT
+    assert (pc.argmax(-1).cpu() == pr.argmax(-1)).all()
+    assert e_inf(xc.grad.cpu(), xr.grad) <= TOL_GRAD
+    worst = {}
+    for n, p in cm.named_parameters():
+        if params[n].grad is None:
+            assert p.grad is None, n
+            continue
+        worst[n] = e_inf(p.grad.cpu(), params[n].grad)
+    assert max(worst.values()) <= TOL_GRAD, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+def _fwd_bwd(model, x, labels, T, N):
+    model.zero_grad(set_to_none=True)
+    xx = x.clone().requires_grad_(True)
+    p = model(xx)
+    masked_ce(p, labels, T, N).backward()
+    return p.detach(), xx.grad.detach(), {n: q.grad.detach().clone() for n, q in model.named_parameters() if q.grad is not None}
+
+
+def test_properties_at_benchmark_size():
+    """T=110, N=1024 (BASELINE.json configs[1] shapes): too big for the CPU oracle in seconds, so
+    check what must hold at any size."""
+    T, N, kind = 110, 1024, "ATV"
+    model = seeded_model(kind, 111).to("cuda").eval()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(T, N, 712, device="cuda", generator=g)
+    labels = torch.randint(0, 6, (T * N,), device="cuda", generator=g)
+    p0, dx0, g0 = _fwd_bwd(model, x, labels, T, N)
+    assert torch.isfinite(p0).all() and torch.isfinite(dx0).all()
+    assert (p0.sum(-1) - 1).abs().max() < 1e-5
+    # (a) run-to-run determinism: bitwise
+    p1, dx1, g1 = _fwd_bwd(model, x, labels, T, N)
+    assert torch.equal(p0, p1) and torch.equal(dx0, dx1)
+    # (b) tile-height invariance (7 vs 8 dialogues per CTA): same arithmetic per dialogue -> bitwise
+    model.rows_per_cta = 8
+    p8, dx8, g8 = _fwd_bwd(model, x, labels, T, N)
+    model.rows_per_cta = 0
+    assert torch.equal(p0, p8) and torch.equal(dx0, dx8)
+    # (c) dialogues are independent: permuting the batch permutes the outputs
+    perm = torch.randperm(N, device="cuda", generator=g)
+    lab_p = labels.view(T, N)[:, perm].reshape(-1)
+    pp, dxp, gp = _fwd_bwd(model, x[:, perm].contiguous(), lab_p, T, N)
+    assert (pp.view(T, N, -1) - p0.view(T, N, -1)[:, perm]).abs().max() < 2e-6
+    assert e_inf(dxp.cpu(), dx0[:, perm].cpu()) < 1e-4
+    for n in g0:
+        assert e_inf(gp[n].cpu(), g0[n].cpu()) < 1e-3, n
+    # (d) inference path (no stash) == training-path forward
+    with torch.no_grad():
+        pi = model(x)
+    assert torch.equal(pi, p0)
+
+
+def test_train_mode_uses_dropout_and_is_seeded():
+    T, N = 9, 40
+    model = seeded_model("ATV", 3).to("cuda").train()
+    x = torch.randn(T, N, 712, device="cuda")
+    torch.manual_seed(1)
+    a = model(x)
+    torch.manual_seed(1)
+    b = model(x)
+    c = model(x)
+    assert torch.equal(a, b) and not torch.equal(a, c)

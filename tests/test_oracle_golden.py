@@ -1,0 +1,72 @@
+"""CPU suite, part 1: pin the oracle.
+
+* torch restatement (oracle/torch_port.py) vs the committed reference-generated fixtures
+  (tests/golden/, made by oracle/make_golden.py from the live reference);
+* the same against the live reference when /root/reference is present (build container only);
+* plain-C restatement (oracle/mab_oracle.c, fp64) of the recurrence forward and of the hand-derived
+  BPTT vs the torch restatement + autograd.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import SPEC, check_against_golden, golden_files, load_golden, port_run, seeded_model
+from oracle import cpu as ocpu
+from oracle import torch_port as tp
+from oracle.ref_shim import attach_tape, load_reference, reference_available
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_torch_port_matches_reference_fixture(path):
+    fix = load_golden(path)
+    probs, loss, dx, grads = port_run(fix)
+    errs = check_against_golden(fix, probs, loss, dx, grads, tol_out=2e-6, tol_grad=2e-5)
+    assert errs["probs"] < 2e-6
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("kind", ["ATV", "AT"])
+def test_torch_port_matches_live_reference(kind):
+    ref = load_reference()
+    cls = ref.MARN_ATV if kind == "ATV" else ref.MARN_AT
+    torch.manual_seed(7)
+    m = cls()
+    ours = seeded_model(kind, 7)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), ours.state_dict().values()))
+    x = torch.randn(8, 4, SPEC[kind]["din"])
+    tape = tp.DropoutTape(3)
+    attach_tape(m, tape)
+    m.train()
+    y = m(x)
+    y2 = tp.mab_forward({k: v.detach() for k, v in m.state_dict().items()}, x, kind, tape.rewind())
+    assert (y - y2).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("kind", ["ATV", "AT"])
+def test_c_oracle_matches_torch_port_and_autograd(kind):
+    torch.set_default_dtype(torch.float64)
+    try:
+        model = seeded_model(kind, 5).double()
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        T, N = 6, 3
+        dh, rd = SPEC[kind]["dh"], SPEC[kind]["rd"]
+        x = torch.randn(T, N, SPEC[kind]["din"])
+        tape = tp.DropoutTape(1)
+        _, hz0, xs = tp.mab_forward(p, x, kind, tape, return_state=True)
+        gx = tp.mab_gate_inputs(p, xs, kind).detach().requires_grad_(True)
+        hz = tp.mab_recurrence(p, gx, kind, tape.rewind())
+        assert (hz - hz0).abs().max() < 1e-12          # hoisted W.x == per-step form
+        mask = tape.stacked("fc.2").numpy()
+        pn = {k: v.detach().numpy() for k, v in p.items()}
+        f = ocpu.mab_forward(pn, gx.detach().numpy(), dh, rd, mask)
+        assert np.abs(f["hz"] - hz.detach().numpy()).max() < 1e-12
+        g = torch.randn_like(hz)
+        names = [k for k in p if k.split(".")[0] in ("att", "fc") or k.startswith("reduce")
+                 or k.endswith(".U.weight") or k.endswith(".V.weight")]
+        gr = torch.autograd.grad((hz * g).sum(), [gx] + [p[k] for k in names])
+        adj, grads = ocpu.mab_backward(pn, g.numpy(), f, dh, rd, mask)
+        assert np.abs(adj["dgx"] - gr[0].numpy()).max() < 1e-12
+        for k, gg in zip(names, gr[1:]):
+            assert np.abs(grads[k] - gg.numpy()).max() < 1e-11, k
+    finally:
+        torch.set_default_dtype(torch.float32)
