@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — utterances/sec of one fwd+bwd of the drop-in HybridRNN_ATV module (BASELINE.json
+configs[1]: audio+text+visual, cross-modal attention + fusion, fp32, 1xB200; configs[4] at N>1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  # our arm (CUDA, C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]           # reference CPU arm (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = zero grads -> forward -> MaskedLoss(CrossEntropy) -> backward (-> gradient allreduce
+complete on every rank when N>1) on one synthetic IEMOCAP-shaped batch x[110, 1024, 712] per GPU
+(weak scaling), train mode.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "utterances/sec fwd+bwd HybridRNN_ATV"
+UNIT = "utterances/s"
+T_LEN, BATCH, D_IN, N_CLS = 110, 1024, 712, 6
+# algorithmic FLOPs per utterance of the serial chain: fwd 999,936; the BPTT adjoint
+# chain is the five transposed products of the same weights = the same count.
+FLOP_FWD_PER_UTT = 999_936
+FLOP_BWD_PER_UTT = 999_936
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ts, line in self.rows:
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_batch(seed, T, B, device=None, pinned=False):
+    """Seeded IEMOCAP-shaped batch (uniform set: every dialogue L = 110)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(T, B, D_IN, generator=g)
+    p = torch.tensor([144, 245, 384, 170, 299, 381], dtype=torch.float32) / 1623.0
+    labels = torch.multinomial(p, T * B, replacement=True, generator=g)
+    umask = torch.ones(B, T)
+    if pinned:
+        x, labels, umask = x.pin_memory(), labels.pin_memory(), umask.pin_memory()
+    if device is not None:
+        x, labels, umask = x.to(device), labels.to(device), umask.to(device)
+    return x, labels, umask
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's torch restatement of the reference, on host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(B, T=T_LEN, seed=111):
+    from oracle import torch_port as tp
+    import lsthm_b200
+    torch.manual_seed(seed)
+    model = lsthm_b200.HybridRNN_ATV.MARN()          # parameter container only (default init, seed 111)
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    x, labels, umask = synthetic_batch(seed, T, B)
+    tape_seed = [0]
+
+    def step():
+        for p in params.values():
+            p.grad = None
+        tape = tp.DropoutTape(tape_seed[0]); tape_seed[0] += 1      # train mode: fresh dropout masks each step
+        probs = tp.mab_forward(params, x, "ATV", tape)
+        loss = tp.masked_loss(probs, labels, umask, "ce")
+        loss.backward()
+        return float(loss.detach())
+    return step, T * B
+
+
+def best_threads(step, candidates):
+    best = None
+    for n in candidates:
+        torch.set_num_threads(n)
+        step()
+        t = time.perf_counter(); step(); dt = time.perf_counter() - t
+        if best is None or dt < best[1]:
+            best = (n, dt)
+    torch.set_num_threads(best[0])
+    return best[0]
+
+
+def run_cpu_baseline(steps=2, B=32):
+    ncpu = os.cpu_count() or 1
+    step, utt = cpu_step_fn(B)
+    cands = sorted({1, min(4, ncpu), min(8, ncpu), ncpu})
+    n = best_threads(step, cands)
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter(); step(); ts.append(time.perf_counter() - t)
+    return {"value": utt / min(ts), "unit": UNIT, "cores": n, "kind": "port",
+            "sample": f"oracle/torch_port.py (torch restatement of the reference) fwd+bwd, train mode, x[{T_LEN},{B},{D_IN}] "
+                      f"fp32, best of {steps} after thread sweep {cands} on {ncpu} host cpus"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 32
+    ncpu = os.cpu_count() or 1
+    step, utt = cpu_step_fn(B)
+    cands = sorted({1, min(4, ncpu), min(8, ncpu), min(16, ncpu), ncpu})
+    n = best_threads(step, cands)
+    for _ in range(max(0, args.warmup - len(cands))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = utt * args.steps / dt
+    sample = (f"reference algorithm via oracle/torch_port.py (the Python reference cannot travel to the GPU box), train mode, "
+              f"x[{T_LEN},{B},{D_IN}] fp32 per step, {n} torch threads (best of sweep {cands}; {ncpu} host cpus)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"HybridRNN_ATV fwd+bwd, T={T_LEN}, sample batch {B} dialogues on host CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": n, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import lsthm_b200
+    from importlib import import_module
+    rec = import_module(lsthm_b200.__name__ + ".recurrence")
+    ddp = import_module(lsthm_b200.__name__ + ".ddp")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, B = args.seq, args.batch
+    torch.manual_seed(111)
+    model = lsthm_b200.HybridRNN_ATV.MARN().to(dev).train()
+    loss_fn = lsthm_b200.MaskedLoss(torch.nn.CrossEntropyLoss)
+    reducer = ddp.GradAllReducer(model, world) if world > 1 else None
+    # two host batches (pinned) so consecutive steps see different data; device-resident copies for `value`
+    host = [synthetic_batch(111 + 7 * rank + i, T, B, pinned=True) for i in range(2)]
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    utt_per_step = T * B * world
+
+    def step_resident(i):
+        x, labels, umask = resident[i & 1]
+        if reducer is not None:
+            reducer.zero_grad()
+        else:
+            model.zero_grad(set_to_none=True)
+        probs = model(x)
+        loss = loss_fn(probs, labels, umask)
+        if reducer is not None:
+            loss = loss * (1.0 / world)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value) with per-kernel CUDA events on the launching stream ----
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start(); time.sleep(0.25)
+    rec.kernel_events = {"fwd": [], "bwd": []}
+    for k in rec.launch_counter:
+        rec.launch_counter[k] = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sum(rec.launch_counter.values()) * world
+    kev, rec.kernel_events = rec.kernel_events, None
+    kms = {k: (sum(a.elapsed_time(b) for a, b in v) / max(1, len(v))) for k, v in kev.items()}
+    clocks = sampler.stop(wall0, wall1) if sampler else None
+    value = utt_per_step * args.steps / (ms * 1e-3)
+
+    e2e_val = e2e_ms = None
+    h2d = d2h = 0
+    if not args.no_e2e:
+        # ---- end to end through the public module API: pinned host inputs -> H2D -> step -> loss D2H ----
+        copy_stream = torch.cuda.Stream(device=dev)
+        dbuf = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i & 1])
+                for dst, src in zip(dbuf[i & 1], host[i & 1]):
+                    dst.copy_(src, non_blocking=True)
+                ready[i & 1].record(copy_stream)
+
+        def step_e2e(i, last):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[i & 1])
+            if not last:
+                prefetch(i + 1)               # next step's H2D overlaps this step's compute
+            x, labels, umask = dbuf[i & 1]
+            if reducer is not None:
+                reducer.zero_grad()
+            else:
+                model.zero_grad(set_to_none=True)
+            loss = loss_fn(model(x), labels, umask)
+            if reducer is not None:
+                loss = loss * (1.0 / world)
+            loss.backward()
+            if reducer is not None:
+                reducer.finish()
+            freed[i & 1].record(cur)
+            return loss.item()                # D2H read of the step's result (also syncs the step)
+
+        for ev in freed:
+            ev.record(torch.cuda.current_stream())
+        n_e2e_warm = max(2, min(args.warmup, 3))
+        prefetch(0)
+        for i in range(n_e2e_warm):
+            step_e2e(i, False)
+        barrier()
+        t0 = time.perf_counter()
+        base = n_e2e_warm
+        for i in range(args.steps):
+            step_e2e(base + i, i == args.steps - 1)
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e_val = utt_per_step * args.steps / (e2e_ms * 1e-3)
+        h2d = sum(t.numel() * t.element_size() for t in host[0]) * world
+        d2h = 4 * world
+
+    if rank == 0:
+        pk = peaks()
+        dom = "bwd" if kms["bwd"] >= kms["fwd"] else "fwd"
+        flop = (FLOP_BWD_PER_UTT if dom == "bwd" else FLOP_FWD_PER_UTT) * T * B
+        achieved = flop / (kms[dom] * 1e-3) / 1e12 if kms[dom] > 0 else 0.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
+        ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"mab_{dom}_kernel", {}).get("dram_bytes_per_launch")
+        info = import_module(lsthm_b200.__name__ + "._lib").mab_launch_info(
+            import_module(lsthm_b200.__name__ + "._lib").make_desc(T, B, (128, 16, 64), (16, 128, 100)))
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"HybridRNN_ATV MARN fwd+bwd (train mode), x[{T},{B},{D_IN}] fp32 per GPU, uniform L={T}, "
+                                   f"MaskedLoss(CrossEntropy); inputs {T * B * D_IN * 4 / 1e6:.0f} MB per step > 126 MB L2, "
+                                   f"two alternating batches", "per_gpu_batch": B, "seq_len": T,
+                       "parallelism": f"dp{world}", "grid": info["grid"], "block": info["block"], "rows_per_cta": info["rows"]},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": (e2e_ms / args.steps) if e2e_ms else None},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": f"mab_{dom}_kernel", "achieved": achieved,
+                         "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                         "traffic": traffic, "peak_source": pk["source"] + " bf16 cuBLAS sustained",
+                         "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
+                         "share_of_step": {k: v / (ms / args.steps) for k, v in kms.items()},
+                         "fp32_ffma": {"achieved": achieved, "peak": ffma_peak, "frac": achieved / ffma_peak,
+                                       "note": f"kernel is fp32 FFMA; peak = 148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock under load)"},
+                         "hbm": {"algorithmic_gbs": None}},
+        }
+        # algorithmic HBM bytes of the dominant kernel: per utterance, fp32
+        D, G, R, MH = 208, 832, 244, 64
+        by = {"fwd": 4 * (G + 2 * D + D + G + G + R + MH + MH), "bwd": 4 * (2 * D + D + D + G + G + MH + MH + G + G + R + MH + D)}
+        out["roofline"]["hbm"] = {"algorithmic_bytes_per_utt": by[dom],
+                                  "achieved_gbs": by[dom] * T * B / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0,
+                                  "peak_gbs": pk["hbm_gbs"]}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = run_cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="dialogues per GPU")
+    ap.add_argument("--seq", type=int, default=T_LEN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

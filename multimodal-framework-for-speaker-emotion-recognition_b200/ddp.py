@@ -1,0 +1,109 @@
+"""Data-parallel gradient exchange for the drop-in modules: one process per GPU, dialogues sharded
+across ranks, ONE summed gradient allreduce per step issued bucket by bucket while the backward is
+still running.
+
+The reference has no distributed code at all (its ``import torch.distributed`` at train.py:12 is
+dead); this is the hookup the north star asks for.  Design:
+  * gradients live in a few flat fp32 buckets (``p.grad`` are views), ordered by the order in which
+    autograd finishes them: head -> recurrence weights -> input projections -> encoders;
+  * a post-accumulate-grad hook per parameter counts a bucket down; when it reaches zero the
+    bucket's ``all_reduce(SUM)`` is enqueued asynchronously (NCCL stream) so it overlaps the rest of
+    the backward; ``finish()`` waits for all buckets;
+  * parameters the model never uses (e.g. ``encoder_*.pos_ffn.fc``) are left out, so
+    their ``.grad`` stays ``None`` exactly as in the single-process reference step (Adam with weight
+    decay would otherwise move them);
+  * loss scaling is the caller's: scale the shard loss by n_shard/n_global and SUM-reduce to equal
+    the single-process step on the concatenated batch (loss.py:21 divides by the batch's utterances).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def unused_parameter_names(model: torch.nn.Module) -> List[str]:
+    """Names of registered-but-never-applied parameters of the drop-in modules."""
+    return [n for n, _ in model.named_parameters() if ".pos_ffn.fc." in n]
+
+
+class GradAllReducer:
+    def __init__(self, model: torch.nn.Module, world_size: int, bucket_bytes: int = 4 << 20,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.world, self.group = world_size, group
+        skip = set(unused_parameter_names(model))
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in skip]
+        # autograd finishes gradients roughly in reverse registration order of use: walk the
+        # parameters backwards so bucket 0 fills first.
+        named = named[::-1]
+        self.buckets: List[torch.Tensor] = []
+        self._members: List[List[torch.nn.Parameter]] = []
+        self._bucket_of: Dict[int, int] = {}
+        cur, cur_bytes = [], 0
+        for n, p in named:
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self._add_bucket(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self._add_bucket(cur)
+        self._pending = [0] * len(self.buckets)
+        self._handles: List = []
+        for b, members in enumerate(self._members):
+            for p in members:
+                p.register_post_accumulate_grad_hook(self._make_hook(b))
+        self.zero_grad()
+
+    def _add_bucket(self, params):
+        total = sum(p.numel() for p in params)
+        flat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
+        o = 0
+        for p in params:
+            p.grad = flat[o:o + p.numel()].view_as(p)
+            self._bucket_of[id(p)] = len(self.buckets)
+            o += p.numel()
+        self.buckets.append(flat)
+        self._members.append(list(params))
+
+    def _make_hook(self, b):
+        def hook(_param):
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and self.world > 1:
+                self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
+                                                     async_op=True))
+        return hook
+
+    def zero_grad(self):
+        """Zero the flat buckets (p.grad stay views of them) and re-arm the per-bucket counters."""
+        for flat in self.buckets:
+            flat.zero_()
+        for b, members in enumerate(self._members):
+            self._pending[b] = len(members)
+            for p in members:
+                if p.grad is None or p.grad.data_ptr() != self._view_ptr(p):
+                    self._rebind(p)
+        self._handles = []
+
+    def _view_ptr(self, p):
+        return p.grad.data_ptr() if p.grad is not None else -1
+
+    def _rebind(self, p):
+        b = self._bucket_of[id(p)]
+        o = 0
+        for q in self._members[b]:
+            if q is p:
+                p.grad = self.buckets[b][o:o + p.numel()].view_as(p)
+                return
+            o += q.numel()
+
+    def finish(self):
+        """Block the current stream until every bucket's allreduce is complete."""
+        for b, n in enumerate(self._pending):
+            if n != 0 and self.world > 1:       # a bucket whose hooks did not all fire (should not happen)
+                self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
+                                                     async_op=True))
+        for h in self._handles:
+            h.wait()
+        self._handles = []

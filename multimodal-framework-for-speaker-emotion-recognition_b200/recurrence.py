@@ -18,6 +18,19 @@ from . import _lib
 
 # Counts launches of OUR kernels (pack/fwd/bwd), for bench.py's `gpu_launches`.
 launch_counter = {"pack": 0, "fwd": 0, "bwd": 0}
+# bench.py sets this to {"fwd": [], "bwd": []} to collect (start, end) CUDA events recorded on the
+# launching stream around each recurrence kernel; None = no events (the default).
+kernel_events = None
+
+
+def _timed(kind, fn, *args):
+    if kernel_events is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(*args)
+    e1.record()
+    kernel_events[kind].append((e0, e1))
 
 
 class MabRecurrenceFn(torch.autograd.Function):
@@ -55,7 +68,7 @@ class MabRecurrenceFn(torch.autograd.Function):
             sC, sG, sA, sR, sU = new(T, N, D), new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h)
         else:
             sC = sG = sA = sR = sU = None
-        _lib.mab_fwd(desc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU)
+        _timed("fwd", _lib.mab_fwd, desc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU)
         launch_counter["fwd"] += 1
         if need_grad:
             ctx.save_for_backward(packed, hz, sC, sG, sA, sR, sU, *weights)
@@ -78,7 +91,8 @@ class MabRecurrenceFn(torch.autograd.Function):
         wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
         new = lambda *s: torch.empty(*s, device=hz.device, dtype=torch.float32)
         dgx, de, dr, dup, dzt = new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h), new(T, N, D)
-        _lib.mab_bwd(desc, wstruct, packed, dhz.contiguous(), ctx.drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt)
+        _timed("bwd", _lib.mab_bwd, desc, wstruct, packed, dhz.contiguous(), ctx.drop_mask, sC, sG, sA, sU,
+               dgx, de, dr, dup, dzt)
         launch_counter["bwd"] += 1
 
         # ---- time-parallel weight-gradient products (fp32; allow_tf32 stays off) ----

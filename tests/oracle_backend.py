@@ -76,3 +76,12 @@ def install(monkeypatch):
 
     monkeypatch.setattr(net, "mab_recurrence", cpu_recurrence)
     return be
+
+
+def install_plain():
+    """Same as install() but without pytest's monkeypatch (for spawned worker processes)."""
+    class _MP:
+        @staticmethod
+        def setattr(obj, name, value):
+            setattr(obj, name, value)
+    return install(_MP)
