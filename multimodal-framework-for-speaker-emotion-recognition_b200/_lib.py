@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "liblsthm_b200.so")
+# LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
+SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
 ABI_VERSION = 1
 MAX_MOD = 3
 

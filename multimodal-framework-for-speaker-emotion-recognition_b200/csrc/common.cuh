@@ -74,57 +74,163 @@ __device__ __forceinline__ float tanhf_(float x) {
 // dialogue rows of the CTA's tile.  Weights are streamed from L2 as float4 (k-major image, row k
 // = 4 adjacent columns), activations are broadcast from shared memory in k-major [k][MTP].
 //   acc[c][m] += W[k][col4 + c] * act[k][m]      k = 0 .. n-1
+// Rows are held as pairs so the inner product runs on the packed fp32x2 FMA of sm_100
+// (SASS FFMA2 with a scalar-broadcast weight operand): half the issue slots of scalar FFMA.
+// The weight loads of the next 4 k-rows are issued before the current 4 are consumed
+// (explicit double buffering) so one L2 round trip is always in flight per thread.
 // ---------------------------------------------------------------------------------------------
-template <int MT, int MTP>
-__device__ __forceinline__ void fma_row(float (&acc)[4][MT], const float4 w, const float *__restrict__ a) {
-    float av[MTP];
-#pragma unroll
-    for (int i = 0; i < MTP / 4; ++i) {
-        const float4 t = reinterpret_cast<const float4 *>(a)[i];
-        av[4 * i + 0] = t.x; av[4 * i + 1] = t.y; av[4 * i + 2] = t.z; av[4 * i + 3] = t.w;
-    }
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-        acc[0][m] = fmaf(w.x, av[m], acc[0][m]);
-        acc[1][m] = fmaf(w.y, av[m], acc[1][m]);
-        acc[2][m] = fmaf(w.z, av[m], acc[2][m]);
-        acc[3][m] = fmaf(w.w, av[m], acc[3][m]);
-    }
-}
-
-template <int MT, int MTP>
-__device__ __forceinline__ void mac(float (&acc)[4][MT], const float4 *__restrict__ w, const int ldw4,
-                                    const float *__restrict__ act, const int n) {
-    int k = 0;
-    for (; k + 4 <= n; k += 4) {
-        const float4 w0 = __ldg(w + (size_t)(k + 0) * ldw4);
-        const float4 w1 = __ldg(w + (size_t)(k + 1) * ldw4);
-        const float4 w2 = __ldg(w + (size_t)(k + 2) * ldw4);
-        const float4 w3 = __ldg(w + (size_t)(k + 3) * ldw4);
-        fma_row<MT, MTP>(acc, w0, act + (k + 0) * MTP);
-        fma_row<MT, MTP>(acc, w1, act + (k + 1) * MTP);
-        fma_row<MT, MTP>(acc, w2, act + (k + 2) * MTP);
-        fma_row<MT, MTP>(acc, w3, act + (k + 3) * MTP);
-    }
-    for (; k < n; ++k) fma_row<MT, MTP>(acc, __ldg(w + (size_t)k * ldw4), act + k * MTP);
-}
-
 template <int MT>
-__device__ __forceinline__ void zero_acc(float (&acc)[4][MT]) {
+struct Acc {
+    static constexpr int NP = (MT + 1) / 2;
+    float2 v[4][NP];
+    __device__ __forceinline__ float get(int c, int m) const { return (m & 1) ? v[c][m >> 1].y : v[c][m >> 1].x; }
+    __device__ __forceinline__ void zero() {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int m = 0; m < MT; ++m) acc[c][m] = 0.f;
+            for (int p = 0; p < NP; ++p) v[c][p] = make_float2(0.f, 0.f);
+    }
+};
+
+template <int MT, int MTP>
+__device__ __forceinline__ void fma_row(Acc<MT> &acc, const float4 w, const float *__restrict__ a) {
+    constexpr int NP = Acc<MT>::NP;
+    float2 av[MTP / 2];
+#pragma unroll
+    for (int i = 0; i < (NP + 1) / 2; ++i) {
+        const float4 t = reinterpret_cast<const float4 *>(a)[i];
+        av[2 * i] = make_float2(t.x, t.y);
+        av[2 * i + 1] = make_float2(t.z, t.w);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        acc.v[0][p] = __ffma2_rn(make_float2(w.x, w.x), av[p], acc.v[0][p]);
+        acc.v[1][p] = __ffma2_rn(make_float2(w.y, w.y), av[p], acc.v[1][p]);
+        acc.v[2][p] = __ffma2_rn(make_float2(w.z, w.z), av[p], acc.v[2][p]);
+        acc.v[3][p] = __ffma2_rn(make_float2(w.w, w.w), av[p], acc.v[3][p]);
+    }
 }
+
+#ifndef LSTHM_MAC_VARIANT
+#define LSTHM_MAC_VARIANT 8
+#endif
+
+#if LSTHM_MAC_VARIANT == 1
+// double-buffered blocks of 4 k-rows (8 weight quads live): deepest prefetch, highest register use
+template <int MT, int MTP>
+__device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, const int ldw4,
+                                    const float *__restrict__ act, const int n) {
+    const int n4 = n & ~3;
+    const size_t ld = (size_t)ldw4;
+    const float4 *p = w;
+    float4 a0, a1, a2, a3, b0, b1, b2, b3;
+    if (n4 > 0) {
+        a0 = __ldg(p); a1 = __ldg(p + ld); a2 = __ldg(p + 2 * ld); a3 = __ldg(p + 3 * ld);
+    }
+    int k = 0;
+#pragma unroll 1
+    for (; k + 8 <= n4; k += 8) {
+        const float4 *pb = p + 4 * ld;
+        b0 = __ldg(pb); b1 = __ldg(pb + ld); b2 = __ldg(pb + 2 * ld); b3 = __ldg(pb + 3 * ld);
+        fma_row<MT, MTP>(acc, a0, act);
+        fma_row<MT, MTP>(acc, a1, act + MTP);
+        fma_row<MT, MTP>(acc, a2, act + 2 * MTP);
+        fma_row<MT, MTP>(acc, a3, act + 3 * MTP);
+        // next block of 4 (clamped to a valid address on the last trip: the reload is never used)
+        const float4 *pa = (k + 8 < n4) ? p + 8 * ld : p;
+        a0 = __ldg(pa); a1 = __ldg(pa + ld); a2 = __ldg(pa + 2 * ld); a3 = __ldg(pa + 3 * ld);
+        fma_row<MT, MTP>(acc, b0, act + 4 * MTP);
+        fma_row<MT, MTP>(acc, b1, act + 5 * MTP);
+        fma_row<MT, MTP>(acc, b2, act + 6 * MTP);
+        fma_row<MT, MTP>(acc, b3, act + 7 * MTP);
+        p += 8 * ld;
+        act += 8 * MTP;
+    }
+    if (k < n4) {   // one remaining block of 4, already in a0..a3
+        fma_row<MT, MTP>(acc, a0, act);
+        fma_row<MT, MTP>(acc, a1, act + MTP);
+        fma_row<MT, MTP>(acc, a2, act + 2 * MTP);
+        fma_row<MT, MTP>(acc, a3, act + 3 * MTP);
+        k += 4;
+        p += 4 * ld;
+        act += 4 * MTP;
+    }
+    for (; k < n; ++k) {
+        fma_row<MT, MTP>(acc, __ldg(p), act);
+        p += ld;
+        act += MTP;
+    }
+}
+#elif LSTHM_MAC_VARIANT == 2
+// double-buffered blocks of 2 k-rows (4 weight quads live)
+template <int MT, int MTP>
+__device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, const int ldw4,
+                                    const float *__restrict__ act, const int n) {
+    const int n2 = n & ~1;
+    const size_t ld = (size_t)ldw4;
+    const float4 *p = w;
+    float4 a0, a1, b0, b1;
+    if (n2 > 0) {
+        a0 = __ldg(p); a1 = __ldg(p + ld);
+    }
+    int k = 0;
+#pragma unroll 1
+    for (; k + 4 <= n2; k += 4) {
+        const float4 *pb = p + 2 * ld;
+        b0 = __ldg(pb); b1 = __ldg(pb + ld);
+        fma_row<MT, MTP>(acc, a0, act);
+        fma_row<MT, MTP>(acc, a1, act + MTP);
+        const float4 *pa = (k + 4 < n2) ? p + 4 * ld : p;
+        a0 = __ldg(pa); a1 = __ldg(pa + ld);
+        fma_row<MT, MTP>(acc, b0, act + 2 * MTP);
+        fma_row<MT, MTP>(acc, b1, act + 3 * MTP);
+        p += 4 * ld;
+        act += 4 * MTP;
+    }
+    if (k < n2) {
+        fma_row<MT, MTP>(acc, a0, act);
+        fma_row<MT, MTP>(acc, a1, act + MTP);
+        k += 2;
+        p += 2 * ld;
+        act += 2 * MTP;
+    }
+    if (k < n) fma_row<MT, MTP>(acc, __ldg(p), act);
+}
+#else
+// single-buffered blocks of LSTHM_MAC_VARIANT (4 or 8) k-rows: all loads of a block first, then the FMAs
+template <int MT, int MTP>
+__device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, const int ldw4,
+                                    const float *__restrict__ act, const int n) {
+    constexpr int KB = LSTHM_MAC_VARIANT;
+    const size_t ld = (size_t)ldw4;
+    const float4 *p = w;
+    int k = 0;
+#pragma unroll 1
+    for (; k + KB <= n; k += KB) {
+        float4 wv[KB];
+#pragma unroll
+        for (int u = 0; u < KB; ++u) wv[u] = __ldg(p + u * ld);
+#pragma unroll
+        for (int u = 0; u < KB; ++u) fma_row<MT, MTP>(acc, wv[u], act + u * MTP);
+        p += KB * ld;
+        act += KB * MTP;
+    }
+    for (; k < n; ++k) {
+        fma_row<MT, MTP>(acc, __ldg(p), act);
+        p += ld;
+        act += MTP;
+    }
+}
+#endif
 
 // Split-K partial sums: part[(split*MTP + m)*J + col]; a thread stores its 4 columns as one float4.
 template <int MT, int MTP>
 __device__ __forceinline__ void store_partial(float *part, const int J, const int split, const int col4,
-                                              const float (&acc)[4][MT]) {
+                                              const Acc<MT> &acc) {
 #pragma unroll
     for (int m = 0; m < MT; ++m)
         *reinterpret_cast<float4 *>(part + (size_t)(split * MTP + m) * J + col4) =
-            make_float4(acc[0][m], acc[1][m], acc[2][m], acc[3][m]);
+            make_float4(acc.get(0, m), acc.get(1, m), acc.get(2, m), acc.get(3, m));
 }
 
 // k-major [k][MTP] vector of one unit: load / store all rows at once (conflict-free 16B accesses).

@@ -48,7 +48,7 @@ static int build_layout(const lsthm_mab_desc *d, MabLayout &L) {
     }
     L.D = D; L.G = 4 * D; L.R = R;
     L.nt = rup(2 * D, 32);
-    if (L.nt > kMaxThreads) return fail("sum of cell sizes too large for one CTA (2*D > 512)");
+    if (L.nt > kMaxThreads) return fail("sum of cell sizes too large for one CTA (2*D > 448)");
     if (R > L.nt || L.MH > L.nt || L.nt < 64) return fail("unsupported dims (R or map_h exceed the CTA width)");
     L.nwarp = L.nt / 32;
     L.ldr = L.G + ((4 - L.G % 32) + 32) % 32;
@@ -106,13 +106,15 @@ static void fwd_smem(const MabLayout &L, int MT, FwdSmem &S) {
     S.u = o; o += L.MH * MTP;
     S.red = o; o += L.nwarp * kHeads * MTP * 2;
     S.fin = o; o += kHeads * MTP * 2;
-    int part = L.G * MTP, p3 = 0;
+    int part = std::max(L.G * MTP, MTP * L.ldr), p3 = 0;
     for (int m = 0; m < L.nm; ++m) { S.s3pb[m] = p3; p3 += L.s3ns[m] * MTP * L.rd[m]; }
     part = std::max(part, p3);
     part = std::max(part, L.s4ns * MTP * L.MH);
     part = std::max(part, L.s5ns * MTP * L.D);
     S.part = o; o += part;
     S.gx = o; o += 2 * MT * L.G;
+    S.mask = o; o += 2 * MT * L.MH;
+    S.batt = o; o += L.G;
     S.total = o;
 }
 

@@ -24,7 +24,10 @@
 namespace lsthm {
 
 constexpr int kHeads = 4;
-constexpr int kMaxThreads = 512;
+#ifndef LSTHM_MAXT
+#define LSTHM_MAXT 448
+#endif
+constexpr int kMaxThreads = LSTHM_MAXT;  // 13-14 warps: leaves up to 144 registers per thread
 
 struct MabLayout {
     int T, N, nm, MH, D, G, R;
@@ -43,7 +46,7 @@ struct MabLayout {
 };
 
 struct FwdSmem {  // float offsets
-    int h, z, c, km, row, r, u, red, fin, part, gx, total;
+    int h, z, c, km, row, r, u, red, fin, part, gx, mask, batt, total;
     int s3pb[kMaxMod];
 };
 struct BwdSmem {
@@ -98,8 +101,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
     float *s_h = smem + a.S.h, *s_z = smem + a.S.z, *s_c = smem + a.S.c, *s_km = smem + a.S.km;
     float *s_row = smem + a.S.row, *s_r = smem + a.S.r, *s_u = smem + a.S.u, *s_red = smem + a.S.red;
     float *s_fin = smem + a.S.fin, *s_part = smem + a.S.part, *s_gx = smem + a.S.gx;
+    float *s_mask = smem + a.S.mask, *s_batt = smem + a.S.batt;
     const float *__restrict__ packed = a.packed;
     const bool stash = a.sC != nullptr;
+    const bool masked = a.mask != nullptr;
 
     for (int i = 8 + tid; i < a.S.total; i += nt) smem[i] = 0.f;
     if (tid == 0) {
@@ -108,11 +113,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
         mbar_fence_init();
     }
     __syncthreads();
-    const uint32_t tile_bytes = (uint32_t)rows * G * sizeof(float);
+    for (int i = tid; i < G; i += nt) s_batt[i] = __ldg(packed + L.batt + i);
+    // per-step tile = this CTA's rows of gx[t] (and of the dropout mask): contiguous in global memory
+    const uint32_t gx_bytes = (uint32_t)rows * G * sizeof(float);
+    const uint32_t mask_bytes = masked ? (uint32_t)rows * MH * sizeof(float) : 0u;
     if (tid == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, tile_bytes);
-        bulk_g2s(s_gx, a.gx + (size_t)n0 * G, tile_bytes, bar);
+        mbar_expect_tx(bar, gx_bytes + mask_bytes);
+        bulk_g2s(s_gx, a.gx + (size_t)n0 * G, gx_bytes, bar);
+        if (masked) bulk_g2s(s_mask, a.mask + (size_t)n0 * MH, mask_bytes, bar);
     }
 
     // step-invariant role of this thread in the gate stage: (hidden unit j, K-half)
@@ -132,13 +141,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
         const int buf = t & 1;
         const size_t tn0 = (size_t)t * N + n0;
         if (tid == 0 && t + 1 < T) {
-            mbar_expect_tx(bar + (buf ^ 1), tile_bytes);
-            bulk_g2s(s_gx + (buf ^ 1) * MT * G, a.gx + (tn0 + N) * G, tile_bytes, bar + (buf ^ 1));
+            mbar_expect_tx(bar + (buf ^ 1), gx_bytes + mask_bytes);
+            bulk_g2s(s_gx + (buf ^ 1) * MT * G, a.gx + (tn0 + N) * G, gx_bytes, bar + (buf ^ 1));
+            if (masked) bulk_g2s(s_mask + (buf ^ 1) * MT * MH, a.mask + (tn0 + N) * MH, mask_bytes, bar + (buf ^ 1));
         }
-        float acc[4][MT];
+        Acc<MT> acc;
         // ---- S1: gate pre-activations  U_m h_{t-1} + V_m z_{t-1}  (+ gx), then the LSTHM cell update
         if (s1_on) {
-            zero_acc<MT>(acc);
+            acc.zero();
             const float4 *wp = reinterpret_cast<const float4 *>(packed + L.wg[m1]) + s1_jl;
             const int e1 = min(s1_k1, s1_dh);
             if (s1_k0 < e1)
@@ -157,10 +167,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             for (int m = 0; m < MT; ++m) {
                 const float4 pp = *reinterpret_cast<const float4 *>(s_part + m * G + s1_goff + 4 * s1_jl);
                 const float *gr = gxs + m * G;
-                const float f = sigmoidf_(acc[0][m] + pp.x + gr[0]);
-                const float ig = sigmoidf_(acc[1][m] + pp.y + gr[s1_dh]);
-                const float og = sigmoidf_(acc[2][m] + pp.z + gr[2 * s1_dh]);
-                const float gg = tanhf_(acc[3][m] + pp.w + gr[3 * s1_dh]);
+                const float f = sigmoidf_(acc.get(0, m) + pp.x + gr[0]);
+                const float ig = sigmoidf_(acc.get(1, m) + pp.y + gr[s1_dh]);
+                const float og = sigmoidf_(acc.get(2, m) + pp.z + gr[2 * s1_dh]);
+                const float gg = tanhf_(acc.get(3, m) + pp.w + gr[3 * s1_dh]);
                 const float c = f * cp[m] + ig * gg;
                 const float h = tanhf_(c) * og;
                 cn[m] = c;
@@ -180,33 +190,32 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             store_rows<MTP>(s_h + s1_j * MTP, hn);
         }
         __syncthreads();
-        // ---- S2: attention logits e = Watt c + b  (4 heads x D), K split in two halves
+        // ---- S2: attention logits e = Watt c + b  (4 heads x D), K split in two halves; each half
+        //      leaves its partial in a padded row layout [m][ldr] (half 0 -> s_row, half 1 -> s_part)
         if (tid < 2 * nq2) {
             const int quad = tid % nq2, half = tid / nq2, kh = D / 2;
-            zero_acc<MT>(acc);
+            acc.zero();
             mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.watt) + (size_t)(half * kh) * nq2 + quad, nq2,
                          s_c + half * kh * MTP, kh);
-            if (half == 1) store_partial<MT, MTP>(s_part, G, 0, 4 * quad, acc);
-        }
-        __syncthreads();
-        if (tid < nq2) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(packed + L.batt) + tid);
+            float *dst = (half ? s_part : s_row) + 4 * quad;
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                const float4 pp = *reinterpret_cast<const float4 *>(s_part + m * G + 4 * tid);
-                *reinterpret_cast<float4 *>(s_row + m * L.ldr + 4 * tid) =
-                    make_float4(acc[0][m] + pp.x + b.x, acc[1][m] + pp.y + b.y, acc[2][m] + pp.z + b.z,
-                                acc[3][m] + pp.w + b.w);
-            }
+            for (int m = 0; m < MT; ++m)
+                *reinterpret_cast<float4 *>(dst + m * L.ldr) =
+                    make_float4(acc.get(0, m), acc.get(1, m), acc.get(2, m), acc.get(3, m));
         }
         __syncthreads();
-        // ---- softmax over the D features per (head, dialogue): per-warp partial (max,sum) ...
+        // ---- softmax over the D features per (head, dialogue): e = p0 + p1 + b, per-warp partial (max,sum) ...
 #pragma unroll
         for (int k = 0; k < kHeads; ++k) {
             float mx = -INFINITY, sm = 0.f;
             if (mvalid) {
-                const float *e = s_row + mm * L.ldr + k * D;
-                for (int j = jb + jj; j < je; j += JL) mx = fmaxf(mx, e[j]);
+                float *e = s_row + mm * L.ldr + k * D;
+                const float *e1 = s_part + mm * L.ldr + k * D, *bb = s_batt + k * D;
+                for (int j = jb + jj; j < je; j += JL) {
+                    const float x = e[j] + e1[j] + bb[j];
+                    e[j] = x;
+                    mx = fmaxf(mx, x);
+                }
                 for (int j = jb + jj; j < je; j += JL) sm += __expf(e[j] - mx);
             }
 #pragma unroll
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             while (local >= L.s3items[m]) { local -= L.s3items[m]; ++m; }
             const int nq = L.rd[m] / 4, quad = local % nq, sp = local / nq;
             const int krow = sp * L.s3chunk[m], head = krow / L.dh[m], js = krow - head * L.dh[m];
-            zero_acc<MT>(acc);
+            acc.zero();
             mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.wr[m]) + (size_t)krow * nq + quad, nq,
                          s_km + (head * D + L.off[m] + js) * MTP, L.s3chunk[m]);
             store_partial<MT, MTP>(s_part + a.S.s3pb[m], L.rd[m], sp, 4 * quad, acc);
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             const int nq = MH / 4, items = nq * L.s4ns;
             for (int item = tid; item < items; item += nt) {
                 const int quad = item % nq, sp = item / nq, k0 = sp * L.s4chunk, n = min(R, k0 + L.s4chunk) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.wf1) + (size_t)k0 * nq + quad, nq,
                                  s_r + k0 * MTP, n);
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
                 for (int sp = 0; sp < L.s4ns; ++sp) s += s_part[(sp * MTP + q) * MH + tid];
                 s = fmaxf(s, 0.f);
                 if (q < rows) {
-                    if (a.mask) s *= __ldg(a.mask + (tn0 + q) * MH + tid);
+                    if (masked) s *= s_mask[buf * MT * MH + q * MH + tid];
                     if (stash) a.sU[(tn0 + q) * MH + tid] = s;
                 }
                 u[q] = s;
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             const int nq = D / 4, items = nq * L.s5ns;
             for (int item = tid; item < items; item += nt) {
                 const int quad = item % nq, sp = item / nq, k0 = sp * L.s5chunk, n = min(MH, k0 + L.s5chunk) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.wf2) + (size_t)k0 * nq + quad, nq,
                                  s_u + k0 * MTP, n);
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 for (int i = tid * 128; i < rows * 2 * D * 4; i += nt * 128) prefetch_l2(d + i);
             }
         }
-        float acc[4][MT];
+        Acc<MT> acc;
         // ---- P0: gh = dL/dh_t + carry, gz = dL/dz_t + carry
         if (tid < 2 * D) {
             const int part = tid / D, j = tid - part * D;
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             const int nq = MH / 4, items = nq * L.b1ns;
             for (int item = tid; item < items; item += nt) {
                 const int quad = item % nq, sp = item / nq, k0 = sp * L.b1chunk, n = min(D, k0 + L.b1chunk) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Wf2) + (size_t)k0 * nq + quad, nq,
                                  s_gz + k0 * MTP, n);
@@ -458,7 +467,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             const int nq = R / 4, items = nq * L.b2ns;
             for (int item = tid; item < items; item += nt) {
                 const int quad = item % nq, sp = item / nq, k0 = sp * L.b2chunk, n = min(MH, k0 + L.b2chunk) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Wf1) + (size_t)k0 * nq + quad, nq,
                                  s_dup + k0 * MTP, n);
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             while (local >= L.b3items[m]) { local -= L.b3items[m]; ++m; }
             const int nq = L.dh[m], quad = local % nq, sp = local / nq;
             const int k0 = sp * L.b3chunk[m], n = min(L.rd[m], k0 + L.b3chunk[m]) - k0;
-            zero_acc<MT>(acc);
+            acc.zero();
             if (n > 0)
                 mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Wr[m]) + (size_t)k0 * nq + quad, nq,
                              s_dr + (L.roff[m] + k0) * MTP, n);
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             const int items = nqd * L.b4ns;
             for (int item = tid; item < items; item += nt) {
                 const int quad = item % nqd, sp = item / nqd, k0 = sp * L.b4chunk, n = min(G, k0 + L.b4chunk) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Watt) + (size_t)k0 * nqd + quad, nqd,
                                  s_km + k0 * MTP, n);
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             const int items = nqd * L.b4ns;
             for (int item = tid; item < items; item += nt) {
                 const int quad = item % nqd, sp = item / nqd, k0 = sp * L.b4chunk, n = min(G, k0 + L.b4chunk) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.packed + L.vcat) + (size_t)k0 * nqd + quad, nqd,
                                  s_km + k0 * MTP, n);
@@ -617,7 +626,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 while (local >= L.b5items[m]) { local -= L.b5items[m]; ++m; }
                 const int nq = L.dh[m] / 4, quad = local % nq, sp = local / nq;
                 const int k0 = sp * L.b5chunk[m], n = min(4 * L.dh[m], k0 + L.b5chunk[m]) - k0;
-                zero_acc<MT>(acc);
+                acc.zero();
                 if (n > 0)
                     mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.U[m]) + (size_t)k0 * nq + quad, nq,
                                  s_km + (L.goff[m] + k0) * MTP, n);
