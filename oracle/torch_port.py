@@ -216,6 +216,135 @@ def mab_head(p: Params, hz: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------
+# lsthm_sps.py  (speaker-state variant, BASELINE.json configs[2])
+# --------------------------------------------------------------------------------------
+def lstm_cell(p: Params, pre: str, x, h, c):
+    """torch.nn.LSTMCell semantics (gate order i,f,g,o; two bias vectors), used for the per-speaker
+    cells lstm_q0 / lstm_q1 (model/lsthm_sps.py:146-147, 183, 188)."""
+    g = F.linear(x, p[pre + ".weight_ih"], p[pre + ".bias_ih"]) + F.linear(h, p[pre + ".weight_hh"], p[pre + ".bias_hh"])
+    d = h.shape[1]
+    i, f, o = torch.sigmoid(g[:, :d]), torch.sigmoid(g[:, d:2 * d]), torch.sigmoid(g[:, 3 * d:])
+    c2 = f * c + i * torch.tanh(g[:, 2 * d:3 * d])
+    return o * torch.tanh(c2), c2
+
+
+def lsthm1_cell(p: Params, pre: str, x, c_prev, h_prev, z_prev, s_prev):
+    """LSTHM1.forward (model/lsthm_sps.py:28-44): LSTHM plus the speaker term S s; gates f,i,o,g."""
+    s = _lin(p, pre + ".W", x) + _lin(p, pre + ".U", h_prev) + _lin(p, pre + ".V", z_prev) + _lin(p, pre + ".S", s_prev)
+    dh = c_prev.shape[1]
+    f, i, o = (torch.sigmoid(s[:, j * dh:(j + 1) * dh]) for j in range(3))
+    g = torch.tanh(s[:, 3 * dh:])
+    c = f * c_prev + i * g
+    return c, torch.tanh(c) * o
+
+
+def cross_attention_cell(p: Params, pre: str, x1, x2, tape, site):
+    """In-cell CrossAttention.forward (model/lsthm_sps.py:59-72), executed the way the reference
+    does (two outer products and a [N,128,128] product); Wv is never used."""
+    dh = x1.shape[1]
+    Q = torch.matmul(x1.unsqueeze(-1), p[pre + ".Wq"])           # [N, D, D]
+    K = torch.matmul(x2.unsqueeze(-1), p[pre + ".Wk"])
+    attn = torch.softmax(torch.matmul(Q / (dh ** 0.5), K), dim=-1)
+    attn = _drop(attn, 0.2, site, tape)
+    return torch.matmul(attn, x2.unsqueeze(-1)).squeeze(-1)
+
+
+def party_rows(qmask_t: torch.Tensor):
+    """Index form of MARN_cell._select_parties (model/lsthm_sps.py:238-259): ascending dialogue
+    ids whose current speaker (argmax of the one-hot row; an all-zero padded row gives 0) is 0 / 1."""
+    idx = torch.argmax(qmask_t, 1)
+    return torch.nonzero(idx == 0).flatten(), torch.nonzero(idx == 1).flatten()
+
+
+def sps_cell(p: Params, pre: str, x_l, x_a, qmask, tape: Optional[DropoutTape] = None):
+    """MARN_cell.forward (model/lsthm_sps.py:156-221).  x_l,x_a [T,N,100], qmask [T,N,2] ->
+    h [T,N,512] = [h_l | h_a | z_l | h_q].  NOTE the reference packs speaker-0 rows before
+    speaker-1 rows and then treats packed row r as dialogue r; restated as is."""
+    T, N, _ = x_l.shape
+    dq = 128
+    z = lambda: x_l.new_zeros(N, dq)
+    h_l, h_a, h_q0, h_q1, c_l, c_a, c_q0, c_q1, z_l = (z() for _ in range(9))
+    q = x_l.new_zeros(N, 2, dq)
+    site = pre + ".dropout"
+    out = []
+    for t in range(T):
+        P0, P1 = party_rows(qmask[t])
+        N0, N1 = P0.numel(), P1.numel()
+        q0_sel = torch.cat([q[P0, 0], x_l.new_zeros(N - N0, dq)], 0) if N0 else None
+        q1_sel = torch.cat([q[P1, 1], x_l.new_zeros(N - N1, dq)], 0) if N1 else None
+        if N0:
+            h_q0, c_q0 = lstm_cell(p, pre + ".lstm_q0", q0_sel, h_q0, c_q0)
+            h_q0 = _drop(h_q0, 0.5, site, tape)
+        if N1:
+            h_q1, c_q1 = lstm_cell(p, pre + ".lstm_q1", q1_sel, h_q1, c_q1)
+            h_q1 = _drop(h_q1, 0.5, site, tape)
+        if N0 and N1:
+            h_q = torch.cat([h_q0[:N0], h_q1[:N1]], 0)
+            h_0 = torch.cat([q0_sel[:N0], q1_sel[:N1]], 0)
+        elif N0:
+            h_q, h_0 = h_q0, q0_sel
+        else:
+            h_q, h_0 = h_q1, q1_sel
+        m = qmask[t].unsqueeze(2)
+        q = h_0.unsqueeze(1) * (1 - m) + h_q.unsqueeze(1) * m
+        c_l, h_l = lsthm1_cell(p, pre + ".lsthm_l", x_l[t], c_l, h_l, z_l, h_q)
+        h_l = _drop(h_l, 0.5, site, tape)
+        c_a, h_a = lsthm1_cell(p, pre + ".lsthm_a", x_a[t], c_a, h_a, z_l, h_q)
+        h_a = _drop(h_a, 0.5, site, tape)
+        z_l = cross_attention_cell(p, pre + ".crossatt_l2a", c_l, c_a, tape, pre + ".crossatt_l2a.dropout")
+        out.append(torch.cat([h_l, h_a, z_l, h_q], 1))
+    return torch.stack(out, 0)
+
+
+def reverse_seq(X: torch.Tensor, umask: torch.Tensor) -> torch.Tensor:
+    """MARN1_sps._reverse_seq (model/lsthm_sps.py:396-410): flip each dialogue over its own length,
+    zero-pad to the longest dialogue.  X [L,B,d], umask [B,L]."""
+    lens = umask.sum(1).int().tolist()
+    Lmax = max(lens)
+    out = X.new_zeros(Lmax, X.shape[1], X.shape[2])
+    for b, n in enumerate(lens):
+        out[:n, b] = torch.flip(X[:n, b], [0])
+    return out
+
+
+def cross_attention_seq(p: Params, pre: str, x1, x2, tape, dk: int = 128):
+    """CrossAttention2/3.forward (model/lsthm_sps.py:88-101, 116-129): dense, UNMASKED attention over
+    the L utterances of each dialogue.  x1,x2 [L,B,*] -> [L,B,128]."""
+    a, b = x1.permute(1, 0, 2), x2.permute(1, 0, 2)
+    Q, K, V = torch.matmul(a, p[pre + ".Wq"]), torch.matmul(b, p[pre + ".Wk"]), torch.matmul(b, p[pre + ".Wv"])
+    attn = torch.softmax(torch.matmul(Q / (dk ** 0.5), K.transpose(1, 2)), dim=-1)
+    attn = _drop(attn, 0.2, pre + ".dropout", tape)
+    return torch.matmul(attn, V).permute(1, 0, 2)
+
+
+def sps_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None, return_state: bool = False):
+    """MARN1_sps.forward (model/lsthm_sps.py:349-394).  x [L,B,1124], qmask [L,B,2], umask [B,L] ->
+    (log-probs [B*L, C] batch-major, x_l [L,B,100], x_a [L,B,100])."""
+    xl = _lin(p, "linear_in", x[:, :, :1024].permute(1, 0, 2))
+    xa = x[:, :, 1024:1124].permute(1, 0, 2)
+    xl1 = encoder_layer(p, "encoder_l", xl, tape)
+    xa1 = encoder_layer(p, "encoder_a", xa, tape)
+    xl = encoder_layer(p, "encoder_l", xl + xl1, tape).permute(1, 0, 2)
+    xa = encoder_layer(p, "encoder_a", xa + xa1, tape).permute(1, 0, 2)
+    h_f = _drop(sps_cell(p, "marn_cell_f", xl, xa, qmask, tape), 0.5, "dropout_rec", tape)
+    h_b = sps_cell(p, "marn_cell_b", reverse_seq(xl, umask), reverse_seq(xa, umask), reverse_seq(qmask, umask), tape)
+    h_b = _drop(reverse_seq(h_b, umask), 0.5, "dropout_rec", tape)
+    h = torch.cat([h_f, h_b], -1)
+    w, v, v1, v2 = p["w"], p["v"], p["v1"], p["v2"]
+    a1 = cross_attention_seq(p, "crossatt_l2a", w * xl, v * xa, tape)
+    a2 = cross_attention_seq(p, "crossatt_a2l", v * xa, w * xl, tape)
+    a1 = cross_attention_seq(p, "crossatt_l2a_1", v * xa, v1 * a1, tape)
+    a2 = cross_attention_seq(p, "crossatt_a2l_1", w * xl, v2 * a2, tape)
+    o = _drop(torch.relu(_lin(p, "fc.0", torch.cat([h, a1, a2], -1))), 0.5, "fc.2", tape)
+    y = _drop(torch.relu(_lin(p, "nn_out.0", o + xl + xa)), 0.5, "nn_out.2", tape)
+    logp = torch.log_softmax(_lin(p, "nn_out.3", y), 2).permute(1, 0, 2)
+    logp = logp.reshape(-1, logp.shape[-1])
+    if return_state:
+        return logp, xl, xa, h
+    return logp, xl, xa
+
+
+# --------------------------------------------------------------------------------------
 # loss.py
 # --------------------------------------------------------------------------------------
 def masked_loss(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, kind: str = "ce"):
