@@ -100,6 +100,72 @@ int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const flo
 int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows,
                           int32_t *smem_fwd, int32_t *smem_bwd);
 
+/* ------------------------------------------------------------------------------------------
+ * lsthm_sps: speaker-state LSTHM cell (one direction of the bidirectional MARN1_sps).
+ * Replaces MARN_cell.forward, model/lsthm_sps.py:156-221: the per-speaker nn.LSTMCell pair on
+ * "packed" rows (_select_parties, :238-259), the party-state update (:204-207), LSTHM1.forward for
+ * text and audio (:28-44, with the speaker term S), dropout on every recurrent state and the in-cell
+ * rank-1 CrossAttention (:59-72).  The input projections W x, the bidirectional wrapper
+ * (_reverse_seq, :396-410), the sequence-level CrossAttention2/3 and the heads stay on the host side.
+ *
+ * Dialogues of a shard are coupled through the packed rows, so the kernels are
+ * cooperative launches over the whole shard: N <= rows_per_cta * #SMs (N <= 1184 on a B200).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t T, N;
+    int32_t rows_per_cta;      /* 0 = auto; else 1..8                                          */
+    float att_p;               /* in-kernel attention dropout prob when att_mask == NULL; 0=off */
+    uint64_t att_seed;
+} lsthm_sps_desc;
+
+typedef struct {               /* all [512][128] in nn.Linear / nn.LSTMCell layout; index 0/1 = l/a or q0/q1 */
+    const float *U[2], *V[2], *S[2];       /* marn_cell.lsthm_{l,a}.{U,V,S}.weight   lsthm_sps.py:17-19 */
+    const float *Wih[2], *Whh[2];          /* marn_cell.lstm_q{0,1}.weight_{ih,hh}   lsthm_sps.py:146-147 */
+    const float *bq[2];                    /* bias_ih + bias_hh [512] (summed by the caller)          */
+    const float *Wq, *Wk;                  /* marn_cell.crossatt_l2a.{Wq,Wk} [128]   lsthm_sps.py:52-53 */
+} lsthm_sps_weights;
+
+typedef struct {               /* dropout masks already scaled by 1/(1-p); any may be NULL (= no dropout) */
+    const float *mq[2];        /* on hq0 / hq1 after the speaker cells  [T][N][128]   lsthm_sps.py:184,189 */
+    const float *ml, *ma;      /* on h_l / h_a                          [T][N][128]   lsthm_sps.py:211,213 */
+    const float *att_mask;     /* on the attention weights              [T][N][128][128] lsthm_sps.py:69  */
+} lsthm_sps_masks;
+
+size_t lsthm_sps_packed_floats(void);
+int lsthm_sps_pack(const lsthm_sps_weights *w, float *packed, void *stream);
+/* floats of caller-provided scratch for the inter-CTA exchange buffers + barrier counter */
+size_t lsthm_sps_workspace_floats(const lsthm_sps_desc *d);
+
+/*
+ *   gx    [T][N][2][512]  W_c x_c + (bW+bU+bV+bS)_c for c = l, a; gate order f|i|o|g
+ *   qmask [T][N][2]       one-hot current speaker (zero rows on padding)
+ *   pi    [T][N] int32    dialogue occupying packed row r (speaker-0 dialogues first, ascending ids)
+ *   n0    [T]    int32    number of speaker-0 dialogues
+ *   out   [T][N][512]     [h_l | h_a | z_l | h_q]                        (lsthm_sps.py:218)
+ *   stash (all or none): sGQ [T][N][2][512] LSTMCell gates i|f|g|o, sCQ/sHQ/sXQ [T][N][2][128] cell state,
+ *         hidden state after dropout, cell input;  sGL [T][N][2][512] LSTHM gates f|i|o|g, sCL/sHL [T][N][2][128]
+ */
+int lsthm_sps_fwd(const lsthm_sps_desc *d, const lsthm_sps_weights *w, const float *packed, const float *gx,
+                  const float *qmask, const int32_t *pi, const int32_t *n0, const lsthm_sps_masks *masks,
+                  float *workspace, float *out, float *sGQ, float *sCQ, float *sHQ, float *sXQ, float *sGL,
+                  float *sCL, float *sHL, void *stream);
+
+/*
+ *   pr   [T][N] int32  packed row of dialogue d (inverse of pi)
+ *   dout [T][N][512]   dL/d out
+ *   dGL  [T][N][2][512] dL/d(LSTHM gate pre-activations)   -> W,U,V,S grads and dx
+ *   dGQ  [T][N][2][512] dL/d(LSTMCell gate pre-activations) -> weight_ih, weight_hh, biases
+ *   dWqk [grid][2][128] per-CTA partial sums of dL/dWq, dL/dWk (sum over the first axis); grid from
+ *        lsthm_sps_launch_info
+ */
+int lsthm_sps_bwd(const lsthm_sps_desc *d, const lsthm_sps_weights *w, const float *qmask, const int32_t *pi,
+                  const int32_t *pr, const int32_t *n0, const lsthm_sps_masks *masks, const float *dout,
+                  const float *sGQ, const float *sCQ, const float *sGL, const float *sCL, float *workspace,
+                  float *dGL, float *dGQ, float *dWqk, void *stream);
+
+int lsthm_sps_launch_info(const lsthm_sps_desc *d, int32_t *grid, int32_t *block, int32_t *rows, int32_t *smem_fwd,
+                          int32_t *smem_bwd);
+
 #ifdef __cplusplus
 }
 #endif

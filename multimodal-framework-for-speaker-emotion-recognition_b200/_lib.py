@@ -34,6 +34,20 @@ class MabWeights(C.Structure):
                 ("Wf1", C.c_void_p), ("bf1", C.c_void_p), ("Wf2", C.c_void_p), ("bf2", C.c_void_p)]
 
 
+class SpsDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("rows_per_cta", C.c_int32), ("att_p", C.c_float),
+                ("att_seed", C.c_uint64)]
+
+
+class SpsWeights(C.Structure):
+    _fields_ = [("U", C.c_void_p * 2), ("V", C.c_void_p * 2), ("S", C.c_void_p * 2), ("Wih", C.c_void_p * 2),
+                ("Whh", C.c_void_p * 2), ("bq", C.c_void_p * 2), ("Wq", C.c_void_p), ("Wk", C.c_void_p)]
+
+
+class SpsMasks(C.Structure):
+    _fields_ = [("mq", C.c_void_p * 2), ("ml", C.c_void_p), ("ma", C.c_void_p), ("att_mask", C.c_void_p)]
+
+
 def build(verbose: bool = False, jobs: int = 8) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_PKG, "csrc"), f"-j{jobs}", "all"]
@@ -69,6 +83,18 @@ def lib() -> C.CDLL:
     L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 13
     L.lsthm_mab_launch_info.restype = C.c_int
     L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 5
+    L.lsthm_sps_packed_floats.restype = C.c_size_t
+    L.lsthm_sps_packed_floats.argtypes = []
+    L.lsthm_sps_workspace_floats.restype = C.c_size_t
+    L.lsthm_sps_workspace_floats.argtypes = [C.POINTER(SpsDesc)]
+    L.lsthm_sps_pack.restype = C.c_int
+    L.lsthm_sps_pack.argtypes = [C.POINTER(SpsWeights), C.c_void_p, C.c_void_p]
+    L.lsthm_sps_fwd.restype = C.c_int
+    L.lsthm_sps_fwd.argtypes = [C.POINTER(SpsDesc), C.POINTER(SpsWeights)] + [C.c_void_p] * 5 + [C.POINTER(SpsMasks)] + [C.c_void_p] * 10
+    L.lsthm_sps_bwd.restype = C.c_int
+    L.lsthm_sps_bwd.argtypes = [C.POINTER(SpsDesc), C.POINTER(SpsWeights)] + [C.c_void_p] * 4 + [C.POINTER(SpsMasks)] + [C.c_void_p] * 10
+    L.lsthm_sps_launch_info.restype = C.c_int
+    L.lsthm_sps_launch_info.argtypes = [C.POINTER(SpsDesc)] + [C.POINTER(C.c_int32)] * 5
     if L.lsthm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"liblsthm_b200.so ABI {L.lsthm_abi_version()} != expected {ABI_VERSION}")
     _lib = L
@@ -147,4 +173,72 @@ def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, drop_mask, sC, sG, sA, sU, d
 def mab_launch_info(d: MabDesc) -> dict:
     v = [C.c_int32() for _ in range(5)]
     _check(lib().lsthm_mab_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab_launch_info")
+    return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))
+
+
+# ------------------------------------------------------------------------------------------------
+# lsthm_sps speaker-state cell
+# ------------------------------------------------------------------------------------------------
+def _int_ptr(t: torch.Tensor, name: str) -> int:
+    if not t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous CUDA int32 tensor")
+    return t.data_ptr()
+
+
+def make_sps_desc(T: int, N: int, rows_per_cta: int = 0, att_p: float = 0.0, att_seed: int = 0) -> SpsDesc:
+    d = SpsDesc()
+    d.T, d.N, d.rows_per_cta, d.att_p, d.att_seed = T, N, rows_per_cta, att_p, att_seed
+    return d
+
+
+def make_sps_weights(U, V, S, Wih, Whh, bq, Wq, Wk) -> SpsWeights:
+    w = SpsWeights()
+    for c in range(2):
+        w.U[c], w.V[c], w.S[c] = _dev_ptr(U[c], "U"), _dev_ptr(V[c], "V"), _dev_ptr(S[c], "S")
+        w.Wih[c], w.Whh[c], w.bq[c] = _dev_ptr(Wih[c], "Wih"), _dev_ptr(Whh[c], "Whh"), _dev_ptr(bq[c], "bq")
+    w.Wq, w.Wk = _dev_ptr(Wq, "Wq"), _dev_ptr(Wk, "Wk")
+    return w
+
+
+def make_sps_masks(mq0=None, mq1=None, ml=None, ma=None, att_mask=None) -> SpsMasks:
+    m = SpsMasks()
+    m.mq[0], m.mq[1] = _dev_ptr(mq0, "mq0"), _dev_ptr(mq1, "mq1")
+    m.ml, m.ma, m.att_mask = _dev_ptr(ml, "ml"), _dev_ptr(ma, "ma"), _dev_ptr(att_mask, "att_mask")
+    return m
+
+
+def sps_packed_floats() -> int:
+    return lib().lsthm_sps_packed_floats()
+
+
+def sps_workspace_floats(d: SpsDesc) -> int:
+    n = lib().lsthm_sps_workspace_floats(C.byref(d))
+    if n == 0:
+        raise RuntimeError(f"bad sps descriptor: {lib().lsthm_last_error().decode()}")
+    return n
+
+
+def sps_pack(w: SpsWeights, packed: torch.Tensor) -> None:
+    _check(lib().lsthm_sps_pack(C.byref(w), _dev_ptr(packed, "packed"), _stream()), "lsthm_sps_pack")
+
+
+def sps_fwd(d, w, packed, gx, qmask, pi, n0, masks, workspace, out, sGQ, sCQ, sHQ, sXQ, sGL, sCL, sHL) -> None:
+    _check(lib().lsthm_sps_fwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(gx, "gx"),
+                               _dev_ptr(qmask, "qmask"), _int_ptr(pi, "pi"), _int_ptr(n0, "n0"), C.byref(masks),
+                               _dev_ptr(workspace, "workspace"), _dev_ptr(out, "out"), _dev_ptr(sGQ, "sGQ"),
+                               _dev_ptr(sCQ, "sCQ"), _dev_ptr(sHQ, "sHQ"), _dev_ptr(sXQ, "sXQ"), _dev_ptr(sGL, "sGL"),
+                               _dev_ptr(sCL, "sCL"), _dev_ptr(sHL, "sHL"), _stream()), "lsthm_sps_fwd")
+
+
+def sps_bwd(d, w, qmask, pi, pr, n0, masks, dout, sGQ, sCQ, sGL, sCL, workspace, dGL, dGQ, dWqk) -> None:
+    _check(lib().lsthm_sps_bwd(C.byref(d), C.byref(w), _dev_ptr(qmask, "qmask"), _int_ptr(pi, "pi"), _int_ptr(pr, "pr"),
+                               _int_ptr(n0, "n0"), C.byref(masks), _dev_ptr(dout, "dout"), _dev_ptr(sGQ, "sGQ"),
+                               _dev_ptr(sCQ, "sCQ"), _dev_ptr(sGL, "sGL"), _dev_ptr(sCL, "sCL"),
+                               _dev_ptr(workspace, "workspace"), _dev_ptr(dGL, "dGL"), _dev_ptr(dGQ, "dGQ"),
+                               _dev_ptr(dWqk, "dWqk"), _stream()), "lsthm_sps_bwd")
+
+
+def sps_launch_info(d: SpsDesc) -> dict:
+    v = [C.c_int32() for _ in range(5)]
+    _check(lib().lsthm_sps_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_sps_launch_info")
     return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))

@@ -181,6 +181,11 @@ static const BwdLaunchFn kBwd[8] = {launch_bwd_1, launch_bwd_2, launch_bwd_3, la
                                     launch_bwd_5, launch_bwd_6, launch_bwd_7, launch_bwd_8};
 
 int set_error(const char *what, cudaError_t e) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
+int fail_msg(const char *msg) { return fail(msg); }
+int launch_pack(const PackJobs &jobs, float *packed, cudaStream_t st) {
+    mab_pack_kernel<<<dim3(32, jobs.n), 256, 0, st>>>(jobs, packed);
+    return check_cuda("weight pack launch");
+}
 
 constexpr size_t kMaxSmemBytes = 227 * 1024;
 

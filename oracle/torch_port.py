@@ -62,6 +62,21 @@ class DropoutTape:
         return torch.stack(self.masks[site], 0)
 
 
+def perturb_ones(params_or_module, seed: int, std: float = 0.1):
+    """The reference initialises every attention projection and fusion scalar of lsthm_sps to ones,
+    which makes the model badly conditioned (SURVEY.md F6, §8c hazards).  Parity is therefore also
+    checked with those tensors perturbed: in registration order, add N(0, std^2) drawn from one seeded
+    generator to every all-ones tensor.  Works on a module or a name->tensor dict (same order)."""
+    g = torch.Generator().manual_seed(seed)
+    items = params_or_module.named_parameters() if hasattr(params_or_module, "named_parameters") \
+        else params_or_module.items()
+    with torch.no_grad():
+        for _, t in items:
+            if t.is_floating_point() and t.numel() > 0 and bool((t == 1).all()):
+                t.add_((std * torch.randn(t.shape, generator=g)).to(t.device))
+    return params_or_module
+
+
 def _drop(x: torch.Tensor, p: float, site: str, tape: Optional[DropoutTape]):
     """nn.Dropout at a named site: identity without a tape (== eval mode)."""
     if tape is None or p == 0.0:

@@ -16,6 +16,38 @@ from oracle import torch_port as tp
 from oracle.ref_shim import attach_tape, load_reference, reference_available
 
 
+@pytest.mark.parametrize("path", golden_files("sps_*.npz"), ids=lambda p: p.split("/")[-1][:-4])
+def test_sps_torch_port_matches_reference_fixture(path):
+    """lsthm_sps: the index-form restatement (vectorised _select_parties, no per-row loop) vs the reference
+    fixtures, eval / perturbed ones-parameters / train with the full dropout mask tape."""
+    from helpers import sps_port_run
+    fix = load_golden(path)
+    logp, loss, dx, grads = sps_port_run(fix)
+    check_against_golden(fix, logp, loss, dx, grads, tol_out=1e-5, tol_grad=2e-4)
+
+
+def test_sps_plan_and_reverse_match_reference_semantics():
+    from importlib import import_module
+    import lsthm_b200
+    sr = import_module(lsthm_b200.__name__ + ".sps_recurrence")
+    g = torch.Generator().manual_seed(0)
+    q = torch.zeros(6, 9, 2)
+    r = torch.rand(6, 9, generator=g)
+    q[..., 0] = (r < 0.45).float()
+    q[..., 1] = ((r >= 0.45) & (r < 0.9)).float()          # the rest are padded rows [0,0] -> speaker 0
+    q[2, :, 0], q[2, :, 1] = 1, 0                            # a step where nobody is speaker 1
+    pi, pr, n0 = sr.party_plan(q)
+    for t in range(6):
+        P0, P1 = tp.party_rows(q[t])
+        assert torch.equal(pi[t], torch.cat([P0, P1]).int()) and int(n0[t]) == P0.numel()
+        assert torch.equal(pr[t][pi[t].long()], torch.arange(9).int())
+    um = torch.zeros(4, 6)
+    for b, n in enumerate([6, 2, 4, 1]):
+        um[b, :n] = 1
+    X = torch.randn(6, 4, 5, generator=g)
+    assert torch.equal(lsthm_b200.lsthm_sps.reverse_seq(X, um), tp.reverse_seq(X, um))
+
+
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
 def test_torch_port_matches_reference_fixture(path):
     fix = load_golden(path)
