@@ -28,10 +28,21 @@ import torch  # noqa: E402
 METRIC = "utterances/sec fwd+bwd HybridRNN_ATV"
 UNIT = "utterances/s"
 T_LEN, BATCH, D_IN, N_CLS = 110, 1024, 712, 6
+# --model sps (BASELINE.json configs[2] shapes, fp32): per-direction FLOPs of the fused cell kernels
+SPS_FLOP_FWD = 524_288 + 786_432 + 82_432
+SPS_FLOP_BWD = 524_288 + 786_432 + 3 * 82_432
 # algorithmic FLOPs per utterance of the serial chain: fwd 999,936; the BPTT adjoint
 # chain is the five transposed products of the same weights = the same count.
 FLOP_FWD_PER_UTT = 999_936
 FLOP_BWD_PER_UTT = 999_936
+
+
+def model_name(kind):
+    return "HybridRNN_ATV" if kind == "ATV" else "MARN1_sps"
+
+
+def metric_name(kind):
+    return f"utterances/sec fwd+bwd {model_name(kind)}"
 
 
 def peaks():
@@ -85,37 +96,51 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_batch(seed, T, B, device=None, pinned=False):
-    """Seeded IEMOCAP-shaped batch (uniform set: every dialogue L = 110)."""
+def synthetic_batch(seed, T, B, device=None, pinned=False, model="ATV"):
+    """Seeded IEMOCAP-shaped batch (uniform set: every dialogue L = 110).  For the sps
+    model also a two-speaker one-hot qmask (first speaker Bernoulli(0.5), switch probability 0.6)."""
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(T, B, D_IN, generator=g)
+    x = torch.randn(T, B, D_IN if model == "ATV" else 1124, generator=g)
     p = torch.tensor([144, 245, 384, 170, 299, 381], dtype=torch.float32) / 1623.0
     labels = torch.multinomial(p, T * B, replacement=True, generator=g)
     umask = torch.ones(B, T)
+    out = [x, labels, umask]
+    if model == "sps":
+        spk = torch.randint(0, 2, (B,), generator=g)
+        qmask = torch.zeros(T, B, 2)
+        for t in range(T):
+            spk = torch.where(torch.rand(B, generator=g) < 0.6, 1 - spk, spk)
+            qmask[t, torch.arange(B), spk] = 1
+        out.append(qmask)
     if pinned:
-        x, labels, umask = x.pin_memory(), labels.pin_memory(), umask.pin_memory()
+        out = [t.pin_memory() for t in out]
     if device is not None:
-        x, labels, umask = x.to(device), labels.to(device), umask.to(device)
-    return x, labels, umask
+        out = [t.to(device) for t in out]
+    return tuple(out)
 
 
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's torch restatement of the reference, on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(B, T=T_LEN, seed=111):
+def cpu_step_fn(B, T=T_LEN, seed=111, model_kind="ATV"):
     from oracle import torch_port as tp
     import lsthm_b200
     torch.manual_seed(seed)
-    model = lsthm_b200.HybridRNN_ATV.MARN()          # parameter container only (default init, seed 111)
+    # parameter container only (default init, seed 111)
+    model = lsthm_b200.HybridRNN_ATV.MARN() if model_kind == "ATV" else lsthm_b200.lsthm_sps.MARN1_sps(6)
     params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-    x, labels, umask = synthetic_batch(seed, T, B)
+    batch = synthetic_batch(seed, T, B, model=model_kind)
+    x, labels, umask = batch[:3]
     tape_seed = [0]
 
     def step():
         for p in params.values():
             p.grad = None
         tape = tp.DropoutTape(tape_seed[0]); tape_seed[0] += 1      # train mode: fresh dropout masks each step
-        probs = tp.mab_forward(params, x, "ATV", tape)
+        if model_kind == "ATV":
+            probs = tp.mab_forward(params, x, "ATV", tape)
+        else:
+            probs = tp.sps_forward(params, x, batch[3], umask, tape)[0]
         loss = tp.masked_loss(probs, labels, umask, "ce")
         loss.backward()
         return float(loss.detach())
@@ -134,16 +159,18 @@ def best_threads(step, candidates):
     return best[0]
 
 
-def run_cpu_baseline(steps=2, B=32):
+def run_cpu_baseline(steps=2, B=32, model_kind="ATV"):
     ncpu = os.cpu_count() or 1
-    step, utt = cpu_step_fn(B)
+    if model_kind == "sps":
+        B = 8                                  # the sps reference path is ~6x slower per utterance on the CPU
+    step, utt = cpu_step_fn(B, model_kind=model_kind)
     cands = sorted({1, min(4, ncpu), min(8, ncpu), ncpu})
     n = best_threads(step, cands)
     ts = []
     for _ in range(steps):
         t = time.perf_counter(); step(); ts.append(time.perf_counter() - t)
     return {"value": utt / min(ts), "unit": UNIT, "cores": n, "kind": "port",
-            "sample": f"oracle/torch_port.py (torch restatement of the reference) fwd+bwd, train mode, x[{T_LEN},{B},{D_IN}] "
+            "sample": f"oracle/torch_port.py (torch restatement of the reference {model_kind}) fwd+bwd, train mode, x[{T_LEN},{B},*] "
                       f"fp32, best of {steps} after thread sweep {cands} on {ncpu} host cpus"}
 
 
@@ -151,9 +178,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = 32
+    B = 32 if args.model == "ATV" else 8
     ncpu = os.cpu_count() or 1
-    step, utt = cpu_step_fn(B)
+    step, utt = cpu_step_fn(B, model_kind=args.model)
     cands = sorted({1, min(4, ncpu), min(8, ncpu), min(16, ncpu), ncpu})
     n = best_threads(step, cands)
     for _ in range(max(0, args.warmup - len(cands))):
@@ -164,12 +191,12 @@ def run_reference_arm(args):
     dt = time.perf_counter() - t0
     val = utt * args.steps / dt
     sample = (f"reference algorithm via oracle/torch_port.py (the Python reference cannot travel to the GPU box), train mode, "
-              f"x[{T_LEN},{B},{D_IN}] fp32 per step, {n} torch threads (best of sweep {cands}; {ncpu} host cpus)")
+              f"{args.model} x[{T_LEN},{B},*] fp32 per step, {n} torch threads (best of sweep {cands}; {ncpu} host cpus)")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.model), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"HybridRNN_ATV fwd+bwd, T={T_LEN}, sample batch {B} dialogues on host CPU"},
+        "config": {"workload": f"{model_name(args.model)} fwd+bwd, T={T_LEN}, sample batch {B} dialogues on host CPU"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": n, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -197,21 +224,34 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.seq, args.batch
     torch.manual_seed(111)
-    model = lsthm_b200.HybridRNN_ATV.MARN().to(dev).train()
+    kind = args.model
+    if kind == "ATV":
+        model = lsthm_b200.HybridRNN_ATV.MARN().to(dev).train()
+    else:
+        tp_mod = import_module("oracle.torch_port")
+        model = lsthm_b200.lsthm_sps.MARN1_sps(6)
+        tp_mod.perturb_ones(model, 114)          # ones-initialised attention makes the stock init degenerate
+        model = model.to(dev).train()
     loss_fn = lsthm_b200.MaskedLoss(torch.nn.CrossEntropyLoss)
+
+    def forward(batch):
+        if kind == "ATV":
+            return model(batch[0])
+        return model(batch[0], batch[3], batch[2])[0]
     reducer = ddp.GradAllReducer(model, world) if world > 1 else None
     # two host batches (pinned) so consecutive steps see different data; device-resident copies for `value`
-    host = [synthetic_batch(111 + 7 * rank + i, T, B, pinned=True) for i in range(2)]
+    host = [synthetic_batch(111 + 7 * rank + i, T, B, pinned=True, model=kind) for i in range(2)]
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     utt_per_step = T * B * world
 
     def step_resident(i):
-        x, labels, umask = resident[i & 1]
+        batch = resident[i & 1]
+        labels, umask = batch[1], batch[2]
         if reducer is not None:
             reducer.zero_grad()
         else:
             model.zero_grad(set_to_none=True)
-        probs = model(x)
+        probs = forward(batch)
         loss = loss_fn(probs, labels, umask)
         if reducer is not None:
             loss = loss * (1.0 / world)
@@ -279,12 +319,13 @@ def run_ours(args):
             cur.wait_event(ready[i & 1])
             if not last:
                 prefetch(i + 1)               # next step's H2D overlaps this step's compute
-            x, labels, umask = dbuf[i & 1]
+            batch = dbuf[i & 1]
+            labels, umask = batch[1], batch[2]
             if reducer is not None:
                 reducer.zero_grad()
             else:
                 model.zero_grad(set_to_none=True)
-            loss = loss_fn(model(x), labels, umask)
+            loss = loss_fn(forward(batch), labels, umask)
             if reducer is not None:
                 loss = loss * (1.0 / world)
             loss.backward()
@@ -312,46 +353,58 @@ def run_ours(args):
 
     if rank == 0:
         pk = peaks()
+        _l = import_module(lsthm_b200.__name__ + "._lib")
         dom = "bwd" if kms["bwd"] >= kms["fwd"] else "fwd"
-        flop = (FLOP_BWD_PER_UTT if dom == "bwd" else FLOP_FWD_PER_UTT) * T * B
+        if kind == "ATV":
+            flop_utt = FLOP_BWD_PER_UTT if dom == "bwd" else FLOP_FWD_PER_UTT
+            kname = f"mab_{dom}_kernel"
+            info = _l.mab_launch_info(_l.make_desc(T, B, (128, 16, 64), (16, 128, 100)))
+            D, G, R, MH = 208, 832, 244, 64
+            # algorithmic HBM bytes per utterance of one launch, fp32
+            by = {"fwd": 4 * (G + 2 * D + D + G + G + R + MH + MH),
+                  "bwd": 4 * (2 * D + D + D + G + G + MH + MH + G + G + R + MH + D)}
+            din = D_IN
+        else:
+            flop_utt = SPS_FLOP_BWD if dom == "bwd" else SPS_FLOP_FWD      # per direction = per launch
+            kname = f"sps_{dom}_kernel"
+            info = _l.sps_launch_info(_l.make_sps_desc(T, B))
+            # one direction: gx 1024 + out 512 + stash (2x1024 gates + 5x256 states); bwd: dout 512 + stash reads + 2x1024 adjoints
+            by = {"fwd": 4 * (1024 + 512 + 2 * 1024 + 5 * 256 + 4 * 128), "bwd": 4 * (512 + 2 * 1024 + 2 * 256 + 2 * 1024 + 4 * 128)}
+            din = 1124
+        flop = flop_utt * T * B
         achieved = flop / (kms[dom] * 1e-3) / 1e12 if kms[dom] > 0 else 0.0
         sm_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
         ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(f"mab_{dom}_kernel", {}).get("dram_bytes_per_launch")
-        info = import_module(lsthm_b200.__name__ + "._lib").mab_launch_info(
-            import_module(lsthm_b200.__name__ + "._lib").make_desc(T, B, (128, 16, 64), (16, 128, 100)))
+            traffic = json.load(open(tpath)).get(kname, {}).get("dram_bytes_per_launch")
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"HybridRNN_ATV MARN fwd+bwd (train mode), x[{T},{B},{D_IN}] fp32 per GPU, uniform L={T}, "
-                                   f"MaskedLoss(CrossEntropy); inputs {T * B * D_IN * 4 / 1e6:.0f} MB per step > 126 MB L2, "
+            "metric": metric_name(kind), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{model_name(kind)} fwd+bwd (train mode), x[{T},{B},{din}] fp32 per GPU, uniform L={T}, "
+                                   f"MaskedLoss(CrossEntropy); inputs {T * B * din * 4 / 1e6:.0f} MB per step > 126 MB L2, "
                                    f"two alternating batches", "per_gpu_batch": B, "seq_len": T,
                        "parallelism": f"dp{world}", "grid": info["grid"], "block": info["block"], "rows_per_cta": info["rows"]},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": (e2e_ms / args.steps) if e2e_ms else None},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": f"mab_{dom}_kernel", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": kname, "achieved": achieved,
                          "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                          "traffic": traffic, "peak_source": pk["source"] + " bf16 cuBLAS sustained",
                          "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
-                         "share_of_step": {k: v / (ms / args.steps) for k, v in kms.items()},
+                         "launches_per_step": {k: len(v) / args.steps for k, v in kev.items()},
+                         "share_of_step": {k: v * len(kev[k]) / args.steps / (ms / args.steps) for k, v in kms.items()},
                          "fp32_ffma": {"achieved": achieved, "peak": ffma_peak, "frac": achieved / ffma_peak,
                                        "note": f"kernel is fp32 FFMA; peak = 148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock under load)"},
-                         "hbm": {"algorithmic_gbs": None}},
+                         "hbm": {"algorithmic_bytes_per_utt": by[dom],
+                                 "achieved_gbs": by[dom] * T * B / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0,
+                                 "peak_gbs": pk["hbm_gbs"]}},
         }
-        # algorithmic HBM bytes of the dominant kernel: per utterance, fp32
-        D, G, R, MH = 208, 832, 244, 64
-        by = {"fwd": 4 * (G + 2 * D + D + G + G + R + MH + MH), "bwd": 4 * (2 * D + D + D + G + G + MH + MH + G + G + R + MH + D)}
-        out["roofline"]["hbm"] = {"algorithmic_bytes_per_utt": by[dom],
-                                  "achieved_gbs": by[dom] * T * B / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0,
-                                  "peak_gbs": pk["hbm_gbs"]}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = run_cpu_baseline()
+            out["cpu_baseline"] = run_cpu_baseline(model_kind=kind)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -366,6 +419,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="dialogues per GPU")
     ap.add_argument("--seq", type=int, default=T_LEN)
+    ap.add_argument("--model", default="ATV", choices=["ATV", "sps"],
+                    help="ATV = BASELINE.json configs[1] (headline); sps = configs[2] shapes (speaker-state model, fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()

@@ -13,6 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
+from . import recurrence as _rec
 from .recurrence import launch_counter
 
 
@@ -58,7 +59,7 @@ class SpsCellFn(torch.autograd.Function):
             sCQ, sHQ, sXQ, sCL, sHL = (new(T, N, 2, 128) for _ in range(5))
         else:
             sGQ = sGL = sCQ = sHQ = sXQ = sCL = sHL = None
-        _lib.sps_fwd(desc, w, packed, gx, qmask, pi, n0, mk, ws, out, sGQ, sCQ, sHQ, sXQ, sGL, sCL, sHL)
+        _rec._timed("fwd", _lib.sps_fwd, desc, w, packed, gx, qmask, pi, n0, mk, ws, out, sGQ, sCQ, sHQ, sXQ, sGL, sCL, sHL)
         launch_counter["fwd"] += 1
         if need_grad:
             ctx.save_for_backward(qmask, pi, pr, n0, out, sGQ, sCQ, sHQ, sXQ, sGL, sCL, sHL, ws, *weights)
@@ -81,7 +82,8 @@ class SpsCellFn(torch.autograd.Function):
         dGL, dGQ = new(T, N, 2, 512), new(T, N, 2, 512)
         grid = _lib.sps_launch_info(desc)["grid"]
         dWqk = new(grid, 2, 128)
-        _lib.sps_bwd(desc, w, qmask, pi, pr, n0, mk, dout.contiguous(), sGQ, sCQ, sGL, sCL, ws, dGL, dGQ, dWqk)
+        _rec._timed("bwd", _lib.sps_bwd, desc, w, qmask, pi, pr, n0, mk, dout.contiguous(), sGQ, sCQ, sGL, sCL, ws, dGL, dGQ,
+                    dWqk)
         launch_counter["bwd"] += 1
         # ---- time-parallel weight-gradient products (fp32) ----
         TN = T * N
