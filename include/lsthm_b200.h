@@ -166,6 +166,21 @@ int lsthm_sps_bwd(const lsthm_sps_desc *d, const lsthm_sps_weights *w, const flo
 int lsthm_sps_launch_info(const lsthm_sps_desc *d, int32_t *grid, int32_t *block, int32_t *rows, int32_t *smem_fwd,
                           int32_t *smem_bwd);
 
+/* ------------------------------------------------------------------------------------------
+ * fp32-accurate dense GEMM on the tcgen05 tensor cores (split-bf16, three UMMAs per k-step) for the
+ * time-parallel products of the path: the hoisted input projections W x (LSTHM.forward line 23 of
+ * model/HybridRNN_ATV.py, LSTHM1.forward line 29 of model/lsthm_sps.py), the nn.Linear layers of
+ * model/encoder.py and of the heads, and the weight-gradient products autograd forms for them.
+ *   mode 0 (NT): C[M][N] = A[M][K] . B[N][K]^T (+ bias[N])     y  = x W^T + b   (torch.nn.functional.linear)
+ *   mode 1 (NN): C[M][N] = A[M][K] . B[K][N]                   dx = dy W
+ *   mode 2 (TN): C[M][N] = A[K][M]^T . B[K][N]                 dW = dy^T x      (split-K, deterministic reduce)
+ * All matrices fp32 row-major, 16-byte aligned, lda/ldb multiples of 4.  `workspace` (may be NULL) holds
+ * the split-K partials: lsthm_gemm3_workspace_floats(mode, M, N, K) floats.
+ * ------------------------------------------------------------------------------------------ */
+size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K);
+int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
+                const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

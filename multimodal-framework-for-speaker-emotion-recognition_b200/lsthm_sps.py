@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .encoder import EncoderLayer
+from .mm3 import linear3
 from .sps_recurrence import sps_cell
 
 
@@ -32,7 +33,7 @@ class LSTHM1(nn.Module):
 
     def gate_input(self, x):
         """W x plus the four biases, for all steps at once (time-parallel part of lines 29-34)."""
-        return F.linear(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias + self.S.bias)
+        return linear3(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias + self.S.bias)
 
 
 class CrossAttention(nn.Module):
@@ -149,7 +150,7 @@ class MARN1_sps(nn.Module):
         self.v2 = nn.Parameter(torch.ones(1))
 
     def forward(self, x, qmask, umask):
-        x_l = self.linear_in(x[:, :, :self.d_r].permute(1, 0, 2))
+        x_l = linear3(x[:, :, :self.d_r].permute(1, 0, 2), self.linear_in.weight, self.linear_in.bias)
         x_a = x[:, :, self.d_r:self.d_r + self.d_a].permute(1, 0, 2)
         x_l_1, _ = self.encoder_l(x_l)
         x_a_1, _ = self.encoder_a(x_a)
@@ -165,6 +166,6 @@ class MARN1_sps(nn.Module):
         attn2 = self.crossatt_a2l(self.v * x_a, self.w * x_l)
         attn1 = self.crossatt_l2a_1(self.v * x_a, self.v1 * attn1)
         attn2 = self.crossatt_a2l_1(self.w * x_l, self.v2 * attn2)
-        output = self.fc(torch.cat([h, attn1, attn2], dim=-1))
+        output = self.fc[2](self.fc[1](linear3(torch.cat([h, attn1, attn2], dim=-1), self.fc[0].weight, self.fc[0].bias)))
         output = F.log_softmax(self.nn_out(output + x_l + x_a), 2).permute(1, 0, 2)
         return output.reshape(-1, output.size(-1)), x_l, x_a

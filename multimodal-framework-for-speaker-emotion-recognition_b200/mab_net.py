@@ -14,6 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .encoder import EncoderLayer
+from .mm3 import linear3
 from .recurrence import mab_recurrence
 
 _MODS = ("l", "a", "v")
@@ -33,7 +34,7 @@ class LSTHM(nn.Module):
 
     def gate_input(self, x: torch.Tensor) -> torch.Tensor:
         """W x + bW + bU + bV for all steps at once (the hoisted, time-parallel part of line 23-27)."""
-        return F.linear(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias)
+        return linear3(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias)
 
 
 class MabNet(nn.Module):
@@ -97,4 +98,7 @@ class MabNet(nn.Module):
         hz = mab_recurrence(gx, self._fc_mask(T, N, x.device), self._dh, self._rd, self._map_h,
                             self.recurrence_weights(), self.rows_per_cta)
         self.last_hz = hz
-        return self.nn_out(hz.view(T * N, -1))       # time-major [T*N, C] probabilities (line 153)
+        y = linear3(hz.view(T * N, -1), self.nn_out[0].weight, self.nn_out[0].bias)
+        for layer in list(self.nn_out)[1:]:
+            y = layer(y)
+        return y                                      # time-major [T*N, C] probabilities (line 153)

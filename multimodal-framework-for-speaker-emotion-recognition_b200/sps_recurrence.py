@@ -14,6 +14,7 @@ import torch
 
 from . import _lib
 from . import recurrence as _rec
+from .mm3 import mm_tn
 from .recurrence import launch_counter
 
 
@@ -92,12 +93,12 @@ class SpsCellFn(torch.autograd.Function):
         for c in range(2):
             ds = dGL[:, :, c]                                     # [T,N,512]
             ds1 = ds[1:].reshape(-1, 512)
-            gU.append(ds1.t() @ sHL[:-1, :, c].reshape(-1, 128))   # h_{t-1} after dropout (lsthm_sps.py:211,213)
-            gV.append(ds1.t() @ z_prev)
-            gS.append(ds.reshape(TN, 512).t() @ hq_t)
+            gU.append(mm_tn(ds1, sHL[:-1, :, c].reshape(-1, 128)))   # h_{t-1} after dropout (lsthm_sps.py:211,213)
+            gV.append(mm_tn(ds1, z_prev))
+            gS.append(mm_tn(ds.reshape(TN, 512), hq_t))
             dg = dGQ[:, :, c]
-            gWih.append(dg.reshape(TN, 512).t() @ sXQ[:, :, c].reshape(TN, 128))
-            gWhh.append(dg[1:].reshape(-1, 512).t() @ sHQ[:-1, :, c].reshape(-1, 128))
+            gWih.append(mm_tn(dg.reshape(TN, 512), sXQ[:, :, c].reshape(TN, 128)))
+            gWhh.append(mm_tn(dg[1:].reshape(-1, 512), sHQ[:-1, :, c].reshape(-1, 128)))
             gbq.append(dg.reshape(TN, 512).sum(0))
         g = dWqk.sum(0)
         grads = (*gU, *gV, *gS, *gWih, *gWhh, *gbq, g[0].view_as(Wq), g[1].view_as(Wk))
