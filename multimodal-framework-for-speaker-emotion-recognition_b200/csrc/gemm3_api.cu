@@ -26,7 +26,7 @@ size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t 
     (void)mode;
     const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
     if (tiles >= 148 || K < 4 * kGemmBK * 8) return 0;
-    const int splits = (int)std::min<long>((K + 255) / 256, (296 + tiles - 1) / tiles);
+    const int splits = (int)std::min<long>((K + 255) / 256, std::max<long>(1, 296 / tiles));   // one full wave: 2 CTAs x 148 SMs
     return splits > 1 ? (size_t)splits * M * N : 0;
 }
 
@@ -43,7 +43,7 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
     const long tiles = (long)tm * tn;
     int splits = 1;
     if (tiles < 148 && K >= 4 * kGemmBK * 8 && workspace) {
-        splits = (int)std::min<long>((K + 255) / 256, (296 + tiles - 1) / tiles);
+        splits = (int)std::min<long>((K + 255) / 256, std::max<long>(1, 296 / tiles));   // one full wave
         while (splits > 1 && (size_t)splits * M * N > workspace_floats) --splits;
     }
     int kps = (K + splits - 1) / splits;

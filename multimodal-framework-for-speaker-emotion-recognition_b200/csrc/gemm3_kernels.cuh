@@ -79,42 +79,52 @@ __device__ __forceinline__ void load8(const float *p, int valid, float (&x)[8]) 
     }
 }
 
-// Stage one operand tile (128 rows of the M/N axis x 32 of K) into hi/lo shared tiles.
-//   MN = 0: src[row][k], k contiguous.   MN = 1: src[k][row], row contiguous.
+// One operand tile (128 rows of the M/N axis x 32 of K) is 512 items of 8 consecutive floats; each of the 256
+// producer threads owns two.  Loading (global -> registers) and storing (split -> shared) are separate so
+// that the loads of k-block kb+1 are in flight while block kb is converted and stored.
+//   MN = 0: src[row][k], k contiguous.   item i: row = i*64 + ptid/4, k-chunk = ptid%4 (4 lanes read a 128 B line)
+//   MN = 1: src[k][row], row contiguous. item i: k = i*16 + ptid/16, row-chunk = ptid%16 (16 lanes read 512 B)
+struct TileRegs {
+    float x[2][8];
+};
+
 template <int MN>
-__device__ __forceinline__ void stage_tile(const float *__restrict__ src, int ld, int row0, int nrows, int k0, int kend,
-                                           uint8_t *hi, uint8_t *lo, int ptid) {
-    float x[8];
-    if (MN == 0) {
-        // item = (row, 8-wide k chunk c): lane -> (row = i*64 + ptid/4, c = ptid%4): 4 lanes read one 128-byte line
+__device__ __forceinline__ void load_tile(const float *__restrict__ src, int ld, int row0, int nrows, int k0, int kend,
+                                          int ptid, TileRegs &t) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2; ++i) {
+        int valid;
+        const float *p;
+        if (MN == 0) {
+            const int r = i * 64 + (ptid >> 2), c = ptid & 3, gr = row0 + r, gk = k0 + 8 * c;
+            valid = gr < nrows ? max(0, min(8, kend - gk)) : 0;
+            p = src + (size_t)gr * ld + gk;
+        } else {
+            const int k = i * 16 + (ptid >> 4), mc = ptid & 15, gk = k0 + k, gr = row0 + 8 * mc;
+            valid = gk < kend ? max(0, min(8, nrows - gr)) : 0;
+            p = src + (size_t)gk * ld + gr;
+        }
+        if (valid > 0) load8(p, valid, t.x[i]);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t.x[i][j] = 0.f;
+        }
+    }
+}
+
+template <int MN>
+__device__ __forceinline__ void store_tile(const TileRegs &t, uint8_t *hi, uint8_t *lo, int ptid) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        int off;
+        if (MN == 0) {
             const int r = i * 64 + (ptid >> 2), c = ptid & 3;
-            const int gr = row0 + r, gk = k0 + 8 * c;
-            const int valid = gr < nrows ? max(0, min(8, kend - gk)) : 0;
-            if (valid > 0) load8(src + (size_t)gr * ld + gk, valid, x);
-            else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = 0.f;
-            }
-            const int off = c * kKLbo + (r >> 3) * kKSbo + (r & 7) * 16;
-            split_store8(x, hi + off, lo + off);
-        }
-    } else {
-        // item = (k, 8-wide row chunk mc): lane -> (k = i*16 + ptid/16, mc = ptid%16): 16 lanes read 512 contiguous bytes
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
+            off = c * kKLbo + (r >> 3) * kKSbo + (r & 7) * 16;
+        } else {
             const int k = i * 16 + (ptid >> 4), mc = ptid & 15;
-            const int gk = k0 + k, gr = row0 + 8 * mc;
-            const int valid = gk < kend ? max(0, min(8, nrows - gr)) : 0;
-            if (valid > 0) load8(src + (size_t)gk * ld + gr, valid, x);
-            else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = 0.f;
-            }
-            const int off = mc * kMnSbo + (k >> 3) * kMnLbo + (k & 7) * 16;
-            split_store8(x, hi + off, lo + off);
+            off = mc * kMnSbo + (k >> 3) * kMnLbo + (k & 7) * 16;
         }
+        split_store8(t.x[i], hi + off, lo + off);
     }
 }
 
@@ -145,13 +155,22 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
 
     if (warp < 8) {
         // ------------------------------ producers ------------------------------
+        TileRegs ta, tb;
+        if (nkb > 0) {
+            load_tile<AMN>(g.A, g.lda, m0, g.M, kbeg, kend, tid, ta);
+            load_tile<BMN>(g.B, g.ldb, n0, g.N, kbeg, kend, tid, tb);
+        }
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % kGemmStages, round = kb / kGemmStages;
             if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);      // the MMAs that read this stage have retired
             uint8_t *st = smem + (size_t)s * kStageBytes;
-            const int k0 = kbeg + kb * kGemmBK;
-            stage_tile<AMN>(g.A, g.lda, m0, g.M, k0, kend, st, st + kTileBytes, tid);
-            stage_tile<BMN>(g.B, g.ldb, n0, g.N, k0, kend, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            store_tile<AMN>(ta, st, st + kTileBytes, tid);
+            store_tile<BMN>(tb, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            if (kb + 1 < nkb) {                                             // next block's loads fly during the fence/arrive/wait
+                const int k1 = kbeg + (kb + 1) * kGemmBK;
+                load_tile<AMN>(g.A, g.lda, m0, g.M, k1, kend, tid, ta);
+                load_tile<BMN>(g.B, g.ldb, n0, g.N, k1, kend, tid, tb);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[s]);
