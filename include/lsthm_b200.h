@@ -181,6 +181,28 @@ size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t 
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention of the utterance encoder (tcgen05, split-bf16, fp32 accuracy).
+ * Replaces ScaledDotProductAttention.forward, model/encoder.py:71-86, as called by
+ * MultiHeadAttention.forward (:27-60) with mask=None: per head  softmax(q k^T * scale) -> dropout -> . v
+ * over the L <= 128 utterances of a dialogue, d_k = d_v = 40; and its autograd backward.
+ * Row i of dialogue b, head h of a matrix X with row stride ldx (floats):  X + (b*L + i)*ldx + h*40.
+ * q/k/v may be three column blocks of one fused projection output (ldq = ldk = ldv = 3*H*40).
+ * Dropout is generated in-kernel from (seed, b, h, i, j); the same call arguments regenerate it in bwd.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t B, L, H, d_head;          /* d_head must be 40                                  */
+    int32_t ldq, ldk, ldv, ldo;       /* row strides (floats), multiples of 4               */
+    float scale;                      /* 1 / temperature = 1/sqrt(d_k)  (encoder.py:22)     */
+    float p_drop;                     /* attention dropout (encoder.py:66), 0 in eval mode  */
+    uint64_t seed;
+} lsthm_attn_desc;
+
+int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, float *out, void *stream);
+/* dq/dk/dv use the row strides ldq/ldk/ldv; out/dout use ldo */
+int lsthm_attn_bwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, const float *out,
+                   const float *dout, float *dq, float *dk, float *dv, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,12 @@ class SpsMasks(C.Structure):
     _fields_ = [("mq", C.c_void_p * 2), ("ml", C.c_void_p), ("ma", C.c_void_p), ("att_mask", C.c_void_p)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("d_head", C.c_int32), ("ldq", C.c_int32),
+                ("ldk", C.c_int32), ("ldv", C.c_int32), ("ldo", C.c_int32), ("scale", C.c_float), ("p_drop", C.c_float),
+                ("seed", C.c_uint64)]
+
+
 def build(verbose: bool = False, jobs: int = 8) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     cmd = ["make", "-C", os.path.join(_PKG, "csrc"), f"-j{jobs}", "all"]
@@ -100,6 +106,10 @@ def lib() -> C.CDLL:
     L.lsthm_gemm3.restype = C.c_int
     L.lsthm_gemm3.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                                 C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.lsthm_attn_fwd.restype = C.c_int
+    L.lsthm_attn_fwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 5
+    L.lsthm_attn_bwd.restype = C.c_int
+    L.lsthm_attn_bwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 9
     if L.lsthm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"liblsthm_b200.so ABI {L.lsthm_abi_version()} != expected {ABI_VERSION}")
     _lib = L
@@ -280,3 +290,30 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
     _check(lib().lsthm_gemm3(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), N,
                              None if ws is None else ws.data_ptr(), nws, _stream()), "lsthm_gemm3")
     return c
+
+
+# ------------------------------------------------------------------------------------------------
+# fused encoder self-attention (tcgen05)
+# ------------------------------------------------------------------------------------------------
+def make_attn_desc(B, L, H, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, d_head=40) -> AttnDesc:
+    d = AttnDesc()
+    d.B, d.L, d.H, d.d_head, d.ldq, d.ldk, d.ldv, d.ldo = B, L, H, d_head, ldq, ldk, ldv, ldo
+    d.scale, d.p_drop, d.seed = scale, p_drop, seed
+    return d
+
+
+def _f32_cuda(t: torch.Tensor, name: str) -> int:
+    if not (t.is_cuda and t.dtype == torch.float32 and t.data_ptr() % 16 == 0):
+        raise RuntimeError(f"{name}: expected a 16-byte aligned float32 CUDA tensor")
+    return t.data_ptr()
+
+
+def attn_fwd(d: AttnDesc, q, k, v, out) -> None:
+    _check(lib().lsthm_attn_fwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
+                                _stream()), "lsthm_attn_fwd")
+
+
+def attn_bwd(d: AttnDesc, q, k, v, out, dout, dq, dk, dv) -> None:
+    _check(lib().lsthm_attn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
+                                _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
+                                _stream()), "lsthm_attn_bwd")

@@ -1,0 +1,351 @@
+// Fused multi-head self-attention of the utterance encoder (model/encoder.py:27-86: per head
+// softmax(q k^T / sqrt(d_k)) -> dropout -> . v, UNMASKED over the L <= 128 utterances of a dialogue,
+// d_k = d_v = 40) on the tcgen05 tensor cores, forward and backward.  One CTA per (dialogue, head):
+// the whole L x L score tile lives in tensor memory, a thread owns one query row for the softmax
+// (tcgen05.ld gives a thread its row), the probabilities go back to shared memory as the next UMMA's
+// operand; nothing of size L x L ever touches HBM (the reference materialises scores, softmax and
+// dropout mask there: [B,8,L,L] x 3 encoders, forward and backward).
+//
+// fp32 accuracy: as in gemm3, every operand is split into bf16 hi + lo and each product is three UMMAs.
+//
+// Operand tiles are stored ONCE, row-major-K ("K-major") in the canonical no-swizzle layout
+//   offset(row, col) = (col/8)*2048 + (row/8)*128 + (row%8)*16 + (col%8)*2      [128 rows]
+// and the same bytes double as the MN-major operand of the transposed product (a core matrix is its
+// own transpose under the major flag): view(m = col, k = row) has LBO = 128, SBO = 2048.
+#pragma once
+#include "gemm3_kernels.cuh"
+
+namespace lsthm {
+
+constexpr int kAttD = 40, kAttDP = 48, kAttLP = 128;
+constexpr int kRowTile = 6 * 2048;          // [128 x 48] bf16
+constexpr int kSqTile = 16 * 2048;          // [128 x 128] bf16
+
+struct AttnArgs {
+    const float *q, *k, *v, *o, *dout;      // row i of dialogue b, head h: base + (b*L + i)*ld + h*40
+    float *out, *dq, *dk, *dv;
+    int B, L, H;
+    int ldq, ldk, ldv, ldo;                 // row strides (floats) of q/k/v (and dq/dk/dv) and of o/out/dout
+    float scale, p_drop;
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ uint32_t att_idesc(int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[128 x N] (+)= A . B over `ksteps` k16 steps, three split terms.  A: hi at a, lo at a + a_lo; same for B.
+__device__ __forceinline__ void umma3(uint32_t tmem_d, uint32_t a, uint32_t a_lo, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
+                                      uint32_t b, uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
+                                      uint32_t idesc, int ksteps) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ah = umma_desc(a + ks * a_step, a_lbo, a_sbo), al = umma_desc(a + a_lo + ks * a_step, a_lbo, a_sbo);
+        const uint64_t bh = umma_desc(b + ks * b_step, b_lbo, b_sbo), bl = umma_desc(b + b_lo + ks * b_step, b_lbo, b_sbo);
+        umma_f16(tmem_d, ah, bh, idesc, ks > 0 ? 1u : 0u);
+        umma_f16(tmem_d, ah, bl, idesc, 1u);
+        umma_f16(tmem_d, al, bh, idesc, 1u);
+    }
+}
+// operand triples used below:  K-major row tile: (k16 step, LBO, SBO) = (4096, 2048, 128);
+//                              MN-major view of the same bytes:         = ( 256,  128, 2048)
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// stage one 40-float row (scaled) of a [L][ld] matrix into a K-major row tile (hi, lo); rows >= L are zero
+__device__ __forceinline__ void stage_row40(const float *base, int ld, int row, int L, float scale, uint8_t *hi, float *keep) {
+    uint8_t *lo = hi + kRowTile;
+    const int roff = (row >> 3) * 128 + (row & 7) * 16;
+    float x[8];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        if (row < L) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * ld) + 2 * c);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * ld) + 2 * c + 1);
+            x[0] = a.x * scale; x[1] = a.y * scale; x[2] = a.z * scale; x[3] = a.w * scale;
+            x[4] = b.x * scale; x[5] = b.y * scale; x[6] = b.z * scale; x[7] = b.w * scale;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        }
+        if (keep) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) keep[8 * c + j] = x[j];
+        }
+        split_store8(x, hi + c * 2048 + roff, lo + c * 2048 + roff);
+    }
+    *reinterpret_cast<uint4 *>(hi + 5 * 2048 + roff) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(lo + 5 * 2048 + roff) = make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ float att_drop_scale(unsigned long long seed, int bh, int i, int j, float p) {
+    unsigned long long x = seed ^ (((unsigned long long)bh << 20) | ((unsigned long long)i << 8) | (unsigned long long)j);
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    const float u = (float)(unsigned)(x >> 40) * (1.0f / 16777216.0f);
+    return u < p ? 0.f : 1.0f / (1.0f - p);
+}
+
+// row-wise softmax statistics of S (TMEM columns [0,128) of this thread's lane), over the first L columns
+__device__ __forceinline__ void row_stats(uint32_t trow, int L, float &mx, float &inv) {
+    float v[16];
+    mx = -INFINITY;
+    for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+        tmem_ld16(trow + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c0 + j < L) mx = fmaxf(mx, v[j]);
+    }
+    float sum = 0.f;
+    for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+        tmem_ld16(trow + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c0 + j < L) sum += __expf(v[j] - mx);
+    }
+    inv = 1.0f / sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward:  out = dropout(softmax(q k^T * scale)) v      SMEM 88 KB -> 2 CTAs / SM
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t tmem_base;
+    uint8_t *sQ = smem, *sK = smem + 2 * kRowTile, *sV = smem + 2 * kSqTile;   // P (64 KB) aliases Q,K after S is done
+    uint8_t *sP = smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
+    const size_t row0 = (size_t)b * L;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, tid, L, a.scale, sQ, nullptr);
+    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, tid, L, 1.f, sK, nullptr);
+    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, tid, L, 1.f, sV, nullptr);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    if (tid == 0) {   // S = Qs K^T : M = query, N = key, K = d (48)
+        umma3(tmem, smem_u32(sQ), kRowTile, 4096u, 2048u, 128u, smem_u32(sK), kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+        umma_commit(&bar[0]);
+    }
+    mbar_wait(&bar[0], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    {
+        float mx, inv;
+        row_stats(trow, L, mx, inv);
+        const int roff = (tid >> 3) * 128 + (tid & 7) * 16;
+        float v[16], p8[8];
+        for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c0 + half * 8 + j;
+                    float p = 0.f;
+                    if (tid < L && col < L) {
+                        p = __expf(v[half * 8 + j] - mx) * inv;
+                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, tid, col, a.p_drop);
+                    }
+                    p8[j] = p;
+                }
+                const int chunk = (c0 >> 3) + half;
+                split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {   // O = P V : M = query, N = d (48, MN-major view of V), K = key (128); overwrites S columns [0,48)
+        umma3(tmem, smem_u32(sP), kSqTile, 4096u, 2048u, 128u, smem_u32(sV), kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
+        umma_commit(&bar[1]);
+    }
+    mbar_wait(&bar[1], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        float v[16];
+        float *orow = a.out + (row0 + tid) * a.ldo + h * kAttD;
+        for (int c0 = 0; c0 < kAttDP; c0 += 16) {
+            tmem_ld16(trow + c0, v);
+            if (tid < L) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4)
+                    if (c0 + 4 * q4 < kAttD)
+                        reinterpret_cast<float4 *>(orow + c0)[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward.  TMEM columns: S [0,128) | dPd [128,256) | dV [256,304) | dQ [304,352) | dK [352,400)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar[3];
+    __shared__ uint32_t tmem_base;
+    uint8_t *sQ = smem, *sK = sQ + 2 * kRowTile, *sV = sK + 2 * kRowTile, *sdO = sV + 2 * kRowTile, *sP = sdO + 2 * kRowTile;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
+    const size_t row0 = (size_t)b * L;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); mbar_fence_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    float dorow[kAttD];
+    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, tid, L, a.scale, sQ, nullptr);
+    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, tid, L, 1.f, sK, nullptr);
+    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, tid, L, 1.f, sV, nullptr);
+    stage_row40(a.dout + row0 * a.ldo + h * kAttD, a.ldo, tid, L, 1.f, sdO, dorow);
+    float delta = 0.f;                         // rowsum(dO * O) = sum_j Pd_ij dPd_ij
+    if (tid < L) {
+        const float *orow = a.o + (row0 + tid) * a.ldo + h * kAttD;
+#pragma unroll
+        for (int d = 0; d < kAttD; d += 4) {
+            const float4 o4 = __ldg(reinterpret_cast<const float4 *>(orow + d));
+            delta += dorow[d] * o4.x + dorow[d + 1] * o4.y + dorow[d + 2] * o4.z + dorow[d + 3] * o4.w;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+    const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), udO = smem_u32(sdO), uP = smem_u32(sP);
+    if (tid == 0) {
+        // S = Qs K^T ; dPd = dO V^T   (both M = query, N = key, K = d)
+        umma3(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+        umma3(tmem + 128, udO, kRowTile, 4096u, 2048u, 128u, uV, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+        umma_commit(&bar[0]);
+    }
+    mbar_wait(&bar[0], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const int roff = (tid >> 3) * 128 + (tid & 7) * 16;
+    float mx, inv;
+    row_stats(trow, L, mx, inv);
+    {   // Pd (dropped, scaled probabilities) -> shared, operand of dV = Pd^T dO
+        float v[16], p8[8];
+        for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c0 + half * 8 + j;
+                    float p = 0.f;
+                    if (tid < L && col < L) {
+                        p = __expf(v[half * 8 + j] - mx) * inv;
+                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, tid, col, a.p_drop);
+                    }
+                    p8[j] = p;
+                }
+                const int chunk = (c0 >> 3) + half;
+                split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {   // dV = Pd^T dO : M = key (MN-major view of P), N = d (MN-major view of dO), K = query
+        umma3(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+        umma_commit(&bar[1]);
+    }
+    mbar_wait(&bar[1], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {   // dS = P * (sc * dPd - delta)  -> overwrites the Pd tile (its only reader, the dV product, has retired)
+        float s[16], g[16], d8[8];
+        for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+            tmem_ld16(trow + c0, s);
+            tmem_ld16(trow + 128 + c0, g);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c0 + half * 8 + j;
+                    float ds = 0.f;
+                    if (tid < L && col < L) {
+                        const float p = __expf(s[half * 8 + j] - mx) * inv;
+                        const float sc = a.p_drop > 0.f ? att_drop_scale(a.seed, blockIdx.x, tid, col, a.p_drop) : 1.f;
+                        ds = p * (sc * g[half * 8 + j] - delta);
+                    }
+                    d8[j] = ds;
+                }
+                const int chunk = (c0 >> 3) + half;
+                split_store8(d8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+            }
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        // dQs = dS K : M = query, N = d (MN view of K), K = key ;  dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
+        umma3(tmem + 304, uP, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
+        umma3(tmem + 352, uP, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+        umma_commit(&bar[2]);
+    }
+    mbar_wait(&bar[2], 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        float v[16];
+        const size_t r = row0 + tid;
+        for (int which = 0; which < 3; ++which) {
+            float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + r * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
+            const float mul = which == 1 ? a.scale : 1.f;              // d/dq = scale * (dS K)
+            const uint32_t tcol = trow + 256 + 48 * which;
+            for (int c0 = 0; c0 < kAttDP; c0 += 16) {
+                tmem_ld16(tcol + c0, v);
+                if (tid < L) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        if (c0 + 4 * q4 < kAttD)
+                            reinterpret_cast<float4 *>(dst + c0)[q4] =
+                                make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    }
+}
+
+}  // namespace lsthm

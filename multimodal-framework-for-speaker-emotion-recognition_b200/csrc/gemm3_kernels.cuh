@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
 }
 
 // C[i] = bias[i % N] + sum_s ws[s][i]   (fixed order -> deterministic)
-__global__ void gemm3_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ bias, float *__restrict__ C,
+static __global__ void gemm3_reduce_kernel(const float *__restrict__ ws, const float *__restrict__ bias, float *__restrict__ C,
                                     int M, int N, int ldc, int splits) {
     const size_t total = (size_t)M * N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {

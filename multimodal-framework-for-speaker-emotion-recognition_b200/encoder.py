@@ -13,12 +13,15 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .fused_attention import fused_self_attention
 from .mm3 import linear3
 
 import os
 # fused library attention for the encoder (measured: 52.4 -> 50.5 ms/step, eval parity unchanged); the explicit
 # softmax path is kept for the dropout-mask-tape tests and when the attention weights are wanted
 _FUSED_SDPA = os.environ.get("LSTHM_FUSED_SDPA", "1") == "1"
+# our own fused attention kernels (csrc/attn_kernels.cuh): tcgen05 split-bf16, scores never leave the SM
+_FUSED_OWN = os.environ.get("LSTHM_FUSED_ATTN", "1") == "1"
 
 
 class ScaledDotProductAttention(nn.Module):
@@ -58,6 +61,15 @@ class MultiHeadAttention(nn.Module):
         B, Lq, Lk = q.size(0), q.size(1), k.size(1)
         H, dk, dv = self.n_head, self.d_k, self.d_v
         res = q
+        if (_FUSED_OWN and q is k and k is v and mask is None and q.is_cuda and q.dtype == torch.float32 and Lq <= 128
+                and dk == 40 and dv == 40 and type(self.attention.dropout) is nn.Dropout and q.shape[-1] % 4 == 0):
+            w_qkv = torch.cat([self.w_qs.weight, self.w_ks.weight, self.w_vs.weight], dim=0)
+            qkv = linear3(q, w_qkv)                                            # one projection GEMM instead of three
+            p = self.attention.dropout.p if self.training else 0.0
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+            ctx = fused_self_attention(qkv, H, 1.0 / self.attention.temperature, p, seed)
+            out = self.layer_norm(self.dropout(linear3(ctx, self.fc.weight)) + res)
+            return out, None
         qh = linear3(q, self.w_qs.weight).view(B, Lq, H, dk).transpose(1, 2)
         kh = linear3(k, self.w_ks.weight).view(B, Lk, H, dk).transpose(1, 2)
         vh = linear3(v, self.w_vs.weight).view(B, Lk, H, dv).transpose(1, 2)

@@ -1,0 +1,43 @@
+"""torch.autograd glue for the fused encoder self-attention kernels (lsthm_attn_fwd/bwd): takes the fused
+projection output qkv[B, L, 3*H*40] and returns the concatenated heads [B, L, H*40]
+(model/encoder.py:38-53: split heads, ScaledDotProductAttention, merge heads)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+launches = {"attn": 0}
+
+
+class FusedSelfAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv: torch.Tensor, n_head: int, scale: float, p_drop: float, seed: int):
+        B, L, W = qkv.shape
+        HD = W // 3
+        qkv = qkv.contiguous()
+        out = torch.empty(B, L, HD, device=qkv.device, dtype=torch.float32)
+        d = _lib.make_attn_desc(B, L, n_head, W, W, W, HD, scale, p_drop, seed)
+        q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
+        _lib.attn_fwd(d, q, k, v, out)
+        launches["attn"] += 1
+        ctx.save_for_backward(qkv, out)
+        ctx.cfg = (n_head, scale, p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: torch.Tensor):
+        qkv, out = ctx.saved_tensors
+        n_head, scale, p_drop, seed = ctx.cfg
+        B, L, W = qkv.shape
+        HD = W // 3
+        dqkv = torch.empty_like(qkv)
+        d = _lib.make_attn_desc(B, L, n_head, W, W, W, HD, scale, p_drop, seed)
+        q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
+        _lib.attn_bwd(d, q, k, v, out, dout.contiguous(), dqkv[:, :, :HD], dqkv[:, :, HD:2 * HD], dqkv[:, :, 2 * HD:])
+        launches["attn"] += 1
+        return dqkv, None, None, None, None
+
+
+def fused_self_attention(qkv: torch.Tensor, n_head: int, scale: float, p_drop: float = 0.0, seed: int = 0) -> torch.Tensor:
+    return FusedSelfAttentionFn.apply(qkv, n_head, float(scale), float(p_drop), int(seed))
