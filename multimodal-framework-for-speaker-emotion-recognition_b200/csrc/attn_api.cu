@@ -32,7 +32,7 @@ int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, con
     const size_t smem = 2 * kSqTile + 2 * kRowTile + 1024;
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_attn_fwd shared-memory opt-in", e);
-    attn_fwd_kernel<<<d->B * d->H, 128, smem, (cudaStream_t)stream>>>(a);
+    attn_fwd_kernel<<<d->B * d->H, 256, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_attn_fwd launch", e);
 }
@@ -47,7 +47,7 @@ int lsthm_attn_bwd(const lsthm_attn_desc *d, const float *q, const float *k, con
     const size_t smem = 8 * kRowTile + 2 * kSqTile + 1024;
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_attn_bwd shared-memory opt-in", e);
-    attn_bwd_kernel<<<d->B * d->H, 128, smem, (cudaStream_t)stream>>>(a);
+    attn_bwd_kernel<<<d->B * d->H, 256, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_attn_bwd launch", e);
 }

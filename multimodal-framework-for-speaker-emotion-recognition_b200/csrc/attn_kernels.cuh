@@ -67,14 +67,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// stage one 40-float row (scaled) of a [L][ld] matrix into a K-major row tile (hi, lo); rows >= L are zero
-__device__ __forceinline__ void stage_row40(const float *base, int ld, int row, int L, float scale, uint8_t *hi, float *keep) {
+// stage chunks [c0, c1) (8 floats each; chunk 5 is the zero padding 40 -> 48) of one 40-float row (scaled) of a
+// [L][ld] matrix into a K-major row tile (hi, lo); rows >= L are zero
+__device__ __forceinline__ void stage_row40(const float *base, int ld, int row, int L, float scale, uint8_t *hi, int c0, int c1) {
     uint8_t *lo = hi + kRowTile;
     const int roff = (row >> 3) * 128 + (row & 7) * 16;
     float x[8];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        if (row < L) {
+    for (int c = 0; c < 6; ++c) {
+        if (c < c0 || c >= c1) continue;
+        if (c < 5 && row < L) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * ld) + 2 * c);
             const float4 b = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * ld) + 2 * c + 1);
             x[0] = a.x * scale; x[1] = a.y * scale; x[2] = a.z * scale; x[3] = a.w * scale;
@@ -83,14 +85,8 @@ __device__ __forceinline__ void stage_row40(const float *base, int ld, int row, 
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = 0.f;
         }
-        if (keep) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) keep[8 * c + j] = x[j];
-        }
         split_store8(x, hi + c * 2048 + roff, lo + c * 2048 + roff);
     }
-    *reinterpret_cast<uint4 *>(hi + 5 * 2048 + roff) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4 *>(lo + 5 * 2048 + roff) = make_uint4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ float att_drop_scale(unsigned long long seed, int bh, int i, int j, float p) {
@@ -100,36 +96,45 @@ __device__ __forceinline__ float att_drop_scale(unsigned long long seed, int bh,
     return u < p ? 0.f : 1.0f / (1.0f - p);
 }
 
-// row-wise softmax statistics of S (TMEM columns [0,128) of this thread's lane), over the first L columns
-__device__ __forceinline__ void row_stats(uint32_t trow, int L, float &mx, float &inv) {
+// Row-wise softmax statistics of S over the first L columns.  Two threads share a query row (tid and tid^128:
+// warps w and w+4 address the same TMEM lanes); each scans its 64-column half and they combine through shared
+// memory.  `ex` is a [2][256] float scratch.  Contains two CTA barriers: call from all 256 threads.
+__device__ __forceinline__ void row_stats(uint32_t trow, int cb, int L, float *ex, float &mx, float &inv) {
     float v[16];
-    mx = -INFINITY;
-    for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+    float m = -INFINITY;
+    for (int c0 = cb; c0 < cb + 64; c0 += 16) {
         tmem_ld16(trow + c0, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            if (c0 + j < L) mx = fmaxf(mx, v[j]);
+            if (c0 + j < L) m = fmaxf(m, v[j]);
     }
+    ex[threadIdx.x] = m;
+    __syncthreads();
+    mx = fmaxf(m, ex[threadIdx.x ^ 128]);
     float sum = 0.f;
-    for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+    for (int c0 = cb; c0 < cb + 64; c0 += 16) {
         tmem_ld16(trow + c0, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
             if (c0 + j < L) sum += __expf(v[j] - mx);
     }
-    inv = 1.0f / sum;
+    ex[256 + threadIdx.x] = sum;
+    __syncthreads();
+    inv = 1.0f / (sum + ex[256 + (threadIdx.x ^ 128)]);
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward:  out = dropout(softmax(q k^T * scale)) v      SMEM 88 KB -> 2 CTAs / SM
+// forward:  out = dropout(softmax(q k^T * scale)) v      256 threads, SMEM 88 KB -> 2 CTAs / SM
+// thread = (query row r = tid%128, column half g = tid/128)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base;
+    __shared__ float ex[512];
     uint8_t *sQ = smem, *sK = smem + 2 * kRowTile, *sV = smem + 2 * kSqTile;   // P (64 KB) aliases Q,K after S is done
     uint8_t *sP = smem;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
     const size_t row0 = (size_t)b * L;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
@@ -137,9 +142,9 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, tid, L, a.scale, sQ, nullptr);
-    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, tid, L, 1.f, sK, nullptr);
-    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, tid, L, 1.f, sV, nullptr);
+    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, r, L, a.scale, sQ, 3 * g, 3 * g + 3);
+    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, r, L, 1.f, sK, 3 * g, 3 * g + 3);
+    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, r, L, 1.f, sV, 3 * g, 3 * g + 3);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -151,13 +156,14 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     }
     mbar_wait(&bar[0], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int cb = 64 * g;
     {
         float mx, inv;
-        row_stats(trow, L, mx, inv);
-        const int roff = (tid >> 3) * 128 + (tid & 7) * 16;
+        row_stats(trow, cb, L, ex, mx, inv);
+        const int roff = (r >> 3) * 128 + (r & 7) * 16;
         float v[16], p8[8];
-        for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+        for (int c0 = cb; c0 < cb + 64; c0 += 16) {
             tmem_ld16(trow + c0, v);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -165,9 +171,9 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
                 for (int j = 0; j < 8; ++j) {
                     const int col = c0 + half * 8 + j;
                     float p = 0.f;
-                    if (tid < L && col < L) {
+                    if (r < L && col < L) {
                         p = __expf(v[half * 8 + j] - mx) * inv;
-                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, tid, col, a.p_drop);
+                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, r, col, a.p_drop);
                     }
                     p8[j] = p;
                 }
@@ -188,10 +194,10 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
         float v[16];
-        float *orow = a.out + (row0 + tid) * a.ldo + h * kAttD;
-        for (int c0 = 0; c0 < kAttDP; c0 += 16) {
+        float *orow = a.out + (row0 + r) * a.ldo + h * kAttD;
+        for (int c0 = 16 * g; c0 < kAttDP; c0 += 32) {
             tmem_ld16(trow + c0, v);
-            if (tid < L) {
+            if (r < L) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                     if (c0 + 4 * q4 < kAttD)
@@ -210,12 +216,13 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // backward.  TMEM columns: S [0,128) | dPd [128,256) | dV [256,304) | dQ [304,352) | dK [352,400)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar[3];
     __shared__ uint32_t tmem_base;
+    __shared__ float ex[512];
     uint8_t *sQ = smem, *sK = sQ + 2 * kRowTile, *sV = sK + 2 * kRowTile, *sdO = sV + 2 * kRowTile, *sP = sdO + 2 * kRowTile;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
     const size_t row0 = (size_t)b * L;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); mbar_fence_init(); }
@@ -223,18 +230,17 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    float dorow[kAttD];
-    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, tid, L, a.scale, sQ, nullptr);
-    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, tid, L, 1.f, sK, nullptr);
-    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, tid, L, 1.f, sV, nullptr);
-    stage_row40(a.dout + row0 * a.ldo + h * kAttD, a.ldo, tid, L, 1.f, sdO, dorow);
-    float delta = 0.f;                         // rowsum(dO * O) = sum_j Pd_ij dPd_ij
-    if (tid < L) {
-        const float *orow = a.o + (row0 + tid) * a.ldo + h * kAttD;
+    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, r, L, a.scale, sQ, 3 * g, 3 * g + 3);
+    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, r, L, 1.f, sK, 3 * g, 3 * g + 3);
+    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, r, L, 1.f, sV, 3 * g, 3 * g + 3);
+    stage_row40(a.dout + row0 * a.ldo + h * kAttD, a.ldo, r, L, 1.f, sdO, 3 * g, 3 * g + 3);
+    float delta = 0.f;                         // rowsum(dO * O) = sum_j Pd_ij dPd_ij  (both threads of a row compute it)
+    if (r < L) {
+        const float *orow = a.o + (row0 + r) * a.ldo + h * kAttD, *drow = a.dout + (row0 + r) * a.ldo + h * kAttD;
 #pragma unroll
         for (int d = 0; d < kAttD; d += 4) {
-            const float4 o4 = __ldg(reinterpret_cast<const float4 *>(orow + d));
-            delta += dorow[d] * o4.x + dorow[d + 1] * o4.y + dorow[d + 2] * o4.z + dorow[d + 3] * o4.w;
+            const float4 o4 = __ldg(reinterpret_cast<const float4 *>(orow + d)), d4 = __ldg(reinterpret_cast<const float4 *>(drow + d));
+            delta += d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -251,13 +257,13 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     }
     mbar_wait(&bar[0], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-    const int roff = (tid >> 3) * 128 + (tid & 7) * 16;
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int roff = (r >> 3) * 128 + (r & 7) * 16, cb = 64 * g;
     float mx, inv;
-    row_stats(trow, L, mx, inv);
+    row_stats(trow, cb, L, ex, mx, inv);
     {   // Pd (dropped, scaled probabilities) -> shared, operand of dV = Pd^T dO
         float v[16], p8[8];
-        for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+        for (int c0 = cb; c0 < cb + 64; c0 += 16) {
             tmem_ld16(trow + c0, v);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -265,9 +271,9 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
                 for (int j = 0; j < 8; ++j) {
                     const int col = c0 + half * 8 + j;
                     float p = 0.f;
-                    if (tid < L && col < L) {
+                    if (r < L && col < L) {
                         p = __expf(v[half * 8 + j] - mx) * inv;
-                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, tid, col, a.p_drop);
+                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, r, col, a.p_drop);
                     }
                     p8[j] = p;
                 }
@@ -287,20 +293,20 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     mbar_wait(&bar[1], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {   // dS = P * (sc * dPd - delta)  -> overwrites the Pd tile (its only reader, the dV product, has retired)
-        float s[16], g[16], d8[8];
-        for (int c0 = 0; c0 < kAttLP; c0 += 16) {
+        float s[16], gg[16], d8[8];
+        for (int c0 = cb; c0 < cb + 64; c0 += 16) {
             tmem_ld16(trow + c0, s);
-            tmem_ld16(trow + 128 + c0, g);
+            tmem_ld16(trow + 128 + c0, gg);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = c0 + half * 8 + j;
                     float ds = 0.f;
-                    if (tid < L && col < L) {
+                    if (r < L && col < L) {
                         const float p = __expf(s[half * 8 + j] - mx) * inv;
-                        const float sc = a.p_drop > 0.f ? att_drop_scale(a.seed, blockIdx.x, tid, col, a.p_drop) : 1.f;
-                        ds = p * (sc * g[half * 8 + j] - delta);
+                        const float sc = a.p_drop > 0.f ? att_drop_scale(a.seed, blockIdx.x, r, col, a.p_drop) : 1.f;
+                        ds = p * (sc * gg[half * 8 + j] - delta);
                     }
                     d8[j] = ds;
                 }
@@ -323,20 +329,19 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
         float v[16];
-        const size_t r = row0 + tid;
-        for (int which = 0; which < 3; ++which) {
-            float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + r * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
+        const size_t gr = row0 + r;
+        // 9 (matrix, 16-column block) items over the two threads of a row: g takes the items with index % 2 == g
+        for (int item = g; item < 9; item += 2) {
+            const int which = item / 3, c0 = 16 * (item % 3);
+            float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + gr * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
             const float mul = which == 1 ? a.scale : 1.f;              // d/dq = scale * (dS K)
-            const uint32_t tcol = trow + 256 + 48 * which;
-            for (int c0 = 0; c0 < kAttDP; c0 += 16) {
-                tmem_ld16(tcol + c0, v);
-                if (tid < L) {
+            tmem_ld16(trow + 256 + 48 * which + c0, v);
+            if (r < L) {
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4)
-                        if (c0 + 4 * q4 < kAttD)
-                            reinterpret_cast<float4 *>(dst + c0)[q4] =
-                                make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
-                }
+                for (int q4 = 0; q4 < 4; ++q4)
+                    if (c0 + 4 * q4 < kAttD)
+                        reinterpret_cast<float4 *>(dst + c0)[q4] =
+                            make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
             }
         }
     }

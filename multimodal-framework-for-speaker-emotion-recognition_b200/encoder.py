@@ -89,8 +89,14 @@ class PositionwiseFeedForward(nn.Module):
         self.fc = nn.Linear(d_in, 100)  # registered but never applied (encoder.py:99,111): grad stays None
 
     def forward(self, x):
-        h = F.relu(linear3(x, self.w_1.weight, self.w_1.bias))
-        return self.layer_norm(self.dropout(linear3(h, self.w_2.weight, self.w_2.bias)) + x)
+        w1, b1, w2 = self.w_1.weight, self.w_1.bias, self.w_2.weight
+        pad = (-w1.shape[0]) % 4
+        if pad and x.is_cuda:
+            # d_inner = 50 (HybridRNN_AT/ATV) is not a multiple of 4: zero-pad the hidden width so both products
+            # run on the tensor-core GEMM (padded units are relu(0) = 0 and meet zero columns of w_2)
+            w1, b1, w2 = F.pad(w1, (0, 0, 0, pad)), F.pad(b1, (0, pad)), F.pad(w2, (0, pad))
+        h = F.relu(linear3(x, w1, b1))
+        return self.layer_norm(self.dropout(linear3(h, w2, self.w_2.bias)) + x)
 
 
 class EncoderLayer(nn.Module):
