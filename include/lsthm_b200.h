@@ -203,6 +203,15 @@ int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, con
 int lsthm_attn_bwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, const float *out,
                    const float *dout, float *dq, float *dk, float *dv, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused Adam step on a flat fp32 buffer.  Replaces `self.optim.step()` of the reference's trainer
+ * (model_trainer.py:82,120: torch.optim.Adam(lr, weight_decay=2e-5), L2-style decay, no amsgrad) for one
+ * gradient bucket; `step` counts from 1 (bias correction).  Parameters whose gradient is None in the
+ * reference (never-used ones) must simply not be part of the buffers.
+ * ------------------------------------------------------------------------------------------ */
+int lsthm_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, size_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
     L.lsthm_attn_fwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 5
     L.lsthm_attn_bwd.restype = C.c_int
     L.lsthm_attn_bwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 9
+    L.lsthm_adam_step.restype = C.c_int
+    L.lsthm_adam_step.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_float] * 5 + [C.c_int32, C.c_void_p]
     if L.lsthm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"liblsthm_b200.so ABI {L.lsthm_abi_version()} != expected {ABI_VERSION}")
     _lib = L
@@ -317,3 +319,14 @@ def attn_bwd(d: AttnDesc, q, k, v, out, dout, dq, dk, dv) -> None:
     _check(lib().lsthm_attn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
                                 _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
                                 _stream()), "lsthm_attn_bwd")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step) -> None:
+    """Fused Adam on flat, contiguous fp32 CUDA buffers of equal length (in place)."""
+    n = param.numel()
+    for t in (grad, exp_avg, exp_avg_sq):
+        if t.numel() != n:
+            raise RuntimeError("adam_step: buffers must have the same length")
+    _check(lib().lsthm_adam_step(_dev_ptr(param, "param"), _dev_ptr(grad, "grad"), _dev_ptr(exp_avg, "exp_avg"),
+                                 _dev_ptr(exp_avg_sq, "exp_avg_sq"), n, lr, beta1, beta2, eps, weight_decay, step, _stream()),
+           "lsthm_adam_step")

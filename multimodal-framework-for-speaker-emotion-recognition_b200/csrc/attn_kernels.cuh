@@ -90,10 +90,7 @@ __device__ __forceinline__ void stage_row40(const float *base, int ld, int row, 
 }
 
 __device__ __forceinline__ float att_drop_scale(unsigned long long seed, int bh, int i, int j, float p) {
-    unsigned long long x = seed ^ (((unsigned long long)bh << 20) | ((unsigned long long)i << 8) | (unsigned long long)j);
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-    const float u = (float)(unsigned)(x >> 40) * (1.0f / 16777216.0f);
-    return u < p ? 0.f : 1.0f / (1.0f - p);
+    return dropout_scale(seed, (uint32_t)bh, (uint32_t)(i << 7 | j), p);
 }
 
 // Row-wise softmax statistics of S over the first L columns.  Two threads share a query row (tid and tid^128:

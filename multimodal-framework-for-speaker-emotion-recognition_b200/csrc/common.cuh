@@ -233,6 +233,16 @@ __device__ __forceinline__ void store_partial(float *part, const int J, const in
             make_float4(acc.get(0, m), acc.get(1, m), acc.get(2, m), acc.get(3, m));
 }
 
+// Counter-based Bernoulli(1-p) keep decision for in-kernel dropout: two rounds of a 32-bit integer finaliser
+// ("lowbias32") over a key built from (seed, row id, column id).  Forward and backward call it with the same
+// arguments, so no mask is ever stored.  Returns the dropout scale: 0 or 1/(1-p).
+__device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t a, uint32_t b, float p) {
+    uint32_t x = (uint32_t)seed ^ (a * 0x9E3779B9u) ^ ((uint32_t)(seed >> 32) + b * 0x85EBCA6Bu);
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    x += a; x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return (float)(x >> 8) * (1.0f / 16777216.0f) < p ? 0.f : 1.0f / (1.0f - p);
+}
+
 // k-major [k][MTP] vector of one unit: load / store all rows at once (conflict-free 16B accesses).
 template <int MTP>
 __device__ __forceinline__ void load_rows(float (&v)[MTP], const float *p) {

@@ -120,7 +120,7 @@ static void fwd_smem(const MabLayout &L, int MT, FwdSmem &S) {
 
 static void bwd_smem(const MabLayout &L, int MT, BwdSmem &S) {
     const int MTP = (MT + 3) & ~3;
-    int o = 0;
+    int o = 8;  // two mbarriers
     S.dh = o; o += L.D * MTP;
     S.dz = o; o += L.D * MTP;
     S.dc = o; o += L.D * MTP;
@@ -142,6 +142,9 @@ static void bwd_smem(const MabLayout &L, int MT, BwdSmem &S) {
     S.p2 = o; o += p2;
     S.red = o; o += L.nwarp * kHeads * MTP;
     S.fin = o; o += kHeads * MTP;
+    S.dhz = o; o += 2 * MT * 2 * L.D;
+    S.uh = o; o += 2 * MT * L.MH;
+    S.mk = o; o += 2 * MT * L.MH;
     S.total = o;
 }
 

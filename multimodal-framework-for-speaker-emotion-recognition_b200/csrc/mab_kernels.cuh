@@ -50,7 +50,7 @@ struct FwdSmem {  // float offsets
     int s3pb[kMaxMod];
 };
 struct BwdSmem {
-    int dh, dz, dc, gh, gz, dup, dr, km, C, A, row, p2, red, fin, total;
+    int dh, dz, dc, gh, gz, dup, dr, km, C, A, row, p2, red, fin, dhz, uh, mk, total;
     int b3pb[kMaxMod], b5pb[kMaxMod];
 };
 
@@ -378,8 +378,31 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
     float *s_pA = s_A;  // B4/B5 partials alias the (by then dead) A tile + dvec rows
     const int nq2 = G / 4, nqd = D / 4;
 
-    for (int i = tid; i < a.S.total; i += nt) smem[i] = 0.f;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    float *s_dhz = smem + a.S.dhz, *s_uh = smem + a.S.uh, *s_mk = smem + a.S.mk;
+    const bool masked = a.mask != nullptr;
+    for (int i = 8 + tid; i < a.S.total; i += nt) smem[i] = 0.f;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_fence_init();
+    }
     __syncthreads();
+    // per-step input tiles (dL/d[h|z], fc hidden, dropout mask) are contiguous rows: bulk-copied one step ahead
+    const uint32_t dhz_bytes = (uint32_t)rows * 2 * D * sizeof(float), uh_bytes = (uint32_t)rows * MH * sizeof(float);
+    const uint32_t tile_bytes = dhz_bytes + uh_bytes + (masked ? uh_bytes : 0u);
+    auto issue_tiles = [&](int t) {
+        const int bf = t & 1;
+        const size_t tn = (size_t)t * N + n0;
+        mbar_expect_tx(bar + bf, tile_bytes);
+        bulk_g2s(s_dhz + bf * MT * 2 * D, a.dhz + tn * 2 * D, dhz_bytes, bar + bf);
+        bulk_g2s(s_uh + bf * MT * MH, a.sU + tn * MH, uh_bytes, bar + bf);
+        if (masked) bulk_g2s(s_mk + bf * MT * MH, a.mask + tn * MH, uh_bytes, bar + bf);
+    };
+    if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_tiles(T - 1);
+    }
 
     const int jj = lane / MTP, mm = lane % MTP;
     const bool mvalid = mm < MT;
@@ -408,10 +431,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             if (t > 0) {
                 const char *c = reinterpret_cast<const char *>(a.sC + (tn0 - N) * D);
                 for (int i = tid * 128; i < rows * D * 4; i += nt * 128) prefetch_l2(c + i);
-                const char *d = reinterpret_cast<const char *>(a.dhz + (tn0 - N) * 2 * D);
-                for (int i = tid * 128; i < rows * 2 * D * 4; i += nt * 128) prefetch_l2(d + i);
             }
         }
+        const int buf = t & 1;
+        if (tid == 0 && t > 0) issue_tiles(t - 1);      // the other slot was last read two barriers ago (step t+1)
         Acc<MT> acc;
         // ---- P0: gh = dL/dh_t + carry, gz = dL/dz_t + carry
         if (tid < 2 * D) {
@@ -420,10 +443,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             load_rows<MTP>(carry, (part ? s_dz : s_dh) + j * MTP);
 #pragma unroll
             for (int q = 0; q < MTP; ++q) v[q] = 0.f;
+            mbar_wait(bar + buf, ((T - 1 - t) >> 1) & 1);
+            const float *dz_s = s_dhz + buf * MT * 2 * D + part * D + j;
 #pragma unroll
             for (int q = 0; q < MT; ++q) {
                 if (q < rows) {
-                    v[q] = __ldg(a.dhz + (tn0 + q) * 2 * D + part * D + j) + carry[q];
+                    v[q] = dz_s[q * 2 * D] + carry[q];
                     if (part) a.dzt[(tn0 + q) * D + j] = v[q];
                 }
             }
@@ -452,9 +477,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 if (q < rows) {
                     float s = 0.f;
                     for (int sp = 0; sp < L.b1ns; ++sp) s += s_p2[(sp * MTP + q) * MH + tid];
-                    const float uh = __ldg(a.sU + (tn0 + q) * MH + tid);
+                    const float uh = s_uh[buf * MT * MH + q * MH + tid];
                     s = (uh != 0.f) ? s : 0.f;
-                    if (a.mask) s *= __ldg(a.mask + (tn0 + q) * MH + tid);
+                    if (masked) s *= s_mk[buf * MT * MH + q * MH + tid];
                     a.dup[(tn0 + q) * MH + tid] = s;
                     v[q] = s;
                 }

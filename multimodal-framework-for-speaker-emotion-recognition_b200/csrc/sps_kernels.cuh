@@ -87,12 +87,9 @@ __device__ __forceinline__ void grid_wait(unsigned *bar, unsigned target) {
     __syncthreads();
 }
 
-// counter-based keep decision for the in-cell attention dropout (same stream in fwd and bwd)
+// in-cell attention dropout: keep decision for element (i, j) of dialogue n at step t (same stream in fwd and bwd)
 __device__ __forceinline__ float att_keep_scale(unsigned long long seed, int t, int n, int i, int j, float p) {
-    unsigned long long x = seed ^ (((unsigned long long)t << 40) | ((unsigned long long)n << 16) | (unsigned long long)(i << 8 | j));
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;   // murmur3 fmix64
-    const float u = (float)(unsigned)(x >> 40) * (1.0f / 16777216.0f);
-    return u < p ? 0.f : 1.0f / (1.0f - p);
+    return dropout_scale(seed, (uint32_t)t * 65536u + (uint32_t)n, (uint32_t)(i << 7 | j), p);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -30,8 +30,10 @@ def unused_parameter_names(model: torch.nn.Module) -> List[str]:
 
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, world_size: int, bucket_bytes: int = 4 << 20,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, flatten_params: bool = False):
         self.world, self.group = world_size, group
+        self.flatten_params = flatten_params
+        self.param_buckets: List[torch.Tensor] = []   # flat parameter storage per bucket (FusedAdam steps on these)
         skip = set(unused_parameter_names(model))
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in skip]
         # autograd finishes gradients roughly in reverse registration order of use: walk the
@@ -66,6 +68,16 @@ class GradAllReducer:
             o += p.numel()
         self.buckets.append(flat)
         self._members.append(list(params))
+        if self.flatten_params:
+            # parameters of a bucket share one flat storage too (p.data become views; values are preserved), so the
+            # optimizer is one fused launch per bucket; offsets are 4-float aligned by construction of `total`
+            pflat = torch.empty(total, device=params[0].device, dtype=params[0].dtype)
+            o = 0
+            for p in params:
+                pflat[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = pflat[o:o + p.numel()].view_as(p)
+                o += p.numel()
+            self.param_buckets.append(pflat)
 
     def _make_hook(self, b):
         def hook(_param):
@@ -107,3 +119,27 @@ class GradAllReducer:
         for h in self._handles:
             h.wait()
         self._handles = []
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (L2-style decay, no amsgrad; what the reference's
+    trainer builds at model_trainer.py:82) as ONE fused CUDA launch per gradient bucket of a
+    ``GradAllReducer(..., flatten_params=True)``.  Parameters that are not in a bucket (never-used ones whose grad
+    is None in the reference) are not touched, exactly as torch skips ``grad is None``."""
+
+    def __init__(self, reducer: GradAllReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        if not reducer.flatten_params:
+            raise RuntimeError("FusedAdam needs GradAllReducer(..., flatten_params=True)")
+        self.reducer, self.lr, self.betas, self.eps, self.weight_decay = reducer, lr, betas, eps, weight_decay
+        self.step_count = 0
+        self.exp_avg = [torch.zeros_like(b) for b in reducer.param_buckets]
+        self.exp_avg_sq = [torch.zeros_like(b) for b in reducer.param_buckets]
+
+    def step(self) -> None:
+        from . import _lib
+        self.step_count += 1
+        for p, g, m, v in zip(self.reducer.param_buckets, self.reducer.buckets, self.exp_avg, self.exp_avg_sq):
+            _lib.adam_step(p, g, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count)
+
+    def zero_grad(self) -> None:
+        self.reducer.zero_grad()

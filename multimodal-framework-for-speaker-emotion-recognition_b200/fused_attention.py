@@ -8,6 +8,19 @@ import torch
 from . import _lib
 
 launches = {"attn": 0}
+# bench.py sets this to a list to collect (start_event, end_event, useful FLOPs) per attention launch
+events = None
+
+
+def _timed(flops, fn, *args):
+    launches["attn"] += 1
+    if events is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(*args)
+    e1.record()
+    events.append((e0, e1, flops))
 
 
 class FusedSelfAttentionFn(torch.autograd.Function):
@@ -19,8 +32,7 @@ class FusedSelfAttentionFn(torch.autograd.Function):
         out = torch.empty(B, L, HD, device=qkv.device, dtype=torch.float32)
         d = _lib.make_attn_desc(B, L, n_head, W, W, W, HD, scale, p_drop, seed)
         q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
-        _lib.attn_fwd(d, q, k, v, out)
-        launches["attn"] += 1
+        _timed(4.0 * B * n_head * L * L * 40, _lib.attn_fwd, d, q, k, v, out)          # QK^T and PV
         ctx.save_for_backward(qkv, out)
         ctx.cfg = (n_head, scale, p_drop, seed)
         return out
@@ -34,8 +46,8 @@ class FusedSelfAttentionFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         d = _lib.make_attn_desc(B, L, n_head, W, W, W, HD, scale, p_drop, seed)
         q, k, v = qkv[:, :, :HD], qkv[:, :, HD:2 * HD], qkv[:, :, 2 * HD:]
-        _lib.attn_bwd(d, q, k, v, out, dout.contiguous(), dqkv[:, :, :HD], dqkv[:, :, HD:2 * HD], dqkv[:, :, 2 * HD:])
-        launches["attn"] += 1
+        _timed(12.0 * B * n_head * L * L * 40, _lib.attn_bwd, d, q, k, v, out, dout.contiguous(), dqkv[:, :, :HD],
+               dqkv[:, :, HD:2 * HD], dqkv[:, :, 2 * HD:])                               # S, dPd, dV, dQ, dK (+ recompute)
         return dqkv, None, None, None, None
 
 

@@ -24,6 +24,21 @@ from . import _lib
 
 _ENABLED = os.environ.get("LSTHM_GEMM3", "1") == "1"
 launches = {"gemm3": 0}
+# bench.py sets this to a list to collect (start_event, end_event, 2*M*N*K) per lsthm_gemm3 launch
+events = None
+
+
+def _gemm(mode, a, b, bias=None):
+    launches["gemm3"] += 1
+    if events is None:
+        return _lib.gemm3(mode, a, b, bias)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    c = _lib.gemm3(mode, a, b, bias)
+    e1.record()
+    k = a.shape[0] if mode == _lib.GEMM_TN else a.shape[1]
+    events.append((e0, e1, 2.0 * c.shape[0] * c.shape[1] * k))
+    return c
 
 
 def set_enabled(flag: bool) -> None:
@@ -54,16 +69,14 @@ def mm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a[K,M]^T @ b[K,N]  (weight-gradient product: reduction over the T*N rows)."""
     if not (_ok(a, b) and _fits(a) and _fits(b)):
         return a.t() @ b
-    launches["gemm3"] += 1
-    return _lib.gemm3(_lib.GEMM_TN, _rows(a), _rows(b))
+    return _gemm(_lib.GEMM_TN, _rows(a), _rows(b))
 
 
 def mm_nn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a[M,K] @ b[K,N]."""
     if not (_ok(a, b) and _fits(a) and _fits(b)):
         return a @ b
-    launches["gemm3"] += 1
-    return _lib.gemm3(_lib.GEMM_NN, _rows(a), _rows(b))
+    return _gemm(_lib.GEMM_NN, _rows(a), _rows(b))
 
 
 class _LinearTC(torch.autograd.Function):
@@ -71,8 +84,7 @@ class _LinearTC(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        launches["gemm3"] += 1
-        return _lib.gemm3(_lib.GEMM_NT, _rows(x), _rows(weight), None if bias is None else bias.contiguous())
+        return _gemm(_lib.GEMM_NT, _rows(x), _rows(weight), None if bias is None else bias.contiguous())
 
     @staticmethod
     def backward(ctx, dy):
