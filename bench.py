@@ -287,7 +287,6 @@ def run_ours(args):
     if sampler:
         sampler.start(); time.sleep(0.25)
     rec.kernel_events = {"fwd": [], "bwd": []}
-    mm3.events, fat.events = [], []
     for cnt in (rec.launch_counter, mm3.launches, fat.launches):
         for k in cnt:
             cnt[k] = 0
@@ -303,6 +302,13 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (sum(rec.launch_counter.values()) + sum(mm3.launches.values()) + sum(fat.launches.values())) * world
     kev, rec.kernel_events = rec.kernel_events, None
+    # the ~60 small tensor-core launches of a step are event-timed in two EXTRA steps outside the timed region
+    # (an event pair per launch would perturb `value`)
+    TC_STEPS = 2
+    mm3.events, fat.events = [], []
+    for i in range(TC_STEPS):
+        step_resident(i)
+    torch.cuda.synchronize()
     gev, mm3.events = mm3.events, None
     aev, fat.events = fat.events, None
 
@@ -314,7 +320,7 @@ def run_ours(args):
         if tot_ms <= 0:
             return None
         tf = fl / (tot_ms * 1e-3) / 1e12
-        return {"launches_per_step": len(evs) / args.steps, "ms_per_step": tot_ms / args.steps, "fp32_equiv_tflops": tf,
+        return {"launches_per_step": len(evs) / TC_STEPS, "ms_per_step": tot_ms / TC_STEPS, "fp32_equiv_tflops": tf,
                 "bf16_umma_tflops": 3 * tf, "frac_of_bf16_peak": 3 * tf / peaks()["bf16_sustained"]}
     kms = {k: (sum(a.elapsed_time(b) for a, b in v) / max(1, len(v))) for k, v in kev.items()}
     clocks = sampler.stop(wall0, wall1) if sampler else None

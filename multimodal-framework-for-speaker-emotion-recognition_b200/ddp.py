@@ -58,25 +58,31 @@ class GradAllReducer:
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
         self.zero_grad()
 
-    def _add_bucket(self, params):
-        total = sum(p.numel() for p in params)
-        flat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
-        o = 0
+    @staticmethod
+    def _offsets(params):
+        """Start offset of each parameter inside its flat bucket, padded to 8 floats so every view keeps the
+        16/32-byte alignment the kernels ask for."""
+        offs, o = [], 0
         for p in params:
+            offs.append(o)
+            o += (p.numel() + 7) // 8 * 8
+        return offs, o
+
+    def _add_bucket(self, params):
+        offs, total = self._offsets(params)
+        flat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
+        for p, o in zip(params, offs):
             p.grad = flat[o:o + p.numel()].view_as(p)
             self._bucket_of[id(p)] = len(self.buckets)
-            o += p.numel()
         self.buckets.append(flat)
         self._members.append(list(params))
         if self.flatten_params:
             # parameters of a bucket share one flat storage too (p.data become views; values are preserved), so the
-            # optimizer is one fused launch per bucket; offsets are 4-float aligned by construction of `total`
-            pflat = torch.empty(total, device=params[0].device, dtype=params[0].dtype)
-            o = 0
-            for p in params:
+            # optimizer is one fused launch per bucket (the padding gaps hold zeros and stay zero under Adam)
+            pflat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
+            for p, o in zip(params, offs):
                 pflat[o:o + p.numel()].copy_(p.data.reshape(-1))
                 p.data = pflat[o:o + p.numel()].view_as(p)
-                o += p.numel()
             self.param_buckets.append(pflat)
 
     def _make_hook(self, b):
@@ -103,12 +109,11 @@ class GradAllReducer:
 
     def _rebind(self, p):
         b = self._bucket_of[id(p)]
-        o = 0
-        for q in self._members[b]:
+        offs, _ = self._offsets(self._members[b])
+        for q, o in zip(self._members[b], offs):
             if q is p:
                 p.grad = self.buckets[b][o:o + p.numel()].view_as(p)
                 return
-            o += q.numel()
 
     def finish(self):
         """Block the current stream until every bucket's allreduce is complete."""

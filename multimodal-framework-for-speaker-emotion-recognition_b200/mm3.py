@@ -52,8 +52,10 @@ def enabled() -> bool:
 
 def _rows(t: torch.Tensor) -> torch.Tensor:
     """2-D view with unit inner stride and 16-byte aligned rows (copy only if the layout forces it)."""
-    if t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
+    if t.stride(1) != 1 or t.stride(0) % 4:
         t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
     return t
 
 
