@@ -42,9 +42,10 @@ def load_reference():
     from models.HybridRNN_ATV import MARN as MARN_ATV  # model/HybridRNN_ATV.py:40
     from models.HybridRNN_AT import MARN as MARN_AT    # model/HybridRNN_AT.py:40
     from models.lsthm_sps import MARN1_sps              # model/lsthm_sps.py:298
+    from models.lsthm_onlysp import MARN1_onlysp        # model/lsthm_onlysp.py:213 (train.py default model)
     from models.encoder import EncoderLayer             # model/encoder.py:116
     import loss as ref_loss                             # loss.py:6
-    ns.MARN_ATV, ns.MARN_AT, ns.MARN1_sps = MARN_ATV, MARN_AT, MARN1_sps
+    ns.MARN_ATV, ns.MARN_AT, ns.MARN1_sps, ns.MARN1_onlysp = MARN_ATV, MARN_AT, MARN1_sps, MARN1_onlysp
     ns.EncoderLayer, ns.MaskedLoss = EncoderLayer, ref_loss.MaskedLoss
     return ns
 

@@ -360,6 +360,69 @@ def sps_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None, 
 
 
 # --------------------------------------------------------------------------------------
+# lsthm_onlysp.py  (the reference's train.py default model, `--model MARN1_onlysp`)
+# --------------------------------------------------------------------------------------
+def gru_cell(p: Params, pre: str, x, h):
+    """torch.nn.GRUCell semantics (gate order r,z,n; n = tanh(W_in x + b_in + r * (W_hn h + b_hn)))."""
+    gi = F.linear(x, p[pre + ".weight_ih"], p[pre + ".bias_ih"])
+    gh = F.linear(h, p[pre + ".weight_hh"], p[pre + ".bias_hh"])
+    d = h.shape[1]
+    r = torch.sigmoid(gi[:, :d] + gh[:, :d])
+    z = torch.sigmoid(gi[:, d:2 * d] + gh[:, d:2 * d])
+    n = torch.tanh(gi[:, 2 * d:] + r * gh[:, 2 * d:])
+    return (1 - z) * n + z * h
+
+
+def onlysp_cell(p: Params, pre: str, x_l, x_a, qmask, tape: Optional[DropoutTape] = None):
+    """MARN_cell.forward of lsthm_onlysp (model/lsthm_onlysp.py:156-206): per-dialogue speaker state through one
+    GRUCell on [x_l|x_a] and a DialogueRNN-style party update; LSTHM1 cells and the in-cell rank-1 attention as in
+    lsthm_sps.  Dialogues are independent here (no packed rows).  Returns h [T,N,512] = [h_l|h_a|z_l|h_s]."""
+    T, N, _ = x_l.shape
+    z = lambda: x_l.new_zeros(N, 128)
+    h_l, h_a, c_l, c_a, z_l = (z() for _ in range(5))
+    q = x_l.new_zeros(N, 2, 128)
+    site = pre + ".dropout"
+    ar = torch.arange(N)
+    out = []
+    for t in range(T):
+        U = torch.cat((x_l[t], x_a[t]), dim=1)
+        qs_0 = q[ar, torch.argmax(qmask[t], 1)]                       # _select_parties, lines 200-205
+        h_s = _drop(gru_cell(p, pre + ".gru_s", U, qs_0), 0.5, site, tape)
+        m = qmask[t].unsqueeze(2)
+        q = q * (1 - m) + h_s.unsqueeze(1) * m
+        c_l, h_l = lsthm1_cell(p, pre + ".lsthm_l", x_l[t], c_l, h_l, z_l, h_s)
+        h_l = _drop(h_l, 0.5, site, tape)
+        c_a, h_a = lsthm1_cell(p, pre + ".lsthm_a", x_a[t], c_a, h_a, z_l, h_s)
+        h_a = _drop(h_a, 0.5, site, tape)
+        z_l = cross_attention_cell(p, pre + ".crossatt_l2a", c_l, c_a, tape, pre + ".crossatt_l2a.dropout")
+        out.append(torch.cat([h_l, h_a, z_l, h_s], 1))
+    return torch.stack(out, 0)
+
+
+def onlysp_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None):
+    """MARN1_onlysp.forward (model/lsthm_onlysp.py:260-301): encoders applied twice WITHOUT residual (264-268),
+    bidirectional cell, sequence cross-attention with the learnable scalars, head directly on the 1280-d concat."""
+    xl = _lin(p, "linear_in", x[:, :, :1024].permute(1, 0, 2))
+    xa = x[:, :, 1024:1124].permute(1, 0, 2)
+    xl = encoder_layer(p, "encoder_l", xl, tape)
+    xa = encoder_layer(p, "encoder_a", xa, tape)
+    xl = encoder_layer(p, "encoder_l", xl, tape).permute(1, 0, 2)
+    xa = encoder_layer(p, "encoder_a", xa, tape).permute(1, 0, 2)
+    h_f = _drop(onlysp_cell(p, "marn_cell_f", xl, xa, qmask, tape), 0.5, "dropout_rec", tape)
+    h_b = onlysp_cell(p, "marn_cell_b", reverse_seq(xl, umask), reverse_seq(xa, umask), reverse_seq(qmask, umask), tape)
+    h_b = _drop(reverse_seq(h_b, umask), 0.5, "dropout_rec", tape)
+    h = torch.cat([h_f, h_b], -1)
+    w, v, v1, v2 = p["w"], p["v"], p["v1"], p["v2"]
+    a1 = cross_attention_seq(p, "crossatt_l2a", w * xl, v * xa, tape)
+    a2 = cross_attention_seq(p, "crossatt_a2l", v * xa, w * xl, tape)
+    a1 = cross_attention_seq(p, "crossatt_l2a_1", v * xa, v1 * a1, tape)
+    a2 = cross_attention_seq(p, "crossatt_a2l_1", w * xl, v2 * a2, tape)
+    y = _drop(torch.relu(_lin(p, "nn_out.0", torch.cat([h, a1, a2], -1))), 0.5, "nn_out.2", tape)
+    logp = torch.log_softmax(_lin(p, "nn_out.3", y), 2).permute(1, 0, 2)
+    return logp.reshape(-1, logp.shape[-1]), xl, xa
+
+
+# --------------------------------------------------------------------------------------
 # loss.py
 # --------------------------------------------------------------------------------------
 def masked_loss(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, kind: str = "ce"):
