@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTHM_ABI_VERSION 1
+#define LSTHM_ABI_VERSION 2
 #define LSTHM_MAX_MOD 3
 
 int lsthm_abi_version(void);
@@ -174,6 +174,7 @@ int lsthm_sps_launch_info(const lsthm_sps_desc *d, int32_t *grid, int32_t *block
  *   mode 0 (NT): C[M][N] = A[M][K] . B[N][K]^T (+ bias[N])     y  = x W^T + b   (torch.nn.functional.linear)
  *   mode 1 (NN): C[M][N] = A[M][K] . B[K][N]                   dx = dy W
  *   mode 2 (TN): C[M][N] = A[K][M]^T . B[K][N]                 dW = dy^T x      (split-K, deterministic reduce)
+ *   mode 3     : mode 0 followed by ReLU in the epilogue       relu(x W^T + b)  (encoder.py:108, w_1 of the FFN)
  * All matrices fp32 row-major, 16-byte aligned, lda/ldb multiples of 4.  `workspace` (may be NULL) holds
  * the split-K partials: lsthm_gemm3_workspace_floats(mode, M, N, K) floats.
  * ------------------------------------------------------------------------------------------ */
@@ -186,9 +187,13 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
  * Replaces ScaledDotProductAttention.forward, model/encoder.py:71-86, as called by
  * MultiHeadAttention.forward (:27-60) with mask=None: per head  softmax(q k^T * scale) -> dropout -> . v
  * over the L <= 128 utterances of a dialogue, d_k = d_v = 40; and its autograd backward.
- * Row i of dialogue b, head h of a matrix X with row stride ldx (floats):  X + (b*L + i)*ldx + h*40.
+ * Row i of dialogue b, head h of a matrix X with row stride ldx (floats):
+ *   X + (b*row_stride_b + i*row_stride_i)*ldx + h*40      (both strides 0 = batch-major [B][L]: b*L + i;
+ *   the reference's time-major activations [L][B][.] are row_stride_b = 1, row_stride_i = B: no permute copy).
  * q/k/v may be three column blocks of one fused projection output (ldq = ldk = ldv = 3*H*40).
  * Dropout is generated in-kernel from (seed, b, h, i, j); the same call arguments regenerate it in bwd.
+ * `lse` [B*H][L] receives each query row's log-sum-exp of the scaled scores (log2 units) in the forward and
+ * must be handed back to the backward, which then needs a single pass over the score tile.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t B, L, H, d_head;          /* d_head must be 40                                  */
@@ -196,12 +201,41 @@ typedef struct {
     float scale;                      /* 1 / temperature = 1/sqrt(d_k)  (encoder.py:22)     */
     float p_drop;                     /* attention dropout (encoder.py:66), 0 in eval mode  */
     uint64_t seed;
+    int64_t row_stride_b, row_stride_i; /* in rows; see above                                */
 } lsthm_attn_desc;
 
-int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, float *out, void *stream);
+int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, float *out, float *lse,
+                   void *stream);
 /* dq/dk/dv use the row strides ldq/ldk/ldv; out/dout use ldo */
 int lsthm_attn_bwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, const float *out,
-                   const float *dout, float *dq, float *dk, float *dv, void *stream);
+                   const float *lse, const float *dout, float *dq, float *dk, float *dv, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused  out = LayerNorm(dropout(y + bias) + residual)  over R rows of width d (4 <= d <= 512, d % 4 == 0), forward and
+ * backward.  Replaces the tail of MultiHeadAttention.forward, model/encoder.py:54-58
+ * (`q = self.dropout(self.fc(q)); q += residual; q = self.layer_norm(q)`) and of PositionwiseFeedForward.forward,
+ * model/encoder.py:106-112.  All matrices fp32 with unit inner stride and row strides (floats) that are
+ * multiples of 4; rows may be in any order (batch- or time-major).
+ *   fwd:  v = dropout(y + bias) + res (kept for the backward, may be NULL in eval; bias [d] may be NULL),  out = LN(v) * gamma + beta
+ *   bwd:  dres = dL/dres (= dL/dv),  dy = dL/dy (= dres * dropout scale; not written when p_drop == 0: it equals
+ *         dres),  dgamma, dbeta [d],  dbias [d] = column sums of dy (bias gradient of the Linear that made y);
+ *         any of the three may be NULL.  `workspace`: lsthm_dln_workspace_floats(d) floats.
+ * Dropout is regenerated in the backward from (seed, row, column).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int64_t R;
+    int32_t d;
+    float eps;                        /* LayerNorm eps (encoder.py:25: 1e-6)                 */
+    float p_drop;
+    uint64_t seed;
+} lsthm_dln_desc;
+
+size_t lsthm_dln_workspace_floats(int32_t d);
+int lsthm_dln_fwd(const lsthm_dln_desc *d, const float *y, int32_t ldy, const float *bias, const float *res, int32_t ldres, const float *gamma,
+                  const float *beta, float *v, int32_t ldv, float *out, int32_t ldo, void *stream);
+int lsthm_dln_bwd(const lsthm_dln_desc *d, const float *dout, int32_t lddo, const float *v, int32_t ldv, const float *gamma,
+                  float *dy, int32_t lddy, float *dres, int32_t lddres, float *dgamma, float *dbeta, float *dbias,
+                  float *workspace, size_t workspace_floats, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adam step on a flat fp32 buffer.  Replaces `self.optim.step()` of the reference's trainer

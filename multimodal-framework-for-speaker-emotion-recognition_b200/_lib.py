@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
 SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_MOD = 3
 
 _f32p = C.POINTER(C.c_float)
@@ -51,7 +51,11 @@ class SpsMasks(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("d_head", C.c_int32), ("ldq", C.c_int32),
                 ("ldk", C.c_int32), ("ldv", C.c_int32), ("ldo", C.c_int32), ("scale", C.c_float), ("p_drop", C.c_float),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("row_stride_b", C.c_int64), ("row_stride_i", C.c_int64)]
+
+
+class DlnDesc(C.Structure):
+    _fields_ = [("R", C.c_int64), ("d", C.c_int32), ("eps", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint64)]
 
 
 def build(verbose: bool = False, jobs: int = 8) -> str:
@@ -107,9 +111,17 @@ def lib() -> C.CDLL:
     L.lsthm_gemm3.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                                 C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]
     L.lsthm_attn_fwd.restype = C.c_int
-    L.lsthm_attn_fwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 5
+    L.lsthm_attn_fwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 6
     L.lsthm_attn_bwd.restype = C.c_int
-    L.lsthm_attn_bwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 9
+    L.lsthm_attn_bwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 10
+    L.lsthm_dln_workspace_floats.restype = C.c_size_t
+    L.lsthm_dln_workspace_floats.argtypes = [C.c_int32]
+    L.lsthm_dln_fwd.restype = C.c_int
+    L.lsthm_dln_fwd.argtypes = [C.POINTER(DlnDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    L.lsthm_dln_bwd.restype = C.c_int
+    L.lsthm_dln_bwd.argtypes = [C.POINTER(DlnDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.lsthm_adam_step.restype = C.c_int
     L.lsthm_adam_step.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_float] * 5 + [C.c_int32, C.c_void_p]
     if L.lsthm_abi_version() != ABI_VERSION:
@@ -264,7 +276,7 @@ def sps_launch_info(d: SpsDesc) -> dict:
 # ------------------------------------------------------------------------------------------------
 # tcgen05 split-bf16 GEMM (time-parallel products)
 # ------------------------------------------------------------------------------------------------
-GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+GEMM_NT, GEMM_NN, GEMM_TN, GEMM_NT_RELU = 0, 1, 2, 3
 
 
 def _mat(t: torch.Tensor, name: str):
@@ -278,7 +290,7 @@ def _mat(t: torch.Tensor, name: str):
 
 def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """mode NT: a[M,K] @ b[N,K]^T (+bias);  NN: a[M,K] @ b[K,N];  TN: a[K,M]^T @ b[K,N]."""
-    if mode == GEMM_NT:
+    if mode in (GEMM_NT, GEMM_NT_RELU):
         M, K = a.shape; N = b.shape[0]; assert b.shape[1] == K
     elif mode == GEMM_NN:
         M, K = a.shape; N = b.shape[1]; assert b.shape[0] == K
@@ -297,10 +309,11 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
 # ------------------------------------------------------------------------------------------------
 # fused encoder self-attention (tcgen05)
 # ------------------------------------------------------------------------------------------------
-def make_attn_desc(B, L, H, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, d_head=40) -> AttnDesc:
+def make_attn_desc(B, L, H, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, d_head=40, time_major=False) -> AttnDesc:
     d = AttnDesc()
     d.B, d.L, d.H, d.d_head, d.ldq, d.ldk, d.ldv, d.ldo = B, L, H, d_head, ldq, ldk, ldv, ldo
     d.scale, d.p_drop, d.seed = scale, p_drop, seed
+    d.row_stride_b, d.row_stride_i = (1, B) if time_major else (L, 1)
     return d
 
 
@@ -310,15 +323,46 @@ def _f32_cuda(t: torch.Tensor, name: str) -> int:
     return t.data_ptr()
 
 
-def attn_fwd(d: AttnDesc, q, k, v, out) -> None:
+def attn_fwd(d: AttnDesc, q, k, v, out, lse) -> None:
     _check(lib().lsthm_attn_fwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
-                                _stream()), "lsthm_attn_fwd")
+                                _f32_cuda(lse, "lse"), _stream()), "lsthm_attn_fwd")
 
 
-def attn_bwd(d: AttnDesc, q, k, v, out, dout, dq, dk, dv) -> None:
+def attn_bwd(d: AttnDesc, q, k, v, out, lse, dout, dq, dk, dv) -> None:
     _check(lib().lsthm_attn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
-                                _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
+                                _f32_cuda(lse, "lse"), _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
                                 _stream()), "lsthm_attn_bwd")
+
+
+def _rows2d(t: torch.Tensor, name: str):
+    """(pointer, row stride) of a 2-D fp32 CUDA matrix with unit inner stride and 16-byte aligned rows."""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0):
+        raise RuntimeError(f"{name}: expected a 2-D float32 CUDA matrix with unit inner stride and 16-byte aligned rows")
+    return t.data_ptr(), t.stride(0)
+
+
+def make_dln_desc(R, d, eps, p_drop=0.0, seed=0) -> DlnDesc:
+    x = DlnDesc()
+    x.R, x.d, x.eps, x.p_drop, x.seed = R, d, eps, p_drop, seed
+    return x
+
+
+def dln_fwd(desc: DlnDesc, y, bias, res, gamma, beta, v, out) -> None:
+    (py, ldy), (pr, ldr), (po, ldo) = _rows2d(y, "y"), _rows2d(res, "res"), _rows2d(out, "out")
+    pv, ldv = _rows2d(v, "v") if v is not None else (None, 0)
+    _check(lib().lsthm_dln_fwd(C.byref(desc), py, ldy, _dev_ptr(bias, "bias"), pr, ldr, _dev_ptr(gamma, "gamma"), _dev_ptr(beta, "beta"), pv, ldv, po, ldo,
+                               _stream()), "lsthm_dln_fwd")
+
+
+def dln_bwd(desc: DlnDesc, dout, v, gamma, dy, dres, dgamma, dbeta, dbias) -> None:
+    (pdo, lddo), (pv, ldv), (pdr, lddr) = _rows2d(dout, "dout"), _rows2d(v, "v"), _rows2d(dres, "dres")
+    pdy, lddy = _rows2d(dy, "dy") if dy is not None else (None, 0)
+    nws = lib().lsthm_dln_workspace_floats(desc.d)
+    ws = torch.empty(nws, device=dout.device, dtype=torch.float32)
+    _check(lib().lsthm_dln_bwd(C.byref(desc), pdo, lddo, pv, ldv, _dev_ptr(gamma, "gamma"), pdy, lddy, pdr, lddr,
+                               _dev_ptr(dgamma, "dgamma"), _dev_ptr(dbeta, "dbeta"), _dev_ptr(dbias, "dbias"), ws.data_ptr(), nws,
+                               _stream()), "lsthm_dln_bwd")
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step) -> None:

@@ -20,12 +20,21 @@ namespace lsthm {
 constexpr int kAttD = 40, kAttDP = 48, kAttLP = 128;
 constexpr int kRowTile = 6 * 2048;          // [128 x 48] bf16
 constexpr int kSqTile = 16 * 2048;          // [128 x 128] bf16
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct AttnArgs {
-    const float *q, *k, *v, *o, *dout;      // row i of dialogue b, head h: base + (b*L + i)*ld + h*40
+    const float *q, *k, *v, *o, *dout;      // row i of dialogue b, head h: base + (b*sb + i*si)*ld + h*40
     float *out, *dq, *dk, *dv;
+    float *lse;                             // [B*H][L] row log-sum-exp of the scaled scores, in log2 units (fwd writes, bwd reads)
     int B, L, H;
     int ldq, ldk, ldv, ldo;                 // row strides (floats) of q/k/v (and dq/dk/dv) and of o/out/dout
+    long long sb, si;                       // row index of (dialogue b, position i) = b*sb + i*si  (batch-major: L,1; time-major: 1,B)
     float scale, p_drop;
     unsigned long long seed;
 };
@@ -56,29 +65,43 @@ __device__ __forceinline__ void umma3(uint32_t tmem_d, uint32_t a, uint32_t a_lo
 // operand triples used below:  K-major row tile: (k16 step, LBO, SBO) = (4096, 2048, 128);
 //                              MN-major view of the same bytes:         = ( 256,  128, 2048)
 
+#define LSTHM_TMEM_LD16_REGS(r, o) \
+    "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7]), \
+    "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : LSTHM_TMEM_LD16_REGS(r, 0)
+                 : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// two 16-column loads (different TMEM addresses) behind one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&va)[16], float (&vb)[16]) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n"
+                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : LSTHM_TMEM_LD16_REGS(r, 0), LSTHM_TMEM_LD16_REGS(r, 16)
+                 : "r"(ta), "r"(tb) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(r[i]); vb[i] = __uint_as_float(r[16 + i]); }
+}
 
-// stage chunks [c0, c1) (8 floats each; chunk 5 is the zero padding 40 -> 48) of one 40-float row (scaled) of a
-// [L][ld] matrix into a K-major row tile (hi, lo); rows >= L are zero
-__device__ __forceinline__ void stage_row40(const float *base, int ld, int row, int L, float scale, uint8_t *hi, int c0, int c1) {
+// stage chunks [c0, c1) (8 floats each; chunk 5 is the zero padding 40 -> 48) of one 40-float row (scaled) into a
+// K-major row tile (hi, lo); src == nullptr (row >= L) stages zeros
+__device__ __forceinline__ void stage_row40(const float *src, int row, float scale, uint8_t *hi, int c0, int c1) {
     uint8_t *lo = hi + kRowTile;
     const int roff = (row >> 3) * 128 + (row & 7) * 16;
     float x[8];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
         if (c < c0 || c >= c1) continue;
-        if (c < 5 && row < L) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * ld) + 2 * c);
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(base + (size_t)row * ld) + 2 * c + 1);
+        if (c < 5 && src != nullptr) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
             x[0] = a.x * scale; x[1] = a.y * scale; x[2] = a.z * scale; x[3] = a.w * scale;
             x[4] = b.x * scale; x[5] = b.y * scale; x[6] = b.z * scale; x[7] = b.w * scale;
         } else {
@@ -89,40 +112,35 @@ __device__ __forceinline__ void stage_row40(const float *base, int ld, int row, 
     }
 }
 
-__device__ __forceinline__ float att_drop_scale(unsigned long long seed, int bh, int i, int j, float p) {
-    return dropout_scale(seed, (uint32_t)bh, (uint32_t)(i << 7 | j), p);
-}
-
-// Row-wise softmax statistics of S over the first L columns.  Two threads share a query row (tid and tid^128:
-// warps w and w+4 address the same TMEM lanes); each scans its 64-column half and they combine through shared
-// memory.  `ex` is a [2][256] float scratch.  Contains two CTA barriers: call from all 256 threads.
-__device__ __forceinline__ void row_stats(uint32_t trow, int cb, int L, float *ex, float &mx, float &inv) {
-    float v[16];
-    float m = -INFINITY;
-    for (int c0 = cb; c0 < cb + 64; c0 += 16) {
-        tmem_ld16(trow + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (c0 + j < L) m = fmaxf(m, v[j]);
+// In-kernel attention dropout: one 32-bit hash per PAIR of adjacent key columns, 16 random bits per element
+// (keep iff bits >= thr, thr = round(p * 65536); the scale is 65536 / (65536 - thr) so the mask is exactly unbiased).
+// Forward and backward evaluate the same function, so no mask is stored.
+struct AttDrop {
+    uint32_t key, thr;
+    float scale;
+    bool on;
+    __device__ __forceinline__ AttDrop(unsigned long long seed, int bh, int row, float p) {
+        on = p > 0.f;
+        thr = (uint32_t)(p * 65536.0f + 0.5f);
+        scale = 65536.0f / (65536.0f - (float)thr);
+        uint32_t x = (uint32_t)seed ^ ((uint32_t)bh * 0x9E3779B9u);
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        key = (x ^ (uint32_t)(seed >> 32)) + (uint32_t)row * 0x85EBCA6Bu;
     }
-    ex[threadIdx.x] = m;
-    __syncthreads();
-    mx = fmaxf(m, ex[threadIdx.x ^ 128]);
-    float sum = 0.f;
-    for (int c0 = cb; c0 < cb + 64; c0 += 16) {
-        tmem_ld16(trow + c0, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (c0 + j < L) sum += __expf(v[j] - mx);
+    // scales for columns (2*pair, 2*pair + 1)
+    __device__ __forceinline__ void pair(int pair_idx, float &s0, float &s1) const {
+        uint32_t x = key + (uint32_t)pair_idx * 0xC2B2AE35u;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        s0 = (x & 0xffffu) >= thr ? scale : 0.f;
+        s1 = (x >> 16) >= thr ? scale : 0.f;
     }
-    ex[256 + threadIdx.x] = sum;
-    __syncthreads();
-    inv = 1.0f / (sum + ex[256 + (threadIdx.x ^ 128)]);
-}
+};
 
 // ---------------------------------------------------------------------------------------------
-// forward:  out = dropout(softmax(q k^T * scale)) v      256 threads, SMEM 88 KB -> 2 CTAs / SM
-// thread = (query row r = tid%128, column half g = tid/128)
+// forward:  out = dropout(softmax(q k^T * scale)) v      256 threads, SMEM 89 KB -> 2 CTAs / SM
+// thread = (query row r = tid%128, column half g = tid/128).  Scores are produced in log2 units (log2(e) is folded
+// into the staged q) so the softmax is one FADD + EX2 per element; the normalisation is applied to the 40 output
+// columns instead of the 128 probabilities.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -133,15 +151,16 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
     uint8_t *sP = smem;
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
-    const size_t row0 = (size_t)b * L;
+    const size_t grow = (size_t)((long long)b * a.sb + (long long)r * a.si);
+    const bool rv = r < L;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, r, L, a.scale, sQ, 3 * g, 3 * g + 3);
-    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, r, L, 1.f, sK, 3 * g, 3 * g + 3);
-    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, r, L, 1.f, sV, 3 * g, 3 * g + 3);
+    stage_row40(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, r, a.scale * kLog2e, sQ, 3 * g, 3 * g + 3);
+    stage_row40(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, r, 1.f, sK, 3 * g, 3 * g + 3);
+    stage_row40(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, r, 1.f, sV, 3 * g, 3 * g + 3);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -155,29 +174,43 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int cb = 64 * g;
+    float mx = -INFINITY, sum = 0.f;
     {
-        float mx, inv;
-        row_stats(trow, cb, L, ex, mx, inv);
+        float v[16];
+        for (int c0 = cb; c0 < cb + 64; c0 += 16) {
+            tmem_ld16(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < L) mx = fmaxf(mx, v[j]);
+        }
+        ex[tid] = mx;
+        __syncthreads();                         
+        mx = fmaxf(mx, ex[tid ^ 128]);
+        const AttDrop drop(a.seed, blockIdx.x, r, a.p_drop);
         const int roff = (r >> 3) * 128 + (r & 7) * 16;
-        float v[16], p8[8];
+        float p8[8];
         for (int c0 = cb; c0 < cb + 64; c0 += 16) {
             tmem_ld16(trow + c0, v);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 8; j += 2) {
                     const int col = c0 + half * 8 + j;
-                    float p = 0.f;
-                    if (r < L && col < L) {
-                        p = __expf(v[half * 8 + j] - mx) * inv;
-                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, r, col, a.p_drop);
+                    float e0 = (rv && col < L) ? fast_exp2(v[half * 8 + j] - mx) : 0.f;
+                    float e1 = (rv && col + 1 < L) ? fast_exp2(v[half * 8 + j + 1] - mx) : 0.f;
+                    sum += e0 + e1;
+                    if (drop.on) {
+                        float s0, s1;
+                        drop.pair(col >> 1, s0, s1);
+                        e0 *= s0; e1 *= s1;
                     }
-                    p8[j] = p;
+                    p8[j] = e0; p8[j + 1] = e1;
                 }
                 const int chunk = (c0 >> 3) + half;
                 split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
             }
         }
+        ex[256 + tid] = sum;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -187,18 +220,22 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
         umma3(tmem, smem_u32(sP), kSqTile, 4096u, 2048u, 128u, smem_u32(sV), kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
         umma_commit(&bar[1]);
     }
+    sum += ex[256 + (tid ^ 128)];
+    const float inv = rv ? 1.0f / sum : 0.f;
+    if (g == 0 && rv && a.lse != nullptr) a.lse[(size_t)blockIdx.x * L + r] = mx + log2f(sum);
     mbar_wait(&bar[1], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
         float v[16];
-        float *orow = a.out + (row0 + r) * a.ldo + h * kAttD;
+        float *orow = a.out + grow * a.ldo + h * kAttD;
         for (int c0 = 16 * g; c0 < kAttDP; c0 += 32) {
             tmem_ld16(trow + c0, v);
-            if (r < L) {
+            if (rv) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                     if (c0 + 4 * q4 < kAttD)
-                        reinterpret_cast<float4 *>(orow + c0)[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        reinterpret_cast<float4 *>(orow + c0)[q4] =
+                            make_float4(v[4 * q4] * inv, v[4 * q4 + 1] * inv, v[4 * q4 + 2] * inv, v[4 * q4 + 3] * inv);
             }
         }
     }
@@ -212,40 +249,46 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
 
 // ---------------------------------------------------------------------------------------------
 // backward.  TMEM columns: S [0,128) | dPd [128,256) | dV [256,304) | dQ [304,352) | dK [352,400)
+// One pass over the score tile: with the forward's row log-sum-exp the probabilities are p = 2^(s - lse), so the
+// dropped probabilities Pd (operand of dV = Pd^T dO) and dS = p (sc dPd - delta) (operand of dQ, dK) are produced
+// together into two shared tiles and the three remaining products are issued back to back.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar[3];
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base;
-    __shared__ float ex[512];
     uint8_t *sQ = smem, *sK = sQ + 2 * kRowTile, *sV = sK + 2 * kRowTile, *sdO = sV + 2 * kRowTile, *sP = sdO + 2 * kRowTile;
+    uint8_t *sD = sP + 2 * kSqTile;
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
-    const size_t row0 = (size_t)b * L;
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); mbar_fence_init(); }
+    const size_t grow = (size_t)((long long)b * a.sb + (long long)r * a.si);
+    const bool rv = r < L;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    stage_row40(a.q + row0 * a.ldq + h * kAttD, a.ldq, r, L, a.scale, sQ, 3 * g, 3 * g + 3);
-    stage_row40(a.k + row0 * a.ldk + h * kAttD, a.ldk, r, L, 1.f, sK, 3 * g, 3 * g + 3);
-    stage_row40(a.v + row0 * a.ldv + h * kAttD, a.ldv, r, L, 1.f, sV, 3 * g, 3 * g + 3);
-    stage_row40(a.dout + row0 * a.ldo + h * kAttD, a.ldo, r, L, 1.f, sdO, 3 * g, 3 * g + 3);
-    float delta = 0.f;                         // rowsum(dO * O) = sum_j Pd_ij dPd_ij  (both threads of a row compute it)
-    if (r < L) {
-        const float *orow = a.o + (row0 + r) * a.ldo + h * kAttD, *drow = a.dout + (row0 + r) * a.ldo + h * kAttD;
+    const float *drow = a.dout + grow * a.ldo + h * kAttD;
+    stage_row40(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, r, a.scale * kLog2e, sQ, 3 * g, 3 * g + 3);
+    stage_row40(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, r, 1.f, sK, 3 * g, 3 * g + 3);
+    stage_row40(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, r, 1.f, sV, 3 * g, 3 * g + 3);
+    stage_row40(rv ? drow : nullptr, r, 1.f, sdO, 3 * g, 3 * g + 3);
+    float delta = 0.f, lse = 0.f;              // delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij  (both threads of a row compute it)
+    if (rv) {
+        const float *orow = a.o + grow * a.ldo + h * kAttD;
 #pragma unroll
         for (int d = 0; d < kAttD; d += 4) {
             const float4 o4 = __ldg(reinterpret_cast<const float4 *>(orow + d)), d4 = __ldg(reinterpret_cast<const float4 *>(drow + d));
             delta += d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
         }
+        lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
-    const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), udO = smem_u32(sdO), uP = smem_u32(sP);
+    const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), udO = smem_u32(sdO), uP = smem_u32(sP), uD = smem_u32(sD);
     if (tid == 0) {
         // S = Qs K^T ; dPd = dO V^T   (both M = query, N = key, K = d)
         umma3(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
@@ -256,59 +299,26 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int roff = (r >> 3) * 128 + (r & 7) * 16, cb = 64 * g;
-    float mx, inv;
-    row_stats(trow, cb, L, ex, mx, inv);
-    {   // Pd (dropped, scaled probabilities) -> shared, operand of dV = Pd^T dO
-        float v[16], p8[8];
+    {
+        const AttDrop drop(a.seed, blockIdx.x, r, a.p_drop);
+        float s[16], gg[16], p8[8], d8[8];
         for (int c0 = cb; c0 < cb + 64; c0 += 16) {
-            tmem_ld16(trow + c0, v);
+            tmem_ld16x2(trow + c0, trow + 128 + c0, s, gg);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = c0 + half * 8 + j;
-                    float p = 0.f;
-                    if (r < L && col < L) {
-                        p = __expf(v[half * 8 + j] - mx) * inv;
-                        if (a.p_drop > 0.f) p *= att_drop_scale(a.seed, blockIdx.x, r, col, a.p_drop);
-                    }
-                    p8[j] = p;
+                for (int j = 0; j < 8; j += 2) {
+                    const int col = c0 + half * 8 + j, i0 = half * 8 + j;
+                    const float p0 = (rv && col < L) ? fast_exp2(s[i0] - lse) : 0.f;
+                    const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - lse) : 0.f;
+                    float s0 = 1.f, s1 = 1.f;
+                    if (drop.on) drop.pair(col >> 1, s0, s1);
+                    p8[j] = p0 * s0; p8[j + 1] = p1 * s1;
+                    d8[j] = p0 * (s0 * gg[i0] - delta); d8[j + 1] = p1 * (s1 * gg[i0 + 1] - delta);
                 }
                 const int chunk = (c0 >> 3) + half;
                 split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
-            }
-        }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {   // dV = Pd^T dO : M = key (MN-major view of P), N = d (MN-major view of dO), K = query
-        umma3(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
-        umma_commit(&bar[1]);
-    }
-    mbar_wait(&bar[1], 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {   // dS = P * (sc * dPd - delta)  -> overwrites the Pd tile (its only reader, the dV product, has retired)
-        float s[16], gg[16], d8[8];
-        for (int c0 = cb; c0 < cb + 64; c0 += 16) {
-            tmem_ld16(trow + c0, s);
-            tmem_ld16(trow + 128 + c0, gg);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = c0 + half * 8 + j;
-                    float ds = 0.f;
-                    if (r < L && col < L) {
-                        const float p = __expf(s[half * 8 + j] - mx) * inv;
-                        const float sc = a.p_drop > 0.f ? att_drop_scale(a.seed, blockIdx.x, r, col, a.p_drop) : 1.f;
-                        ds = p * (sc * gg[half * 8 + j] - delta);
-                    }
-                    d8[j] = ds;
-                }
-                const int chunk = (c0 >> 3) + half;
-                split_store8(d8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+                split_store8(d8, sD + chunk * 2048 + roff, sD + kSqTile + chunk * 2048 + roff);
             }
         }
     }
@@ -317,23 +327,25 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) {
+        // dV = Pd^T dO : M = key (MN-major view of Pd), N = d (MN-major view of dO), K = query
+        umma3(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
         // dQs = dS K : M = query, N = d (MN view of K), K = key ;  dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
-        umma3(tmem + 304, uP, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
-        umma3(tmem + 352, uP, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
-        umma_commit(&bar[2]);
+        umma3(tmem + 304, uD, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
+        umma3(tmem + 352, uD, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+        umma_commit(&bar[1]);
     }
-    mbar_wait(&bar[2], 0);
+    mbar_wait(&bar[1], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
         float v[16];
-        const size_t gr = row0 + r;
         // 9 (matrix, 16-column block) items over the two threads of a row: g takes the items with index % 2 == g
         for (int item = g; item < 9; item += 2) {
             const int which = item / 3, c0 = 16 * (item % 3);
-            float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + gr * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
-            const float mul = which == 1 ? a.scale : 1.f;              // d/dq = scale * (dS K)
+            float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + grow * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
+            // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
+            const float mul = which == 1 ? a.scale : which == 2 ? kLn2 : 1.f;
             tmem_ld16(trow + 256 + 48 * which + c0, v);
-            if (r < L) {
+            if (rv) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                     if (c0 + 4 * q4 < kAttD)

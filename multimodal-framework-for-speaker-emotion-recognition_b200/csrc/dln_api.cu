@@ -1,0 +1,72 @@
+// Host side of lsthm_dln_fwd / lsthm_dln_bwd (include/lsthm_b200.h): fused dropout + residual + LayerNorm.
+#include "../../include/lsthm_b200.h"
+#include "dln_kernels.cuh"
+
+namespace lsthm {
+int set_error(const char *what, cudaError_t e);
+int fail_msg(const char *msg);
+}  // namespace lsthm
+using namespace lsthm;
+
+static constexpr int kDlnMaxGrid = 148 * 4;   // 4 resident CTAs of 8 warps per SM
+
+static int dln_grid(long long R) {
+    const long long need = (R + kDlnWarps - 1) / kDlnWarps;
+    return (int)(need < kDlnMaxGrid ? (need < 1 ? 1 : need) : kDlnMaxGrid);
+}
+static int dln_check(const lsthm_dln_desc *d) {
+    if (!d) return fail_msg("null dln descriptor");
+    if (d->R < 0) return fail_msg("lsthm_dln: R < 0");
+    if (d->d < 4 || d->d > 128 * kDlnMaxC || (d->d & 3)) return fail_msg("lsthm_dln: need 4 <= d <= 512, d % 4 == 0");
+    if (d->p_drop < 0.f || d->p_drop >= 1.f) return fail_msg("lsthm_dln: p_drop must be in [0,1)");
+    return 0;
+}
+static bool bad_ld(int ld, int d) { return ld < d || (ld & 3); }
+
+extern "C" {
+
+size_t lsthm_dln_workspace_floats(int32_t d) { return (size_t)kDlnMaxGrid * 3 * (size_t)d; }
+
+int lsthm_dln_fwd(const lsthm_dln_desc *d, const float *y, int32_t ldy, const float *bias, const float *res, int32_t ldres, const float *gamma,
+                  const float *beta, float *v, int32_t ldv, float *out, int32_t ldo, void *stream) {
+    if (dln_check(d)) return 1;
+    if (!y || !res || !gamma || !beta || !out) return fail_msg("lsthm_dln_fwd: null pointer");
+    if (bad_ld(ldy, d->d) || bad_ld(ldres, d->d) || bad_ld(ldo, d->d) || (v && bad_ld(ldv, d->d)))
+        return fail_msg("lsthm_dln_fwd: row strides must be >= d and multiples of 4 floats");
+    if (d->R == 0) return 0;
+    DlnArgs a{};
+    a.R = d->R; a.d = d->d; a.eps = d->eps; a.p_drop = d->p_drop; a.seed = d->seed;
+    a.y = y; a.ldy = ldy; a.bias = bias; a.res = res; a.ldres = ldres; a.gamma = gamma; a.beta = beta; a.v = v; a.ldv = ldv; a.out = out; a.ldo = ldo;
+    const int grid = dln_grid(d->R);
+    if (d->d <= 128) dln_fwd_kernel<1><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
+    else if (d->d <= 256) dln_fwd_kernel<2><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
+    else dln_fwd_kernel<4><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_dln_fwd launch", e);
+}
+
+int lsthm_dln_bwd(const lsthm_dln_desc *d, const float *dout, int32_t lddo, const float *v, int32_t ldv, const float *gamma,
+                  float *dy, int32_t lddy, float *dres, int32_t lddres, float *dgamma, float *dbeta, float *dbias,
+                  float *workspace, size_t workspace_floats, void *stream) {
+    if (dln_check(d)) return 1;
+    if (!dout || !v || !gamma || !dres || !workspace) return fail_msg("lsthm_dln_bwd: null pointer");
+    if (d->p_drop > 0.f && !dy) return fail_msg("lsthm_dln_bwd: dy is required when p_drop > 0 (it equals dres otherwise)");
+    if (bad_ld(lddo, d->d) || bad_ld(ldv, d->d) || bad_ld(lddres, d->d) || (dy && bad_ld(lddy, d->d)))
+        return fail_msg("lsthm_dln_bwd: row strides must be >= d and multiples of 4 floats");
+    if (workspace_floats < lsthm_dln_workspace_floats(d->d)) return fail_msg("lsthm_dln_bwd: workspace too small");
+    DlnArgs a{};
+    a.R = d->R; a.d = d->d; a.eps = d->eps; a.p_drop = d->p_drop; a.seed = d->seed;
+    a.dout = dout; a.lddo = lddo; a.vin = v; a.ldv = ldv; a.gamma = gamma; a.dy = dy; a.lddy = lddy; a.dres = dres; a.lddres = lddres;
+    a.partial = workspace;
+    const int grid = dln_grid(d->R);
+    if (d->d <= 128) dln_bwd_kernel<1><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
+    else if (d->d <= 256) dln_bwd_kernel<2><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
+    else dln_bwd_kernel<4><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("lsthm_dln_bwd launch", e);
+    dln_reduce_kernel<<<(3 * d->d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, grid, d->d, dgamma, dbeta, dbias);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_dln_bwd reduce launch", e);
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// Fused  out = LayerNorm(dropout(y + bias) + residual)  of the utterance encoder, forward and backward
+// (model/encoder.py:54-58 — `q = self.dropout(self.fc(q)); q += residual; q = self.layer_norm(q)` — and
+// :106-112, the same tail after the position-wise feed-forward).  Row-wise and HBM-bound: one warp owns a
+// row (d <= 512 floats in registers as float4 chunks), rows are walked grid-stride, every tensor is read or
+// written exactly once.  The reference (and stock PyTorch) spends a dropout kernel + mask tensor, an add and a
+// LayerNorm kernel on this in the forward and four kernels in the backward.
+//
+// Dropout is regenerated from (seed, row, column) in the backward — no mask tensor.  The backward also
+// emits the column sums every caller needs next: dgamma, dbeta and the bias gradient of the Linear that
+// produced y (= column sums of dy), as per-block partials reduced in a fixed order (deterministic).
+#pragma once
+#include "common.cuh"
+
+namespace lsthm {
+
+constexpr int kDlnMaxC = 4;          // float4 chunks per lane -> d <= 512
+constexpr int kDlnWarps = 8;
+
+struct DlnArgs {
+    long long R;
+    int d;
+    const float *y, *bias, *res, *gamma, *beta, *dout, *vin;   // bias (may be NULL): y + bias before the dropout
+    float *v, *out, *dy, *dres, *partial;     // partial: [gridDim.x][3][d]  (dgamma, dbeta, dbias)
+    int ldy, ldres, ldv, ldo, lddo, lddy, lddres;
+    float eps, p_drop;
+    unsigned long long seed;
+};
+
+// 16 random bits per element, one 32-bit hash per pair of elements (same construction as the attention dropout)
+struct RowDrop {
+    uint32_t key, thr;
+    float scale;
+    bool on;
+    __device__ __forceinline__ RowDrop(unsigned long long seed, float p) {
+        on = p > 0.f;
+        thr = (uint32_t)(p * 65536.0f + 0.5f);
+        scale = 65536.0f / (65536.0f - (float)thr);
+        uint32_t x = (uint32_t)seed * 0x9E3779B9u + 0x7F4A7C15u;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        key = x ^ (uint32_t)(seed >> 32);
+    }
+    // scales of the 4 elements of float4 chunk number `chunk` (global index over the whole matrix)
+    __device__ __forceinline__ float4 quad(unsigned long long chunk) const {
+        const uint32_t base = key + (uint32_t)(chunk >> 31) * 0x85EBCA6Bu;
+        uint32_t x = base + (uint32_t)(2 * chunk) * 0xC2B2AE35u, z = base + (uint32_t)(2 * chunk + 1) * 0xC2B2AE35u;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        z ^= z >> 16; z *= 0x7feb352du; z ^= z >> 15; z *= 0x846ca68bu; z ^= z >> 16;
+        return make_float4((x & 0xffffu) >= thr ? scale : 0.f, (x >> 16) >= thr ? scale : 0.f,
+                           (z & 0xffffu) >= thr ? scale : 0.f, (z >> 16) >= thr ? scale : 0.f);
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NC>   // float4 chunks per lane: d <= 128 * NC
+__global__ void __launch_bounds__(32 * kDlnWarps, NC == 4 ? 2 : NC == 2 ? 3 : 4) dln_fwd_kernel(const __grid_constant__ DlnArgs a) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nc = a.d >> 2;
+    const float inv_d = 1.0f / (float)a.d;
+    const RowDrop drop(a.seed, a.p_drop);
+    float4 gm[NC], bt[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        gm[i] = bt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nc) {
+            gm[i] = __ldg(reinterpret_cast<const float4 *>(a.gamma) + c);
+            bt[i] = __ldg(reinterpret_cast<const float4 *>(a.beta) + c);
+        }
+    }
+    for (long long row = (long long)blockIdx.x * kDlnWarps + wib; row < a.R; row += (long long)gridDim.x * kDlnWarps) {
+        float4 x[NC];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nc) {
+                float4 y = __ldcs(reinterpret_cast<const float4 *>(a.y + row * a.ldy) + c);
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(a.res + row * a.ldres) + c);
+                if (a.bias != nullptr) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias) + c);
+                    y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+                }
+                if (drop.on) {
+                    const float4 m = drop.quad((unsigned long long)row * nc + c);
+                    y.x *= m.x; y.y *= m.y; y.z *= m.z; y.w *= m.w;
+                }
+                x[i] = make_float4(y.x + r.x, y.y + r.y, y.z + r.z, y.w + r.w);
+                s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+            }
+        }
+        const float mean = warp_sum(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            if (lane + 32 * i < nc) {
+                const float dx = x[i].x - mean, dy = x[i].y - mean, dz = x[i].z - mean, dw = x[i].w - mean;
+                q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + a.eps);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nc) {
+                if (a.v != nullptr) reinterpret_cast<float4 *>(a.v + row * a.ldv)[c] = x[i];
+                float4 o;
+                o.x = (x[i].x - mean) * rstd * gm[i].x + bt[i].x;
+                o.y = (x[i].y - mean) * rstd * gm[i].y + bt[i].y;
+                o.z = (x[i].z - mean) * rstd * gm[i].z + bt[i].z;
+                o.w = (x[i].w - mean) * rstd * gm[i].w + bt[i].w;
+                reinterpret_cast<float4 *>(a.out + row * a.ldo)[c] = o;
+            }
+        }
+    }
+}
+
+// dv = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dout * gamma,  xhat = (v - mean) * rstd
+// dres = dv,  dy = dv * dropout scale;  partial sums of (dout * xhat, dout, dy) per column
+template <int NC>
+__global__ void __launch_bounds__(32 * kDlnWarps, NC == 4 ? 2 : NC == 2 ? 3 : 4) dln_bwd_kernel(const __grid_constant__ DlnArgs a) {
+    __shared__ float4 red[kDlnWarps][3][32 * NC];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nc = a.d >> 2;
+    const float inv_d = 1.0f / (float)a.d;
+    const RowDrop drop(a.seed, a.p_drop);
+    float4 gm[NC], ag[NC], ab[NC], ay[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int c = lane + 32 * i;
+        gm[i] = ag[i] = ab[i] = ay[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < nc) gm[i] = __ldg(reinterpret_cast<const float4 *>(a.gamma) + c);
+    }
+    for (long long row = (long long)blockIdx.x * kDlnWarps + wib; row < a.R; row += (long long)gridDim.x * kDlnWarps) {
+        float4 x[NC], g[NC];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            x[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < nc) {
+                x[i] = __ldcs(reinterpret_cast<const float4 *>(a.vin + row * a.ldv) + c);
+                g[i] = __ldcs(reinterpret_cast<const float4 *>(a.dout + row * a.lddo) + c);
+                s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+            }
+        }
+        const float mean = warp_sum(s) * inv_d;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            if (lane + 32 * i < nc) {
+                x[i].x -= mean; x[i].y -= mean; x[i].z -= mean; x[i].w -= mean;
+                q += (x[i].x * x[i].x + x[i].y * x[i].y) + (x[i].z * x[i].z + x[i].w * x[i].w);
+            }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) * inv_d + a.eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            if (lane + 32 * i < nc) {
+                x[i].x *= rstd; x[i].y *= rstd; x[i].z *= rstd; x[i].w *= rstd;           // xhat
+                ag[i].x += g[i].x * x[i].x; ag[i].y += g[i].y * x[i].y; ag[i].z += g[i].z * x[i].z; ag[i].w += g[i].w * x[i].w;
+                ab[i].x += g[i].x; ab[i].y += g[i].y; ab[i].z += g[i].z; ab[i].w += g[i].w;
+                g[i].x *= gm[i].x; g[i].y *= gm[i].y; g[i].z *= gm[i].z; g[i].w *= gm[i].w;
+                sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+                sgx += (g[i].x * x[i].x + g[i].y * x[i].y) + (g[i].z * x[i].z + g[i].w * x[i].w);
+            }
+        }
+        const float mg = warp_sum(sg) * inv_d, mgx = warp_sum(sgx) * inv_d;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nc) {
+                float4 dv;
+                dv.x = rstd * (g[i].x - mg - x[i].x * mgx);
+                dv.y = rstd * (g[i].y - mg - x[i].y * mgx);
+                dv.z = rstd * (g[i].z - mg - x[i].z * mgx);
+                dv.w = rstd * (g[i].w - mg - x[i].w * mgx);
+                reinterpret_cast<float4 *>(a.dres + row * a.lddres)[c] = dv;
+                if (drop.on) {
+                    const float4 m = drop.quad((unsigned long long)row * nc + c);
+                    dv.x *= m.x; dv.y *= m.y; dv.z *= m.z; dv.w *= m.w;
+                    reinterpret_cast<float4 *>(a.dy + row * a.lddy)[c] = dv;
+                }
+                ay[i].x += dv.x; ay[i].y += dv.y; ay[i].z += dv.z; ay[i].w += dv.w;
+            }
+        }
+    }
+    // block partials, fixed warp order
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        red[wib][0][lane + 32 * i] = ag[i];
+        red[wib][1][lane + 32 * i] = ab[i];
+        red[wib][2][lane + 32 * i] = ay[i];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 3 * nc; idx += blockDim.x) {
+        const int which = idx / nc, c = idx - which * nc;
+        float4 t = red[0][which][c];
+        for (int w = 1; w < kDlnWarps; ++w) {
+            const float4 u = red[w][which][c];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        reinterpret_cast<float4 *>(a.partial + ((size_t)blockIdx.x * 3 + which) * a.d)[c] = t;
+    }
+}
+
+// out[which][col] = sum over blocks of partial[blk][which][col]  (fixed order)
+static __global__ void dln_reduce_kernel(const float *__restrict__ partial, int nblk, int d, float *dgamma, float *dbeta, float *dbias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * d) return;
+    const int which = i / d, col = i - which * d;
+    float *dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
+    if (dst == nullptr) return;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * 3 + which) * d + col];
+    dst[col] = s;
+}
+
+}  // namespace lsthm

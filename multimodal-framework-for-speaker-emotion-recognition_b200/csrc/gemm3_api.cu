@@ -23,7 +23,7 @@ using namespace lsthm;
 extern "C" {
 
 size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K) {
-    (void)mode;
+    if (mode == 3) return 0;
     const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
     if (tiles >= 148 || K < 4 * kGemmBK * 8) return 0;
     const int splits = (int)std::min<long>((K + 255) / 256, std::max<long>(1, 296 / tiles));   // one full wave: 2 CTAs x 148 SMs
@@ -32,17 +32,18 @@ size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t 
 
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream) {
-    if (mode < 0 || mode > 2) return fail_msg("lsthm_gemm3: mode must be 0 (NT), 1 (NN) or 2 (TN)");
+    if (mode < 0 || mode > 3) return fail_msg("lsthm_gemm3: mode must be 0 (NT), 1 (NN), 2 (TN) or 3 (NT + ReLU)");
     if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return fail_msg("lsthm_gemm3: bad shape or null pointer");
     if ((lda & 3) || (ldb & 3)) return fail_msg("lsthm_gemm3: lda and ldb must be multiples of 4 floats");
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
         return fail_msg("lsthm_gemm3: operands must be 16-byte aligned");
     GemmArgs g;
+    g.relu = mode == 3 ? 1 : 0;
     g.A = A; g.B = B; g.bias = bias; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
     const int tm = (M + kGemmBM - 1) / kGemmBM, tn = (N + kGemmBN - 1) / kGemmBN;
     const long tiles = (long)tm * tn;
     int splits = 1;
-    if (tiles < 148 && K >= 4 * kGemmBK * 8 && workspace) {
+    if (tiles < 148 && K >= 4 * kGemmBK * 8 && workspace && mode != 3) {
         splits = (int)std::min<long>((K + 255) / 256, std::max<long>(1, 296 / tiles));   // one full wave
         while (splits > 1 && (size_t)splits * M * N > workspace_floats) --splits;
     }
@@ -53,7 +54,7 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
     if (splits > 1) { g.C = workspace; g.ldc = N; }
     const dim3 grid(tn, tm, splits);
     int rc;
-    if (mode == 0) rc = launch_gemm<0, 0>(g, grid, (cudaStream_t)stream);
+    if (mode == 0 || mode == 3) rc = launch_gemm<0, 0>(g, grid, (cudaStream_t)stream);
     else if (mode == 1) rc = launch_gemm<0, 1>(g, grid, (cudaStream_t)stream);
     else rc = launch_gemm<1, 1>(g, grid, (cudaStream_t)stream);
     if (rc) return rc;

@@ -40,6 +40,7 @@ struct GemmArgs {
     int M, N, K, lda, ldb, ldc;
     int k_per_split;   // multiple of kGemmBK
     int splits;
+    int relu;          // NT epilogue: C = max(0, A.B^T + bias)  (splits == 1 only)
 };
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -53,16 +54,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
 }
-// split 8 consecutive fp32 values into bf16 hi / lo and store each as one 16-byte chunk
+// split 8 consecutive fp32 values into bf16 hi / lo and store each as one 16-byte chunk.
+// Two values per packed conversion (cvt.rn.bf16x2.f32 -> one F2FP): hi = rn(x), lo = rn(x - hi).
 __device__ __forceinline__ void split_store8(const float (&x)[8], uint8_t *hi, uint8_t *lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        const float r0 = x[2 * i] - __bfloat162float(h0), r1 = x[2 * i + 1] - __bfloat162float(h1);
-        __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
-        h[i] = *reinterpret_cast<uint32_t *>(&hv);
-        l[i] = pack_bf16(r0, r1);
+        h[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+        const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+        l[i] = pack_bf16(x[2 * i] - h0, x[2 * i + 1] - h1);
     }
     *reinterpret_cast<uint4 *>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -232,12 +232,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
                             const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + c0) + q);
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
+                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                         reinterpret_cast<float4 *>(crow + c0)[q] = o;
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
-                        if (n0 + c0 + j < g.N) crow[c0 + j] = __uint_as_float(v[j]) + (add_bias ? __ldg(g.bias + n0 + c0 + j) : 0.f);
+                        if (n0 + c0 + j < g.N) {
+                            const float o = __uint_as_float(v[j]) + (add_bias ? __ldg(g.bias + n0 + c0 + j) : 0.f);
+                            crow[c0 + j] = g.relu ? fmaxf(o, 0.f) : o;
+                        }
                 }
             }
         }

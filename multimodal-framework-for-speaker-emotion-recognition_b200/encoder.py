@@ -1,9 +1,13 @@
-"""Host-side mirror of the reference's per-modality utterance encoder (model/encoder.py).
+"""Host-side mirror of the reference's per-modality utterance encoder (model/encoder.py) — the first "next"
+row of SURVEY.md §8(f).
 
-Time-parallel, GEMM-shaped and outside the recurrence, so it stays ordinary PyTorch (cuBLAS);
-a fused kernel for it is the first "next" row of SURVEY.md §8(f).  Parameter names, shapes and
-construction order equal the reference's (encoder.py:10-25, 92-99, 124-127) so that state_dicts
-load both ways and a fixed seed yields identical initial weights.
+Parameter names, shapes and construction order equal the reference's (encoder.py:10-25, 92-99, 124-127) so
+that state_dicts load both ways and a fixed seed yields identical initial weights.  On a CUDA device the whole
+layer runs on our own kernels over a 2-D row view of the activations (``EncoderLayer._fast``): fused QKV
+projection and the other Linear layers on ``lsthm_gemm3`` (tcgen05), self-attention on ``lsthm_attn_*`` (tcgen05,
+reads time-major rows in place), and both ``LayerNorm(dropout(.) + residual)`` tails on ``lsthm_dln_*``.  The
+module-by-module path below it is the same arithmetic in PyTorch ops and is what runs when a test swaps the
+dropout modules for a mask tape, or on shapes the kernels do not cover.
 """
 from __future__ import annotations
 
@@ -14,7 +18,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .fused_attention import fused_self_attention
-from .mm3 import linear3
+from .fused_dln import drop_res_layer_norm
+from .mm3 import linear3, rows_view, _LinearTC
+from . import mm3
 
 import os
 # fused library attention for the encoder (measured: 52.4 -> 50.5 ms/step, eval parity unchanged); the explicit
@@ -99,12 +105,54 @@ class PositionwiseFeedForward(nn.Module):
         return self.layer_norm(self.dropout(linear3(h, w2, self.w_2.bias)) + x)
 
 
+def _seed(p: float) -> int:
+    return int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+
+
 class EncoderLayer(nn.Module):
     def __init__(self, d_model, d_inner, n_head, d_k, d_v, dropout=0.1):
         super().__init__()
         self.slf_attn = MultiHeadAttention(n_head, d_model, d_model, d_k, d_v, dropout=dropout)
         self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=dropout)
 
+    def _fast_ok(self, x: torch.Tensor, mask) -> bool:
+        a, f = self.slf_attn, self.pos_ffn
+        plain = all(type(m) is nn.Dropout for m in (a.dropout, a.attention.dropout, f.dropout))
+        return (_FUSED_OWN and mm3.enabled() and mask is None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
+                and x.shape[1] <= 128 and a.d_k == 40 and a.d_v == 40 and x.shape[-1] % 4 == 0 and x.shape[-1] <= 512
+                and plain and x.data_ptr() % 16 == 0)
+
+    def _fast(self, x: torch.Tensor) -> torch.Tensor:
+        """The whole layer on 2-D rows; ``x`` is [B, L, d] logically, in whatever row order its storage has."""
+        a, f = self.slf_attn, self.pos_ffn
+        B, L, d = x.shape
+        rv = rows_view(x)
+        if rv is None:
+            x = x.contiguous()
+            rv = rows_view(x)
+        rows, time_major = rv                                   # rows [R, d]; time_major: row = i*B + b
+        train = self.training
+        H, W = a.n_head, 3 * a.n_head * 40
+        w_qkv = torch.cat([a.w_qs.weight, a.w_ks.weight, a.w_vs.weight], dim=0)
+        qkv = _LinearTC.apply(rows, w_qkv, None, False)         # one projection GEMM instead of three (encoder.py:38-40)
+        p_att = a.attention.dropout.p if train else 0.0
+        qkv3 = qkv.view(L, B, W) if time_major else qkv.view(B, L, W)
+        ctx = fused_self_attention(qkv3, H, 1.0 / a.attention.temperature, p_att, _seed(p_att), time_major)
+        y = _LinearTC.apply(ctx.view(B * L, H * 40), a.fc.weight, None, False)
+        p1 = a.dropout.p if train else 0.0
+        x1 = drop_res_layer_norm(y, None, rows, a.layer_norm.weight, a.layer_norm.bias, a.layer_norm.eps, p1, _seed(p1))
+        w1, b1, w2 = f.w_1.weight, f.w_1.bias, f.w_2.weight
+        pad = (-w1.shape[0]) % 4
+        if pad:   # d_inner = 50 (HybridRNN_AT/ATV): zero-pad the hidden width to a multiple of 4 (relu(0) = 0 meets zero columns)
+            w1, b1, w2 = F.pad(w1, (0, 0, 0, pad)), F.pad(b1, (0, pad)), F.pad(w2, (0, pad))
+        h = _LinearTC.apply(x1, w1, b1, True)                   # relu(w_1 x + b) with the ReLU in the GEMM epilogue
+        y2 = _LinearTC.apply(h, w2, None, False)                # w_2's bias is added by the fused tail (its gradient comes from there)
+        p2 = f.dropout.p if train else 0.0
+        out = drop_res_layer_norm(y2, f.w_2.bias, x1, f.layer_norm.weight, f.layer_norm.bias, f.layer_norm.eps, p2, _seed(p2))
+        return out.view(L, B, d).transpose(0, 1) if time_major else out.view(B, L, d)
+
     def forward(self, enc_input, slf_attn_mask=None):
+        if self._fast_ok(enc_input, slf_attn_mask):
+            return self._fast(enc_input), None
         y, attn = self.slf_attn(enc_input, enc_input, enc_input, mask=slf_attn_mask)
         return self.pos_ffn(y), attn

@@ -82,27 +82,61 @@ def mm_nn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 class _LinearTC(torch.autograd.Function):
+    """y = x W^T (+ b) (optionally followed by ReLU in the GEMM epilogue) on 2-D row matrices."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        return _gemm(_lib.GEMM_NT, _rows(x), _rows(weight), None if bias is None else bias.contiguous())
+    def forward(ctx, x, weight, bias, relu):
+        ctx.has_bias, ctx.relu = bias is not None, relu
+        y = _gemm(_lib.GEMM_NT_RELU if relu else _lib.GEMM_NT, _rows(x), _rows(weight), None if bias is None else bias.contiguous())
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, y = ctx.saved_tensors
+        if ctx.relu:
+            dy = torch.ops.aten.threshold_backward(dy, y, 0.0)
         dy = _rows(dy)
         dx = mm_nn(dy, weight) if ctx.needs_input_grad[0] else None
         dw = mm_tn(dy, x) if ctx.needs_input_grad[1] else None
         db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db
+        return dx, dw, db, None
 
 
-def linear3(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
-    """Drop-in for F.linear on the time-parallel projections (x [..., K], weight [N, K])."""
+def rows_view(x: torch.Tensor):
+    """A 3-D activation [A, B, K] as a 2-D row matrix WITHOUT a copy when its storage allows it.
+
+    Returns (rows[R, K], swapped): ``swapped`` is True when the rows are in [B, A] order, i.e. ``x`` is a permuted
+    view of time-major storage such as ``x_time_major.permute(1, 0, 2)`` (the reference hands its encoders exactly
+    that, model/HybridRNN_ATV.py:90-92).  Row-wise ops don't care about the order; whoever needs it (the attention
+    kernel) is told through its row strides.  None if no copy-free row view exists.
+    """
+    A, B, K = x.shape
+    if x.stride(2) != 1:
+        return None
+    s0, s1 = x.stride(0), x.stride(1)
+    if s0 == B * s1 and s1 % 4 == 0 and s1 >= K:
+        return x.as_strided((A * B, K), (s1, 1)), False
+    if s1 == A * s0 and s0 % 4 == 0 and s0 >= K:
+        return x.as_strided((B * A, K), (s0, 1)), True
+    return None
+
+
+def linear3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False) -> torch.Tensor:
+    """Drop-in for F.linear (+ optional ReLU) on the time-parallel projections (x [..., K], weight [N, K]).
+    3-D inputs that are permuted views of time-major storage are processed in place (no permute copy) and the
+    result is returned as the same kind of view."""
     K, N = x.shape[-1], weight.shape[0]
     if not (_ok(x, weight) and K % 4 == 0 and N % 4 == 0):
-        return F.linear(x, weight, bias)
+        y = F.linear(x, weight, bias)
+        return F.relu(y) if relu else y
+    if x.dim() == 3 and x.data_ptr() % 16 == 0:
+        rv = rows_view(x)
+        if rv is not None:
+            rows, swapped = rv
+            y = _LinearTC.apply(rows, weight, bias, relu)
+            A, B = x.shape[0], x.shape[1]
+            return y.view(B, A, N).transpose(0, 1) if swapped else y.view(A, B, N)
     lead = x.shape[:-1]
-    y = _LinearTC.apply(x.reshape(-1, K), weight, bias)
+    y = _LinearTC.apply(x.reshape(-1, K), weight, bias, relu)
     return y.view(*lead, N)

@@ -221,17 +221,97 @@ def sps_run_module(fix, device="cuda", rows_per_cta=0):
     return logp.detach().cpu(), loss.detach().cpu(), x.grad.detach().cpu(), grads
 
 
-def check_against_fp64_truth(fix, probs, loss, dx, grads, tol_out=TOL_OUT, tol_grad=TOL_GRAD, slack=3.0):
+class relu_kinks:
+    """Records every ``torch.relu`` pre-activation of an oracle run (call order = site id) and can force the on/off
+    decision of chosen units: ``force = {site: [(flat_index, on), ...]}``.  A ReLU whose pre-activation is closer to
+    zero than the forward parity tolerance has no defined derivative at that resolution; the sps parity test uses
+    this to enumerate the subgradient choices the fp64 truth could equally have made (see ``sps_kink_truths``)."""
+
+    def __init__(self, force=None):
+        self.force, self.z = force or {}, []
+
+    def __enter__(self):
+        self._orig = torch.relu
+
+        def patched(z):
+            i = len(self.z)
+            self.z.append(z.detach())
+            m = z > 0
+            if i in self.force:
+                m = m.clone()
+                for idx, on in self.force[i]:
+                    m.view(-1)[idx] = on
+            return z * m.to(z.dtype)
+        torch.relu = patched
+        return self
+
+    def __exit__(self, *exc):
+        torch.relu = self._orig
+
+
+def sps_port_run64(fix, force=None):
+    """fp64 run of the oracle restatement (eval fixtures only) -> truth dict shaped like the fixture's fp64 fields,
+    plus the recorded ReLU pre-activations."""
+    assert not int(fix["train"])
+    model = sps_seeded_model(fix["seed"], int(fix["perturb"]))
+    params = {k: v.detach().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    x = torch.from_numpy(fix["x"]).double().requires_grad_(True)
+    qmask, umask = torch.from_numpy(fix["qmask"]).double(), torch.from_numpy(fix["umask"]).double()
+    with relu_kinks(force) as rk:
+        logp, _, _ = tp.sps_forward(params, x, qmask, umask, None)
+        loss = tp.masked_loss(logp, torch.from_numpy(fix["labels"]).view(-1), umask, "ce")
+        loss.backward()
+    stride = int(fix["sample_stride"])
+    truth = {"probs64": logp.detach().numpy(), "loss64": np.array(loss.item()), "dx64": x.grad.numpy()}
+    for k, v in params.items():
+        if v.grad is None:
+            continue
+        flat = v.grad.reshape(-1).numpy()
+        truth["gnorm64/" + k] = np.array(np.linalg.norm(flat))
+        truth["gsamp64/" + k] = flat if flat.size <= 4096 else flat[::stride]
+    return truth, rk.z
+
+
+def sps_kink_truths(fix, rel=TOL_OUT, kmax=5):
+    """Alternative fp64 truths of an eval fixture: one per non-empty subset of the (at most kmax) ReLU units whose
+    pre-activation lies within ``rel`` x the layer's largest pre-activation of zero — i.e. within the FORWARD parity
+    tolerance of their kink — with those units' on/off decisions flipped."""
+    import itertools
+    base, zs = sps_port_run64(fix)
+    assert e_inf(base["dx64"], fix["dx64"]) < 1e-7 and e_inf(base["probs64"], fix["probs64"]) < 1e-9   # oracle == reference (fp64)
+    near = []
+    for site, z in enumerate(zs):
+        a = z.abs().reshape(-1)
+        thr = rel * float(a.max())
+        for idx in torch.nonzero(a < thr).reshape(-1).tolist():
+            near.append((float(a[idx]) / float(a.max()), site, idx, bool(z.reshape(-1)[idx] > 0)))
+    near = sorted(near)[:kmax]
+    for r in range(1, len(near) + 1):
+        for sub in itertools.combinations(near, r):
+            force = {}
+            for _, site, idx, on in sub:
+                force.setdefault(site, []).append((idx, not on))
+            yield sub, sps_port_run64(fix, force)[0]
+
+
+def check_against_fp64_truth(fix, probs, loss, dx, grads, tol_out=TOL_OUT, tol_grad=TOL_GRAD, slack=3.0, truth=None):
     """Parity bar for the ill-conditioned lsthm_sps: against the fp64 run of the reference,
     err(ours, fp64) <= max(tol, slack * err(reference fp32, fp64)), per tensor.  Also requires identical argmax
-    with the fp32 reference wherever its top-2 margin exceeds 1e-3."""
-    def bar(tol, ref32, truth):
-        return max(tol, slack * e_inf(ref32, truth))
+    with the fp32 reference wherever its top-2 margin exceeds 1e-3.  ``truth`` (optional) replaces the fp64
+    comparator (a kink-flipped truth from ``sps_kink_truths``); the bars always come from the fixture."""
+    def bar(tol, ref32, truth_):
+        return max(tol, slack * e_inf(ref32, truth_))
+    bars = {"probs": bar(tol_out, fix["probs"], fix["probs64"]), "dx": bar(tol_grad, fix["dx"], fix["dx64"])}
+    gbars = {k[8:]: bar(tol_grad, fix["gsamp/" + k[8:]], fix[k]) for k in fix if k.startswith("gsamp64/")}
+    orig = fix
+    if truth is not None:
+        fix = dict(fix)
+        fix.update(truth)
     errs = {"probs": e_inf(probs, fix["probs64"]), "dx": e_inf(dx, fix["dx64"]),
             "loss": abs(float(loss) - float(fix["loss64"])) / abs(float(fix["loss64"]))}
-    assert errs["probs"] <= bar(tol_out, fix["probs"], fix["probs64"]), errs
-    assert errs["dx"] <= bar(tol_grad, fix["dx"], fix["dx64"]), errs
-    assert errs["loss"] <= max(tol_out, slack * abs(float(fix["loss"]) - float(fix["loss64"])) / abs(float(fix["loss64"]))), errs
+    assert errs["probs"] <= bars["probs"], errs
+    assert errs["dx"] <= bars["dx"], errs
+    assert errs["loss"] <= max(tol_out, slack * abs(float(orig["loss"]) - float(orig["loss64"])) / abs(float(orig["loss64"]))), errs
     ref = fix["probs"]
     top2 = np.sort(ref, -1)[:, -2:]
     decided = (top2[:, 1] - top2[:, 0]) > 1e-3
@@ -253,7 +333,7 @@ def check_against_fp64_truth(fix, probs, loss, dx, grads, tol_out=TOL_OUT, tol_g
             continue
         samp = flat if flat.size <= 4096 else flat[::stride]
         err = e_inf(samp, fix[key])
-        lim = bar(tol_grad, fix["gsamp/" + name], fix[key])
+        lim = gbars[name]
         worst = max(worst, err / lim)
         assert err <= lim, (name, err, lim)
     errs["worst_grad_over_bar"] = worst

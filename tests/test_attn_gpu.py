@@ -36,6 +36,22 @@ def test_forward_backward_vs_fp64(B, L):
     assert eo < 2e-5 and eg < 5e-5, (eo, eg)
 
 
+def test_time_major_layout_matches_batch_major():
+    """[L, B, .] activations (the reference's own layout) are read in place through the row strides."""
+    B, L = 3, 37
+    g = torch.Generator(device="cuda").manual_seed(5)
+    qkv = torch.randn(B, L, 3 * H * D, device="cuda", generator=g)
+    w = torch.randn(B, L, H * D, device="cuda", generator=g)
+    scale = D ** -0.5
+    a = qkv.clone().requires_grad_(True)
+    oa = fa.fused_self_attention(a, H, scale, 0.1, 3)
+    (oa * w).sum().backward()
+    bt = qkv.transpose(0, 1).contiguous().requires_grad_(True)
+    ob = fa.fused_self_attention(bt, H, scale, 0.1, 3, time_major=True)
+    (ob * w.transpose(0, 1)).sum().backward()
+    assert torch.equal(oa, ob.transpose(0, 1)) and torch.equal(a.grad, bt.grad.transpose(0, 1))
+
+
 def test_dropout_is_seeded_and_consistent_between_fwd_and_bwd():
     B, L, p = 2, 50, 0.1
     g = torch.Generator(device="cuda").manual_seed(7)
