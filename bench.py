@@ -213,6 +213,7 @@ def run_ours(args):
     ddp = import_module(lsthm_b200.__name__ + ".ddp")
     mm3 = import_module(lsthm_b200.__name__ + ".mm3")
     fat = import_module(lsthm_b200.__name__ + ".fused_attention")
+    fdl = import_module(lsthm_b200.__name__ + ".fused_dln")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -287,7 +288,7 @@ def run_ours(args):
     if sampler:
         sampler.start(); time.sleep(0.25)
     rec.kernel_events = {"fwd": [], "bwd": []}
-    for cnt in (rec.launch_counter, mm3.launches, fat.launches):
+    for cnt in (rec.launch_counter, mm3.launches, fat.launches, fdl.launches):
         for k in cnt:
             cnt[k] = 0
     barrier()
@@ -300,7 +301,8 @@ def run_ours(args):
     barrier()
     wall1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = (sum(rec.launch_counter.values()) + sum(mm3.launches.values()) + sum(fat.launches.values())) * world
+    launches = (sum(rec.launch_counter.values()) + sum(mm3.launches.values()) + sum(fat.launches.values())
+                + sum(fdl.launches.values())) * world
     kev, rec.kernel_events = rec.kernel_events, None
     # the ~60 small tensor-core launches of a step are event-timed in two EXTRA steps outside the timed region
     # (an event pair per launch would perturb `value`)

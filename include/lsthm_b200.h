@@ -182,6 +182,14 @@ size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t 
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream);
 
+/* The same product for modes 0, 1 and 3 when B is a layer WEIGHT W and M = T*N is large: W is split once into
+ * bf16 hi/lo tile images in the UMMA shared-memory layout (`pack`, lsthm_gemm3w_pack_bytes(N, K) bytes, written by
+ * the call), the main kernel converts only the activation operand, fetches weight tiles with bulk async copies and
+ * owns 128 x 256 output tiles.  Same numerics as lsthm_gemm3. */
+size_t lsthm_gemm3w_pack_bytes(int32_t N, int32_t K);
+int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *W, int32_t ldw,
+                 const float *bias, float *C, int32_t ldc, void *pack, size_t pack_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head self-attention of the utterance encoder (tcgen05, split-bf16, fp32 accuracy).
  * Replaces ScaledDotProductAttention.forward, model/encoder.py:71-86, as called by
@@ -236,6 +244,13 @@ int lsthm_dln_fwd(const lsthm_dln_desc *d, const float *y, int32_t ldy, const fl
 int lsthm_dln_bwd(const lsthm_dln_desc *d, const float *dout, int32_t lddo, const float *v, int32_t ldv, const float *gamma,
                   float *dy, int32_t lddy, float *dres, int32_t lddres, float *dgamma, float *dbeta, float *dbias,
                   float *workspace, size_t workspace_floats, void *stream);
+
+/* Column sums out[C] = sum_r A[r][c] of a row-major fp32 matrix (C % 4 == 0, ld % 4 == 0): the bias gradients
+ * autograd forms as dy.sum(0) for every nn.Linear on the path, over all T*N rows.  Deterministic (fixed order).
+ * `workspace`: lsthm_colsum_workspace_floats(R, C) floats. */
+size_t lsthm_colsum_workspace_floats(int64_t R, int32_t C);
+int lsthm_colsum(int64_t R, int32_t C, const float *A, int32_t ld, float *out, float *workspace, size_t workspace_floats,
+                 void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adam step on a flat fp32 buffer.  Replaces `self.optim.step()` of the reference's trainer

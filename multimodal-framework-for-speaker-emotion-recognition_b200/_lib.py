@@ -122,6 +122,15 @@ def lib() -> C.CDLL:
     L.lsthm_dln_bwd.restype = C.c_int
     L.lsthm_dln_bwd.argtypes = [C.POINTER(DlnDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.lsthm_gemm3w_pack_bytes.restype = C.c_size_t
+    L.lsthm_gemm3w_pack_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.lsthm_gemm3w.restype = C.c_int
+    L.lsthm_gemm3w.argtypes = [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                               C.c_void_p, C.c_size_t, C.c_void_p]
+    L.lsthm_colsum_workspace_floats.restype = C.c_size_t
+    L.lsthm_colsum_workspace_floats.argtypes = [C.c_int64, C.c_int32]
+    L.lsthm_colsum.restype = C.c_int
+    L.lsthm_colsum.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.lsthm_adam_step.restype = C.c_int
     L.lsthm_adam_step.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_float] * 5 + [C.c_int32, C.c_void_p]
     if L.lsthm_abi_version() != ABI_VERSION:
@@ -277,6 +286,7 @@ def sps_launch_info(d: SpsDesc) -> dict:
 # tcgen05 split-bf16 GEMM (time-parallel products)
 # ------------------------------------------------------------------------------------------------
 GEMM_NT, GEMM_NN, GEMM_TN, GEMM_NT_RELU = 0, 1, 2, 3
+GEMM3W_MIN_ROWS = int(os.environ.get("LSTHM_GEMM3W_MIN_ROWS", "2048"))
 
 
 def _mat(t: torch.Tensor, name: str):
@@ -299,6 +309,13 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
     pa, lda = _mat(a, "a")
     pb, ldb = _mat(b, "b")
     c = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    if mode != GEMM_TN and M >= GEMM3W_MIN_ROWS:
+        # B is a layer weight and there are many rows: pre-split weight images + 128 x 256 tiles
+        nbytes = lib().lsthm_gemm3w_pack_bytes(N, K)
+        pack = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
+        _check(lib().lsthm_gemm3w(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), N, pack.data_ptr(), nbytes,
+                                  _stream()), "lsthm_gemm3w")
+        return c
     nws = lib().lsthm_gemm3_workspace_floats(mode, M, N, K)
     ws = torch.empty(nws, device=a.device, dtype=torch.float32) if nws else None
     _check(lib().lsthm_gemm3(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), N,
@@ -363,6 +380,17 @@ def dln_bwd(desc: DlnDesc, dout, v, gamma, dy, dres, dgamma, dbeta, dbias) -> No
     _check(lib().lsthm_dln_bwd(C.byref(desc), pdo, lddo, pv, ldv, _dev_ptr(gamma, "gamma"), pdy, lddy, pdr, lddr,
                                _dev_ptr(dgamma, "dgamma"), _dev_ptr(dbeta, "dbeta"), _dev_ptr(dbias, "dbias"), ws.data_ptr(), nws,
                                _stream()), "lsthm_dln_bwd")
+
+
+def colsum(a: torch.Tensor) -> torch.Tensor:
+    """Column sums of a 2-D fp32 CUDA matrix (unit inner stride, 16-byte aligned rows, width % 4 == 0)."""
+    pa, ld = _rows2d(a, "a")
+    R, Cc = a.shape
+    out = torch.empty(Cc, device=a.device, dtype=torch.float32)
+    nws = lib().lsthm_colsum_workspace_floats(R, Cc)
+    ws = torch.empty(nws, device=a.device, dtype=torch.float32)
+    _check(lib().lsthm_colsum(R, Cc, pa, ld, out.data_ptr(), ws.data_ptr(), nws, _stream()), "lsthm_colsum")
+    return out
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step) -> None:

@@ -90,25 +90,32 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&va
     for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(r[i]); vb[i] = __uint_as_float(r[16 + i]); }
 }
 
-// stage chunks [c0, c1) (8 floats each; chunk 5 is the zero padding 40 -> 48) of one 40-float row (scaled) into a
-// K-major row tile (hi, lo); src == nullptr (row >= L) stages zeros
-__device__ __forceinline__ void stage_row40(const float *src, int row, float scale, uint8_t *hi, int c0, int c1) {
+// Staging of one 40-float row into a K-major [128 x 48] row tile (hi, lo), split in two phases so that a thread's
+// global loads for ALL operand tiles are in flight before the first conversion: a thread owns three of the six
+// 8-float chunks of its row (chunk 5 is the zero padding 40 -> 48); src == nullptr (row >= L) stages zeros.
+struct RowRegs {
+    float4 v[6];
+};
+__device__ __forceinline__ void row_load(const float *src, int c0, RowRegs &r) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int c = c0 + i;
+        if (c < 5 && src != nullptr) {
+            r.v[2 * i] = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c);
+            r.v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
+        } else {
+            r.v[2 * i] = r.v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+__device__ __forceinline__ void row_store(const RowRegs &r, int row, float scale, uint8_t *hi, int c0) {
     uint8_t *lo = hi + kRowTile;
     const int roff = (row >> 3) * 128 + (row & 7) * 16;
-    float x[8];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        if (c < c0 || c >= c1) continue;
-        if (c < 5 && src != nullptr) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c);
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
-            x[0] = a.x * scale; x[1] = a.y * scale; x[2] = a.z * scale; x[3] = a.w * scale;
-            x[4] = b.x * scale; x[5] = b.y * scale; x[6] = b.z * scale; x[7] = b.w * scale;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = 0.f;
-        }
-        split_store8(x, hi + c * 2048 + roff, lo + c * 2048 + roff);
+    for (int i = 0; i < 3; ++i) {
+        const float4 a = r.v[2 * i], b = r.v[2 * i + 1];
+        const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+        split_store8(x, hi + (c0 + i) * 2048 + roff, lo + (c0 + i) * 2048 + roff);
     }
 }
 
@@ -158,9 +165,15 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    stage_row40(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, r, a.scale * kLog2e, sQ, 3 * g, 3 * g + 3);
-    stage_row40(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, r, 1.f, sK, 3 * g, 3 * g + 3);
-    stage_row40(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, r, 1.f, sV, 3 * g, 3 * g + 3);
+    {
+        RowRegs rq, rk, rw;
+        row_load(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, 3 * g, rq);
+        row_load(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, 3 * g, rk);
+        row_load(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, 3 * g, rw);
+        row_store(rq, r, a.scale * kLog2e, sQ, 3 * g);
+        row_store(rk, r, 1.f, sK, 3 * g);
+        row_store(rw, r, 1.f, sV, 3 * g);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -269,19 +282,16 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const float *drow = a.dout + grow * a.ldo + h * kAttD;
-    stage_row40(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, r, a.scale * kLog2e, sQ, 3 * g, 3 * g + 3);
-    stage_row40(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, r, 1.f, sK, 3 * g, 3 * g + 3);
-    stage_row40(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, r, 1.f, sV, 3 * g, 3 * g + 3);
-    stage_row40(rv ? drow : nullptr, r, 1.f, sdO, 3 * g, 3 * g + 3);
-    float delta = 0.f, lse = 0.f;              // delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij  (both threads of a row compute it)
-    if (rv) {
-        const float *orow = a.o + grow * a.ldo + h * kAttD;
-#pragma unroll
-        for (int d = 0; d < kAttD; d += 4) {
-            const float4 o4 = __ldg(reinterpret_cast<const float4 *>(orow + d)), d4 = __ldg(reinterpret_cast<const float4 *>(drow + d));
-            delta += d4.x * o4.x + d4.y * o4.y + d4.z * o4.z + d4.w * o4.w;
-        }
-        lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
+    {
+        RowRegs rq, rk, rw, rd;
+        row_load(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, 3 * g, rq);
+        row_load(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, 3 * g, rk);
+        row_load(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, 3 * g, rw);
+        row_load(rv ? drow : nullptr, 3 * g, rd);
+        row_store(rq, r, a.scale * kLog2e, sQ, 3 * g);
+        row_store(rk, r, 1.f, sK, 3 * g);
+        row_store(rw, r, 1.f, sV, 3 * g);
+        row_store(rd, r, 1.f, sdO, 3 * g);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -294,6 +304,20 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
         umma3(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
         umma3(tmem + 128, udO, kRowTile, 4096u, 2048u, 128u, uV, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
         umma_commit(&bar[0]);
+    }
+    // while the tensor core works: delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij (both threads of a row compute it) and the row's lse
+    float delta = 0.f, lse = 0.f;
+    if (rv) {
+        const float *orow = a.o + grow * a.ldo + h * kAttD;
+        float4 o4[10], d4[10];
+#pragma unroll
+        for (int d = 0; d < 10; ++d) {
+            o4[d] = __ldg(reinterpret_cast<const float4 *>(orow) + d);
+            d4[d] = __ldg(reinterpret_cast<const float4 *>(drow) + d);
+        }
+        lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
+#pragma unroll
+        for (int d = 0; d < 10; ++d) delta += d4[d].x * o4[d].x + d4[d].y * o4[d].y + d4[d].z * o4[d].z + d4[d].w * o4[d].w;
     }
     mbar_wait(&bar[0], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

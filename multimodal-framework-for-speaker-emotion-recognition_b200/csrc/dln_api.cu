@@ -64,9 +64,33 @@ int lsthm_dln_bwd(const lsthm_dln_desc *d, const float *dout, int32_t lddo, cons
     else dln_bwd_kernel<4><<<grid, 32 * kDlnWarps, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("lsthm_dln_bwd launch", e);
-    dln_reduce_kernel<<<(3 * d->d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(workspace, grid, d->d, dgamma, dbeta, dbias);
+    dln_reduce_kernel<<<(3 * d->d + 31) / 32, 256, 0, (cudaStream_t)stream>>>(workspace, grid, d->d, dgamma, dbeta, dbias);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_dln_bwd reduce launch", e);
+}
+
+static int colsum_chunks(long long R, int C) {
+    const int coltiles = (C + 127) / 128;
+    long long n = kDlnMaxGrid / coltiles;
+    if (n < 1) n = 1;
+    const long long maxc = (R + 63) / 64;                         // at least 64 rows per chunk
+    return (int)(n < maxc ? n : (maxc < 1 ? 1 : maxc));
+}
+
+size_t lsthm_colsum_workspace_floats(int64_t R, int32_t C) { return (size_t)colsum_chunks(R, C) * (size_t)C; }
+
+int lsthm_colsum(int64_t R, int32_t C, const float *A, int32_t ld, float *out, float *workspace, size_t workspace_floats, void *stream) {
+    if (R < 1 || C < 4 || (C & 3) || !A || !out || !workspace) return fail_msg("lsthm_colsum: need R >= 1, C % 4 == 0 and non-null pointers");
+    if (ld < C || (ld & 3) || (reinterpret_cast<uintptr_t>(A) & 15)) return fail_msg("lsthm_colsum: rows must be 16-byte aligned (ld % 4 == 0)");
+    const int nchunk = colsum_chunks(R, C);
+    if (workspace_floats < (size_t)nchunk * C) return fail_msg("lsthm_colsum: workspace too small");
+    const int rpc = (int)((R + nchunk - 1) / nchunk);
+    colsum_partial_kernel<<<dim3((C + 127) / 128, nchunk), 256, 0, (cudaStream_t)stream>>>(A, R, C, ld, rpc, workspace);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("lsthm_colsum launch", e);
+    colsum_final_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(workspace, nchunk, C, out);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_colsum final launch", e);
 }
 
 }  // extern "C"

@@ -208,16 +208,79 @@ __global__ void __launch_bounds__(32 * kDlnWarps, NC == 4 ? 2 : NC == 2 ? 3 : 4)
     }
 }
 
-// out[which][col] = sum over blocks of partial[blk][which][col]  (fixed order)
-static __global__ void dln_reduce_kernel(const float *__restrict__ partial, int nblk, int d, float *dgamma, float *dbeta, float *dbias) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * d) return;
-    const int which = i / d, col = i - which * d;
-    float *dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
-    if (dst == nullptr) return;
+// out[which][col] = sum over blocks of partial[blk][which][col]  (fixed order: 8 interleaved row groups, then the groups)
+static __global__ void __launch_bounds__(256) dln_reduce_kernel(const float *__restrict__ partial, int nblk, int d, float *dgamma,
+                                                                float *dbeta, float *dbias) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cx;                      // column of the [3*d] vector
     float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * 3 + which) * d + col];
-    dst[col] = s;
+    if (i < 3 * d)
+        for (int b = ry; b < nblk; b += 8) s += partial[(size_t)b * 3 * d + i];
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && i < 3 * d) {
+        float t = red[0][cx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += red[r][cx];
+        const int which = i / d, col = i - which * d;
+        float *dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias;
+        if (dst != nullptr) dst[col] = t;
+    }
 }
 
+}  // namespace lsthm
+
+// ---------------------------------------------------------------------------------------------
+// Column sums of a row-major matrix A[R][C] (bias gradients: db = sum over all T*N rows of dy), two stages, fixed
+// summation order.  Stage 1: a CTA owns 128 columns (32 float4 lanes) x one chunk of rows, 8 row lanes.
+// ---------------------------------------------------------------------------------------------
+namespace lsthm {
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float *__restrict__ A, long long R, int C, int ld, int rows_per_chunk,
+                                                             float *__restrict__ partial) {
+    __shared__ float4 red[8][32];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c4 = blockIdx.x * 32 + cx;                         // float4 column index
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * c4 < C) {
+        const float4 *p = reinterpret_cast<const float4 *>(A) + c4;
+        const size_t ld4 = (size_t)(ld >> 2);
+        long long r = r0 + ry;
+        for (; r + 24 < r1; r += 32) {                            // 4 independent loads in flight per thread
+            const float4 a = __ldcs(p + (size_t)r * ld4), b = __ldcs(p + (size_t)(r + 8) * ld4);
+            const float4 c = __ldcs(p + (size_t)(r + 16) * ld4), d = __ldcs(p + (size_t)(r + 24) * ld4);
+            s.x += (a.x + b.x) + (c.x + d.x); s.y += (a.y + b.y) + (c.y + d.y);
+            s.z += (a.z + b.z) + (c.z + d.z); s.w += (a.w + b.w) + (c.w + d.w);
+        }
+        for (; r < r1; r += 8) {
+            const float4 a = __ldcs(p + (size_t)r * ld4);
+            s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        }
+    }
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && 4 * c4 < C) {
+        float4 t = red[0][cx];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { t.x += red[k][cx].x; t.y += red[k][cx].y; t.z += red[k][cx].z; t.w += red[k][cx].w; }
+        reinterpret_cast<float4 *>(partial + (size_t)blockIdx.y * C)[c4] = t;
+    }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float *__restrict__ partial, int nchunk, int C, float *__restrict__ out) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    float s = 0.f;
+    if (c < C)
+        for (int b = ry; b < nchunk; b += 8) s += partial[(size_t)b * C + c];
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float t = red[0][cx];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += red[k][cx];
+        out[c] = t;
+    }
+}
 }  // namespace lsthm

@@ -16,6 +16,21 @@ static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st) {
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_gemm3 launch", e);
 }
+
+template <int BMN>
+static int launch_gemm_w(const GemmWArgs &g, const float *W, int ldw, uint8_t *img, dim3 grid, cudaStream_t st) {
+    const int nch = (g.N + kWNC - 1) / kWNC;
+    const size_t chunks = (size_t)nch * g.nkb * 1024;
+    const int pblocks = (int)std::min<size_t>((chunks + 255) / 256, 148 * 8);
+    gemm3w_pack_kernel<BMN><<<pblocks, 256, 0, st>>>(W, ldw, g.N, g.K, g.nkb, img, chunks);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("lsthm_gemm3w pack launch", e);
+    e = cudaFuncSetAttribute(gemm3w_kernel<BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWSmemBytes);
+    if (e != cudaSuccess) return set_error("lsthm_gemm3w shared-memory opt-in", e);
+    gemm3w_kernel<BMN><<<grid, kGemmThreads, kWSmemBytes, st>>>(g);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_gemm3w launch", e);
+}
 }  // namespace lsthm
 
 using namespace lsthm;
@@ -66,6 +81,27 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
         if (e != cudaSuccess) return set_error("lsthm_gemm3 reduce launch", e);
     }
     return 0;
+}
+
+size_t lsthm_gemm3w_pack_bytes(int32_t N, int32_t K) {
+    if (N < 1 || K < 1) return 0;
+    return (size_t)((N + kWNC - 1) / kWNC) * ((K + kGemmBK - 1) / kGemmBK) * 2 * (size_t)kWImgBytes;
+}
+
+int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *W, int32_t ldw,
+                 const float *bias, float *C, int32_t ldc, void *pack, size_t pack_bytes, void *stream) {
+    if (mode != 0 && mode != 1 && mode != 3) return fail_msg("lsthm_gemm3w: mode must be 0 (NT), 1 (NN) or 3 (NT + ReLU)");
+    if (M < 1 || N < 1 || K < 1 || !A || !W || !C || !pack) return fail_msg("lsthm_gemm3w: bad shape or null pointer");
+    if ((lda & 3) || (ldw & 3)) return fail_msg("lsthm_gemm3w: lda and ldw must be multiples of 4 floats");
+    if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(pack)) & 15)
+        return fail_msg("lsthm_gemm3w: operands must be 16-byte aligned");
+    if (pack_bytes < lsthm_gemm3w_pack_bytes(N, K)) return fail_msg("lsthm_gemm3w: pack buffer too small");
+    GemmWArgs g;
+    g.A = A; g.bias = bias; g.img = static_cast<const uint8_t *>(pack); g.C = C;
+    g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldc = ldc; g.nkb = (K + kGemmBK - 1) / kGemmBK; g.relu = mode == 3 ? 1 : 0;
+    const dim3 grid((N + kWNC - 1) / kWNC, (M + kGemmBM - 1) / kGemmBM, 1);
+    if (mode == 1) return launch_gemm_w<1>(g, W, ldw, static_cast<uint8_t *>(pack), grid, (cudaStream_t)stream);
+    return launch_gemm_w<0>(g, W, ldw, static_cast<uint8_t *>(pack), grid, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -266,4 +266,185 @@ static __global__ void gemm3_reduce_kernel(const float *__restrict__ ws, const f
     }
 }
 
+
+// =============================================================================================
+// gemm3w: the same split-bf16 product for the case "B is a WEIGHT" (y = x W^T: NT; dx = dy W: NN), where M = T*N rows
+// is huge and N, K are a layer's widths.  Differences to gemm3_kernel:
+//   * the weight is split ONCE per call into bf16 hi/lo tile images already in the canonical UMMA layout
+//     (gemm3w_pack_kernel, a few hundred KB), so the main kernel's producers only convert the activation operand and
+//     the weight tiles arrive by one 32 KB bulk async copy (TMA engine) per k-block;
+//   * a CTA owns 128 rows x up to 256 output columns (one UMMA of N = 256 per term): half the redundant activation
+//     conversions of the 128-wide tile, 256 TMEM columns -> still 2 CTAs per SM;
+//   * all 8 producer warps drain the accumulator (2 warps per TMEM lane quarter).
+// =============================================================================================
+constexpr int kWNC = 256, kWStages = 2;
+constexpr int kWImgBytes = kWNC * kGemmBK * 2;                 // one bf16 image (hi or lo) of a [256 x 32] weight block
+constexpr int kWStageBytes = 2 * kTileBytes + 2 * kWImgBytes;   // A_hi, A_lo (padded gemm3 layout) + B_hi, B_lo images
+constexpr size_t kWSmemBytes = (size_t)kWStages * kWStageBytes + 1024;
+
+// image index: ((n_chunk * nkb + kb) * 2 + part) ; within an image
+//   BMN = 0 (W[n][k], K-major):  (k/8)*4096 + (n/8)*128 + (n%8)*16 + (k%8)*2        LBO 4096, SBO 128, k16 step 8192
+//   BMN = 1 (W[k][n], MN-major): (n/8)*512 + (k/8)*128 + (k%8)*16 + (n%8)*2         LBO 128,  SBO 512, k16 step 256
+template <int BMN>
+__global__ void __launch_bounds__(256) gemm3w_pack_kernel(const float *__restrict__ W, int ldw, int N, int K, int nkb, uint8_t *__restrict__ img,
+                                                          size_t total_chunks) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 1023);                         // 16-byte chunk inside an image
+        const size_t blk = i >> 10;                            // n_chunk * nkb + kb
+        const int kb = (int)(blk % nkb), nch = (int)(blk / nkb);
+        float x[8];
+        if (BMN == 0) {
+            const int kc = c >> 8, n = c & 255;                // chunk = 8 consecutive k of row n
+            const int gn = nch * kWNC + n, gk = kb * kGemmBK + 8 * kc;
+            const int valid = gn < N ? max(0, min(8, K - gk)) : 0;
+            if (valid > 0) load8(W + (size_t)gn * ldw + gk, valid, x);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+        } else {
+            const int mc = c >> 5, k = c & 31;                 // chunk = 8 consecutive n at row k: c = mc*32 + (k/8)*8 + k%8
+            const int gk = kb * kGemmBK + k, gn = nch * kWNC + 8 * mc;
+            const int valid = gk < K ? max(0, min(8, N - gn)) : 0;
+            if (valid > 0) load8(W + (size_t)gk * ldw + gn, valid, x);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+        }
+        uint8_t *hi = img + blk * (2 * (size_t)kWImgBytes) + (size_t)c * 16;
+        split_store8(x, hi, hi + kWImgBytes);
+    }
+}
+
+struct GemmWArgs {
+    const float *A, *bias;
+    const uint8_t *img;   // packed weight images
+    float *C;
+    int M, N, K, lda, ldc, nkb, relu;
+};
+
+template <int BMN>
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_constant__ GemmWArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw;
+    __shared__ __align__(8) uint64_t full_bar[kWStages], empty_bar[kWStages], done_bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * kGemmBM, nch = blockIdx.x, n0 = nch * kWNC;
+    const int ncols = min(kWNC, g.N - n0);                     // valid output columns of this CTA
+    const int nkb = g.nkb;
+
+    if (tid == 0) {
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&full_bar[s], 9); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&done_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(kWNC));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base;
+
+    if (warp < 8) {
+        // ------------------------------ producers: convert A, fetch the packed weight block ------------------------------
+        TileRegs ta;
+        load_tile<0>(g.A, g.lda, m0, g.M, 0, g.K, tid, ta);
+        const uint8_t *wsrc = g.img + (size_t)nch * nkb * (2 * (size_t)kWImgBytes);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kWStages, round = kb / kWStages;
+            if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);      // the MMAs that read this stage have retired
+            uint8_t *st = smem + (size_t)s * kWStageBytes;
+            if (tid == 0) {
+                mbar_expect_tx(&full_bar[s], 2 * kWImgBytes);
+                bulk_g2s(st + 2 * kTileBytes, wsrc + (size_t)kb * (2 * (size_t)kWImgBytes), 2 * kWImgBytes, &full_bar[s]);
+            }
+            store_tile<0>(ta, st, st + kTileBytes, tid);
+            if (kb + 1 < nkb) load_tile<0>(g.A, g.lda, m0, g.M, (kb + 1) * kGemmBK, g.K, tid, ta);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+    } else if (lane == 0) {
+        // ------------------------------ MMA issuer ------------------------------
+        const int n_mma = (ncols + 15) & ~15;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)BMN << 16) | ((uint32_t)(n_mma >> 3) << 17) |
+                               ((uint32_t)(kGemmBM >> 4) << 24);
+        constexpr uint32_t b_lbo = BMN ? 128 : 4096, b_sbo = BMN ? 512 : 128, b_step = BMN ? 256 : 8192;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % kWStages, round = kb / kWStages;
+            mbar_wait(&full_bar[s], round & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem_u32(smem + (size_t)s * kWStageBytes);
+#pragma unroll
+            for (int ks = 0; ks < kGemmBK / 16; ++ks) {
+                const uint64_t ah = umma_desc(base + ks * 2 * kKLbo, kKLbo, kKSbo);
+                const uint64_t al = umma_desc(base + kTileBytes + ks * 2 * kKLbo, kKLbo, kKSbo);
+                const uint64_t bh = umma_desc(base + 2 * kTileBytes + ks * b_step, b_lbo, b_sbo);
+                const uint64_t bl = umma_desc(base + 2 * kTileBytes + kWImgBytes + ks * b_step, b_lbo, b_sbo);
+                const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem), "l"(ah), "l"(bh), "r"(idesc), "r"(acc0) : "memory");
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&done_bar)) : "memory");
+    }
+
+    // ------------------------------ epilogue: warps 0-7, two per TMEM lane quarter ------------------------------
+    if (warp < 8) {
+        mbar_wait(&done_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3, chalf = warp >> 2;
+        const int gm = m0 + q * 32 + lane;
+        float *crow = g.C + (size_t)gm * g.ldc + n0;
+        const bool vec = (g.ldc & 3) == 0;
+#pragma unroll 1
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128 && c0 < ncols; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         "tcgen05.wait::ld.sync.aligned;"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(taddr) : "memory");
+            if (gm < g.M) {
+                if (c0 + 16 <= ncols && vec) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float4 o = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
+                                               __uint_as_float(v[4 * q4 + 3]));
+                        if (g.bias != nullptr) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + c0) + q4);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        reinterpret_cast<float4 *>(crow + c0)[q4] = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < ncols) {
+                            const float o = __uint_as_float(v[j]) + (g.bias != nullptr ? __ldg(g.bias + n0 + c0 + j) : 0.f);
+                            crow[c0 + j] = g.relu ? fmaxf(o, 0.f) : o;
+                        }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kWNC));
+    }
+}
+
 }  // namespace lsthm

@@ -81,6 +81,15 @@ def mm_nn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return _gemm(_lib.GEMM_NN, _rows(a), _rows(b))
 
 
+def colsum(a: torch.Tensor) -> torch.Tensor:
+    """a.sum(0) for a 2-D matrix — the bias gradient of a Linear over all T*N rows — on our deterministic kernel."""
+    if (_ENABLED and a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0 and a.shape[1] % 4 == 0
+            and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0):
+        launches["gemm3"] += 2
+        return _lib.colsum(a)
+    return a.sum(0)
+
+
 class _LinearTC(torch.autograd.Function):
     """y = x W^T (+ b) (optionally followed by ReLU in the GEMM epilogue) on 2-D row matrices."""
 
@@ -99,7 +108,7 @@ class _LinearTC(torch.autograd.Function):
         dy = _rows(dy)
         dx = mm_nn(dy, weight) if ctx.needs_input_grad[0] else None
         dw = mm_tn(dy, x) if ctx.needs_input_grad[1] else None
-        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        db = colsum(dy) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db, None
 
 

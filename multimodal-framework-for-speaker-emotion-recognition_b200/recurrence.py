@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .mm3 import mm_tn
+from .mm3 import mm_tn, colsum
 
 # Counts launches of OUR kernels (pack/fwd/bwd), for bench.py's `gpu_launches`.
 launch_counter = {"pack": 0, "fwd": 0, "bwd": 0}
@@ -111,7 +111,7 @@ class MabRecurrenceFn(torch.autograd.Function):
             gV.append(full[4 * o:4 * o + 4 * dh[m], D:])
             o += dh[m]
         de2, c2 = de.view(TN, G), sC.view(TN, D)
-        gWatt, gbatt = mm_tn(de2, c2), de2.sum(0)
+        gWatt, gbatt = mm_tn(de2, c2), colsum(de2)
         att = sA.view(TN, 4, D) * c2.unsqueeze(1)           # attended = a * cs (HybridRNN_ATV.py:125)
         dr2 = dr.view(TN, R)
         gWr, gbr = [], []
@@ -120,12 +120,12 @@ class MabRecurrenceFn(torch.autograd.Function):
             vec = att[:, :, o:o + dh[m]].reshape(TN, 4 * dh[m])  # head-major regroup (lines 126-128)
             drm = dr2[:, ro:ro + rd[m]]
             gWr.append(mm_tn(drm, vec))
-            gbr.append(drm.sum(0))
+            gbr.append(colsum(drm))
             o += dh[m]
             ro += rd[m]
         dup2, dzt2 = dup.view(TN, map_h), dzt.view(TN, D)
-        gWf1, gbf1 = mm_tn(dup2, sR.view(TN, R)), dup2.sum(0)
-        gWf2, gbf2 = mm_tn(dzt2, sU.view(TN, map_h)), dzt2.sum(0)
+        gWf1, gbf1 = mm_tn(dup2, sR.view(TN, R)), colsum(dup2)
+        gWf2, gbf2 = mm_tn(dzt2, sU.view(TN, map_h)), colsum(dzt2)
         grads = (*gU, *gV, gWatt, gbatt, *gWr, *gbr, gWf1, gbf1, gWf2, gbf2)
         return (dgx, None, None, *grads)
 

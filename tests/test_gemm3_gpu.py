@@ -52,3 +52,35 @@ def test_strided_views():
     act = torch.randn(6000, 416, device="cuda")
     a, b = big[:, 512:576], act[:, 208:]
     assert _err(lib.gemm3(lib.GEMM_TN, a, b), a.double().t() @ b.double()) < 2e-5
+
+
+@pytest.mark.parametrize("R,C,off,ld", [(112640, 832, 0, 832), (1000, 100, 4, 120), (7, 4, 0, 4), (513, 244, 16, 260), (65, 1024, 0, 1024)])
+def test_colsum_matches_fp64_and_is_deterministic(R, C, off, ld):
+    from importlib import import_module
+    mm3 = import_module(lsthm_b200.__name__ + ".mm3")
+    g = torch.Generator(device="cuda").manual_seed(R + C)
+    big = torch.randn(R, ld, device="cuda", generator=g)
+    a = big[:, off:off + C]
+    s1, s2 = mm3.colsum(a), mm3.colsum(a)
+    ref = a.double().sum(0)
+    assert torch.equal(s1, s2)
+    assert ((s1.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 960, 100), (3000, 100, 320), (2500, 52, 512), (2049, 244, 64), (9000, 512, 100),
+                                   (2300, 8, 1024), (2100, 300, 36)])
+def test_weight_stationary_path_nt_nn_relu(M, N, K):
+    """Rows >= GEMM3W_MIN_ROWS route NT/NN through lsthm_gemm3w (pre-split weight images, 128 x 256 tiles): ragged
+    N and K, N spanning several 256-column chunks, bias and the ReLU epilogue, strided activations."""
+    assert M >= lib.GEMM3W_MIN_ROWS
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    xw = torch.randn(M, K + 8, device="cuda", generator=g)
+    x = xw[:, 4:4 + K]
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.1
+    b = torch.randn(N, device="cuda", generator=g)
+    ref = x.double() @ w.double().t() + b.double()
+    assert _err(lib.gemm3(lib.GEMM_NT, x, w, b), ref) < 2e-5
+    assert _err(lib.gemm3(lib.GEMM_NT, x, w), ref - b.double()) < 2e-5
+    assert _err(lib.gemm3(lib.GEMM_NT_RELU, x, w, b), ref.clamp_min(0)) < 2e-5
+    dy = torch.randn(M, N, device="cuda", generator=g)
+    assert _err(lib.gemm3(lib.GEMM_NN, dy, w), dy.double() @ w.double()) < 2e-5
