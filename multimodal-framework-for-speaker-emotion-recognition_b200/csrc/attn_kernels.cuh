@@ -282,12 +282,23 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const float *drow = a.dout + grow * a.ldo + h * kAttD;
+    float4 o4[10], d4[10];
+    float delta = 0.f, lse = 0.f;
     {
         RowRegs rq, rk, rw, rd;
         row_load(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, 3 * g, rq);
         row_load(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, 3 * g, rk);
         row_load(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, 3 * g, rw);
         row_load(rv ? drow : nullptr, 3 * g, rd);
+        if (rv) {   // the delta operands (row of O, row of dO, lse): loads in flight during the conversions, used after the MMA issue
+            const float *orow = a.o + grow * a.ldo + h * kAttD;
+#pragma unroll
+            for (int d = 0; d < 10; ++d) {
+                o4[d] = __ldg(reinterpret_cast<const float4 *>(orow) + d);
+                d4[d] = __ldg(reinterpret_cast<const float4 *>(drow) + d);
+            }
+            lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
+        }
         row_store(rq, r, a.scale * kLog2e, sQ, 3 * g);
         row_store(rk, r, 1.f, sK, 3 * g);
         row_store(rw, r, 1.f, sV, 3 * g);
@@ -306,16 +317,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
         umma_commit(&bar[0]);
     }
     // while the tensor core works: delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij (both threads of a row compute it) and the row's lse
-    float delta = 0.f, lse = 0.f;
     if (rv) {
-        const float *orow = a.o + grow * a.ldo + h * kAttD;
-        float4 o4[10], d4[10];
-#pragma unroll
-        for (int d = 0; d < 10; ++d) {
-            o4[d] = __ldg(reinterpret_cast<const float4 *>(orow) + d);
-            d4[d] = __ldg(reinterpret_cast<const float4 *>(drow) + d);
-        }
-        lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
 #pragma unroll
         for (int d = 0; d < 10; ++d) delta += d4[d].x * o4[d].x + d4[d].y * o4[d].y + d4[d].z * o4[d].z + d4[d].w * o4[d].w;
     }

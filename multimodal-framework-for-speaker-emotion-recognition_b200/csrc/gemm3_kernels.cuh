@@ -399,36 +399,41 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_co
     }
 
     // ------------------------------ epilogue: warps 0-7, two per TMEM lane quarter ------------------------------
+    // A thread owns an accumulator ROW (TMEM lane); storing it directly would scatter 16-byte pieces over 32 rows per
+    // instruction.  Each warp therefore transposes 64 columns at a time through its own shared-memory patch (the
+    // operand stages are dead by now) and writes whole 256-byte row segments: 4 cache lines per store instruction.
     if (warp < 8) {
         mbar_wait(&done_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3, chalf = warp >> 2;
-        const int gm = m0 + q * 32 + lane;
-        float *crow = g.C + (size_t)gm * g.ldc + n0;
-        const bool vec = (g.ldc & 3) == 0;
+        const int gm0 = m0 + q * 32;
+        const bool vec = (g.ldc & 3) == 0 && (g.N & 3) == 0;
+        float *patch = reinterpret_cast<float *>(smem) + warp * (32 * 68);
 #pragma unroll 1
-        for (int c0 = chalf * 128; c0 < chalf * 128 + 128 && c0 < ncols; c0 += 16) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-                         "tcgen05.wait::ld.sync.aligned;"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(taddr) : "memory");
-            if (gm < g.M) {
-                if (c0 + 16 <= ncols && vec) {
+        for (int cb = chalf * 128; cb < chalf * 128 + 128 && cb < ncols; cb += 64) {
+#pragma unroll 1
+            for (int c0 = cb; c0 < cb + 64 && c0 < ncols; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                             "tcgen05.wait::ld.sync.aligned;"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(taddr) : "memory");
+                if (vec) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         float4 o = make_float4(__uint_as_float(v[4 * q4]), __uint_as_float(v[4 * q4 + 1]), __uint_as_float(v[4 * q4 + 2]),
                                                __uint_as_float(v[4 * q4 + 3]));
-                        if (g.bias != nullptr) {
+                        if (g.bias != nullptr && c0 + 4 * q4 < ncols) {
                             const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + c0) + q4);
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
                         if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        reinterpret_cast<float4 *>(crow + c0)[q4] = o;
+                        *reinterpret_cast<float4 *>(patch + lane * 68 + (c0 - cb) + 4 * q4) = o;
                     }
-                } else {
+                } else if (gm0 + lane < g.M) {
+                    float *crow = g.C + (size_t)(gm0 + lane) * g.ldc + n0;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (c0 + j < ncols) {
@@ -436,6 +441,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_co
                             crow[c0 + j] = g.relu ? fmaxf(o, 0.f) : o;
                         }
                 }
+            }
+            if (vec) {
+                __syncwarp();
+                const int col = (lane & 15) * 4, rsub = lane >> 4;
+                if (cb + col < ncols) {
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int row = 2 * i + rsub;
+                        if (gm0 + row < g.M)
+                            *reinterpret_cast<float4 *>(g.C + (size_t)(gm0 + row) * g.ldc + n0 + cb + col) =
+                                *reinterpret_cast<const float4 *>(patch + row * 68 + col);
+                    }
+                }
+                __syncwarp();
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

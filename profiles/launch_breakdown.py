@@ -31,5 +31,5 @@ for n, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 if "--detail" in sys.argv:
     print()
     for d in seg:
-        if "gemm3_kernel" in d[ki] or "attn" in d[ki]:
+        if "gemm3" in d[ki] and "reduce" not in d[ki] and "pack" not in d[ki] or "attn" in d[ki]:
             print(f"{float(d[vi]) / 1e3:9.1f} us  grid {d[gi]:>16} {re.sub(r'.*lsthm::', '', d[ki])[:40]}")
