@@ -228,6 +228,7 @@ def run_ours(args):
     T, B = args.seq, args.batch
     torch.manual_seed(111)
     kind = args.model
+    import_module(lsthm_b200.__name__ + "._lib").set_precision("bf16" if args.dtype == "bf16" else "fp32")
     if kind == "ATV":
         model = lsthm_b200.HybridRNN_ATV.MARN().to(dev).train()
     else:
@@ -412,7 +413,7 @@ def run_ours(args):
         out = {
             "metric": metric_name(kind), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{model_name(kind)} fwd+bwd (train mode), x[{T},{B},{din}] fp32 per GPU, uniform L={T}, "
                                    f"MaskedLoss(CrossEntropy); inputs {T * B * din * 4 / 1e6:.0f} MB per step > 126 MB L2, "
                                    f"two alternating batches", "per_gpu_batch": B, "seq_len": T,
@@ -452,6 +453,9 @@ def main():
     ap.add_argument("--seq", type=int, default=T_LEN)
     ap.add_argument("--model", default="ATV", choices=["ATV", "sps"],
                     help="ATV = BASELINE.json configs[1] (headline); sps = configs[2] shapes (speaker-state model, fp32)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="f32: every tensor-core product is the fp32-accurate split (parity mode, the metric's precision); "
+                         "bf16: time-parallel products with bf16 operands (tests/test_bf16_gpu.py states the tolerance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()

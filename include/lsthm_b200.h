@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTHM_ABI_VERSION 2
+#define LSTHM_ABI_VERSION 3
 #define LSTHM_MAX_MOD 3
 
 int lsthm_abi_version(void);
@@ -178,6 +178,9 @@ int lsthm_sps_launch_info(const lsthm_sps_desc *d, int32_t *grid, int32_t *block
  * All matrices fp32 row-major, 16-byte aligned, lda/ldb multiples of 4.  `workspace` (may be NULL) holds
  * the split-K partials: lsthm_gemm3_workspace_floats(mode, M, N, K) floats.
  * ------------------------------------------------------------------------------------------ */
+/* OR this into `mode` for the bf16 mode of BASELINE.json (stated separately from fp32 parity): operands are rounded
+ * to bf16 while they are staged and each k-step is ONE UMMA (fp32 accumulation) instead of the three split terms. */
+#define LSTHM_GEMM_BF16 0x10
 size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K);
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream);
@@ -210,6 +213,9 @@ typedef struct {
     float p_drop;                     /* attention dropout (encoder.py:66), 0 in eval mode  */
     uint64_t seed;
     int64_t row_stride_b, row_stride_i; /* in rows; see above                                */
+    int32_t precision;                /* 0: fp32-accurate (operands split in bf16 hi + lo, three UMMAs per k-step);
+                                         1: bf16 mode (operands rounded to bf16, one UMMA per k-step, fp32 softmax) */
+    int32_t reserved;
 } lsthm_attn_desc;
 
 int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, const float *v, float *out, float *lse,
@@ -251,6 +257,13 @@ int lsthm_dln_bwd(const lsthm_dln_desc *d, const float *dout, int32_t lddo, cons
 size_t lsthm_colsum_workspace_floats(int64_t R, int32_t C);
 int lsthm_colsum(int64_t R, int32_t C, const float *A, int32_t ld, float *out, float *workspace, size_t workspace_floats,
                  void *stream);
+
+/* Batch assembly of the reference trainer, model_trainer.py:104-105 (`textf = (r1 + r2 + r3 + r4) / 4` followed by
+ * `torch.cat((textf, acouf), dim=-1)`), in one pass over R = L*B utterances: r1..r4 [R][d_text] are the four RoBERTa
+ * layers of dataloader.py:29-32, acouf [R][d_audio], x [R][d_text + d_audio].  All contiguous fp32, widths % 4 == 0.
+ * Same operation order as the reference, so the result is bit-identical. */
+int lsthm_assemble_input(int64_t R, int32_t d_text, int32_t d_audio, const float *r1, const float *r2, const float *r3, const float *r4,
+                         const float *acouf, float *x, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused Adam step on a flat fp32 buffer.  Replaces `self.optim.step()` of the reference's trainer

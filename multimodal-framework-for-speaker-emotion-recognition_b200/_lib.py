@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
 SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_MOD = 3
 
 _f32p = C.POINTER(C.c_float)
@@ -51,7 +51,8 @@ class SpsMasks(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("d_head", C.c_int32), ("ldq", C.c_int32),
                 ("ldk", C.c_int32), ("ldv", C.c_int32), ("ldo", C.c_int32), ("scale", C.c_float), ("p_drop", C.c_float),
-                ("seed", C.c_uint64), ("row_stride_b", C.c_int64), ("row_stride_i", C.c_int64)]
+                ("seed", C.c_uint64), ("row_stride_b", C.c_int64), ("row_stride_i", C.c_int64),
+                ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DlnDesc(C.Structure):
@@ -131,6 +132,8 @@ def lib() -> C.CDLL:
     L.lsthm_colsum_workspace_floats.argtypes = [C.c_int64, C.c_int32]
     L.lsthm_colsum.restype = C.c_int
     L.lsthm_colsum.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.lsthm_assemble_input.restype = C.c_int
+    L.lsthm_assemble_input.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.lsthm_adam_step.restype = C.c_int
     L.lsthm_adam_step.argtypes = [C.c_void_p] * 4 + [C.c_size_t] + [C.c_float] * 5 + [C.c_int32, C.c_void_p]
     if L.lsthm_abi_version() != ABI_VERSION:
@@ -286,6 +289,17 @@ def sps_launch_info(d: SpsDesc) -> dict:
 # tcgen05 split-bf16 GEMM (time-parallel products)
 # ------------------------------------------------------------------------------------------------
 GEMM_NT, GEMM_NN, GEMM_TN, GEMM_NT_RELU = 0, 1, 2, 3
+GEMM_BF16 = 0x10
+# "fp32": every tensor-core product is the fp32-accurate three-term bf16 split (parity mode, the default).
+# "bf16": operands rounded to bf16, one UMMA per k-step (BASELINE.json's bf16 mode; tolerance stated in tests/test_bf16_gpu.py).
+PRECISION = os.environ.get("LSTHM_PRECISION", "fp32")
+
+
+def set_precision(mode: str) -> None:
+    global PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    PRECISION = mode
 GEMM3W_MIN_ROWS = int(os.environ.get("LSTHM_GEMM3W_MIN_ROWS", "2048"))
 
 
@@ -309,7 +323,10 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
     pa, lda = _mat(a, "a")
     pb, ldb = _mat(b, "b")
     c = torch.empty(M, N, device=a.device, dtype=torch.float32)
-    if mode != GEMM_TN and M >= GEMM3W_MIN_ROWS:
+    base_mode = mode
+    if PRECISION == "bf16":
+        mode |= GEMM_BF16
+    if base_mode != GEMM_TN and M >= GEMM3W_MIN_ROWS:
         # B is a layer weight and there are many rows: pre-split weight images + 128 x 256 tiles
         nbytes = lib().lsthm_gemm3w_pack_bytes(N, K)
         pack = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
@@ -331,6 +348,7 @@ def make_attn_desc(B, L, H, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, d_hea
     d.B, d.L, d.H, d.d_head, d.ldq, d.ldk, d.ldv, d.ldo = B, L, H, d_head, ldq, ldk, ldv, ldo
     d.scale, d.p_drop, d.seed = scale, p_drop, seed
     d.row_stride_b, d.row_stride_i = (1, B) if time_major else (L, 1)
+    d.precision = 1 if PRECISION == "bf16" else 0
     return d
 
 
@@ -391,6 +409,21 @@ def colsum(a: torch.Tensor) -> torch.Tensor:
     ws = torch.empty(nws, device=a.device, dtype=torch.float32)
     _check(lib().lsthm_colsum(R, Cc, pa, ld, out.data_ptr(), ws.data_ptr(), nws, _stream()), "lsthm_colsum")
     return out
+
+
+def assemble_input(r1, r2, r3, r4, acouf) -> torch.Tensor:
+    """x = cat((r1 + r2 + r3 + r4) / 4, acouf) over the last dim (model_trainer.py:104-105), one fused pass."""
+    lead, dt, da = r1.shape[:-1], r1.shape[-1], acouf.shape[-1]
+    for t in (r2, r3, r4):
+        if t.shape != r1.shape:
+            raise RuntimeError("assemble_input: the four text layers must have the same shape")
+    if acouf.shape[:-1] != lead:
+        raise RuntimeError("assemble_input: acouf must share the leading dims of the text layers")
+    x = torch.empty(*lead, dt + da, device=r1.device, dtype=torch.float32)
+    R = x.numel() // (dt + da)
+    _check(lib().lsthm_assemble_input(R, dt, da, _dev_ptr(r1, "r1"), _dev_ptr(r2, "r2"), _dev_ptr(r3, "r3"), _dev_ptr(r4, "r4"),
+                                      _dev_ptr(acouf, "acouf"), x.data_ptr(), _stream()), "lsthm_assemble_input")
+    return x
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step) -> None:

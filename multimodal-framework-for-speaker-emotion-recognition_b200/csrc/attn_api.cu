@@ -14,6 +14,7 @@ static int attn_check(const lsthm_attn_desc *d) {
     if (d->d_head != kAttD) return fail_msg("lsthm_attn: d_k = d_v = 40 only (encoder.py: d_k = d_v = 40)");
     if ((d->ldq | d->ldk | d->ldv | d->ldo) & 3) return fail_msg("lsthm_attn: row strides must be multiples of 4 floats");
     if (d->p_drop < 0.f || d->p_drop >= 1.f) return fail_msg("lsthm_attn: p_drop must be in [0,1)");
+    if (d->precision != 0 && d->precision != 1) return fail_msg("lsthm_attn: precision must be 0 (fp32-accurate split) or 1 (bf16 operands)");
     if (d->row_stride_b < 0 || d->row_stride_i < 0) return fail_msg("lsthm_attn: row strides must be >= 0");
     return 0;
 }
@@ -36,9 +37,10 @@ int lsthm_attn_fwd(const lsthm_attn_desc *d, const float *q, const float *k, con
     attn_fill(d, a);
     a.q = q; a.k = k; a.v = v; a.out = out; a.lse = lse;
     const size_t smem = 2 * kSqTile + 2 * kRowTile + 1024;
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = d->precision == 1 ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_attn_fwd shared-memory opt-in", e);
-    attn_fwd_kernel<<<d->B * d->H, 256, smem, (cudaStream_t)stream>>>(a);
+    kern<<<d->B * d->H, 256, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_attn_fwd launch", e);
 }
@@ -50,10 +52,11 @@ int lsthm_attn_bwd(const lsthm_attn_desc *d, const float *q, const float *k, con
     AttnArgs a{};
     attn_fill(d, a);
     a.q = q; a.k = k; a.v = v; a.o = out; a.lse = const_cast<float *>(lse); a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv;
-    const size_t smem = 8 * kRowTile + 4 * kSqTile + 1024;
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = 8 * kRowTile + 4 * kSqTile;
+    auto kern = d->precision == 1 ? attn_bwd_kernel<true> : attn_bwd_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_attn_bwd shared-memory opt-in", e);
-    attn_bwd_kernel<<<d->B * d->H, 256, smem, (cudaStream_t)stream>>>(a);
+    kern<<<d->B * d->H, kAttBwdThreads, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_attn_bwd launch", e);
 }

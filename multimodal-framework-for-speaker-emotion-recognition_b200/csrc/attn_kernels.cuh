@@ -51,6 +51,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // D[128 x N] (+)= A . B over `ksteps` k16 steps, three split terms.  A: hi at a, lo at a + a_lo; same for B.
+template <bool BF16 = false>
 __device__ __forceinline__ void umma3(uint32_t tmem_d, uint32_t a, uint32_t a_lo, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
                                       uint32_t b, uint32_t b_lo, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
                                       uint32_t idesc, int ksteps) {
@@ -58,8 +59,10 @@ __device__ __forceinline__ void umma3(uint32_t tmem_d, uint32_t a, uint32_t a_lo
         const uint64_t ah = umma_desc(a + ks * a_step, a_lbo, a_sbo), al = umma_desc(a + a_lo + ks * a_step, a_lbo, a_sbo);
         const uint64_t bh = umma_desc(b + ks * b_step, b_lbo, b_sbo), bl = umma_desc(b + b_lo + ks * b_step, b_lbo, b_sbo);
         umma_f16(tmem_d, ah, bh, idesc, ks > 0 ? 1u : 0u);
-        umma_f16(tmem_d, ah, bl, idesc, 1u);
-        umma_f16(tmem_d, al, bh, idesc, 1u);
+        if (!BF16) {                                   // bf16 mode: operands rounded to bf16, one UMMA per k-step
+            umma_f16(tmem_d, ah, bl, idesc, 1u);
+            umma_f16(tmem_d, al, bh, idesc, 1u);
+        }
     }
 }
 // operand triples used below:  K-major row tile: (k16 step, LBO, SBO) = (4096, 2048, 128);
@@ -90,6 +93,12 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&va
     for (int i = 0; i < 16; ++i) { va[i] = __uint_as_float(r[i]); vb[i] = __uint_as_float(r[16 + i]); }
 }
 
+template <bool BF16>
+__device__ __forceinline__ void put8(const float (&x)[8], uint8_t *hi, uint8_t *lo) {
+    if (BF16) store8_hi(x, hi);
+    else split_store8(x, hi, lo);
+}
+
 // Staging of one 40-float row into a K-major [128 x 48] row tile (hi, lo), split in two phases so that a thread's
 // global loads for ALL operand tiles are in flight before the first conversion: a thread owns three of the six
 // 8-float chunks of its row (chunk 5 is the zero padding 40 -> 48); src == nullptr (row >= L) stages zeros.
@@ -108,6 +117,7 @@ __device__ __forceinline__ void row_load(const float *src, int c0, RowRegs &r) {
         }
     }
 }
+template <bool BF16>
 __device__ __forceinline__ void row_store(const RowRegs &r, int row, float scale, uint8_t *hi, int c0) {
     uint8_t *lo = hi + kRowTile;
     const int roff = (row >> 3) * 128 + (row & 7) * 16;
@@ -115,7 +125,7 @@ __device__ __forceinline__ void row_store(const RowRegs &r, int row, float scale
     for (int i = 0; i < 3; ++i) {
         const float4 a = r.v[2 * i], b = r.v[2 * i + 1];
         const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
-        split_store8(x, hi + (c0 + i) * 2048 + roff, lo + (c0 + i) * 2048 + roff);
+        put8<BF16>(x, hi + (c0 + i) * 2048 + roff, lo + (c0 + i) * 2048 + roff);
     }
 }
 
@@ -149,6 +159,7 @@ struct AttDrop {
 // into the staged q) so the softmax is one FADD + EX2 per element; the normalisation is applied to the 40 output
 // columns instead of the 128 probabilities.
 // ---------------------------------------------------------------------------------------------
+template <bool BF16>
 __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar[2];
@@ -170,9 +181,9 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
         row_load(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, 3 * g, rq);
         row_load(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, 3 * g, rk);
         row_load(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, 3 * g, rw);
-        row_store(rq, r, a.scale * kLog2e, sQ, 3 * g);
-        row_store(rk, r, 1.f, sK, 3 * g);
-        row_store(rw, r, 1.f, sV, 3 * g);
+        row_store<BF16>(rq, r, a.scale * kLog2e, sQ, 3 * g);
+        row_store<BF16>(rk, r, 1.f, sK, 3 * g);
+        row_store<BF16>(rw, r, 1.f, sV, 3 * g);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
     if (tid == 0) {   // S = Qs K^T : M = query, N = key, K = d (48)
-        umma3(tmem, smem_u32(sQ), kRowTile, 4096u, 2048u, 128u, smem_u32(sK), kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+        umma3<BF16>(tmem, smem_u32(sQ), kRowTile, 4096u, 2048u, 128u, smem_u32(sK), kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
         umma_commit(&bar[0]);
     }
     mbar_wait(&bar[0], 0);
@@ -220,7 +231,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
                     p8[j] = e0; p8[j + 1] = e1;
                 }
                 const int chunk = (c0 >> 3) + half;
-                split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+                put8<BF16>(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
             }
         }
         ex[256 + tid] = sum;
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) {   // O = P V : M = query, N = d (48, MN-major view of V), K = key (128); overwrites S columns [0,48)
-        umma3(tmem, smem_u32(sP), kSqTile, 4096u, 2048u, 128u, smem_u32(sV), kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
+        umma3<BF16>(tmem, smem_u32(sP), kSqTile, 4096u, 2048u, 128u, smem_u32(sV), kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
         umma_commit(&bar[1]);
     }
     sum += ex[256 + (tid ^ 128)];
@@ -266,8 +277,43 @@ __global__ void __launch_bounds__(256, 2) attn_fwd_kernel(const __grid_constant_
 // dropped probabilities Pd (operand of dV = Pd^T dO) and dS = p (sc dPd - delta) (operand of dQ, dK) are produced
 // together into two shared tiles and the three remaining products are issued back to back.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+// 512 threads: four threads share a query row (tid, tid+128, tid+256, tid+384 address the same TMEM lanes), each
+// owns 32 of the 128 key columns -> 4 warps per scheduler hide the TMEM / MUFU / shared-memory latencies of the pass.
+constexpr int kAttBwdThreads = 512;
+
+// the one or two 8-float chunks of a 40 (+8 zero) float row a thread of group g stages: chunks g and g + 4 (< 6)
+struct RowRegs2 {
+    float4 v[4];
+};
+__device__ __forceinline__ void row_load2(const float *src, int g, RowRegs2 &r) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = g + 4 * i;
+        if (c < 5 && src != nullptr) {
+            r.v[2 * i] = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c);
+            r.v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
+        } else {
+            r.v[2 * i] = r.v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ void row_store2(const RowRegs2 &r, int row, float scale, uint8_t *hi, int g) {
+    uint8_t *lo = hi + kRowTile;
+    const int roff = (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = g + 4 * i;
+        if (c >= 6) continue;
+        const float4 a = r.v[2 * i], b = r.v[2 * i + 1];
+        const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+        put8<BF16>(x, hi + c * 2048 + roff, lo + c * 2048 + roff);
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kAttBwdThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];   // no-swizzle operands need 16-byte alignment only; 224 KB + 2 KB static fit 227 KB
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base;
     uint8_t *sQ = smem, *sK = sQ + 2 * kRowTile, *sV = sK + 2 * kRowTile, *sdO = sV + 2 * kRowTile, *sP = sdO + 2 * kRowTile;
@@ -282,27 +328,30 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const float *drow = a.dout + grow * a.ldo + h * kAttD;
-    float4 o4[10], d4[10];
-    float delta = 0.f, lse = 0.f;
+    float lse = 0.f, delta = 0.f;
     {
-        RowRegs rq, rk, rw, rd;
-        row_load(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, 3 * g, rq);
-        row_load(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, 3 * g, rk);
-        row_load(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, 3 * g, rw);
-        row_load(rv ? drow : nullptr, 3 * g, rd);
-        if (rv) {   // the delta operands (row of O, row of dO, lse): loads in flight during the conversions, used after the MMA issue
+        RowRegs2 rq, rk, rw, rd;
+        row_load2(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, g, rq);
+        row_load2(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, g, rk);
+        row_load2(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, g, rw);
+        row_load2(rv ? drow : nullptr, g, rd);
+        // delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij (each of the row's four threads computes it: 2 x 160 B, L1-resident)
+        if (rv) {
             const float *orow = a.o + grow * a.ldo + h * kAttD;
+            float4 o4[10], d4[10];
 #pragma unroll
             for (int d = 0; d < 10; ++d) {
                 o4[d] = __ldg(reinterpret_cast<const float4 *>(orow) + d);
                 d4[d] = __ldg(reinterpret_cast<const float4 *>(drow) + d);
             }
             lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
+#pragma unroll
+            for (int d = 0; d < 10; ++d) delta += d4[d].x * o4[d].x + d4[d].y * o4[d].y + d4[d].z * o4[d].z + d4[d].w * o4[d].w;
         }
-        row_store(rq, r, a.scale * kLog2e, sQ, 3 * g);
-        row_store(rk, r, 1.f, sK, 3 * g);
-        row_store(rw, r, 1.f, sV, 3 * g);
-        row_store(rd, r, 1.f, sdO, 3 * g);
+        row_store2<BF16>(rq, r, a.scale * kLog2e, sQ, g);
+        row_store2<BF16>(rk, r, 1.f, sK, g);
+        row_store2<BF16>(rw, r, 1.f, sV, g);
+        row_store2<BF16>(rd, r, 1.f, sdO, g);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -312,23 +361,19 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
     const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), udO = smem_u32(sdO), uP = smem_u32(sP), uD = smem_u32(sD);
     if (tid == 0) {
         // S = Qs K^T ; dPd = dO V^T   (both M = query, N = key, K = d)
-        umma3(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
-        umma3(tmem + 128, udO, kRowTile, 4096u, 2048u, 128u, uV, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+        umma3<BF16>(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+        umma3<BF16>(tmem + 128, udO, kRowTile, 4096u, 2048u, 128u, uV, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
         umma_commit(&bar[0]);
-    }
-    // while the tensor core works: delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij (both threads of a row compute it) and the row's lse
-    if (rv) {
-#pragma unroll
-        for (int d = 0; d < 10; ++d) delta += d4[d].x * o4[d].x + d4[d].y * o4[d].y + d4[d].z * o4[d].z + d4[d].w * o4[d].w;
     }
     mbar_wait(&bar[0], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int roff = (r >> 3) * 128 + (r & 7) * 16, cb = 64 * g;
+    const int roff = (r >> 3) * 128 + (r & 7) * 16, cb = 32 * g;
     {
         const AttDrop drop(a.seed, blockIdx.x, r, a.p_drop);
         float s[16], gg[16], p8[8], d8[8];
-        for (int c0 = cb; c0 < cb + 64; c0 += 16) {
+#pragma unroll
+        for (int c0 = cb; c0 < cb + 32; c0 += 16) {
             tmem_ld16x2(trow + c0, trow + 128 + c0, s, gg);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -343,8 +388,8 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
                     d8[j] = p0 * (s0 * gg[i0] - delta); d8[j + 1] = p1 * (s1 * gg[i0 + 1] - delta);
                 }
                 const int chunk = (c0 >> 3) + half;
-                split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
-                split_store8(d8, sD + chunk * 2048 + roff, sD + kSqTile + chunk * 2048 + roff);
+                put8<BF16>(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+                put8<BF16>(d8, sD + chunk * 2048 + roff, sD + kSqTile + chunk * 2048 + roff);
             }
         }
     }
@@ -354,18 +399,18 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (tid == 0) {
         // dV = Pd^T dO : M = key (MN-major view of Pd), N = d (MN-major view of dO), K = query
-        umma3(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+        umma3<BF16>(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
         // dQs = dS K : M = query, N = d (MN view of K), K = key ;  dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
-        umma3(tmem + 304, uD, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
-        umma3(tmem + 352, uD, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+        umma3<BF16>(tmem + 304, uD, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
+        umma3<BF16>(tmem + 352, uD, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
         umma_commit(&bar[1]);
     }
     mbar_wait(&bar[1], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
         float v[16];
-        // 9 (matrix, 16-column block) items over the two threads of a row: g takes the items with index % 2 == g
-        for (int item = g; item < 9; item += 2) {
+        // 9 (matrix, 16-column block) items over the four threads of a row: g takes the items with index % 4 == g
+        for (int item = g; item < 9; item += 4) {
             const int which = item / 3, c0 = 16 * (item % 3);
             float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + grow * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
             // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)

@@ -1,4 +1,6 @@
 // Host side of lsthm_dln_fwd / lsthm_dln_bwd (include/lsthm_b200.h): fused dropout + residual + LayerNorm.
+#include <algorithm>
+
 #include "../../include/lsthm_b200.h"
 #include "dln_kernels.cuh"
 
@@ -91,6 +93,23 @@ int lsthm_colsum(int64_t R, int32_t C, const float *A, int32_t ld, float *out, f
     colsum_final_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(workspace, nchunk, C, out);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_colsum final launch", e);
+}
+
+int lsthm_assemble_input(int64_t R, int32_t d_text, int32_t d_audio, const float *r1, const float *r2, const float *r3, const float *r4,
+                         const float *acouf, float *x, void *stream) {
+    if (R < 0 || d_text < 4 || d_audio < 4 || (d_text & 3) || (d_audio & 3)) return fail_msg("lsthm_assemble_input: widths must be positive multiples of 4");
+    if (!r1 || !r2 || !r3 || !r4 || !acouf || !x) return fail_msg("lsthm_assemble_input: null pointer");
+    if ((reinterpret_cast<uintptr_t>(r1) | reinterpret_cast<uintptr_t>(r2) | reinterpret_cast<uintptr_t>(r3) | reinterpret_cast<uintptr_t>(r4) |
+         reinterpret_cast<uintptr_t>(acouf) | reinterpret_cast<uintptr_t>(x)) & 15)
+        return fail_msg("lsthm_assemble_input: operands must be 16-byte aligned");
+    if (R == 0) return 0;
+    const long long total = R * ((d_text + d_audio) / 4);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    assemble_input_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(r1), reinterpret_cast<const float4 *>(r2), reinterpret_cast<const float4 *>(r3),
+        reinterpret_cast<const float4 *>(r4), reinterpret_cast<const float4 *>(acouf), reinterpret_cast<float4 *>(x), R, d_text / 4, d_audio / 4);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_assemble_input launch", e);
 }
 
 }  // extern "C"

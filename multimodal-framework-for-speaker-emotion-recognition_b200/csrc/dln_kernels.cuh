@@ -284,3 +284,31 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float *__restri
     }
 }
 }  // namespace lsthm
+
+// ---------------------------------------------------------------------------------------------
+// Batch assembly of the trainer (model_trainer.py:104-105):  x = cat(((r1 + r2) + r3 + r4) / 4, acouf)  per utterance,
+// one pass: 4 x d_text + d_audio floats read, d_text + d_audio written (the reference runs 3 adds, a divide and a cat:
+// seven passes over the 1024-wide RoBERTa layers).  Same operation order as the reference -> bit-identical.
+// ---------------------------------------------------------------------------------------------
+namespace lsthm {
+__global__ void __launch_bounds__(256) assemble_input_kernel(const float4 *__restrict__ r1, const float4 *__restrict__ r2,
+                                                             const float4 *__restrict__ r3, const float4 *__restrict__ r4,
+                                                             const float4 *__restrict__ ac, float4 *__restrict__ x, long long R, int dt4, int da4) {
+    const int w4 = dt4 + da4;
+    const long long total = R * w4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / w4;
+        const int c = (int)(i - row * w4);
+        float4 o;
+        if (c < dt4) {
+            const long long j = row * dt4 + c;
+            const float4 a = __ldcs(r1 + j), b = __ldcs(r2 + j), cc = __ldcs(r3 + j), d = __ldcs(r4 + j);
+            o.x = (((a.x + b.x) + cc.x) + d.x) / 4.0f; o.y = (((a.y + b.y) + cc.y) + d.y) / 4.0f;
+            o.z = (((a.z + b.z) + cc.z) + d.z) / 4.0f; o.w = (((a.w + b.w) + cc.w) + d.w) / 4.0f;
+        } else {
+            o = __ldcs(ac + row * da4 + (c - dt4));
+        }
+        x[i] = o;
+    }
+}
+}  // namespace lsthm

@@ -8,16 +8,16 @@ namespace lsthm {
 int set_error(const char *what, cudaError_t e);
 int fail_msg(const char *msg);
 
-template <int AMN, int BMN>
+template <int AMN, int BMN, bool BF16>
 static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm3_kernel<AMN, BMN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
     if (e != cudaSuccess) return set_error("lsthm_gemm3 shared-memory opt-in", e);
-    gemm3_kernel<AMN, BMN><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(g);
+    gemm3_kernel<AMN, BMN, BF16><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(g);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_gemm3 launch", e);
 }
 
-template <int BMN>
+template <int BMN, bool BF16>
 static int launch_gemm_w(const GemmWArgs &g, const float *W, int ldw, uint8_t *img, dim3 grid, cudaStream_t st) {
     const int nch = (g.N + kWNC - 1) / kWNC;
     const size_t chunks = (size_t)nch * g.nkb * 1024;
@@ -25,9 +25,9 @@ static int launch_gemm_w(const GemmWArgs &g, const float *W, int ldw, uint8_t *i
     gemm3w_pack_kernel<BMN><<<pblocks, 256, 0, st>>>(W, ldw, g.N, g.K, g.nkb, img, chunks);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error("lsthm_gemm3w pack launch", e);
-    e = cudaFuncSetAttribute(gemm3w_kernel<BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWSmemBytes);
+    e = cudaFuncSetAttribute(gemm3w_kernel<BMN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWSmemBytes);
     if (e != cudaSuccess) return set_error("lsthm_gemm3w shared-memory opt-in", e);
-    gemm3w_kernel<BMN><<<grid, kGemmThreads, kWSmemBytes, st>>>(g);
+    gemm3w_kernel<BMN, BF16><<<grid, kGemmThreads, kWSmemBytes, st>>>(g);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_gemm3w launch", e);
 }
@@ -38,6 +38,7 @@ using namespace lsthm;
 extern "C" {
 
 size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K) {
+    mode &= ~LSTHM_GEMM_BF16;
     if (mode == 3) return 0;
     const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
     if (tiles >= 148 || K < 4 * kGemmBK * 8) return 0;
@@ -47,6 +48,8 @@ size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t 
 
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream) {
+    const bool bf16 = (mode & LSTHM_GEMM_BF16) != 0;
+    mode &= ~LSTHM_GEMM_BF16;
     if (mode < 0 || mode > 3) return fail_msg("lsthm_gemm3: mode must be 0 (NT), 1 (NN), 2 (TN) or 3 (NT + ReLU)");
     if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return fail_msg("lsthm_gemm3: bad shape or null pointer");
     if ((lda & 3) || (ldb & 3)) return fail_msg("lsthm_gemm3: lda and ldb must be multiples of 4 floats");
@@ -69,9 +72,10 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
     if (splits > 1) { g.C = workspace; g.ldc = N; }
     const dim3 grid(tn, tm, splits);
     int rc;
-    if (mode == 0 || mode == 3) rc = launch_gemm<0, 0>(g, grid, (cudaStream_t)stream);
-    else if (mode == 1) rc = launch_gemm<0, 1>(g, grid, (cudaStream_t)stream);
-    else rc = launch_gemm<1, 1>(g, grid, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0 || mode == 3) rc = bf16 ? launch_gemm<0, 0, true>(g, grid, st) : launch_gemm<0, 0, false>(g, grid, st);
+    else if (mode == 1) rc = bf16 ? launch_gemm<0, 1, true>(g, grid, st) : launch_gemm<0, 1, false>(g, grid, st);
+    else rc = bf16 ? launch_gemm<1, 1, true>(g, grid, st) : launch_gemm<1, 1, false>(g, grid, st);
     if (rc) return rc;
     if (splits > 1) {
         const size_t total = (size_t)M * N;
@@ -90,6 +94,8 @@ size_t lsthm_gemm3w_pack_bytes(int32_t N, int32_t K) {
 
 int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *W, int32_t ldw,
                  const float *bias, float *C, int32_t ldc, void *pack, size_t pack_bytes, void *stream) {
+    const bool bf16 = (mode & LSTHM_GEMM_BF16) != 0;
+    mode &= ~LSTHM_GEMM_BF16;
     if (mode != 0 && mode != 1 && mode != 3) return fail_msg("lsthm_gemm3w: mode must be 0 (NT), 1 (NN) or 3 (NT + ReLU)");
     if (M < 1 || N < 1 || K < 1 || !A || !W || !C || !pack) return fail_msg("lsthm_gemm3w: bad shape or null pointer");
     if ((lda & 3) || (ldw & 3)) return fail_msg("lsthm_gemm3w: lda and ldw must be multiples of 4 floats");
@@ -100,8 +106,10 @@ int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, 
     g.A = A; g.bias = bias; g.img = static_cast<const uint8_t *>(pack); g.C = C;
     g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldc = ldc; g.nkb = (K + kGemmBK - 1) / kGemmBK; g.relu = mode == 3 ? 1 : 0;
     const dim3 grid((N + kWNC - 1) / kWNC, (M + kGemmBM - 1) / kGemmBM, 1);
-    if (mode == 1) return launch_gemm_w<1>(g, W, ldw, static_cast<uint8_t *>(pack), grid, (cudaStream_t)stream);
-    return launch_gemm_w<0>(g, W, ldw, static_cast<uint8_t *>(pack), grid, (cudaStream_t)stream);
+    uint8_t *img = static_cast<uint8_t *>(pack);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 1) return bf16 ? launch_gemm_w<1, true>(g, W, ldw, img, grid, st) : launch_gemm_w<1, false>(g, W, ldw, img, grid, st);
+    return bf16 ? launch_gemm_w<0, true>(g, W, ldw, img, grid, st) : launch_gemm_w<0, false>(g, W, ldw, img, grid, st);
 }
 
 }  // extern "C"

@@ -68,6 +68,11 @@ __device__ __forceinline__ void split_store8(const float (&x)[8], uint8_t *hi, u
     *reinterpret_cast<uint4 *>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// bf16 mode (one UMMA per k-step, operands rounded to bf16): only the hi image is produced
+__device__ __forceinline__ void store8_hi(const float (&x)[8], uint8_t *hi) {
+    *reinterpret_cast<uint4 *>(hi) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+}
+
 // Load 8 consecutive floats p[0..7] where only the first `valid` (<= 8) are in range; the rest are zero.
 __device__ __forceinline__ void load8(const float *p, int valid, float (&x)[8]) {
     if (valid >= 8) {
@@ -112,7 +117,7 @@ __device__ __forceinline__ void load_tile(const float *__restrict__ src, int ld,
     }
 }
 
-template <int MN>
+template <int MN, bool BF16 = false>
 __device__ __forceinline__ void store_tile(const TileRegs &t, uint8_t *hi, uint8_t *lo, int ptid) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -124,11 +129,12 @@ __device__ __forceinline__ void store_tile(const TileRegs &t, uint8_t *hi, uint8
             const int k = i * 16 + (ptid >> 4), mc = ptid & 15;
             off = mc * kMnSbo + (k >> 3) * kMnLbo + (k & 7) * 16;
         }
-        split_store8(t.x[i], hi + off, lo + off);
+        if (BF16) store8_hi(t.x[i], hi + off);
+        else split_store8(t.x[i], hi + off, lo + off);
     }
 }
 
-template <int AMN, int BMN>
+template <int AMN, int BMN, bool BF16 = false>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_constant__ GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw;
@@ -164,8 +170,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
             const int s = kb % kGemmStages, round = kb / kGemmStages;
             if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);      // the MMAs that read this stage have retired
             uint8_t *st = smem + (size_t)s * kStageBytes;
-            store_tile<AMN>(ta, st, st + kTileBytes, tid);
-            store_tile<BMN>(tb, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            store_tile<AMN, BF16>(ta, st, st + kTileBytes, tid);
+            store_tile<BMN, BF16>(tb, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
             if (kb + 1 < nkb) {                                             // next block's loads fly during the fence/arrive/wait
                 const int k1 = kbeg + (kb + 1) * kGemmBK;
                 load_tile<AMN>(g.A, g.lda, m0, g.M, k1, kend, tid, ta);
@@ -195,10 +201,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
                 const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem), "l"(ah), "l"(bh), "r"(idesc), "r"(acc0) : "memory");
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                             ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                             ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                if (!BF16) {
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                }
             }
             // commit: arrives on the barrier when all MMAs issued so far have completed (implies before_thread_sync)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
@@ -324,7 +332,7 @@ struct GemmWArgs {
     int M, N, K, lda, ldc, nkb, relu;
 };
 
-template <int BMN>
+template <int BMN, bool BF16 = false>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_constant__ GemmWArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw;
@@ -359,10 +367,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_co
             if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);      // the MMAs that read this stage have retired
             uint8_t *st = smem + (size_t)s * kWStageBytes;
             if (tid == 0) {
-                mbar_expect_tx(&full_bar[s], 2 * kWImgBytes);
-                bulk_g2s(st + 2 * kTileBytes, wsrc + (size_t)kb * (2 * (size_t)kWImgBytes), 2 * kWImgBytes, &full_bar[s]);
+                constexpr uint32_t wbytes = BF16 ? kWImgBytes : 2 * kWImgBytes;           // bf16 mode: the hi image only
+                mbar_expect_tx(&full_bar[s], wbytes);
+                bulk_g2s(st + 2 * kTileBytes, wsrc + (size_t)kb * (2 * (size_t)kWImgBytes), wbytes, &full_bar[s]);
             }
-            store_tile<0>(ta, st, st + kTileBytes, tid);
+            store_tile<0, BF16>(ta, st, st + kTileBytes, tid);
             if (kb + 1 < nkb) load_tile<0>(g.A, g.lda, m0, g.M, (kb + 1) * kGemmBK, g.K, tid, ta);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -388,10 +397,12 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_co
                 const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem), "l"(ah), "l"(bh), "r"(idesc), "r"(acc0) : "memory");
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                             ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
-                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                             ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                if (!BF16) {
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                }
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty_bar[s])) : "memory");
         }

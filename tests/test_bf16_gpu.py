@@ -1,0 +1,76 @@
+"""bf16 mode (BASELINE.json names it for configs[2]; the north star asks for its tolerance to be stated separately from
+fp32 parity).  What the mode is: every TIME-PARALLEL tensor-core product of the path (input / encoder / FFN / head
+projections, their input- and weight-gradient products, and the encoder self-attention products) takes its operands
+rounded to bf16 and issues ONE UMMA per k-step with fp32 accumulation, instead of the fp32-accurate three-term split.
+The recurrence itself (cell state, gates, in-cell attention, softmaxes), LayerNorm, the losses and lsthm_sps's
+sequence-level CrossAttention2/3 stay fp32.
+
+Stated tolerance (the one SURVEY.md §8d derived for a bf16 mode), against the reference's fp32 outputs on the committed
+fixtures (measured on B200: probabilities 2.0e-4 .. 2.6e-4, loss < 1e-6, dx E_2 1.3e-2 .. 2.3e-2, argmax identical):
+    probabilities  E_inf <= 5e-4      loss  rel <= 1e-3      d loss / d x  E_2 <= 3e-2      argmax agreement >= 99.9 %
+and against fp64 for the kernels themselves:  GEMM E_inf <= 1e-2,  attention out / grads E_inf <= 2e-2.
+Each test also checks that the mode is really active (error above the fp32-mode bar)."""
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+
+import lsthm_b200
+from helpers import e_inf, golden_files, load_golden, run_module
+
+pytestmark = pytest.mark.gpu
+lib = import_module(lsthm_b200.__name__ + "._lib")
+fa = import_module(lsthm_b200.__name__ + ".fused_attention")
+
+
+@pytest.fixture
+def bf16_mode():
+    lib.set_precision("bf16")
+    yield
+    lib.set_precision("fp32")
+
+
+def _err(c, ref):
+    return ((c.double() - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 960, 100), (1000, 320, 512)])
+def test_gemm_modes(bf16_mode, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.1
+    dy = torch.randn(M, N, device="cuda", generator=g)
+    for got, ref in ((lib.gemm3(lib.GEMM_NT, x, w), x.double() @ w.double().t()),
+                     (lib.gemm3(lib.GEMM_NN, dy, w), dy.double() @ w.double()),
+                     (lib.gemm3(lib.GEMM_TN, dy, x), dy.double().t() @ x.double())):
+        e = _err(got, ref)
+        assert 1e-4 < e < 1e-2, e
+
+
+def test_attention(bf16_mode):
+    B, L, H, D = 3, 110, 8, 40
+    g = torch.Generator(device="cuda").manual_seed(1)
+    qkv = torch.randn(B, L, 3 * H * D, device="cuda", generator=g).requires_grad_(True)
+    w = torch.randn(B, L, H * D, device="cuda", generator=g)
+    out = fa.fused_self_attention(qkv, H, D ** -0.5)
+    (out * w).sum().backward()
+    q64 = qkv.detach().double().requires_grad_(True)
+    q, k, v = (t.view(B, L, H, D).transpose(1, 2) for t in q64.split(H * D, dim=-1))
+    ref = (torch.softmax((q * D ** -0.5) @ k.transpose(-2, -1), -1) @ v).transpose(1, 2).reshape(B, L, H * D)
+    (ref * w.double()).sum().backward()
+    eo, eg = _err(out.detach(), ref.detach()), _err(qkv.grad, q64.grad)
+    assert 1e-4 < eo < 2e-2 and 1e-4 < eg < 2e-2, (eo, eg)
+
+
+@pytest.mark.parametrize("path", golden_files("mab_*eval.npz"), ids=lambda p: p.split("/")[-1][:-4])
+def test_module_within_stated_bf16_tolerance(bf16_mode, path):
+    fix = load_golden(path)
+    probs, loss, dx, _ = run_module(fix, "cuda")
+    e2 = lambda a, b: float(np.linalg.norm(np.asarray(a, np.float64) - b) / np.linalg.norm(b))
+    errs = {"probs": e_inf(probs, fix["probs"]), "loss": abs(float(loss) - float(fix["loss"])) / abs(float(fix["loss"])),
+            "dx_E2": e2(dx, fix["dx"].astype(np.float64)),
+            "argmax": float((np.argmax(np.asarray(probs), -1) == np.argmax(fix["probs"], -1)).mean())}
+    print(path.split("/")[-1], errs)
+    assert errs["probs"] <= 5e-4 and errs["loss"] <= 1e-3 and errs["dx_E2"] <= 3e-2 and errs["argmax"] >= 0.999, errs
+    assert errs["probs"] > 1e-6                                   # the mode is on
