@@ -56,7 +56,14 @@ int lsthm_attn_bwd(const lsthm_attn_desc *d, const float *q, const float *k, con
     auto kern = d->precision == 1 ? attn_bwd_kernel<true> : attn_bwd_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_attn_bwd shared-memory opt-in", e);
-    kern<<<d->B * d->H, kAttBwdThreads, smem, (cudaStream_t)stream>>>(a);
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+            sm_count = 148;
+    }
+    const int items = d->B * d->H;
+    kern<<<items < sm_count ? items : sm_count, kAttBwdThreads, smem, (cudaStream_t)stream>>>(a);   // persistent: one CTA per SM
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_attn_bwd launch", e);
 }

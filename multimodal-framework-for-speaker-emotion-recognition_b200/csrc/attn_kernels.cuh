@@ -290,8 +290,8 @@ __device__ __forceinline__ void row_load2(const float *src, int g, RowRegs2 &r) 
     for (int i = 0; i < 2; ++i) {
         const int c = g + 4 * i;
         if (c < 5 && src != nullptr) {
-            r.v[2 * i] = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c);
-            r.v[2 * i + 1] = __ldg(reinterpret_cast<const float4 *>(src) + 2 * c + 1);
+            r.v[2 * i] = reinterpret_cast<const float4 *>(src)[2 * c];
+            r.v[2 * i + 1] = reinterpret_cast<const float4 *>(src)[2 * c + 1];
         } else {
             r.v[2 * i] = r.v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -311,121 +311,158 @@ __device__ __forceinline__ void row_store2(const RowRegs2 &r, int row, float sca
     }
 }
 
+// Persistent: one CTA per SM walks the (dialogue, head) items blockIdx.x, blockIdx.x + gridDim.x, ...  With 224 KB of
+// shared memory only one CTA fits an SM, so nothing else can hide an item's memory phases; instead the rows of item
+// i+1 (q, k, v, dO, O: 5 x L slices of 160 bytes) are fetched by bulk async copies (TMA engine, mbarrier
+// complete_tx) into a raw fp32 patch that aliases the Pd / dS tiles, issued as soon as item i's last products have
+// retired, so they land while item i's gradients are drained from TMEM and stored.
 template <bool BF16>
 __global__ void __launch_bounds__(kAttBwdThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];   // no-swizzle operands need 16-byte alignment only; 224 KB + 2 KB static fit 227 KB
-    __shared__ __align__(8) uint64_t bar[2];
+    extern __shared__ __align__(128) uint8_t smem[];   // no-swizzle operands need 16-byte alignment only
+    __shared__ __align__(8) uint64_t bar[3];           // 0: S,dPd done   1: dV,dQ,dK done   2: raw rows of the next item landed
     __shared__ uint32_t tmem_base;
     uint8_t *sQ = smem, *sK = sQ + 2 * kRowTile, *sV = sK + 2 * kRowTile, *sdO = sV + 2 * kRowTile, *sP = sdO + 2 * kRowTile;
     uint8_t *sD = sP + 2 * kSqTile;
+    constexpr int kRawLd = 44;                                  // floats per raw row: 176 B stride -> conflict-free 16-byte reads by row
+    float *raw = reinterpret_cast<float *>(sP);                 // [5][128][kRawLd] = 112.6 KB <= 128 KB (sP + sD)
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
-    const int b = blockIdx.x / a.H, h = blockIdx.x % a.H, L = a.L;
-    const size_t grow = (size_t)((long long)b * a.sb + (long long)r * a.si);
+    const int L = a.L, nitems = a.B * a.H;
     const bool rv = r < L;
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1); mbar_fence_init(); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    const float *drow = a.dout + grow * a.ldo + h * kAttD;
-    float lse = 0.f, delta = 0.f;
-    {
-        RowRegs2 rq, rk, rw, rd;
-        row_load2(rv ? a.q + grow * a.ldq + h * kAttD : nullptr, g, rq);
-        row_load2(rv ? a.k + grow * a.ldk + h * kAttD : nullptr, g, rk);
-        row_load2(rv ? a.v + grow * a.ldv + h * kAttD : nullptr, g, rw);
-        row_load2(rv ? drow : nullptr, g, rd);
-        // delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij (each of the row's four threads computes it: 2 x 160 B, L1-resident)
-        if (rv) {
-            const float *orow = a.o + grow * a.ldo + h * kAttD;
-            float4 o4[10], d4[10];
-#pragma unroll
-            for (int d = 0; d < 10; ++d) {
-                o4[d] = __ldg(reinterpret_cast<const float4 *>(orow) + d);
-                d4[d] = __ldg(reinterpret_cast<const float4 *>(drow) + d);
-            }
-            lse = __ldg(a.lse + (size_t)blockIdx.x * L + r);
-#pragma unroll
-            for (int d = 0; d < 10; ++d) delta += d4[d].x * o4[d].x + d4[d].y * o4[d].y + d4[d].z * o4[d].z + d4[d].w * o4[d].w;
-        }
-        row_store2<BF16>(rq, r, a.scale * kLog2e, sQ, g);
-        row_store2<BF16>(rk, r, 1.f, sK, g);
-        row_store2<BF16>(rw, r, 1.f, sV, g);
-        row_store2<BF16>(rd, r, 1.f, sdO, g);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
     const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV), udO = smem_u32(sdO), uP = smem_u32(sP), uD = smem_u32(sD);
-    if (tid == 0) {
-        // S = Qs K^T ; dPd = dO V^T   (both M = query, N = key, K = d)
-        umma3<BF16>(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
-        umma3<BF16>(tmem + 128, udO, kRowTile, 4096u, 2048u, 128u, uV, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
-        umma_commit(&bar[0]);
-    }
-    mbar_wait(&bar[0], 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int roff = (r >> 3) * 128 + (r & 7) * 16, cb = 32 * g;
-    {
-        const AttDrop drop(a.seed, blockIdx.x, r, a.p_drop);
-        float s[16], gg[16], p8[8], d8[8];
+
+    // bulk copies of one item's rows: 5 arrays x L rows x 160 B, spread over the CTA's threads; thread 0 posts the byte count
+    auto fetch = [&](int item) {
+        const int b = item / a.H, h = item % a.H;
+        if (tid == 0) mbar_expect_tx(&bar[2], (uint32_t)(5 * L * kAttD * sizeof(float)));
+        for (int idx = tid; idx < 5 * L; idx += kAttBwdThreads) {
+            const int arr = idx / L, row = idx - arr * L;
+            const size_t gr = (size_t)((long long)b * a.sb + (long long)row * a.si);
+            const float *src = (arr == 0 ? a.q + gr * a.ldq : arr == 1 ? a.k + gr * a.ldk : arr == 2 ? a.v + gr * a.ldv
+                                : arr == 3 ? a.dout + gr * a.ldo : a.o + gr * a.ldo) + h * kAttD;
+            bulk_g2s(raw + (arr * 128 + row) * kRawLd, src, kAttD * sizeof(float), &bar[2]);
+        }
+    };
+    int item = blockIdx.x;
+    float lse_next = 0.f;
+    if (item < nitems) {
+        fetch(item);
+        if (rv) lse_next = __ldg(a.lse + (size_t)item * L + r);
+    }
+    for (int it = 0; item < nitems; item += gridDim.x, ++it) {
+        const int b = item / a.H, h = item % a.H;
+        const uint32_t ph = it & 1;
+        const size_t grow = (size_t)((long long)b * a.sb + (long long)r * a.si);
+        const float lse = lse_next;
+        float delta = 0.f;
+        mbar_wait(&bar[2], ph);                                   // this item's raw rows have landed
+        {
+            RowRegs2 rq, rk, rw, rd;
+            auto raw_row = [&](int arr) { return rv ? raw + (arr * 128 + r) * kRawLd : nullptr; };
+            row_load2(raw_row(0), g, rq);
+            row_load2(raw_row(1), g, rk);
+            row_load2(raw_row(2), g, rw);
+            row_load2(raw_row(3), g, rd);
+            if (rv) {   // delta = rowsum(dO * O) = sum_j Pd_ij dPd_ij (each of the row's four threads computes it from the raw patch)
+                const float4 *d4 = reinterpret_cast<const float4 *>(raw + (3 * 128 + r) * kRawLd);
+                const float4 *o4 = reinterpret_cast<const float4 *>(raw + (4 * 128 + r) * kRawLd);
 #pragma unroll
-        for (int c0 = cb; c0 < cb + 32; c0 += 16) {
-            tmem_ld16x2(trow + c0, trow + 128 + c0, s, gg);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                    const int col = c0 + half * 8 + j, i0 = half * 8 + j;
-                    const float p0 = (rv && col < L) ? fast_exp2(s[i0] - lse) : 0.f;
-                    const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - lse) : 0.f;
-                    float s0 = 1.f, s1 = 1.f;
-                    if (drop.on) drop.pair(col >> 1, s0, s1);
-                    p8[j] = p0 * s0; p8[j + 1] = p1 * s1;
-                    d8[j] = p0 * (s0 * gg[i0] - delta); d8[j + 1] = p1 * (s1 * gg[i0 + 1] - delta);
+                for (int d = 0; d < 10; ++d) {
+                    const float4 x = d4[d], y = o4[d];
+                    delta += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
                 }
-                const int chunk = (c0 >> 3) + half;
-                put8<BF16>(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
-                put8<BF16>(d8, sD + chunk * 2048 + roff, sD + kSqTile + chunk * 2048 + roff);
             }
+            row_store2<BF16>(rq, r, a.scale * kLog2e, sQ, g);
+            row_store2<BF16>(rk, r, 1.f, sK, g);
+            row_store2<BF16>(rw, r, 1.f, sV, g);
+            row_store2<BF16>(rd, r, 1.f, sdO, g);
         }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {
-        // dV = Pd^T dO : M = key (MN-major view of Pd), N = d (MN-major view of dO), K = query
-        umma3<BF16>(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
-        // dQs = dS K : M = query, N = d (MN view of K), K = key ;  dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
-        umma3<BF16>(tmem + 304, uD, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
-        umma3<BF16>(tmem + 352, uD, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
-        umma_commit(&bar[1]);
-    }
-    mbar_wait(&bar[1], 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-        float v[16];
-        // 9 (matrix, 16-column block) items over the four threads of a row: g takes the items with index % 4 == g
-        for (int item = g; item < 9; item += 4) {
-            const int which = item / 3, c0 = 16 * (item % 3);
-            float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + grow * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
-            // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
-            const float mul = which == 1 ? a.scale : which == 2 ? kLn2 : 1.f;
-            tmem_ld16(trow + 256 + 48 * which + c0, v);
-            if (rv) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                          // tiles complete; raw patch fully consumed; previous item's TMEM reads done
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            // S = Qs K^T ; dPd = dO V^T   (both M = query, N = key, K = d)
+            umma3<BF16>(tmem, uQ, kRowTile, 4096u, 2048u, 128u, uK, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+            umma3<BF16>(tmem + 128, udO, kRowTile, 4096u, 2048u, 128u, uV, kRowTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 3);
+            umma_commit(&bar[0]);
+        }
+        mbar_wait(&bar[0], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const AttDrop drop(a.seed, item, r, a.p_drop);
+            float s[16], gg[16], p8[8], d8[8];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4)
-                    if (c0 + 4 * q4 < kAttD)
-                        reinterpret_cast<float4 *>(dst + c0)[q4] =
-                            make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
+            for (int c0 = cb; c0 < cb + 32; c0 += 16) {
+                tmem_ld16x2(trow + c0, trow + 128 + c0, s, gg);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const int col = c0 + half * 8 + j, i0 = half * 8 + j;
+                        const float p0 = (rv && col < L) ? fast_exp2(s[i0] - lse) : 0.f;
+                        const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - lse) : 0.f;
+                        float s0 = 1.f, s1 = 1.f;
+                        if (drop.on) drop.pair(col >> 1, s0, s1);
+                        p8[j] = p0 * s0; p8[j + 1] = p1 * s1;
+                        d8[j] = p0 * (s0 * gg[i0] - delta); d8[j + 1] = p1 * (s1 * gg[i0 + 1] - delta);
+                    }
+                    const int chunk = (c0 >> 3) + half;
+                    put8<BF16>(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+                    put8<BF16>(d8, sD + chunk * 2048 + roff, sD + kSqTile + chunk * 2048 + roff);
+                }
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            // dV = Pd^T dO : M = key (MN-major view of Pd), N = d (MN-major view of dO), K = query
+            umma3<BF16>(tmem + 256, uP, kSqTile, 256u, 128u, 2048u, udO, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+            // dQs = dS K : M = query, N = d (MN view of K), K = key ;  dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
+            umma3<BF16>(tmem + 304, uD, kSqTile, 4096u, 2048u, 128u, uK, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 0, 1), 8);
+            umma3<BF16>(tmem + 352, uD, kSqTile, 256u, 128u, 2048u, uQ, kRowTile, 256u, 128u, 2048u, att_idesc(kAttDP, 1, 1), 8);
+            umma_commit(&bar[1]);
+        }
+        mbar_wait(&bar[1], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // every product of this item has retired: the Pd / dS tiles (= the raw patch) are free -> start the next item's rows
+        const int next = item + gridDim.x;
+        if (next < nitems) {
+            fetch(next);
+            if (rv) lse_next = __ldg(a.lse + (size_t)next * L + r);
+        }
+        {
+            float v[16];
+            // 9 (matrix, 16-column block) items over the four threads of a row: g takes the items with index % 4 == g
+            for (int blk = g; blk < 9; blk += 4) {
+                const int which = blk / 3, c0 = 16 * (blk % 3);
+                float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + grow * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
+                // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
+                const float mul = which == 1 ? a.scale : which == 2 ? kLn2 : 1.f;
+                tmem_ld16(trow + 256 + 48 * which + c0, v);
+                if (rv) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4)
+                        if (c0 + 4 * q4 < kAttD)
+                            reinterpret_cast<float4 *>(dst + c0)[q4] =
+                                make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -73,8 +73,8 @@ def segments(kernel):
 
 
 lines = [f"# ncu summary `{tag}`", "",
-         "Source: `ncu --set full --clock-control none [--import-source on] -k regex:<kernel>` on `bench.py --steps 2 --warmup 3 "
-         "--no-e2e --no-cpu-baseline` (`--model sps --steps 1` for the sps cell), 1 GPU (B200); each run was preceded by the same "
+         "Source: `ncu --set full --clock-control none [--import-source on] -k regex:<kernel>` on `bench.py --steps 1..2 --warmup 1..3 "
+         "--no-e2e --no-cpu-baseline` (`--model sps --steps 1` for the sps cell; from r01n on: profiles/capture_ncu.sh), 1 GPU (B200); each run was preceded by the same "
          "command without ncu exiting 0.  The raw/source pages were exported to CSV on the GPU box "
          "(the .ncu-rep files exceed the 64 MiB return limit).  Numbers are per launch; durations under ncu are cold-cache "
          "and serialised.", ""]
@@ -104,9 +104,12 @@ for grp in ("mab", "sps", "attn"):
                       "segment after the BAR):", "", "| seg | share | FFMA/FFMA2 instrs | UMMA instrs |", "|---|---|---|---|"]
             lines += [f"| {i} | {s:.1f}% | {f} | {t} |" for i, (s, f, t) in enumerate(seg)]
         lines.append("")
-hdr, units, data = raw_rows("gemm")
-if data:
-    lines += ["## lsthm::gemm3_kernel — all launches of one step", "",
+for grp, title in (("gemm", "lsthm::gemm3_kernel (general operands; the weight-gradient TN products)"),
+                   ("gemmw", "lsthm::gemm3w_kernel (weight-stationary NT / NN products)"),
+                   ("dln", "row-wise HBM-bound kernels (fused dropout+residual+LayerNorm, column sums)")):
+  hdr, units, data = raw_rows(grp)
+  if data:
+    lines += [f"## {title} — all launches of one step", "",
               "| variant | grid | ms | tensor pipe active % | issue active % | DRAM thr % | L2 thr % | DRAM MB (r+w) |", "|---|---|---|---|---|---|---|---|"]
     tot = 0.0
     for d in data:
