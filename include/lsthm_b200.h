@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTHM_ABI_VERSION 3
+#define LSTHM_ABI_VERSION 4
 #define LSTHM_MAX_MOD 3
 
 int lsthm_abi_version(void);
@@ -90,11 +90,14 @@ int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx,
  *   dr   [T][N][R]   dL/d(reduce outputs)        -> d reduce_dim_nn_*
  *   dup  [T][N][map_h] dL/d(fc.0 pre-activation) -> d fc.0
  *   dzt  [T][N][D]   total dL/dz_t               -> d fc.3
+ *   att  [T][N][4D]  (optional, may be NULL) the attended features a * c of the forward, regrouped per modality and
+ *                    head-major inside a modality (columns 4*off_m + head*dh_m + j): column block m is the operand
+ *                    of d reduce_dim_nn_m, so the host needs no elementwise product / regroup copy for it
  */
 int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed,
                   const float *dhz, const float *drop_mask,
                   const float *sC, const float *sG, const float *sA, const float *sU,
-                  float *dgx, float *de, float *dr, float *dup, float *dzt, void *stream);
+                  float *dgx, float *de, float *dr, float *dup, float *dzt, float *att, void *stream);
 
 /* Launch geometry the library would use (for roofline bookkeeping in bench.py). */
 int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows,

@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
 SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_MOD = 3
 
 _f32p = C.POINTER(C.c_float)
@@ -91,7 +91,7 @@ def lib() -> C.CDLL:
     L.lsthm_mab_fwd.restype = C.c_int
     L.lsthm_mab_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 10
     L.lsthm_mab_bwd.restype = C.c_int
-    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 13
+    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 14
     L.lsthm_mab_launch_info.restype = C.c_int
     L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 5
     L.lsthm_sps_packed_floats.restype = C.c_size_t
@@ -203,11 +203,11 @@ def mab_fwd(d: MabDesc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU) -> None:
                                _stream()), "lsthm_mab_fwd")
 
 
-def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt) -> None:
+def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt, att=None) -> None:
     _check(lib().lsthm_mab_bwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"),
                                _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"),
                                _dev_ptr(sA, "sA"), _dev_ptr(sU, "sU"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
-                               _dev_ptr(dr, "dr"), _dev_ptr(dup, "dup"), _dev_ptr(dzt, "dzt"), _stream()),
+                               _dev_ptr(dr, "dr"), _dev_ptr(dup, "dup"), _dev_ptr(dzt, "dzt"), _dev_ptr(att, "att"), _stream()),
            "lsthm_mab_bwd")
 
 

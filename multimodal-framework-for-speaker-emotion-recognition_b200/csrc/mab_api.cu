@@ -272,7 +272,7 @@ int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx,
 
 int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed, const float *dhz,
                   const float *drop_mask, const float *sC, const float *sG, const float *sA, const float *sU,
-                  float *dgx, float *de, float *dr, float *dup, float *dzt, void *stream) {
+                  float *dgx, float *de, float *dr, float *dup, float *dzt, float *att, void *stream) {
     BwdArgs a;
     if (build_layout(d, a.L)) return 1;
     if (!w || !packed || !dhz || !sC || !sG || !sA || !sU || !dgx || !de || !dr || !dup || !dzt)
@@ -285,7 +285,7 @@ int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const flo
     for (int m = 0; m < kMaxMod; ++m) { a.U[m] = w->U[m]; a.Wr[m] = w->Wr[m]; }
     a.Watt = w->Watt; a.Wf1 = w->Wf1; a.Wf2 = w->Wf2;
     a.dhz = dhz; a.mask = drop_mask; a.sC = sC; a.sG = sG; a.sA = sA; a.sU = sU;
-    a.dgx = dgx; a.de = de; a.dr = dr; a.dup = dup; a.dzt = dzt;
+    a.dgx = dgx; a.de = de; a.dr = dr; a.dup = dup; a.dzt = dzt; a.att = att;
     const int grid = cdiv(a.L.N, MT);
     return kBwd[MT - 1](a, grid, bytes, (cudaStream_t)stream);
 }

@@ -67,6 +67,7 @@ struct BwdArgs {
     const float *U[kMaxMod], *Wr[kMaxMod], *Watt, *Wf1, *Wf2;
     const float *dhz, *mask, *sC, *sG, *sA, *sU;
     float *dgx, *de, *dr, *dup, *dzt;
+    float *att;   // [T][N][G] attended = a * c regrouped per modality, head-major (HybridRNN_ATV.py:125-128): the operand of d reduce_m
 };
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -569,13 +570,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             for (int j = jb + jj; j < je; j += JL) {
                 const float cv = s_C[mm * L.ldc + j];
                 float direct = 0.f;
+                int mj = 0;
+                while (mj + 1 < L.nm && j >= L.off[mj + 1]) ++mj;
+                const int abase = 4 * L.off[mj] + (j - L.off[mj]), adh = L.dh[mj];   // column of (modality, head 0, feature) in `att`
 #pragma unroll
                 for (int k = 0; k < kHeads; ++k) {
                     const float av = s_A[mm * L.ldr + k * D + j], dv = s_row[mm * L.ldr + k * D + j];
                     direct += dv * av;
                     const float dev = av * (dv * cv - dot[k]);
                     s_km[(k * D + j) * MTP + mm] = dev;
-                    if (mm < rows) a.de[(tn0 + mm) * G + k * D + j] = dev;
+                    if (mm < rows) {
+                        a.de[(tn0 + mm) * G + k * D + j] = dev;
+                        if (a.att != nullptr) a.att[(tn0 + mm) * G + abase + k * adh] = av * cv;
+                    }
                 }
                 s_dc[j * MTP + mm] += direct;
             }

@@ -92,8 +92,9 @@ class MabRecurrenceFn(torch.autograd.Function):
         wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
         new = lambda *s: torch.empty(*s, device=hz.device, dtype=torch.float32)
         dgx, de, dr, dup, dzt = new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h), new(T, N, D)
+        att = new(T, N, G)     # attended = a * cs (HybridRNN_ATV.py:125), regrouped per modality head-major (lines 126-128) by the kernel
         _timed("bwd", _lib.mab_bwd, desc, wstruct, packed, dhz.contiguous(), ctx.drop_mask, sC, sG, sA, sU,
-               dgx, de, dr, dup, dzt)
+               dgx, de, dr, dup, dzt, att)
         launch_counter["bwd"] += 1
 
         # ---- time-parallel weight-gradient products (fp32; allow_tf32 stays off) ----
@@ -112,12 +113,12 @@ class MabRecurrenceFn(torch.autograd.Function):
             o += dh[m]
         de2, c2 = de.view(TN, G), sC.view(TN, D)
         gWatt, gbatt = mm_tn(de2, c2), colsum(de2)
-        att = sA.view(TN, 4, D) * c2.unsqueeze(1)           # attended = a * cs (HybridRNN_ATV.py:125)
+        att2 = att.view(TN, G)
         dr2 = dr.view(TN, R)
         gWr, gbr = [], []
         o = ro = 0
         for m in range(M):
-            vec = att[:, :, o:o + dh[m]].reshape(TN, 4 * dh[m])  # head-major regroup (lines 126-128)
+            vec = att2[:, 4 * o:4 * o + 4 * dh[m]]              # column block m: [head][feature], no copy
             drm = dr2[:, ro:ro + rd[m]]
             gWr.append(mm_tn(drm, vec))
             gbr.append(colsum(drm))

@@ -47,7 +47,7 @@ class OracleBackend:
             for t, k in ((sC, "C"), (sG, "G"), (sA, "A"), (sR, "R"), (sU, "UH")):
                 t.copy_(torch.from_numpy(f[k]).reshape(t.shape))
 
-    def mab_bwd(self, d, w, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt):
+    def mab_bwd(self, d, w, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt, att=None):
         dh, rd = self._dims(d)
         T, N = d.T, d.N
         D = sum(dh)
@@ -59,6 +59,12 @@ class OracleBackend:
                                    None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
         for t, k in ((dgx, "dgx"), (de, "de"), (dr, "dr"), (dup, "dup"), (dzt, "dzt")):
             t.copy_(torch.from_numpy(adj[k]).reshape(t.shape))
+        if att is not None:   # attended = a * c regrouped per modality, head-major (include/lsthm_b200.h: lsthm_mab_bwd)
+            a4 = sA.reshape(T, N, 4, D) * sC.reshape(T, N, 1, D)
+            o = 0
+            for h in dh:
+                att[:, :, 4 * o:4 * o + 4 * h] = a4[:, :, :, o:o + h].reshape(T, N, 4 * h)
+                o += h
 
 
 def install(monkeypatch):

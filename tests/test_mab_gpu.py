@@ -63,9 +63,16 @@ def _run_kernels(c, T, N):
     mask = None if c["mask"] is None else c["mask"].to(dev)
     lib.mab_fwd(d, packed, gx, mask, out["hz"], out["C"], out["G"], out["A"], out["R"], out["UH"])
     adj = dict(dgx=new(T, N, 4 * D), de=new(T, N, 4 * D), dr=new(T, N, R), dup=new(T, N, MH), dzt=new(T, N, D))
+    att = new(T, N, 4 * D)
     lib.mab_bwd(d, ws, packed, c["dhz"].to(dev), mask, out["C"], out["G"], out["A"], out["UH"],
-                adj["dgx"], adj["de"], adj["dr"], adj["dup"], adj["dzt"])
+                adj["dgx"], adj["de"], adj["dr"], adj["dup"], adj["dzt"], att)
     torch.cuda.synchronize()
+    # the regrouped attended features the backward also emits: a * c, per modality, head-major (HybridRNN_ATV.py:125-128)
+    a4 = out["A"].view(T, N, 4, D) * out["C"].view(T, N, 1, D)
+    o = 0
+    for h in dh:
+        assert torch.equal(att[:, :, 4 * o:4 * o + 4 * h], a4[:, :, :, o:o + h].reshape(T, N, 4 * h))
+        o += h
     return {k: v.cpu().numpy() for k, v in out.items()}, {k: v.cpu().numpy() for k, v in adj.items()}
 
 
