@@ -62,11 +62,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Pointwise math.  fp32 mode must stay well inside 1e-4 (logits) / 1e-3 (grads) of the fp32
 // reference, so no tanh.approx / ex2.approx-only shortcuts with 1e-3 relative error here.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// The divisions are MUFU.RCP based (__fdividef: <= 2 ulp, denominators here are in [1, 2^126]) instead of the IEEE
+// division sequence: a third of the instructions of the gate nonlinearities, same 1e-7 absolute accuracy.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_(float x) {
-    // 1 - 2/(e^{2x}+1): abs error ~1e-7, saturates cleanly for |x| large.
+    // 1 - 2/(e^{2x}+1): abs error ~1e-7, saturates cleanly for |x| large (e = inf -> 2/inf = 0).
     const float e = __expf(2.0f * x);
-    return 1.0f - 2.0f / (e + 1.0f);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
 // ---------------------------------------------------------------------------------------------
