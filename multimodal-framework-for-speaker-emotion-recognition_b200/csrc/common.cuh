@@ -245,6 +245,32 @@ __device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t
     return (float)(x >> 8) * (1.0f / 16777216.0f) < p ? 0.f : 1.0f / (1.0f - p);
 }
 
+// Cheaper variant for dense attention dropout: ONE one-round hash per PAIR of adjacent columns, 16 random bits per
+// element (keep iff bits >= round(p * 65536); scale 65536 / (65536 - thr), so the mask is exactly unbiased).  `a`
+// names the (step, dialogue) tile, `row` / `col` the element; forward and backward evaluate the same function.
+struct PairDrop {
+    uint32_t base, thr;
+    float scale;
+    __device__ __forceinline__ PairDrop(unsigned long long seed, uint32_t a, float p) {
+        thr = (uint32_t)(p * 65536.0f + 0.5f);
+        scale = 65536.0f / (65536.0f - (float)thr);
+        uint32_t x = (uint32_t)seed ^ (a * 0x9E3779B9u);
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        base = x ^ (uint32_t)(seed >> 32);
+    }
+    __device__ __forceinline__ void pair(uint32_t row, uint32_t pair_idx, float &s0, float &s1) const {
+        uint32_t x = base + row * 0x85EBCA6Bu + pair_idx * 0xC2B2AE35u;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        s0 = (x & 0xffffu) >= thr ? scale : 0.f;
+        s1 = (x >> 16) >= thr ? scale : 0.f;
+    }
+    __device__ __forceinline__ float one(uint32_t row, uint32_t col) const {
+        float s0, s1;
+        pair(row, col >> 1, s0, s1);
+        return (col & 1) ? s1 : s0;
+    }
+};
+
 // k-major [k][MTP] vector of one unit: load / store all rows at once (conflict-free 16B accesses).
 template <int MTP>
 __device__ __forceinline__ void load_rows(float (&v)[MTP], const float *p) {

@@ -87,10 +87,8 @@ __device__ __forceinline__ void grid_wait(unsigned *bar, unsigned target) {
     __syncthreads();
 }
 
-// in-cell attention dropout: keep decision for element (i, j) of dialogue n at step t (same stream in fwd and bwd)
-__device__ __forceinline__ float att_keep_scale(unsigned long long seed, int t, int n, int i, int j, float p) {
-    return dropout_scale(seed, (uint32_t)t * 65536u + (uint32_t)n, (uint32_t)(i << 7 | j), p);
-}
+// in-cell attention dropout: PairDrop (common.cuh) keyed by (step, dialogue), row i, column pair j/2 — the same
+// stream in forward and backward, no mask tensor
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -293,10 +291,13 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
                         num = fmaf(e * __ldg(am + j), car[j], num);
                     }
                 } else if (a.att_p > 0.f) {
-                    for (int j = 0; j < kU; ++j) {
-                        const float e = __expf(ai * s_wk[j] - mx);
-                        den += e;
-                        num = fmaf(e * att_keep_scale(a.att_seed, t, n, i, j, a.att_p), car[j], num);
+                    const PairDrop pd(a.att_seed, (uint32_t)t * 65536u + (uint32_t)n, a.att_p);
+                    for (int j = 0; j < kU; j += 2) {
+                        float s0, s1;
+                        pd.pair(i, j >> 1, s0, s1);
+                        const float e0 = __expf(ai * s_wk[j] - mx), e1 = __expf(ai * s_wk[j + 1] - mx);
+                        den += e0; den += e1;
+                        num = fmaf(e0 * s0, car[j], num); num = fmaf(e1 * s1, car[j + 1], num);
                     }
                 } else {
 #pragma unroll 4
@@ -389,14 +390,17 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_co
                 const int n = r0 + m;
                 const float *am = a.att_mask ? a.att_mask + (((size_t)t * N + n) * kU + i) * kU : nullptr;
                 float den = 0.f, n1s = 0.f, n2s = 0.f, n3s = 0.f;
-                for (int j = 0; j < kU; ++j) {
-                    const float wk = s_wk[j];
-                    const float e = __expf(ai * wk - mx);
-                    float sc = 1.f;
-                    if (am) sc = __ldg(am + j);
-                    else if (a.att_p > 0.f) sc = att_keep_scale(a.att_seed, t, n, i, j, a.att_p);
-                    const float ex = e * sc * car[j];
-                    den += e; n1s += ex; n2s = fmaf(ex, wk, n2s); n3s = fmaf(e, wk, n3s);
+                const bool hashed = am == nullptr && a.att_p > 0.f;
+                const PairDrop pd(a.att_seed, (uint32_t)t * 65536u + (uint32_t)n, a.att_p);
+                for (int j = 0; j < kU; j += 2) {
+                    float s0 = 1.f, s1 = 1.f;
+                    if (am) { s0 = __ldg(am + j); s1 = __ldg(am + j + 1); }
+                    else if (hashed) pd.pair(i, j >> 1, s0, s1);
+                    const float wk0 = s_wk[j], wk1 = s_wk[j + 1];
+                    const float e0 = __expf(ai * wk0 - mx), e1 = __expf(ai * wk1 - mx);
+                    const float ex0 = e0 * s0 * car[j], ex1 = e1 * s1 * car[j + 1];
+                    den += e0; n1s += ex0; n2s = fmaf(ex0, wk0, n2s); n3s = fmaf(e0, wk0, n3s);
+                    den += e1; n1s += ex1; n2s = fmaf(ex1, wk1, n2s); n3s = fmaf(e1, wk1, n3s);
                 }
                 const float inv = 1.0f / den, out = n1s * inv, go = r_gz[m * LDA + i];
                 const float g = go * (n2s - out * n3s) * inv;
@@ -423,12 +427,13 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_co
                 const float wk = s_wk[j], x2 = r_ca[m * LDA + j];
                 const int n = r0 + m;
                 float dca = 0.f;
+                const PairDrop pd(a.att_seed, (uint32_t)t * 65536u + (uint32_t)n, a.att_p);
                 for (int i = 0; i < kU; ++i) {
                     const float ai = r_ai[m * LDA + i];
                     const float p = __expf(ai * wk - r_mx[m * LDA + i]) * r_id[m * LDA + i];
                     float sc = 1.f;
                     if (a.att_mask) sc = __ldg(a.att_mask + (((size_t)t * N + n) * kU + i) * kU + j);
-                    else if (a.att_p > 0.f) sc = att_keep_scale(a.att_seed, t, n, i, j, a.att_p);
+                    else if (a.att_p > 0.f) sc = pd.one(i, j);
                     const float go = r_gz[m * LDA + i];
                     dca = fmaf(go * p, sc, dca);
                     dwk = fmaf(p * (sc * x2 - r_out[m * LDA + i]), ai * go, dwk);
