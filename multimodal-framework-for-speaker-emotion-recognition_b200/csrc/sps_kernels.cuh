@@ -419,28 +419,36 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_co
             if (lane == 0) s_dsm[warp] = s * 0.08838834764831845f;   // dL/d(Wq.ca)
         }
         __syncthreads();
-        // ---- P2b: per (dialogue, j): dc_a (direct + through s), per-row dWk contribution
-        for (int pair = tid; pair < MT * kU; pair += nt) {
-            const int m = pair >> 7, j = pair & 127;
-            float dwk = 0.f;
+        // ---- P2b: per (dialogue, column pair j, j+1): dc_a (direct + through s), per-row dWk contribution.
+        //      A thread owns two adjacent columns so one dropout hash (and one set of row constants) serves both.
+        for (int pair = tid; pair < MT * (kU / 2); pair += nt) {
+            const int m = pair >> 6, j = (pair & 63) * 2;
+            float dwk0 = 0.f, dwk1 = 0.f;
             if (m < rows) {
-                const float wk = s_wk[j], x2 = r_ca[m * LDA + j];
+                const float wk0 = s_wk[j], wk1 = s_wk[j + 1], x20 = r_ca[m * LDA + j], x21 = r_ca[m * LDA + j + 1];
                 const int n = r0 + m;
-                float dca = 0.f;
+                float dca0 = 0.f, dca1 = 0.f;
                 const PairDrop pd(a.att_seed, (uint32_t)t * 65536u + (uint32_t)n, a.att_p);
+                const bool hashed = a.att_mask == nullptr && a.att_p > 0.f;
                 for (int i = 0; i < kU; ++i) {
-                    const float ai = r_ai[m * LDA + i];
-                    const float p = __expf(ai * wk - r_mx[m * LDA + i]) * r_id[m * LDA + i];
-                    float sc = 1.f;
-                    if (a.att_mask) sc = __ldg(a.att_mask + (((size_t)t * N + n) * kU + i) * kU + j);
-                    else if (a.att_p > 0.f) sc = pd.one(i, j);
-                    const float go = r_gz[m * LDA + i];
-                    dca = fmaf(go * p, sc, dca);
-                    dwk = fmaf(p * (sc * x2 - r_out[m * LDA + i]), ai * go, dwk);
+                    const float ai = r_ai[m * LDA + i], mxi = r_mx[m * LDA + i], idi = r_id[m * LDA + i];
+                    const float p0 = __expf(ai * wk0 - mxi) * idi, p1 = __expf(ai * wk1 - mxi) * idi;
+                    float s0 = 1.f, s1 = 1.f;
+                    if (a.att_mask) {
+                        const float2 mk = __ldg(reinterpret_cast<const float2 *>(a.att_mask + (((size_t)t * N + n) * kU + i) * kU + j));
+                        s0 = mk.x; s1 = mk.y;
+                    } else if (hashed) pd.pair(i, j >> 1, s0, s1);
+                    const float go = r_gz[m * LDA + i], oi = r_out[m * LDA + i], ag = ai * go;
+                    dca0 = fmaf(go * p0, s0, dca0);
+                    dca1 = fmaf(go * p1, s1, dca1);
+                    dwk0 = fmaf(p0 * (s0 * x20 - oi), ag, dwk0);
+                    dwk1 = fmaf(p1 * (s1 * x21 - oi), ag, dwk1);
                 }
-                s_Gca[j * MTP + m] += dca + s_wq[j] * s_dsm[m];
+                s_Gca[j * MTP + m] += dca0 + s_wq[j] * s_dsm[m];
+                s_Gca[(j + 1) * MTP + m] += dca1 + s_wq[j + 1] * s_dsm[m];
             }
-            r_tmp[m * LDA + j] = dwk;
+            r_tmp[m * LDA + j] = dwk0;
+            r_tmp[m * LDA + j + 1] = dwk1;
         }
         __syncthreads();
         if (tid < kU) {                                       // fixed-order reduction over the tile's dialogues
