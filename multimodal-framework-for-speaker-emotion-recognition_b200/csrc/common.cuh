@@ -119,7 +119,7 @@ __device__ __forceinline__ void fma_row(Acc<MT> &acc, const float4 w, const floa
 
 #if LSTHM_MAC_VARIANT == 1
 // double-buffered blocks of 4 k-rows (8 weight quads live): deepest prefetch, highest register use
-template <int MT, int MTP>
+template <int MT, int MTP, int KB_UNUSED = 0>
 __device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, const int ldw4,
                                     const float *__restrict__ act, const int n) {
     const int n4 = n & ~3;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, 
 }
 #elif LSTHM_MAC_VARIANT == 2
 // double-buffered blocks of 2 k-rows (4 weight quads live)
-template <int MT, int MTP>
+template <int MT, int MTP, int KB_UNUSED = 0>
 __device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, const int ldw4,
                                     const float *__restrict__ act, const int n) {
     const int n2 = n & ~1;
@@ -199,11 +199,15 @@ __device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, 
     if (k < n) fma_row<MT, MTP>(acc, __ldg(p), act);
 }
 #else
-// single-buffered blocks of LSTHM_MAC_VARIANT (4 or 8) k-rows: all loads of a block first, then the FMAs
-template <int MT, int MTP>
+// single-buffered blocks of KB (4 or 8) k-rows: all loads of a block first, then the FMAs.  Measured on B200 (N=1024,
+// T=110): mab_fwd is fastest with KB = 8 (5.00 vs 5.22 ms), mab_bwd with KB = 4 (5.40 vs 5.82 ms), both sps kernels
+// with KB = 8 (sps_bwd 7.86 vs 8.50 ms).
+#ifndef LSTHM_MAC_BWD
+#define LSTHM_MAC_BWD 4
+#endif
+template <int MT, int MTP, int KB = LSTHM_MAC_VARIANT>
 __device__ __forceinline__ void mac(Acc<MT> &acc, const float4 *__restrict__ w, const int ldw4,
                                     const float *__restrict__ act, const int n) {
-    constexpr int KB = LSTHM_MAC_VARIANT;
     const size_t ld = (size_t)ldw4;
     const float4 *p = w;
     int k = 0;
@@ -235,17 +239,7 @@ __device__ __forceinline__ void store_partial(float *part, const int J, const in
             make_float4(acc.get(0, m), acc.get(1, m), acc.get(2, m), acc.get(3, m));
 }
 
-// Counter-based Bernoulli(1-p) keep decision for in-kernel dropout: two rounds of a 32-bit integer finaliser
-// ("lowbias32") over a key built from (seed, row id, column id).  Forward and backward call it with the same
-// arguments, so no mask is ever stored.  Returns the dropout scale: 0 or 1/(1-p).
-__device__ __forceinline__ float dropout_scale(unsigned long long seed, uint32_t a, uint32_t b, float p) {
-    uint32_t x = (uint32_t)seed ^ (a * 0x9E3779B9u) ^ ((uint32_t)(seed >> 32) + b * 0x85EBCA6Bu);
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    x += a; x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return (float)(x >> 8) * (1.0f / 16777216.0f) < p ? 0.f : 1.0f / (1.0f - p);
-}
-
-// Cheaper variant for dense attention dropout: ONE one-round hash per PAIR of adjacent columns, 16 random bits per
+// Counter-based in-kernel dropout for dense attention tiles: ONE one-round 32-bit integer finaliser ("lowbias32") per PAIR of adjacent columns, 16 random bits per
 // element (keep iff bits >= round(p * 65536); scale 65536 / (65536 - thr), so the mask is exactly unbiased).  `a`
 // names the (step, dialogue) tile, `row` / `col` the element; forward and backward evaluate the same function.
 struct PairDrop {

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 const int quad = item % nq, sp = item / nq, k0 = sp * L.b1chunk, n = min(D, k0 + L.b1chunk) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Wf2) + (size_t)k0 * nq + quad, nq,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Wf2) + (size_t)k0 * nq + quad, nq,
                                  s_gz + k0 * MTP, n);
                 store_partial<MT, MTP>(s_p2, MH, sp, 4 * quad, acc);
             }
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 const int quad = item % nq, sp = item / nq, k0 = sp * L.b2chunk, n = min(MH, k0 + L.b2chunk) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Wf1) + (size_t)k0 * nq + quad, nq,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Wf1) + (size_t)k0 * nq + quad, nq,
                                  s_dup + k0 * MTP, n);
                 store_partial<MT, MTP>(s_p2, R, sp, 4 * quad, acc);
             }
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
             const int k0 = sp * L.b3chunk[m], n = min(L.rd[m], k0 + L.b3chunk[m]) - k0;
             acc.zero();
             if (n > 0)
-                mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Wr[m]) + (size_t)k0 * nq + quad, nq,
+                mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Wr[m]) + (size_t)k0 * nq + quad, nq,
                              s_dr + (L.roff[m] + k0) * MTP, n);
             store_partial<MT, MTP>(s_p2 + a.S.b3pb[m], 4 * L.dh[m], sp, 4 * quad, acc);
         }
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 const int quad = item % nqd, sp = item / nqd, k0 = sp * L.b4chunk, n = min(G, k0 + L.b4chunk) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Watt) + (size_t)k0 * nqd + quad, nqd,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Watt) + (size_t)k0 * nqd + quad, nqd,
                                  s_km + k0 * MTP, n);
                 store_partial<MT, MTP>(s_pA, D, sp, 4 * quad, acc);
             }
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 const int quad = item % nqd, sp = item / nqd, k0 = sp * L.b4chunk, n = min(G, k0 + L.b4chunk) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.packed + L.vcat) + (size_t)k0 * nqd + quad, nqd,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.packed + L.vcat) + (size_t)k0 * nqd + quad, nqd,
                                  s_km + k0 * MTP, n);
                 store_partial<MT, MTP>(s_pA, D, sp, 4 * quad, acc);
             }
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                 const int k0 = sp * L.b5chunk[m], n = min(4 * L.dh[m], k0 + L.b5chunk[m]) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.U[m]) + (size_t)k0 * nq + quad, nq,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.U[m]) + (size_t)k0 * nq + quad, nq,
                                  s_km + (L.goff[m] + k0) * MTP, n);
                 store_partial<MT, MTP>(s_p2 + a.S.b5pb[m], L.dh[m], sp, 4 * quad, acc);
             }
