@@ -224,9 +224,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # the contract is ONE line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # the contract is ONE line on stdout: NCCL prints its "NCCL version ..." banner (any NCCL_DEBUG level >= VERSION)
+        # to stdout unless told otherwise, so send NCCL's log stream to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.seq, args.batch
     torch.manual_seed(111)
