@@ -224,8 +224,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # the contract is ONE line on stdout: NCCL prints its "NCCL version ..." banner (any NCCL_DEBUG level >= VERSION)
-        # to stdout unless told otherwise, so send NCCL's log stream to stderr
+        # the contract is ONE line on stdout: NCCL prints its "NCCL version ..." banner to stdout at NCCL_DEBUG=VERSION
+        # (what this image sets) and honours NCCL_DEBUG_FILE only above that level -> raise to WARN and log to stderr
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     T, B = args.seq, args.batch
