@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTHM_ABI_VERSION 4
+#define LSTHM_ABI_VERSION 5
 #define LSTHM_MAX_MOD 3
 
 int lsthm_abi_version(void);
@@ -62,42 +62,49 @@ typedef struct {
     const float *Wf2, *bf2;           /* fc.3 [D][map_h]                                      */
 } lsthm_mab_weights;
 
-/* Number of floats of the packed (k-major / gate-interleaved) weight image the kernels stream. */
+/* Number of floats of the packed weight image the kernels stream (k-major / gate-interleaved copies of U and Watt,
+ * and the COMPOSITE weights: the chain has no nonlinearity between reduce_dim_nn_m and fc.0 (HybridRNN_ATV.py:126-129),
+ * nor between fc.3 and the V term of the next step's gates (:129 -> :25), so the kernels use
+ *     W1 = Wf1 . blockdiag(Wr_m)  [map_h x 4D],  b1 = Wf1 br + bf1      and      W2 = Vcat . Wf2  [4D x map_h],  bv = Vcat bf2
+ * (composed in fp64 at pack time): three dependent products per step instead of five, 28 % fewer serial MACs). */
 size_t lsthm_mab_packed_floats(const lsthm_mab_desc *d);
 
-/* Re-layout the weights into `packed` (call after every optimizer step, before fwd/bwd). */
+/* Re-layout / compose the weights into `packed` (call after every optimizer step, before fwd/bwd). */
 int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, float *packed, void *stream);
 
 /*
  * Forward recurrence over all T steps.
  *   gx        [T][N][4D]   W_m x_m + bW_m + bU_m + bV_m, cell-major, f|i|o|g inside a cell
  *   drop_mask [T][N][map_h] keep/(1-p) mask of fc's Dropout, or NULL (eval mode)
- *   hz        [T][N][2D]   out: [h_t | z_t]   (what nn_out consumes, HybridRNN_ATV.py:139)
+ *   hz        [T][N][2D]   out: the h_t half of [h_t | z_t] (what nn_out consumes, HybridRNN_ATV.py:139); the z_t half is
+ *                          NOT written: z_t = fc.3(u_t) = u_t Wf2^T + bf2 is one time-parallel product over all T*N rows
+ *                          that the caller forms from `u` (nothing on the serial path needs z_t any more)
+ *   u         [T][N][map_h] out: fc hidden after ReLU and dropout (HybridRNN_ATV.py:66)
  *   stash (all out, may ALL be NULL for inference):
- *     sC [T][N][D]  cell states      sG [T][N][4D] gates after sigmoid/tanh (layout of gx)
- *     sA [T][N][4][D] softmax weights   sR [T][N][R] reduce outputs   sU [T][N][map_h] fc hidden
+ *     sC [T][N][D]  cell states      sG [T][N][4D] gates after sigmoid/tanh (layout of gx)      sA [T][N][4][D] softmax weights
  */
 int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx, const float *drop_mask,
-                  float *hz, float *sC, float *sG, float *sA, float *sR, float *sU, void *stream);
+                  float *hz, float *u, float *sC, float *sG, float *sA, void *stream);
 
 /*
- * BPTT.  `w` gives the native-layout weights (the transposed products read them directly),
- * `packed` the image from lsthm_mab_pack (for the concatenated V).
- *   dhz  [T][N][2D]  dL/d[h_t|z_t] from the head
+ * BPTT.  `w` gives the native-layout weights (the transposed products of U and Watt read them directly),
+ * `packed` the image from lsthm_mab_pack (composite weights).
+ *   dhz  [T][N][2D]  dL/d[h_t|z_t] from the head (the kernel reads the h half)
+ *   duz  [T][N][map_h]  (dL/dz_t from the head) . Wf2 — the head's gradient pulled through fc.3, one time-parallel
+ *                    product formed by the caller
  * out (the adjoints the time-parallel weight-gradient products consume):
- *   dgx  [T][N][4D]  dL/d(gate pre-activations)  -> dW,dU,dV,db and dx
+ *   dgx  [T][N][4D]  dL/d(gate pre-activations) ds_t  -> dW,dU,dV,db and dx; also the carried part of dL/dz:
+ *                    dL/dz_t(total) = dL/dz_t(head) + ds_{t+1} . Vcat  -> d fc.3
  *   de   [T][N][4D]  dL/d(att logits)            -> d att.0
- *   dr   [T][N][R]   dL/d(reduce outputs)        -> d reduce_dim_nn_*
- *   dup  [T][N][map_h] dL/d(fc.0 pre-activation) -> d fc.0
- *   dzt  [T][N][D]   total dL/dz_t               -> d fc.3
+ *   dup  [T][N][map_h] dL/d(fc.0 pre-activation) -> d fc.0, and dr = dup . Wf1 -> d reduce_dim_nn_*
  *   att  [T][N][4D]  (optional, may be NULL) the attended features a * c of the forward, regrouped per modality and
  *                    head-major inside a modality (columns 4*off_m + head*dh_m + j): column block m is the operand
- *                    of d reduce_dim_nn_m, so the host needs no elementwise product / regroup copy for it
+ *                    of d reduce_dim_nn_m and of the recomputed reduce outputs r_m = att_m Wr_m^T + br_m
  */
 int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed,
-                  const float *dhz, const float *drop_mask,
-                  const float *sC, const float *sG, const float *sA, const float *sU,
-                  float *dgx, float *de, float *dr, float *dup, float *dzt, float *att, void *stream);
+                  const float *dhz, const float *duz, const float *drop_mask,
+                  const float *sC, const float *sG, const float *sA, const float *u,
+                  float *dgx, float *de, float *dup, float *att, void *stream);
 
 /* Launch geometry the library would use (for roofline bookkeeping in bench.py). */
 int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows,

@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
 SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_MOD = 3
 
 _f32p = C.POINTER(C.c_float)
@@ -89,9 +89,9 @@ def lib() -> C.CDLL:
     L.lsthm_mab_pack.restype = C.c_int
     L.lsthm_mab_pack.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights), C.c_void_p, C.c_void_p]
     L.lsthm_mab_fwd.restype = C.c_int
-    L.lsthm_mab_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 10
+    L.lsthm_mab_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 9
     L.lsthm_mab_bwd.restype = C.c_int
-    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 14
+    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 13
     L.lsthm_mab_launch_info.restype = C.c_int
     L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 5
     L.lsthm_sps_packed_floats.restype = C.c_size_t
@@ -196,18 +196,18 @@ def mab_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
     _check(lib().lsthm_mab_pack(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _stream()), "lsthm_mab_pack")
 
 
-def mab_fwd(d: MabDesc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU) -> None:
+def mab_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sG, sA) -> None:
+    """Writes the h half of hz[T,N,2D] and u[T,N,map_h]; the caller forms z = u Wf2^T + bf2 (include/lsthm_b200.h)."""
     _check(lib().lsthm_mab_fwd(C.byref(d), _dev_ptr(packed, "packed"), _dev_ptr(gx, "gx"),
-                               _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(hz, "hz"), _dev_ptr(sC, "sC"),
-                               _dev_ptr(sG, "sG"), _dev_ptr(sA, "sA"), _dev_ptr(sR, "sR"), _dev_ptr(sU, "sU"),
-                               _stream()), "lsthm_mab_fwd")
+                               _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(hz, "hz"), _dev_ptr(u, "u"), _dev_ptr(sC, "sC"),
+                               _dev_ptr(sG, "sG"), _dev_ptr(sA, "sA"), _stream()), "lsthm_mab_fwd")
 
 
-def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt, att=None) -> None:
-    _check(lib().lsthm_mab_bwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"),
+def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, duz, drop_mask, sC, sG, sA, u, dgx, de, dup, att=None) -> None:
+    _check(lib().lsthm_mab_bwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"), _dev_ptr(duz, "duz"),
                                _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"),
-                               _dev_ptr(sA, "sA"), _dev_ptr(sU, "sU"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
-                               _dev_ptr(dr, "dr"), _dev_ptr(dup, "dup"), _dev_ptr(dzt, "dzt"), _dev_ptr(att, "att"), _stream()),
+                               _dev_ptr(sA, "sA"), _dev_ptr(u, "u"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
+                               _dev_ptr(dup, "dup"), _dev_ptr(att, "att"), _stream()),
            "lsthm_mab_bwd")
 
 
@@ -312,8 +312,10 @@ def _mat(t: torch.Tensor, name: str):
     return t.data_ptr(), t.stride(0)
 
 
-def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """mode NT: a[M,K] @ b[N,K]^T (+bias);  NN: a[M,K] @ b[K,N];  TN: a[K,M]^T @ b[K,N]."""
+def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mode NT: a[M,K] @ b[N,K]^T (+bias);  NN: a[M,K] @ b[K,N];  TN: a[K,M]^T @ b[K,N].
+    ``out`` (optional): a 2-D fp32 CUDA view [M, N] with unit inner stride (e.g. a column block of a wider matrix)."""
     if mode in (GEMM_NT, GEMM_NT_RELU):
         M, K = a.shape; N = b.shape[0]; assert b.shape[1] == K
     elif mode == GEMM_NN:
@@ -322,7 +324,13 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
         K, M = a.shape; N = b.shape[1]; assert b.shape[0] == K
     pa, lda = _mat(a, "a")
     pb, ldb = _mat(b, "b")
-    c = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    if out is None:
+        c, ldc = torch.empty(M, N, device=a.device, dtype=torch.float32), N
+    else:
+        if tuple(out.shape) != (M, N):
+            raise RuntimeError(f"gemm3: out has shape {tuple(out.shape)}, expected {(M, N)}")
+        c = out
+        _, ldc = _mat(out, "out")
     base_mode = mode
     if PRECISION == "bf16":
         mode |= GEMM_BF16
@@ -330,12 +338,12 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
         # B is a layer weight and there are many rows: pre-split weight images + 128 x 256 tiles
         nbytes = lib().lsthm_gemm3w_pack_bytes(N, K)
         pack = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
-        _check(lib().lsthm_gemm3w(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), N, pack.data_ptr(), nbytes,
+        _check(lib().lsthm_gemm3w(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), ldc, pack.data_ptr(), nbytes,
                                   _stream()), "lsthm_gemm3w")
         return c
     nws = lib().lsthm_gemm3_workspace_floats(mode, M, N, K)
     ws = torch.empty(nws, device=a.device, dtype=torch.float32) if nws else None
-    _check(lib().lsthm_gemm3(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), N,
+    _check(lib().lsthm_gemm3(mode, M, N, K, pa, lda, pb, ldb, _dev_ptr(bias, "bias"), c.data_ptr(), ldc,
                              None if ws is None else ws.data_ptr(), nws, _stream()), "lsthm_gemm3")
     return c
 

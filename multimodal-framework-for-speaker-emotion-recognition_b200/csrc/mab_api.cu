@@ -21,6 +21,53 @@ __global__ void mab_pack_kernel(const __grid_constant__ PackJobs jobs, float *__
 }
 
 
+// Composite weights (fp64 accumulation, rounded once to fp32):
+//   W1 = Wf1 . blockdiag(Wr_m)  [MH x 4D]  (columns in the attended order k = head*D + j),   b1 = Wf1 br + bf1
+//   W2 = Vcat . Wf2             [4D x MH]  (rows in the native gate order),                  bv = Vcat bf2
+// written to every image that uses them (see MabLayout).
+__global__ void mab_compose_kernel(const __grid_constant__ ComposeArgs a, float *__restrict__ packed) {
+    const MabLayout &L = a.L;
+    const int D = L.D, G = L.G, MH = L.MH, R = L.R;
+    const int n1 = MH * G, n2 = G * MH, total = n1 + n2 + MH + G;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        if (idx < n1) {                                        // W1[col][k]
+            const int col = idx / G, k = idx - col * G, head = k / D, j = k - head * D;
+            int m = 0;
+            while (m + 1 < L.nm && j >= L.off[m + 1]) ++m;
+            const int jl = j - L.off[m], dh = L.dh[m];
+            double s = 0.0;
+            for (int r = 0; r < L.rd[m]; ++r)
+                s += (double)__ldg(a.Wf1 + (size_t)col * R + L.roff[m] + r) * (double)__ldg(a.Wr[m] + (size_t)r * 4 * dh + head * dh + jl);
+            packed[L.w1 + (size_t)k * MH + col] = (float)s;
+            packed[L.w1n + (size_t)col * G + k] = (float)s;
+        } else if (idx < n1 + n2) {                            // W2[g][q], g = goff_m + gate*dh_m + jl
+            const int i2 = idx - n1, g = i2 / MH, q = i2 - g * MH;
+            int m = 0;
+            while (m + 1 < L.nm && g >= L.goff[m + 1]) ++m;
+            const int lg = g - L.goff[m], dh = L.dh[m], gate = lg / dh, jl = lg - gate * dh;
+            const float *vrow = a.V[m] + (size_t)lg * D;
+            double s = 0.0;
+            for (int j = 0; j < D; ++j) s += (double)__ldg(vrow + j) * (double)__ldg(a.Wf2 + (size_t)j * MH + q);
+            packed[L.w2n + (size_t)g * MH + q] = (float)s;
+            packed[L.wg[m] + (size_t)(dh + q) * 4 * dh + 4 * jl + gate] = (float)s;      // forward image: row dh+q, gate-interleaved column
+        } else if (idx < n1 + n2 + MH) {                       // b1
+            const int col = idx - n1 - n2;
+            double s = (double)__ldg(a.bf1 + col);
+            for (int m = 0; m < L.nm; ++m)
+                for (int r = 0; r < L.rd[m]; ++r) s += (double)__ldg(a.Wf1 + (size_t)col * R + L.roff[m] + r) * (double)__ldg(a.br[m] + r);
+            packed[L.b1 + col] = (float)s;
+        } else {                                               // bv
+            const int g = idx - n1 - n2 - MH;
+            int m = 0;
+            while (m + 1 < L.nm && g >= L.goff[m + 1]) ++m;
+            const float *vrow = a.V[m] + (size_t)(g - L.goff[m]) * D;
+            double s = 0.0;
+            for (int j = 0; j < D; ++j) s += (double)__ldg(vrow + j) * (double)__ldg(a.bf2 + j);
+            packed[L.bvz + g] = (float)s;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -55,42 +102,27 @@ static int build_layout(const lsthm_mab_desc *d, MabLayout &L) {
     L.ldc = L.D + ((4 - L.D % 32) + 32) % 32;
     L.smchunk = rup(cdiv(D, L.nwarp), 8);
     int o = 0;
-    for (int m = 0; m < L.nm; ++m) { L.wg[m] = o; o += (L.dh[m] + D) * 4 * L.dh[m]; }
+    for (int m = 0; m < L.nm; ++m) { L.wg[m] = o; o += (L.dh[m] + L.MH) * 4 * L.dh[m]; }
     L.watt = o; o += D * L.G;
-    for (int m = 0; m < L.nm; ++m) { L.wr[m] = o; o += 4 * L.dh[m] * L.rd[m]; }
-    L.wf1 = o; o += R * L.MH;
-    L.wf2 = o; o += L.MH * D;
+    L.w1 = o; o += L.G * L.MH;
+    L.w1n = o; o += L.MH * L.G;
+    L.w2n = o; o += L.G * L.MH;
     L.batt = o; o += L.G;
-    L.br = o; o += R;
-    L.bf1 = o; o += L.MH;
-    L.bf2 = o; o += D;
-    L.vcat = o; o += L.G * D;
+    L.b1 = o; o += L.MH;
+    L.bvz = o; o += L.G;
     L.total = o;
-    // forward split-K plans
-    L.s3total = 0;
-    for (int m = 0; m < L.nm; ++m) {
-        L.s3chunk[m] = L.dh[m] >= 32 ? 32 : L.dh[m];
-        if (L.dh[m] % L.s3chunk[m]) return fail("cell size must be <32 or a multiple of 32");
-        L.s3ns[m] = 4 * L.dh[m] / L.s3chunk[m];
-        L.s3items[m] = (L.rd[m] / 4) * L.s3ns[m];
-        L.s3total += L.s3items[m];
-    }
-    L.s4chunk = 16; L.s4ns = cdiv(R, 16);
-    L.s5chunk = 8;  L.s5ns = cdiv(L.MH, 8);
+    if (D + L.MH > L.nt) return fail("unsupported dims (D + map_h exceeds the CTA width)");
+    // forward split-K plan of the fused reduce+fc.0 product (K = 4D)
+    L.s34chunk = 64; L.s34ns = cdiv(L.G, 64);
     // backward split-K plans
-    L.b1ns = 16; L.b1chunk = cdiv(D, 16);
-    L.b2chunk = 16; L.b2ns = cdiv(L.MH, 16);
-    L.b3total = 0; L.b5total = 0;
+    L.b5total = 0;
     for (int m = 0; m < L.nm; ++m) {
-        L.b3ns[m] = std::min(4, std::max(1, L.rd[m] / 32));
-        L.b3chunk[m] = cdiv(L.rd[m], L.b3ns[m]);
-        L.b3items[m] = L.dh[m] * L.b3ns[m];
-        L.b3total += L.b3items[m];
         L.b5chunk[m] = 64; L.b5ns[m] = cdiv(4 * L.dh[m], 64);
         L.b5items[m] = (L.dh[m] / 4) * L.b5ns[m];
         L.b5total += L.b5items[m];
     }
     L.b4ns = 8; L.b4chunk = cdiv(L.G, 8);
+    L.b5uchunk = 64; L.b5uns = cdiv(L.G, 64);
     return 0;
 }
 
@@ -98,19 +130,14 @@ static void fwd_smem(const MabLayout &L, int MT, FwdSmem &S) {
     const int MTP = (MT + 3) & ~3;
     int o = 8;  // two mbarriers
     S.h = o; o += L.D * MTP;
-    S.z = o; o += L.D * MTP;
     S.c = o; o += L.D * MTP;
     S.km = o; o += L.G * MTP;
     S.row = o; o += MTP * L.ldr;
-    S.r = o; o += L.R * MTP;
     S.u = o; o += L.MH * MTP;
     S.red = o; o += L.nwarp * kHeads * MTP * 2;
     S.fin = o; o += kHeads * MTP * 2;
-    int part = std::max(L.G * MTP, MTP * L.ldr), p3 = 0;
-    for (int m = 0; m < L.nm; ++m) { S.s3pb[m] = p3; p3 += L.s3ns[m] * MTP * L.rd[m]; }
-    part = std::max(part, p3);
-    part = std::max(part, L.s4ns * MTP * L.MH);
-    part = std::max(part, L.s5ns * MTP * L.D);
+    int part = std::max(L.G * MTP, MTP * L.ldr);
+    part = std::max(part, L.s34ns * MTP * L.MH);
     S.part = o; o += part;
     S.gx = o; o += 2 * MT * L.G;
     S.mask = o; o += 2 * MT * L.MH;
@@ -122,27 +149,21 @@ static void bwd_smem(const MabLayout &L, int MT, BwdSmem &S) {
     const int MTP = (MT + 3) & ~3;
     int o = 8;  // two mbarriers
     S.dh = o; o += L.D * MTP;
-    S.dz = o; o += L.D * MTP;
+    S.du = o; o += L.MH * MTP;
     S.dc = o; o += L.D * MTP;
     S.gh = o; o += L.D * MTP;
-    S.gz = o; o += L.D * MTP;
     S.dup = o; o += L.MH * MTP;
-    S.dr = o; o += L.R * MTP;
     S.km = o; o += L.G * MTP;
     S.C = o; o += MTP * L.ldc;
-    S.A = o; o += MTP * L.ldr;      // A tile, then (with the dvec rows) the B4/B5 dz partials
+    S.A = o; o += MTP * L.ldr;      // A tile, then (with the dvec rows) the B4 dc / B5 du partials
     S.row = o; o += MTP * L.ldr;
-    int p2 = L.b1ns * MTP * L.MH, p3 = 0, p5 = 0;
-    p2 = std::max(p2, L.b2ns * MTP * L.R);
-    for (int m = 0; m < L.nm; ++m) {
-        S.b3pb[m] = p3; p3 += L.b3ns[m] * MTP * 4 * L.dh[m];
-        S.b5pb[m] = p5; p5 += L.b5ns[m] * MTP * L.dh[m];
-    }
-    p2 = std::max(p2, std::max(p3, p5));
-    S.p2 = o; o += p2;
+    int p5 = 0;
+    for (int m = 0; m < L.nm; ++m) { S.b5pb[m] = p5; p5 += L.b5ns[m] * MTP * L.dh[m]; }
+    S.p2 = o; o += p5;
     S.red = o; o += L.nwarp * kHeads * MTP;
     S.fin = o; o += kHeads * MTP;
     S.dhz = o; o += 2 * MT * 2 * L.D;
+    S.duz = o; o += 2 * MT * L.MH;
     S.uh = o; o += 2 * MT * L.MH;
     S.mk = o; o += 2 * MT * L.MH;
     S.total = o;
@@ -236,56 +257,53 @@ int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, float *p
         if (!w->U[m] || !w->V[m] || !w->Wr[m] || !w->br[m]) return fail("null weight pointer");
         const int dh = L.dh[m];
         add(w->U[m], L.wg[m], 4 * dh, dh, 4 * dh, 0, dh);
-        add(w->V[m], L.wg[m], 4 * dh, L.D, 4 * dh, dh, dh);
-        add(w->Wr[m], L.wr[m], L.rd[m], 4 * dh, L.rd[m], 0, 0);
-        add(w->br[m], L.br + L.roff[m], L.rd[m], 1, L.rd[m], 0, 0);
-        add(w->V[m], L.vcat + L.goff[m] * L.D, 1, 4 * dh * L.D, 1, 0, 0);
     }
     if (!w->Watt || !w->batt || !w->Wf1 || !w->bf1 || !w->Wf2 || !w->bf2) return fail("null weight pointer");
     add(w->Watt, L.watt, L.G, L.D, L.G, 0, 0);
     add(w->batt, L.batt, L.G, 1, L.G, 0, 0);
-    add(w->Wf1, L.wf1, L.MH, L.R, L.MH, 0, 0);
-    add(w->bf1, L.bf1, L.MH, 1, L.MH, 0, 0);
-    add(w->Wf2, L.wf2, L.D, L.MH, L.D, 0, 0);
-    add(w->bf2, L.bf2, L.D, 1, L.D, 0, 0);
     jobs.n = n;
     mab_pack_kernel<<<dim3(32, n), 256, 0, (cudaStream_t)stream>>>(jobs, packed);
-    return check_cuda("lsthm_mab_pack launch");
+    if (check_cuda("lsthm_mab_pack launch")) return 1;
+    ComposeArgs c;
+    c.L = L;
+    for (int m = 0; m < kMaxMod; ++m) { c.V[m] = w->V[m]; c.Wr[m] = w->Wr[m]; c.br[m] = w->br[m]; }
+    c.Wf1 = w->Wf1; c.bf1 = w->bf1; c.Wf2 = w->Wf2; c.bf2 = w->bf2;
+    mab_compose_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(c, packed);
+    return check_cuda("lsthm_mab_pack compose launch");
 }
 
 int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx, const float *drop_mask, float *hz,
-                  float *sC, float *sG, float *sA, float *sR, float *sU, void *stream) {
+                  float *u, float *sC, float *sG, float *sA, void *stream) {
     FwdArgs a;
     if (build_layout(d, a.L)) return 1;
-    if (!packed || !gx || !hz) return fail("null packed/gx/hz pointer");
-    const bool any = sC || sG || sA || sR || sU, all = sC && sG && sA && sR && sU;
+    if (!packed || !gx || !hz || !u) return fail("null packed/gx/hz/u pointer");
+    const bool any = sC || sG || sA, all = sC && sG && sA;
     if (any && !all) return fail("stash pointers must be all set or all NULL");
     const int MT = pick_rows(d, true);
     fwd_smem(a.L, MT, a.S);
     const size_t bytes = (size_t)a.S.total * 4;
     if (bytes > kMaxSmemBytes) return fail("forward tile does not fit in shared memory");
     a.packed = packed; a.gx = gx; a.mask = drop_mask;
-    a.hz = hz; a.sC = sC; a.sG = sG; a.sA = sA; a.sR = sR; a.sU = sU;
+    a.hz = hz; a.sC = sC; a.sG = sG; a.sA = sA; a.sU = u;
     const int grid = cdiv(a.L.N, MT);
     return kFwd[MT - 1](a, grid, bytes, (cudaStream_t)stream);
 }
 
 int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed, const float *dhz,
-                  const float *drop_mask, const float *sC, const float *sG, const float *sA, const float *sU,
-                  float *dgx, float *de, float *dr, float *dup, float *dzt, float *att, void *stream) {
+                  const float *duz, const float *drop_mask, const float *sC, const float *sG, const float *sA, const float *u,
+                  float *dgx, float *de, float *dup, float *att, void *stream) {
     BwdArgs a;
     if (build_layout(d, a.L)) return 1;
-    if (!w || !packed || !dhz || !sC || !sG || !sA || !sU || !dgx || !de || !dr || !dup || !dzt)
-        return fail("null pointer argument");
+    if (!w || !packed || !dhz || !duz || !sC || !sG || !sA || !u || !dgx || !de || !dup) return fail("null pointer argument");
     const int MT = pick_rows(d, true);
     bwd_smem(a.L, MT, a.S);
     const size_t bytes = (size_t)a.S.total * 4;
     if (bytes > kMaxSmemBytes) return fail("backward tile does not fit in shared memory");
     a.packed = packed;
-    for (int m = 0; m < kMaxMod; ++m) { a.U[m] = w->U[m]; a.Wr[m] = w->Wr[m]; }
-    a.Watt = w->Watt; a.Wf1 = w->Wf1; a.Wf2 = w->Wf2;
-    a.dhz = dhz; a.mask = drop_mask; a.sC = sC; a.sG = sG; a.sA = sA; a.sU = sU;
-    a.dgx = dgx; a.de = de; a.dr = dr; a.dup = dup; a.dzt = dzt; a.att = att;
+    for (int m = 0; m < kMaxMod; ++m) a.U[m] = w->U[m];
+    a.Watt = w->Watt;
+    a.dhz = dhz; a.duz = duz; a.mask = drop_mask; a.sC = sC; a.sG = sG; a.sA = sA; a.sU = u;
+    a.dgx = dgx; a.de = de; a.dup = dup; a.att = att;
     const int grid = cdiv(a.L.N, MT);
     return kBwd[MT - 1](a, grid, bytes, (cudaStream_t)stream);
 }

@@ -33,40 +33,44 @@ struct MabLayout {
     int T, N, nm, MH, D, G, R;
     int dh[kMaxMod], off[kMaxMod], goff[kMaxMod], rd[kMaxMod], roff[kMaxMod];
     // packed weight image (float offsets)
-    int wg[kMaxMod], watt, wr[kMaxMod], wf1, wf2, batt, br, bf1, bf2, vcat, total;
+    // packed image offsets (floats).  Composite weights (the chain has no nonlinearity between reduce_m and fc.0, nor
+    // between fc.3 and the V term of the next step's gates):  W1 = Wf1 . blockdiag(Wr_m) [MH x 4D],  b1 = Wf1 br + bf1,
+    // W2 = Vcat . Wf2 [4D x MH],  bv = Vcat bf2.
+    //   wg[m]  [(dh_m + MH)][4 dh_m]  rows: U_m^T then W2_m^T, columns gate-interleaved        (forward gates)
+    //   watt   [D][4D]                 Watt^T                                                   (forward logits)
+    //   w1     [4D][MH]                W1^T, rows in the attended order k = head*D + j           (forward fused reduce+fc.0)
+    //   w1n    [MH][4D]                W1                                                       (backward d attended)
+    //   w2n    [4D][MH]                W2, rows in the native gate order                         (backward du carry)
+    int wg[kMaxMod], watt, w1, w1n, w2n, batt, b1, bvz, total;
     int nt, nwarp, ldr, ldc, smchunk;
     // split-K plans (forward)
-    int s3chunk[kMaxMod], s3ns[kMaxMod], s3items[kMaxMod], s3total;
-    int s4ns, s4chunk, s5ns, s5chunk;
+    int s34ns, s34chunk;
     // split-K plans (backward)
-    int b1ns, b1chunk, b2ns, b2chunk;
-    int b3ns[kMaxMod], b3chunk[kMaxMod], b3items[kMaxMod], b3total;
-    int b4ns, b4chunk;
+    int b4ns, b4chunk, b5uns, b5uchunk;
     int b5ns[kMaxMod], b5chunk[kMaxMod], b5items[kMaxMod], b5total;
 };
 
 struct FwdSmem {  // float offsets
-    int h, z, c, km, row, r, u, red, fin, part, gx, mask, batt, total;
-    int s3pb[kMaxMod];
+    int h, c, km, row, u, red, fin, part, gx, mask, batt, total;
 };
 struct BwdSmem {
-    int dh, dz, dc, gh, gz, dup, dr, km, C, A, row, p2, red, fin, dhz, uh, mk, total;
-    int b3pb[kMaxMod], b5pb[kMaxMod];
+    int dh, du, dc, gh, dup, km, C, A, row, p2, red, fin, dhz, duz, uh, mk, total;
+    int b5pb[kMaxMod];
 };
 
 struct FwdArgs {
     MabLayout L;
     FwdSmem S;
     const float *packed, *gx, *mask;
-    float *hz, *sC, *sG, *sA, *sR, *sU;
+    float *hz, *sC, *sG, *sA, *sU;
 };
 struct BwdArgs {
     MabLayout L;
     BwdSmem S;
     const float *packed;
-    const float *U[kMaxMod], *Wr[kMaxMod], *Watt, *Wf1, *Wf2;
-    const float *dhz, *mask, *sC, *sG, *sA, *sU;
-    float *dgx, *de, *dr, *dup, *dzt;
+    const float *U[kMaxMod], *Watt;
+    const float *dhz, *duz, *mask, *sC, *sG, *sA, *sU;
+    float *dgx, *de, *dup;
     float *att;   // [T][N][G] attended = a * c regrouped per modality, head-major (HybridRNN_ATV.py:125-128): the operand of d reduce_m
 };
 
@@ -84,6 +88,10 @@ struct PackJobs {
     PackJob j[24];
     int n;
 };
+struct ComposeArgs {          // inputs of the composite-weight kernel (native nn.Linear layouts)
+    MabLayout L;
+    const float *V[kMaxMod], *Wr[kMaxMod], *br[kMaxMod], *Wf1, *bf1, *Wf2, *bf2;
+};
 
 // ---------------------------------------------------------------------------------------------
 // forward
@@ -95,12 +103,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
     extern __shared__ __align__(16) float smem[];
     const MabLayout &L = a.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int D = L.D, G = L.G, R = L.R, MH = L.MH, N = L.N, T = L.T;
+    const int D = L.D, G = L.G, MH = L.MH, N = L.N, T = L.T;
     const int n0 = blockIdx.x * MT;
     const int rows = min(MT, N - n0);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    float *s_h = smem + a.S.h, *s_z = smem + a.S.z, *s_c = smem + a.S.c, *s_km = smem + a.S.km;
-    float *s_row = smem + a.S.row, *s_r = smem + a.S.r, *s_u = smem + a.S.u, *s_red = smem + a.S.red;
+    float *s_h = smem + a.S.h, *s_c = smem + a.S.c, *s_km = smem + a.S.km;
+    float *s_row = smem + a.S.row, *s_u = smem + a.S.u, *s_red = smem + a.S.red;
     float *s_fin = smem + a.S.fin, *s_part = smem + a.S.part, *s_gx = smem + a.S.gx;
     float *s_mask = smem + a.S.mask, *s_batt = smem + a.S.batt;
     const float *__restrict__ packed = a.packed;
@@ -125,13 +133,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
         if (masked) bulk_g2s(s_mask, a.mask + (size_t)n0 * MH, mask_bytes, bar);
     }
 
-    // step-invariant role of this thread in the gate stage: (hidden unit j, K-half)
+    // step-invariant role of this thread in the gate stage: (hidden unit j, K-half); K = [h_m (dh_m) ; u (MH)]
     const bool s1_on = tid < 2 * D;
     const int s1_j = tid % D, s1_half = tid / D;
     int m1 = 0;
     while (m1 + 1 < L.nm && s1_j >= L.off[m1 + 1]) ++m1;
     const int s1_dh = L.dh[m1], s1_jl = s1_j - L.off[m1], s1_goff = L.goff[m1];
-    const int s1_kh = (s1_dh + D) / 2, s1_k0 = s1_half * s1_kh, s1_k1 = s1_k0 + s1_kh;
+    const int s1_kh = (s1_dh + MH) / 2, s1_k0 = s1_half * s1_kh, s1_k1 = s1_k0 + s1_kh;
+    // bv = Vcat bf2 of this unit's four gates: the constant part of V z_{t-1} = W2 u_{t-1} + bv for t >= 1 (z_{-1} = 0)
+    float bv4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (s1_on && s1_half == 0) {
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) bv4[g4] = __ldg(packed + L.bvz + s1_goff + g4 * s1_dh + s1_jl);
+    }
     const int nq2 = G / 4;
     // softmax lane mapping: lane = (jj, mm); warp w owns features [jb, je)
     const int jj = lane / MTP, mm = lane % MTP;
@@ -141,13 +155,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
     for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
         const size_t tn0 = (size_t)t * N + n0;
+        const float bvon = t > 0 ? 1.f : 0.f;
         if (tid == 0 && t + 1 < T) {
             mbar_expect_tx(bar + (buf ^ 1), gx_bytes + mask_bytes);
             bulk_g2s(s_gx + (buf ^ 1) * MT * G, a.gx + (tn0 + N) * G, gx_bytes, bar + (buf ^ 1));
             if (masked) bulk_g2s(s_mask + (buf ^ 1) * MT * MH, a.mask + (tn0 + N) * MH, mask_bytes, bar + (buf ^ 1));
         }
         Acc<MT> acc;
-        // ---- S1: gate pre-activations  U_m h_{t-1} + V_m z_{t-1}  (+ gx), then the LSTHM cell update
+        // ---- S1: gate pre-activations  U_m h_{t-1} + W2_m u_{t-1}  (+ gx + bv), then the LSTHM cell update
         if (s1_on) {
             acc.zero();
             const float4 *wp = reinterpret_cast<const float4 *>(packed + L.wg[m1]) + s1_jl;
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             if (s1_k0 < e1)
                 mac<MT, MTP>(acc, wp + (size_t)s1_k0 * s1_dh, s1_dh, s_h + (L.off[m1] + s1_k0) * MTP, e1 - s1_k0);
             const int b2 = max(s1_k0, s1_dh);
-            if (b2 < s1_k1) mac<MT, MTP>(acc, wp + (size_t)b2 * s1_dh, s1_dh, s_z + (b2 - s1_dh) * MTP, s1_k1 - b2);
+            if (b2 < s1_k1) mac<MT, MTP>(acc, wp + (size_t)b2 * s1_dh, s1_dh, s_u + (b2 - s1_dh) * MTP, s1_k1 - b2);
             if (s1_half == 1) store_partial<MT, MTP>(s_part, G, 0, s1_goff + 4 * s1_jl, acc);
         }
         __syncthreads();
@@ -168,10 +183,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             for (int m = 0; m < MT; ++m) {
                 const float4 pp = *reinterpret_cast<const float4 *>(s_part + m * G + s1_goff + 4 * s1_jl);
                 const float *gr = gxs + m * G;
-                const float f = sigmoidf_(acc.get(0, m) + pp.x + gr[0]);
-                const float ig = sigmoidf_(acc.get(1, m) + pp.y + gr[s1_dh]);
-                const float og = sigmoidf_(acc.get(2, m) + pp.z + gr[2 * s1_dh]);
-                const float gg = tanhf_(acc.get(3, m) + pp.w + gr[3 * s1_dh]);
+                const float f = sigmoidf_(acc.get(0, m) + pp.x + gr[0] + bvon * bv4[0]);
+                const float ig = sigmoidf_(acc.get(1, m) + pp.y + gr[s1_dh] + bvon * bv4[1]);
+                const float og = sigmoidf_(acc.get(2, m) + pp.z + gr[2 * s1_dh] + bvon * bv4[2]);
+                const float gg = tanhf_(acc.get(3, m) + pp.w + gr[3 * s1_dh] + bvon * bv4[3]);
                 const float c = f * cp[m] + ig * gg;
                 const float h = tanhf_(c) * og;
                 cn[m] = c;
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             s_fin[tid * 2 + 1] = 1.0f / S;
         }
         __syncthreads();
-        // ... and applied: a = softmax, attended = a * c  (k-major for the reduce products)
+        // ... and applied: a = softmax, attended = a * c  (k-major, row index head*D + j: the K order of W1)
         if (mvalid) {
 #pragma unroll
             for (int k = 0; k < kHeads; ++k) {
@@ -258,7 +273,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
             }
         }
         __syncthreads();
-        // ---- S3: per-modality reduce layers (head-major regroup), split-K items; + A tile copy-out
+        // ---- S34: fc hidden pre-activation straight from the attended features, v = W1 att + b1 with
+        //      W1 = Wf1 . blockdiag(Wr_m) composed at pack time (reduce_m and fc.0 have no nonlinearity between them);
+        //      + A tile copy-out
         if (stash) {
             for (int i = tid; i < rows * nq2; i += nt) {
                 const int m = i / nq2, c4 = i - m * nq2;
@@ -266,101 +283,49 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
                     *reinterpret_cast<const float4 *>(s_row + m * L.ldr + 4 * c4);
             }
         }
-        for (int item = tid; item < L.s3total; item += nt) {
-            int m = 0, local = item;
-            while (local >= L.s3items[m]) { local -= L.s3items[m]; ++m; }
-            const int nq = L.rd[m] / 4, quad = local % nq, sp = local / nq;
-            const int krow = sp * L.s3chunk[m], head = krow / L.dh[m], js = krow - head * L.dh[m];
-            acc.zero();
-            mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.wr[m]) + (size_t)krow * nq + quad, nq,
-                         s_km + (head * D + L.off[m] + js) * MTP, L.s3chunk[m]);
-            store_partial<MT, MTP>(s_part + a.S.s3pb[m], L.rd[m], sp, 4 * quad, acc);
-        }
-        __syncthreads();
-        if (tid < R) {
-            int m = 0;
-            while (m + 1 < L.nm && tid >= L.roff[m + 1]) ++m;
-            const int cl = tid - L.roff[m], rdm = L.rd[m], ns = L.s3ns[m];
-            const float *pb = s_part + a.S.s3pb[m] + cl;
-            const float b = __ldg(packed + L.br + tid);
-            float r[MTP];
-#pragma unroll
-            for (int q = 0; q < MTP; ++q) r[q] = 0.f;
-#pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                float s = b;
-                for (int sp = 0; sp < ns; ++sp) s += pb[(sp * MTP + q) * rdm];
-                r[q] = s;
-                if (stash && q < rows) a.sR[(tn0 + q) * R + tid] = s;
-            }
-            store_rows<MTP>(s_r + tid * MTP, r);
-        }
-        __syncthreads();
-        // ---- S4: fc.0 + ReLU (+ dropout mask)
         {
-            const int nq = MH / 4, items = nq * L.s4ns;
+            const int nq = MH / 4, items = nq * L.s34ns;
             for (int item = tid; item < items; item += nt) {
-                const int quad = item % nq, sp = item / nq, k0 = sp * L.s4chunk, n = min(R, k0 + L.s4chunk) - k0;
+                const int quad = item % nq, sp = item / nq, k0 = sp * L.s34chunk, n = min(G, k0 + L.s34chunk) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.wf1) + (size_t)k0 * nq + quad, nq,
-                                 s_r + k0 * MTP, n);
+                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.w1) + (size_t)k0 * nq + quad, nq,
+                                 s_km + k0 * MTP, n);
                 store_partial<MT, MTP>(s_part, MH, sp, 4 * quad, acc);
             }
         }
         __syncthreads();
+        // ---- ReLU (+ dropout mask): u_t, the state the next step's gates consume (z_t = fc.3(u_t) is formed by the
+        //      host for all steps at once: nothing on the serial path needs it any more)
         if (tid < MH) {
-            const float b = __ldg(packed + L.bf1 + tid);
+            const float b = __ldg(packed + L.b1 + tid);
             float u[MTP];
 #pragma unroll
             for (int q = 0; q < MTP; ++q) u[q] = 0.f;
 #pragma unroll
             for (int q = 0; q < MT; ++q) {
                 float s = b;
-                for (int sp = 0; sp < L.s4ns; ++sp) s += s_part[(sp * MTP + q) * MH + tid];
+                for (int sp = 0; sp < L.s34ns; ++sp) s += s_part[(sp * MTP + q) * MH + tid];
                 s = fmaxf(s, 0.f);
                 if (q < rows) {
                     if (masked) s *= s_mask[buf * MT * MH + q * MH + tid];
-                    if (stash) a.sU[(tn0 + q) * MH + tid] = s;
+                    a.sU[(tn0 + q) * MH + tid] = s;      // always written: the host forms z_t = fc.3(u_t) from it
+                } else {
+                    s = 0.f;
                 }
                 u[q] = s;
             }
             store_rows<MTP>(s_u + tid * MTP, u);
         }
         __syncthreads();
-        // ---- S5: fc.3 -> z_t
-        {
-            const int nq = D / 4, items = nq * L.s5ns;
-            for (int item = tid; item < items; item += nt) {
-                const int quad = item % nq, sp = item / nq, k0 = sp * L.s5chunk, n = min(MH, k0 + L.s5chunk) - k0;
-                acc.zero();
-                if (n > 0)
-                    mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(packed + L.wf2) + (size_t)k0 * nq + quad, nq,
-                                 s_u + k0 * MTP, n);
-                store_partial<MT, MTP>(s_part, D, sp, 4 * quad, acc);
-            }
-        }
-        __syncthreads();
-        if (tid < D) {
-            const float b = __ldg(packed + L.bf2 + tid);
-            float z[MTP];
-#pragma unroll
-            for (int q = 0; q < MTP; ++q) z[q] = 0.f;
-#pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                float s = b;
-                for (int sp = 0; sp < L.s5ns; ++sp) s += s_part[(sp * MTP + q) * D + tid];
-                z[q] = s;
-                if (q < rows) a.hz[(tn0 + q) * 2 * D + D + tid] = s;
-            }
-            store_rows<MTP>(s_z + tid * MTP, z);
-        }
-        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward (BPTT).  Carries dh, dz, dc live in shared memory across steps.
+// backward (BPTT).  Carries dh, du, dc live in shared memory across steps.  With the composite weights the adjoint
+// chain of a step is:  du_t = duz_t + W2^T ds_{t+1}  ->  (ReLU, mask)  ->  d att = W1^T dup  ->  softmax backward
+// ->  dc += Watt^T de  ->  cell backward (ds_t)  ->  carries  du = W2^T ds_t,  dh_m = U_m^T ds_{t,m}.
+// duz_t = (dL/dz_t from the head) . Wf2 is formed by the host for all steps at once.
 // ---------------------------------------------------------------------------------------------
 template <int MT>
 __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_constant__ BwdArgs a) {
@@ -369,18 +334,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
     extern __shared__ __align__(16) float smem[];
     const MabLayout &L = a.L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int D = L.D, G = L.G, R = L.R, MH = L.MH, N = L.N, T = L.T;
+    const int D = L.D, G = L.G, MH = L.MH, N = L.N, T = L.T;
     const int n0 = blockIdx.x * MT;
     const int rows = min(MT, N - n0);
-    float *s_dh = smem + a.S.dh, *s_dz = smem + a.S.dz, *s_dc = smem + a.S.dc, *s_gh = smem + a.S.gh;
-    float *s_gz = smem + a.S.gz, *s_dup = smem + a.S.dup, *s_dr = smem + a.S.dr, *s_km = smem + a.S.km;
+    float *s_dh = smem + a.S.dh, *s_du = smem + a.S.du, *s_dc = smem + a.S.dc, *s_gh = smem + a.S.gh;
+    float *s_dup = smem + a.S.dup, *s_km = smem + a.S.km;
     float *s_C = smem + a.S.C, *s_A = smem + a.S.A, *s_row = smem + a.S.row, *s_p2 = smem + a.S.p2;
     float *s_red = smem + a.S.red, *s_fin = smem + a.S.fin;
     float *s_pA = s_A;  // B4/B5 partials alias the (by then dead) A tile + dvec rows
     const int nq2 = G / 4, nqd = D / 4;
+    const float *__restrict__ packed = a.packed;
 
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    float *s_dhz = smem + a.S.dhz, *s_uh = smem + a.S.uh, *s_mk = smem + a.S.mk;
+    float *s_dhz = smem + a.S.dhz, *s_duz = smem + a.S.duz, *s_uh = smem + a.S.uh, *s_mk = smem + a.S.mk;
     const bool masked = a.mask != nullptr;
     for (int i = 8 + tid; i < a.S.total; i += nt) smem[i] = 0.f;
     if (tid == 0) {
@@ -389,14 +355,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
         mbar_fence_init();
     }
     __syncthreads();
-    // per-step input tiles (dL/d[h|z], fc hidden, dropout mask) are contiguous rows: bulk-copied one step ahead
+    // per-step input tiles (dL/d[h|z], duz, fc hidden, dropout mask) are contiguous rows: bulk-copied one step ahead
     const uint32_t dhz_bytes = (uint32_t)rows * 2 * D * sizeof(float), uh_bytes = (uint32_t)rows * MH * sizeof(float);
-    const uint32_t tile_bytes = dhz_bytes + uh_bytes + (masked ? uh_bytes : 0u);
+    const uint32_t tile_bytes = dhz_bytes + 2 * uh_bytes + (masked ? uh_bytes : 0u);
     auto issue_tiles = [&](int t) {
         const int bf = t & 1;
         const size_t tn = (size_t)t * N + n0;
         mbar_expect_tx(bar + bf, tile_bytes);
         bulk_g2s(s_dhz + bf * MT * 2 * D, a.dhz + tn * 2 * D, dhz_bytes, bar + bf);
+        bulk_g2s(s_duz + bf * MT * MH, a.duz + tn * MH, uh_bytes, bar + bf);
         bulk_g2s(s_uh + bf * MT * MH, a.sU + tn * MH, uh_bytes, bar + bf);
         if (masked) bulk_g2s(s_mk + bf * MT * MH, a.mask + tn * MH, uh_bytes, bar + bf);
     };
@@ -437,109 +404,47 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
         const int buf = t & 1;
         if (tid == 0 && t > 0) issue_tiles(t - 1);      // the other slot was last read two barriers ago (step t+1)
         Acc<MT> acc;
-        // ---- P0: gh = dL/dh_t + carry, gz = dL/dz_t + carry
-        if (tid < 2 * D) {
-            const int part = tid / D, j = tid - part * D;
-            float carry[MTP], v[MTP];
-            load_rows<MTP>(carry, (part ? s_dz : s_dh) + j * MTP);
+        // ---- P0: gh = dL/dh_t + carry;  dup = (duz_t + carry_u) through ReLU and the dropout mask
+        if (tid < D + MH) {
+            float v[MTP];
 #pragma unroll
             for (int q = 0; q < MTP; ++q) v[q] = 0.f;
             mbar_wait(bar + buf, ((T - 1 - t) >> 1) & 1);
-            const float *dz_s = s_dhz + buf * MT * 2 * D + part * D + j;
+            if (tid < D) {
+                float carry[MTP];
+                load_rows<MTP>(carry, s_dh + tid * MTP);
+                const float *dh_s = s_dhz + buf * MT * 2 * D + tid;
 #pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                if (q < rows) {
-                    v[q] = dz_s[q * 2 * D] + carry[q];
-                    if (part) a.dzt[(tn0 + q) * D + j] = v[q];
+                for (int q = 0; q < MT; ++q)
+                    if (q < rows) v[q] = dh_s[q * 2 * D] + carry[q];
+                store_rows<MTP>(s_gh + tid * MTP, v);
+            } else {
+                const int j = tid - D;
+                float carry[MTP];
+                load_rows<MTP>(carry, s_du + j * MTP);
+#pragma unroll
+                for (int q = 0; q < MT; ++q) {
+                    if (q < rows) {
+                        float s = s_duz[buf * MT * MH + q * MH + j] + carry[q];
+                        const float uh = s_uh[buf * MT * MH + q * MH + j];
+                        s = (uh != 0.f) ? s : 0.f;
+                        if (masked) s *= s_mk[buf * MT * MH + q * MH + j];
+                        a.dup[(tn0 + q) * MH + j] = s;
+                        v[q] = s;
+                    }
                 }
-            }
-            store_rows<MTP>((part ? s_gz : s_gh) + j * MTP, v);
-        }
-        __syncthreads();
-        // ---- B1: d(fc hidden) = Wf2^T gz, through ReLU and the dropout mask
-        {
-            const int nq = MH / 4, items = nq * L.b1ns;
-            for (int item = tid; item < items; item += nt) {
-                const int quad = item % nq, sp = item / nq, k0 = sp * L.b1chunk, n = min(D, k0 + L.b1chunk) - k0;
-                acc.zero();
-                if (n > 0)
-                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Wf2) + (size_t)k0 * nq + quad, nq,
-                                 s_gz + k0 * MTP, n);
-                store_partial<MT, MTP>(s_p2, MH, sp, 4 * quad, acc);
+                store_rows<MTP>(s_dup + j * MTP, v);
             }
         }
         __syncthreads();
-        if (tid < MH) {
-            float v[MTP];
-#pragma unroll
-            for (int q = 0; q < MTP; ++q) v[q] = 0.f;
-#pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                if (q < rows) {
-                    float s = 0.f;
-                    for (int sp = 0; sp < L.b1ns; ++sp) s += s_p2[(sp * MTP + q) * MH + tid];
-                    const float uh = s_uh[buf * MT * MH + q * MH + tid];
-                    s = (uh != 0.f) ? s : 0.f;
-                    if (masked) s *= s_mk[buf * MT * MH + q * MH + tid];
-                    a.dup[(tn0 + q) * MH + tid] = s;
-                    v[q] = s;
-                }
-            }
-            store_rows<MTP>(s_dup + tid * MTP, v);
-        }
-        __syncthreads();
-        // ---- B2: d(reduce outputs) = Wf1^T dup
-        {
-            const int nq = R / 4, items = nq * L.b2ns;
-            for (int item = tid; item < items; item += nt) {
-                const int quad = item % nq, sp = item / nq, k0 = sp * L.b2chunk, n = min(MH, k0 + L.b2chunk) - k0;
-                acc.zero();
-                if (n > 0)
-                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Wf1) + (size_t)k0 * nq + quad, nq,
-                                 s_dup + k0 * MTP, n);
-                store_partial<MT, MTP>(s_p2, R, sp, 4 * quad, acc);
-            }
-        }
-        __syncthreads();
-        if (tid < R) {
-            float v[MTP];
-#pragma unroll
-            for (int q = 0; q < MTP; ++q) v[q] = 0.f;
-#pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                float s = 0.f;
-                for (int sp = 0; sp < L.b2ns; ++sp) s += s_p2[(sp * MTP + q) * R + tid];
-                v[q] = s;
-                if (q < rows) a.dr[(tn0 + q) * R + tid] = s;
-            }
-            store_rows<MTP>(s_dr + tid * MTP, v);
-        }
-        __syncthreads();
-        // ---- B3: d(attended) = Wr_m^T dr_m  (columns head-major inside each modality)
-        for (int item = tid; item < L.b3total; item += nt) {
-            int m = 0, local = item;
-            while (local >= L.b3items[m]) { local -= L.b3items[m]; ++m; }
-            const int nq = L.dh[m], quad = local % nq, sp = local / nq;
-            const int k0 = sp * L.b3chunk[m], n = min(L.rd[m], k0 + L.b3chunk[m]) - k0;
+        // ---- B23: d(attended) = W1^T dup  (K = MH in one go: no split, each thread writes its 4 columns of the dvec rows)
+        for (int quad = tid; quad < nq2; quad += nt) {
             acc.zero();
-            if (n > 0)
-                mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.Wr[m]) + (size_t)k0 * nq + quad, nq,
-                             s_dr + (L.roff[m] + k0) * MTP, n);
-            store_partial<MT, MTP>(s_p2 + a.S.b3pb[m], 4 * L.dh[m], sp, 4 * quad, acc);
-        }
-        __syncthreads();
-        for (int c = tid; c < G; c += nt) {
-            int m = 0;
-            while (m + 1 < L.nm && c >= L.goff[m + 1]) ++m;
-            const int lc = c - L.goff[m], dhm = L.dh[m], head = lc / dhm, j = lc - head * dhm, Jm = 4 * dhm;
-            const float *pb = s_p2 + a.S.b3pb[m] + lc;
-            const int ns = L.b3ns[m];
+            mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(packed + L.w1n) + quad, nq2, s_dup, MH);
 #pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                float s = 0.f;
-                for (int sp = 0; sp < ns; ++sp) s += pb[(sp * MTP + q) * Jm];
-                s_row[q * L.ldr + head * D + L.off[m] + j] = s;
-            }
+            for (int m = 0; m < MT; ++m)
+                *reinterpret_cast<float4 *>(s_row + m * L.ldr + 4 * quad) =
+                    make_float4(acc.get(0, m), acc.get(1, m), acc.get(2, m), acc.get(3, m));
         }
         cp_async_wait_all();
         __syncthreads();
@@ -642,42 +547,43 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_bwd_kernel(const __grid_co
                     make_float4(ds[g][0], ds[g][1], ds[g][2], ds[g][3]);
         }
         __syncthreads();
-        // ---- B5: carries into step t-1:  dz = Vcat^T ds,  dh_m = U_m^T ds_m
+        // ---- B5: carries into step t-1:  du = W2^T ds  (through fc.3 and V in one product),  dh_m = U_m^T ds_m
         {
-            const int items = nqd * L.b4ns;
+            const int nq = MH / 4, items = nq * L.b5uns;
             for (int item = tid; item < items; item += nt) {
-                const int quad = item % nqd, sp = item / nqd, k0 = sp * L.b4chunk, n = min(G, k0 + L.b4chunk) - k0;
+                const int quad = item % nq, sp = item / nq, k0 = sp * L.b5uchunk, n = min(G, k0 + L.b5uchunk) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.packed + L.vcat) + (size_t)k0 * nqd + quad, nqd,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(packed + L.w2n) + (size_t)k0 * nq + quad, nq,
                                  s_km + k0 * MTP, n);
-                store_partial<MT, MTP>(s_pA, D, sp, 4 * quad, acc);
+                store_partial<MT, MTP>(s_pA, MH, sp, 4 * quad, acc);
             }
             for (int item = tid; item < L.b5total; item += nt) {
                 int m = 0, local = item;
                 while (local >= L.b5items[m]) { local -= L.b5items[m]; ++m; }
-                const int nq = L.dh[m] / 4, quad = local % nq, sp = local / nq;
+                const int nq5 = L.dh[m] / 4, quad = local % nq5, sp = local / nq5;
                 const int k0 = sp * L.b5chunk[m], n = min(4 * L.dh[m], k0 + L.b5chunk[m]) - k0;
                 acc.zero();
                 if (n > 0)
-                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.U[m]) + (size_t)k0 * nq + quad, nq,
+                    mac<MT, MTP, LSTHM_MAC_BWD>(acc, reinterpret_cast<const float4 *>(a.U[m]) + (size_t)k0 * nq5 + quad, nq5,
                                  s_km + (L.goff[m] + k0) * MTP, n);
                 store_partial<MT, MTP>(s_p2 + a.S.b5pb[m], L.dh[m], sp, 4 * quad, acc);
             }
         }
         __syncthreads();
-        if (tid < 2 * D) {
+        if (tid < D + MH) {
             float v[MTP];
 #pragma unroll
             for (int q = 0; q < MTP; ++q) v[q] = 0.f;
-            if (tid < D) {
+            if (tid >= D) {
+                const int j = tid - D;
 #pragma unroll
                 for (int q = 0; q < MT; ++q) {
                     float s = 0.f;
-                    for (int sp = 0; sp < L.b4ns; ++sp) s += s_pA[(sp * MTP + q) * D + tid];
+                    for (int sp = 0; sp < L.b5uns; ++sp) s += s_pA[(sp * MTP + q) * MH + j];
                     v[q] = s;
                 }
-                store_rows<MTP>(s_dz + tid * MTP, v);
+                store_rows<MTP>(s_du + j * MTP, v);
             } else {
                 const float *pb = s_p2 + a.S.b5pb[mc] + c_jl;
                 const int ns = L.b5ns[mc];

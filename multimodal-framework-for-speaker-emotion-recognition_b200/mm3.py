@@ -112,6 +112,17 @@ class _LinearTC(torch.autograd.Function):
         return dx, dw, db, None
 
 
+def linear_into(x: torch.Tensor, weight: torch.Tensor, bias, out: torch.Tensor) -> None:
+    """out[:] = x @ weight^T + bias for 2-D operands, written straight into ``out`` (may be a column block of a wider
+    matrix); no autograd (used inside custom backward/forward bodies)."""
+    if (_ok(x, weight, out) and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and out.stride(1) == 1 and out.stride(0) % 4 == 0
+            and out.data_ptr() % 16 == 0 and _fits(x)):
+        launches["gemm3"] += 1
+        _lib.gemm3(_lib.GEMM_NT, _rows(x), _rows(weight), None if bias is None else bias.contiguous(), out=out)
+    else:
+        out.copy_(F.linear(x, weight, bias))
+
+
 def rows_view(x: torch.Tensor):
     """A 3-D activation [A, B, K] as a 2-D row matrix WITHOUT a copy when its storage allows it.
 

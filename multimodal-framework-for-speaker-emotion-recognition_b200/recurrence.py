@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .mm3 import mm_tn, colsum
+from .mm3 import mm_tn, mm_nn, colsum, linear_into
 
 # Counts launches of OUR kernels (pack/fwd/bwd), for bench.py's `gpu_launches`.
 launch_counter = {"pack": 0, "fwd": 0, "bwd": 0}
@@ -39,6 +39,11 @@ class MabRecurrenceFn(torch.autograd.Function):
 
     Argument order after (gx, drop_mask, dims): U_0..U_{M-1}, V_0.., Watt, batt, Wr_0.., br_0..,
     Wf1, bf1, Wf2, bf2  — all in nn.Linear layout, i.e. the modules' own parameter storage.
+
+    The kernels run the chain with composite weights (include/lsthm_b200.h): per step  gates(h, u) -> cell ->
+    attention -> u' = relu(W1 attended + b1).  What they no longer touch is formed here as time-parallel products over
+    all T*N rows:  z = u Wf2^T + bf2  (forward),  duz = dz_head Wf2  (into the BPTT),  and for the weight gradients
+    r = attended Wr^T + br,  dr = dup Wf1,  dz_total = dz_head + ds_{t+1} Vcat.
     """
 
     @staticmethod
@@ -61,29 +66,32 @@ class MabRecurrenceFn(torch.autograd.Function):
         _lib.mab_pack(desc, wstruct, packed)
         launch_counter["pack"] += 1
         new = lambda *s: torch.empty(*s, device=gx.device, dtype=torch.float32)
-        hz = new(T, N, 2 * D)
+        hz, u = new(T, N, 2 * D), new(T, N, map_h)
         need_grad = any(ctx.needs_input_grad)
         if drop_mask is not None:
             drop_mask = drop_mask.contiguous()
         if need_grad:
-            sC, sG, sA, sR, sU = new(T, N, D), new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h)
+            sC, sG, sA = new(T, N, D), new(T, N, G), new(T, N, G)
         else:
-            sC = sG = sA = sR = sU = None
-        _timed("fwd", _lib.mab_fwd, desc, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU)
+            sC = sG = sA = None
+        _timed("fwd", _lib.mab_fwd, desc, packed, gx, drop_mask, hz, u, sC, sG, sA)
         launch_counter["fwd"] += 1
+        # z_t = fc.3(u_t) for all steps at once, written into the z half of hz (HybridRNN_ATV.py:129)
+        linear_into(u.view(T * N, map_h), Wf2, bf2, hz.view(T * N, 2 * D)[:, D:])
         if need_grad:
-            ctx.save_for_backward(packed, hz, sC, sG, sA, sR, sU, *weights)
+            ctx.save_for_backward(packed, hz, u, sC, sG, sA, *weights)
             ctx.drop_mask = drop_mask
             ctx.dims = dims
         return hz
 
     @staticmethod
     def backward(ctx, dhz: torch.Tensor):
-        packed, hz, sC, sG, sA, sR, sU, *weights = ctx.saved_tensors
+        packed, hz, u, sC, sG, sA, *weights = ctx.saved_tensors
         dh, rd, map_h, rows_per_cta = ctx.dims
         M = len(dh)
         T, N, _ = hz.shape
         D, R, G = sum(dh), sum(rd), 4 * sum(dh)
+        TN = T * N
         U, V = weights[0:M], weights[M:2 * M]
         Watt, batt = weights[2 * M], weights[2 * M + 1]
         Wr, br = weights[2 * M + 2:3 * M + 2], weights[3 * M + 2:4 * M + 2]
@@ -91,14 +99,16 @@ class MabRecurrenceFn(torch.autograd.Function):
         desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
         wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
         new = lambda *s: torch.empty(*s, device=hz.device, dtype=torch.float32)
-        dgx, de, dr, dup, dzt = new(T, N, G), new(T, N, G), new(T, N, R), new(T, N, map_h), new(T, N, D)
+        dhz = dhz.contiguous()
+        dz_head = dhz.view(TN, 2 * D)[:, D:]
+        duz = mm_nn(dz_head, Wf2)                              # the head's dL/dz pulled through fc.3: [TN, map_h]
+        dgx, de, dup = new(T, N, G), new(T, N, G), new(T, N, map_h)
         att = new(T, N, G)     # attended = a * cs (HybridRNN_ATV.py:125), regrouped per modality head-major (lines 126-128) by the kernel
-        _timed("bwd", _lib.mab_bwd, desc, wstruct, packed, dhz.contiguous(), ctx.drop_mask, sC, sG, sA, sU,
-               dgx, de, dr, dup, dzt, att)
+        _timed("bwd", _lib.mab_bwd, desc, wstruct, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sC, sG, sA, u,
+               dgx, de, dup, att)
         launch_counter["bwd"] += 1
 
-        # ---- time-parallel weight-gradient products (fp32; allow_tf32 stays off) ----
-        TN = T * N
+        # ---- time-parallel weight-gradient products (fp32-accurate; allow_tf32 stays off) ----
         gU: List[torch.Tensor] = []
         gV: List[torch.Tensor] = []
         if T > 1:
@@ -113,20 +123,24 @@ class MabRecurrenceFn(torch.autograd.Function):
             o += dh[m]
         de2, c2 = de.view(TN, G), sC.view(TN, D)
         gWatt, gbatt = mm_tn(de2, c2), colsum(de2)
-        att2 = att.view(TN, G)
-        dr2 = dr.view(TN, R)
+        att2, dup2, u2 = att.view(TN, G), dup.view(TN, map_h), u.view(TN, map_h)
+        dr2 = mm_nn(dup2, Wf1)                                  # dL/d(reduce outputs) = dup Wf1: [TN, R]
+        r2 = new(TN, R)                                          # reduce outputs r_m = attended_m Wr_m^T + br_m (lines 126-128)
         gWr, gbr = [], []
         o = ro = 0
         for m in range(M):
             vec = att2[:, 4 * o:4 * o + 4 * dh[m]]              # column block m: [head][feature], no copy
+            linear_into(vec, Wr[m], br[m], r2[:, ro:ro + rd[m]])
             drm = dr2[:, ro:ro + rd[m]]
             gWr.append(mm_tn(drm, vec))
             gbr.append(colsum(drm))
             o += dh[m]
             ro += rd[m]
-        dup2, dzt2 = dup.view(TN, map_h), dzt.view(TN, D)
-        gWf1, gbf1 = mm_tn(dup2, sR.view(TN, R)), colsum(dup2)
-        gWf2, gbf2 = mm_tn(dzt2, sU.view(TN, map_h)), colsum(dzt2)
+        gWf1, gbf1 = mm_tn(dup2, r2), colsum(dup2)
+        # total dL/dz_t = head part + the part carried by the next step's gates through V: ds_{t+1} Vcat
+        dzt = dz_head.clone() if T == 1 else torch.cat(
+            [dz_head[:TN - N] + mm_nn(dgx[1:].reshape(-1, G), torch.cat(list(V), dim=0)), dz_head[TN - N:]], dim=0)
+        gWf2, gbf2 = mm_tn(dzt, u2), colsum(dzt)
         grads = (*gU, *gV, gWatt, gbatt, *gWr, *gbr, gWf1, gbf1, gWf2, gbf2)
         return (dgx, None, None, *grads)
 

@@ -37,16 +37,16 @@ def main():
     new = lambda *s: torch.empty(*s, device=dev)
     gx, dhz = torch.randn(T, N, 4 * D, device=dev), torch.randn(T, N, 2 * D, device=dev)
     mask = (torch.rand(T, N, MH, device=dev) < 0.7).float() / 0.7
-    hz, sC, sG, sA, sR, sU = new(T, N, 2 * D), new(T, N, D), new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, R), new(T, N, MH)
-    dgx, de, dr, dup, dzt = new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, R), new(T, N, MH), new(T, N, D)
+    hz, sC, sG, sA, sU = new(T, N, 2 * D), new(T, N, D), new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, MH)
+    dgx, de, dup, att, duz = new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, MH), new(T, N, 4 * D), torch.randn(T, N, MH, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     tf, tb = [], []
     for i in range(a.reps + 2):
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
-        lib.mab_fwd(d, packed, gx, mask, hz, sC, sG, sA, sR, sU)
+        lib.mab_fwd(d, packed, gx, mask, hz, sU, sC, sG, sA)
         e1.record()
-        lib.mab_bwd(d, ws, packed, dhz, mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt)
+        lib.mab_bwd(d, ws, packed, dhz, duz, mask, sC, sG, sA, sU, dgx, de, dup, att)
         e2.record()
         torch.cuda.synchronize()
         if i >= 2:

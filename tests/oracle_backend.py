@@ -38,26 +38,28 @@ class OracleBackend:
     def _dims(d):
         return tuple(d.dh[i] for i in range(d.n_mod)), tuple(d.rd[i] for i in range(d.n_mod))
 
-    def mab_fwd(self, d, packed, gx, drop_mask, hz, sC, sG, sA, sR, sU):
+    def mab_fwd(self, d, packed, gx, drop_mask, hz, u, sC, sG, sA):
         dh, rd = self._dims(d)
         f = ocpu.mab_forward(self.weights, gx.double().numpy(), dh, rd,
                              None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
-        hz.copy_(torch.from_numpy(f["hz"]))
+        hz.copy_(torch.from_numpy(f["hz"]))            # the library writes only the h half; the host overwrites the z half
+        u.copy_(torch.from_numpy(f["UH"]).reshape(u.shape))
         if sC is not None:
-            for t, k in ((sC, "C"), (sG, "G"), (sA, "A"), (sR, "R"), (sU, "UH")):
+            for t, k in ((sC, "C"), (sG, "G"), (sA, "A")):
                 t.copy_(torch.from_numpy(f[k]).reshape(t.shape))
 
-    def mab_bwd(self, d, w, packed, dhz, drop_mask, sC, sG, sA, sU, dgx, de, dr, dup, dzt, att=None):
+    def mab_bwd(self, d, w, packed, dhz, duz, drop_mask, sC, sG, sA, u, dgx, de, dup, att=None):
         dh, rd = self._dims(d)
         T, N = d.T, d.N
         D = sum(dh)
-        # hz / R feed only the oracle's own weight-gradient accumulation, which is not used here
+        # hz / R feed only the oracle's own weight-gradient accumulation, which is not used here; the oracle takes the
+        # head's dL/dz directly (dhz carries it), so `duz` (= dz_head Wf2, what the CUDA kernel consumes) is not needed
         f = dict(hz=np.zeros((T, N, 2 * D)), C=sC.double().numpy(), G=sG.double().numpy(),
                  A=np.ascontiguousarray(sA.double().numpy().reshape(T, N, 4, D)),
-                 R=np.zeros((T, N, sum(rd))), UH=sU.double().numpy())
+                 R=np.zeros((T, N, sum(rd))), UH=u.double().numpy())
         adj, _ = ocpu.mab_backward(self.weights, dhz.double().numpy(), f, dh, rd,
                                    None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
-        for t, k in ((dgx, "dgx"), (de, "de"), (dr, "dr"), (dup, "dup"), (dzt, "dzt")):
+        for t, k in ((dgx, "dgx"), (de, "de"), (dup, "dup")):
             t.copy_(torch.from_numpy(adj[k]).reshape(t.shape))
         if att is not None:   # attended = a * c regrouped per modality, head-major (include/lsthm_b200.h: lsthm_mab_bwd)
             a4 = sA.reshape(T, N, 4, D) * sC.reshape(T, N, 1, D)

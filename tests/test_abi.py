@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_layout_queries_and_errors():
     d = lib.make_desc(110, 1024, (128, 16, 64), (16, 128, 100))
-    assert lib.mab_packed_floats(d) > 500000
+    assert lib.mab_packed_floats(d) > 400000
     info = lib.mab_launch_info(d)
     assert info["rows"] == 7 and info["grid"] == 147 and info["block"] == 416
     assert info["smem_fwd"] <= 227 * 1024 and info["smem_bwd"] <= 227 * 1024
@@ -50,5 +50,5 @@ def test_layout_queries_and_errors():
 def test_binding_rejects_host_tensors():
     d = lib.make_desc(2, 2, (128, 16), (16, 128))
     with pytest.raises(RuntimeError, match="CUDA tensor"):
-        lib.mab_fwd(d, torch.zeros(8), torch.zeros(2, 2, 576), None, torch.zeros(2, 2, 288),
-                    None, None, None, None, None)
+        lib.mab_fwd(d, torch.zeros(8), torch.zeros(2, 2, 576), None, torch.zeros(2, 2, 288), torch.zeros(2, 2, 64),
+                    None, None, None)
