@@ -397,8 +397,9 @@ def run_ours(args):
             info = _l.mab_launch_info(_l.make_desc(T, B, (128, 16, 64), (16, 128, 100)))
             D, G, R, MH = 208, 832, 244, 64
             # algorithmic HBM bytes per utterance of one launch, fp32
-            by = {"fwd": 4 * (G + 2 * D + D + G + G + R + MH + MH),
-                  "bwd": 4 * (2 * D + D + D + G + G + MH + MH + G + G + R + MH + D)}
+            # fwd: read gx, mask; write h, u, stash C/G/A.   bwd: read dhz, duz, u, mask, C_t, C_{t-1}, G, A; write dgx, de, dup, att
+            by = {"fwd": 4 * (G + MH + D + MH + D + G + G),
+                  "bwd": 4 * (2 * D + MH + MH + MH + 2 * D + G + G + G + G + MH + G)}
             din = D_IN
         else:
             flop_utt = SPS_FLOP_BWD if dom == "bwd" else SPS_FLOP_FWD      # per direction = per launch
