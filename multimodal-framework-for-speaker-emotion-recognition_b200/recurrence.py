@@ -42,8 +42,8 @@ class MabRecurrenceFn(torch.autograd.Function):
 
     The kernels run the chain with composite weights (include/lsthm_b200.h): per step  gates(h, u) -> cell ->
     attention -> u' = relu(W1 attended + b1).  What they no longer touch is formed here as time-parallel products over
-    all T*N rows:  z = u Wf2^T + bf2  (forward),  duz = dz_head Wf2  (into the BPTT),  and for the weight gradients
-    r = attended Wr^T + br,  dr = dup Wf1,  dz_total = dz_head + ds_{t+1} Vcat.
+    all T*N rows:  z = u Wf2^T + bf2  (forward),  duz = dz_head Wf2  (into the BPTT);  the weight gradients of the composed
+    layers follow from three products with K = T*N (ds^T [h|u], dup^T attended, dz_head^T u) and a few tiny matrix products.
     """
 
     @staticmethod
@@ -109,38 +109,45 @@ class MabRecurrenceFn(torch.autograd.Function):
         launch_counter["bwd"] += 1
 
         # ---- time-parallel weight-gradient products (fp32-accurate; allow_tf32 stays off) ----
+        # z never has to be touched here: with z_{t-1} = u_{t-1} Wf2^T + bf2 and X = ds[1:]^T [h_{t-1} | u_{t-1}]  (K = (T-1) N)
+        #   dU_m = block of X_h,     dV = X_u Wf2^T + colsum(ds[1:]) bf2^T,
+        #   dWf2 = dz_head^T u + Vcat^T X_u,     dbf2 = colsum(dz_head) + Vcat^T colsum(ds[1:])
+        # (the carried part of dL/dz_t is ds_{t+1} Vcat, and its product with u_t is Vcat^T X_u again).
+        u2 = u.view(TN, map_h)
+        Vcat = torch.cat(list(V), dim=0)                        # [G, D], native gate order = column order of dgx
+        if T > 1:
+            ds1 = dgx[1:].reshape(-1, G)
+            Xh = mm_tn(ds1, hz[:-1].reshape(-1, 2 * D)[:, :D])  # [G, D]
+            Xu = mm_tn(ds1, u2[:TN - N])                        # [G, map_h]
+            cs1 = colsum(ds1)                                   # [G]
+        else:
+            Xh, Xu, cs1 = dgx.new_zeros(G, D), dgx.new_zeros(G, map_h), dgx.new_zeros(G)
+        gVfull = Xu @ Wf2.t() + torch.outer(cs1, bf2)           # [G, D] (tiny products: fp32 SGEMM)
         gU: List[torch.Tensor] = []
         gV: List[torch.Tensor] = []
-        if T > 1:
-            # [G, 2D] = dgx[1:]^T @ [h_{t-1} | z_{t-1}]; U_m / V_m grads are blocks of it
-            full = mm_tn(dgx[1:].reshape(-1, G), hz[:-1].reshape(-1, 2 * D))
-        else:
-            full = dgx.new_zeros(G, 2 * D)
         o = 0
         for m in range(M):
-            gU.append(full[4 * o:4 * o + 4 * dh[m], o:o + dh[m]])
-            gV.append(full[4 * o:4 * o + 4 * dh[m], D:])
+            gU.append(Xh[4 * o:4 * o + 4 * dh[m], o:o + dh[m]])
+            gV.append(gVfull[4 * o:4 * o + 4 * dh[m]])
             o += dh[m]
+        gWf2 = mm_tn(dz_head, u2) + Vcat.t() @ Xu               # [D, map_h]
+        gbf2 = colsum(dz_head) + Vcat.t() @ cs1
         de2, c2 = de.view(TN, G), sC.view(TN, D)
         gWatt, gbatt = mm_tn(de2, c2), colsum(de2)
-        att2, dup2, u2 = att.view(TN, G), dup.view(TN, map_h), u.view(TN, map_h)
-        dr2 = mm_nn(dup2, Wf1)                                  # dL/d(reduce outputs) = dup Wf1: [TN, R]
-        r2 = new(TN, R)                                          # reduce outputs r_m = attended_m Wr_m^T + br_m (lines 126-128)
-        gWr, gbr = [], []
+        # reduce_m / fc.0: with r = attended Wr^T + br and dr = dup Wf1, one product Y = dup^T attended [map_h, G] gives both:
+        #   dWr_m = Wf1_m^T Y_m,  dbr_m = Wf1_m^T colsum(dup),  dWf1[:, m] = Y_m Wr_m^T + colsum(dup) br_m^T,  dbf1 = colsum(dup)
+        att2, dup2 = att.view(TN, G), dup.view(TN, map_h)
+        Y, cdup = mm_tn(dup2, att2), colsum(dup2)
+        gWr, gbr, gWf1_parts = [], [], []
         o = ro = 0
         for m in range(M):
-            vec = att2[:, 4 * o:4 * o + 4 * dh[m]]              # column block m: [head][feature], no copy
-            linear_into(vec, Wr[m], br[m], r2[:, ro:ro + rd[m]])
-            drm = dr2[:, ro:ro + rd[m]]
-            gWr.append(mm_tn(drm, vec))
-            gbr.append(colsum(drm))
+            Ym, Wf1m = Y[:, 4 * o:4 * o + 4 * dh[m]], Wf1[:, ro:ro + rd[m]]
+            gWr.append(Wf1m.t() @ Ym)
+            gbr.append(Wf1m.t() @ cdup)
+            gWf1_parts.append(Ym @ Wr[m].t() + torch.outer(cdup, br[m]))
             o += dh[m]
             ro += rd[m]
-        gWf1, gbf1 = mm_tn(dup2, r2), colsum(dup2)
-        # total dL/dz_t = head part + the part carried by the next step's gates through V: ds_{t+1} Vcat
-        dzt = dz_head.clone() if T == 1 else torch.cat(
-            [dz_head[:TN - N] + mm_nn(dgx[1:].reshape(-1, G), torch.cat(list(V), dim=0)), dz_head[TN - N:]], dim=0)
-        gWf2, gbf2 = mm_tn(dzt, u2), colsum(dzt)
+        gWf1, gbf1 = torch.cat(gWf1_parts, dim=1), cdup
         grads = (*gU, *gV, gWatt, gbatt, *gWr, *gbr, gWf1, gbf1, gWf2, gbf2)
         return (dgx, None, None, *grads)
 
