@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(kAttBwdThreads, 1) attn_bwd_kernel(const __gri
     uint8_t *sD = sP + 2 * kSqTile;
     constexpr int kRawLd = 44;                                  // floats per raw row: 176 B stride -> conflict-free 16-byte reads by row
     float *raw = reinterpret_cast<float *>(sP);                 // [5][128][kRawLd] = 112.6 KB <= 128 KB (sP + sD)
+    constexpr int kPatchRows = (4 * kSqTile - 5 * 128 * kRawLd * 4) / (kAttD * 4);   // rows of the epilogue patch behind it: 115
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int L = a.L, nitems = a.B * a.H;
     const bool rv = r < L;
@@ -443,13 +444,41 @@ __global__ void __launch_bounds__(kAttBwdThreads, 1) attn_bwd_kernel(const __gri
             fetch(next);
             if (rv) lse_next = __ldg(a.lse + (size_t)next * L + r);
         }
-        {
+        if (L <= kPatchRows) {
+            // Coalesced epilogue: a thread owns an accumulator ROW, so storing from registers would put 16 bytes into
+            // each of 32 rows per instruction.  Each gradient matrix goes through a [L][40] fp32 patch in the 18 KB of
+            // the Pd/dS region that the next item's raw rows do not use, and leaves as whole 160-byte row slices.
+            float *patch = reinterpret_cast<float *>(sP) + 5 * 128 * kRawLd;
+            float v[16];
+            for (int which = 0; which < 3; ++which) {
+                // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
+                const float mul = which == 1 ? a.scale : which == 2 ? kLn2 : 1.f;
+                if (g < 3) {                                  // warp-uniform: column block 16*g of the 40 (+8) columns
+                    tmem_ld16(trow + 256 + 48 * which + 16 * g, v);
+                    if (rv) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            if (16 * g + 4 * q4 < kAttD)
+                                *reinterpret_cast<float4 *>(patch + r * kAttD + 16 * g + 4 * q4) =
+                                    make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
+                    }
+                }
+                __syncthreads();
+                float *base = which == 0 ? a.dv : which == 1 ? a.dq : a.dk;
+                const int ld = which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk;
+                for (int idx = tid; idx < L * (kAttD / 4); idx += kAttBwdThreads) {
+                    const int row = idx / (kAttD / 4), f4 = idx - row * (kAttD / 4);
+                    const size_t gr = (size_t)((long long)b * a.sb + (long long)row * a.si);
+                    reinterpret_cast<float4 *>(base + gr * ld + h * kAttD)[f4] = reinterpret_cast<const float4 *>(patch + row * kAttD)[f4];
+                }
+                __syncthreads();
+            }
+        } else {
             float v[16];
             // 9 (matrix, 16-column block) items over the four threads of a row: g takes the items with index % 4 == g
             for (int blk = g; blk < 9; blk += 4) {
                 const int which = blk / 3, c0 = 16 * (blk % 3);
                 float *dst = (which == 0 ? a.dv : which == 1 ? a.dq : a.dk) + grow * (which == 0 ? a.ldv : which == 1 ? a.ldq : a.ldk) + h * kAttD;
-                // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
                 const float mul = which == 1 ? a.scale : which == 2 ? kLn2 : 1.f;
                 tmem_ld16(trow + 256 + 48 * which + c0, v);
                 if (rv) {
