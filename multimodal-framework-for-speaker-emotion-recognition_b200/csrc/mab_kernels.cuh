@@ -297,25 +297,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) mab_fwd_kernel(const __grid_co
         __syncthreads();
         // ---- ReLU (+ dropout mask): u_t, the state the next step's gates consume (z_t = fc.3(u_t) is formed by the
         //      host for all steps at once: nothing on the serial path needs it any more)
-        if (tid < MH) {
-            const float b = __ldg(packed + L.b1 + tid);
-            float u[MTP];
-#pragma unroll
-            for (int q = 0; q < MTP; ++q) u[q] = 0.f;
-#pragma unroll
-            for (int q = 0; q < MT; ++q) {
-                float s = b;
-                for (int sp = 0; sp < L.s34ns; ++sp) s += s_part[(sp * MTP + q) * MH + tid];
+        // one (hidden unit, dialogue) pair per thread: 13 partials each instead of 7 x 13 on 64 threads
+        for (int idx = tid; idx < MH * MTP; idx += nt) {
+            const int j = idx % MH, q = idx / MH;
+            float s = 0.f;
+            if (q < rows) {
+                s = __ldg(packed + L.b1 + j);
+                for (int sp = 0; sp < L.s34ns; ++sp) s += s_part[(sp * MTP + q) * MH + j];
                 s = fmaxf(s, 0.f);
-                if (q < rows) {
-                    if (masked) s *= s_mask[buf * MT * MH + q * MH + tid];
-                    a.sU[(tn0 + q) * MH + tid] = s;      // always written: the host forms z_t = fc.3(u_t) from it
-                } else {
-                    s = 0.f;
-                }
-                u[q] = s;
+                if (masked) s *= s_mask[buf * MT * MH + q * MH + j];
+                a.sU[(tn0 + q) * MH + j] = s;      // always written: the host forms z_t = fc.3(u_t) from it
             }
-            store_rows<MTP>(s_u + tid * MTP, u);
+            s_u[j * MTP + q] = s;
         }
         __syncthreads();
     }
