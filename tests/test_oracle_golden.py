@@ -102,3 +102,43 @@ def test_c_oracle_matches_torch_port_and_autograd(kind):
             assert np.abs(grads[k] - gg.numpy()).max() < 1e-11, k
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("train,perturb", [(False, False), (False, True), (True, True)])
+def test_onlysp_port_matches_live_reference(train, perturb):
+    """lsthm_onlysp (the reference's train.py default model, next variant to get a kernel): the oracle restatement vs the
+    live reference — log-probs, loss and every gradient, eval / perturbed ones-parameters / train with the mask tape,
+    ragged dialogue lengths."""
+    from oracle.make_golden import synth_dialogues
+    ref = load_reference()
+    torch.manual_seed(31)
+    m = ref.MARN1_onlysp(6)
+    if perturb:
+        tp.perturb_ones(m, 5)
+    x, qmask, umask, labels = synth_dialogues(17, 9, [9, 4, 7, 9, 5])
+    x.requires_grad_(True)
+    tape = None
+    if train:
+        tape = tp.DropoutTape(4)
+        attach_tape(m, tape)
+        m.train()
+    else:
+        m.eval()
+    logp, _, _ = m(x, qmask, umask)
+    loss = ref.MaskedLoss(torch.nn.CrossEntropyLoss)(logp, labels.view(-1), umask)
+    loss.backward()
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    x2 = x.detach().clone().requires_grad_(True)
+    logp2, _, _ = tp.onlysp_forward(p, x2, qmask, umask, tape.rewind() if train else None)
+    loss2 = tp.masked_loss(logp2, labels.view(-1), umask, "ce")
+    loss2.backward()
+    e = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    assert e(logp2.detach(), logp.detach()) < 2e-5 and abs(float(loss2.detach()) - float(loss.detach())) / abs(float(loss.detach())) < 1e-5
+    assert e(x2.grad, x.grad) < 5e-4
+    gmax = max(float(q.grad.norm()) for q in m.parameters() if q.grad is not None)
+    for n, q in m.named_parameters():
+        if q.grad is None:
+            assert p[n].grad is None or float(p[n].grad.abs().max()) == 0.0, n
+        elif float(q.grad.norm()) > 1e-6 * gmax:
+            assert e(p[n].grad, q.grad) < 1e-3, (n, e(p[n].grad, q.grad))
