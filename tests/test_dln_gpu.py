@@ -99,3 +99,32 @@ def test_encoder_layer_fast_path_matches_module_path():
         for k, v in layer64.named_parameters():
             if v.grad is not None:
                 assert _rel(ga[k], v.grad) < 1e-4, k
+
+
+def test_encoder_layer_fast_path_train_mode_is_seeded_and_differentiates_its_own_mask():
+    """Train mode of the fused layer (in-kernel dropout in the attention and in both LayerNorm tails, no mask tensors):
+    the torch RNG seeds it, and the backward regenerates exactly the forward's masks (directional derivative)."""
+    enc_mod = import_module(lsthm_b200.__name__ + ".encoder")
+    torch.manual_seed(1)
+    L, B, d = 31, 6, 100
+    layer = enc_mod.EncoderLayer(d, 50, 8, 40, 40).cuda().train()
+    x = torch.randn(L, B, d, device="cuda")
+    w = torch.randn(B, L, d, device="cuda")
+
+    def f(inp, seed):
+        torch.manual_seed(seed)
+        y, _ = layer(inp.permute(1, 0, 2))
+        return (y * w).sum()
+
+    a, b, c = f(x, 5), f(x, 5), f(x, 6)
+    assert a.item() == b.item() and a.item() != c.item()
+    layer.eval()
+    assert f(x, 5).item() == f(x, 6).item() and f(x, 5).item() != a.item()      # eval: no dropout anywhere
+    layer.train()
+    xg = x.clone().requires_grad_(True)
+    f(xg, 5).backward()
+    dirn = torch.randn_like(x)
+    eps = 1e-3
+    num = (f(x + eps * dirn, 5).double() - f(x - eps * dirn, 5).double()) / (2 * eps)
+    ana = (xg.grad.double() * dirn).sum()
+    assert abs(num - ana) / abs(ana) < 2e-2, (num.item(), ana.item())
