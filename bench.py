@@ -412,6 +412,7 @@ def run_ours(args):
         achieved = flop / (kms[dom] * 1e-3) / 1e12 if kms[dom] > 0 else 0.0
         sm_mhz = (clocks or {}).get("sm_mhz") or pk["sm_max_mhz"]
         ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        hbm_gbs = by[dom] * T * B / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
@@ -428,18 +429,23 @@ def run_ours(args):
                     "ms_per_step": (e2e_ms / args.steps) if e2e_ms else None},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": kname, "achieved": achieved,
-                         "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                         "traffic": traffic, "peak_source": pk["source"] + " bf16 cuBLAS sustained",
+            # Of the two rooflines the contract offers, HBM is the one nearer to binding for the dominant kernel (its
+            # algorithmic bytes at the measured copy bandwidth take longer than its algorithmic FLOPs at the measured bf16
+            # tensor peak), so the headline roofline is "hbm"; the kernel itself is an fp32 FFMA latency/L2-stream bound
+            # chain and the other views are reported next to it.
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": hbm_gbs,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / pk["hbm_gbs"],
+                         "traffic": traffic, "peak_source": pk["source"] + " copy bandwidth",
+                         "algorithmic_bytes_per_utt": by[dom],
                          "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
                          "launches_per_step": {k: len(v) / args.steps for k, v in kev.items()},
                          "share_of_step": {k: v * len(kev[k]) / args.steps / (ms / args.steps) for k, v in kms.items()},
+                         "tensor": {"achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                                    "frac": achieved / pk["bf16_sustained"],
+                                    "note": "reference-algorithmic FLOPs of the dominant kernel vs the measured bf16 cuBLAS peak; the kernel issues no tensor work"},
                          "tensor_core_kernels": {"gemm3": tc_summary(gev), "attention": tc_summary(aev)},
                          "fp32_ffma": {"achieved": achieved, "peak": ffma_peak, "frac": achieved / ffma_peak,
-                                       "note": f"kernel is fp32 FFMA; peak = 148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock under load)"},
-                         "hbm": {"algorithmic_bytes_per_utt": by[dom],
-                                 "achieved_gbs": by[dom] * T * B / (kms[dom] * 1e-3) / 1e9 if kms[dom] > 0 else 0.0,
-                                 "peak_gbs": pk["hbm_gbs"]}},
+                                       "note": f"kernel is fp32 FFMA; peak = 148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz (clock under load)"}},
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = run_cpu_baseline(model_kind=kind)
