@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTHM_ABI_VERSION 5
+#define LSTHM_ABI_VERSION 6
 #define LSTHM_MAX_MOD 3
 
 int lsthm_abi_version(void);
@@ -109,6 +109,48 @@ int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const flo
 /* Launch geometry the library would use (for roofline bookkeeping in bench.py). */
 int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows,
                           int32_t *smem_fwd, int32_t *smem_bwd);
+
+/* ------------------------------------------------------------------------------------------
+ * AT / ATV recurrence, weight-stationary tensor-core form (lsthm_mab2_*): the same operator boundary as lsthm_mab_*
+ * (the body of the time loop of MARN.forward, model/HybridRNN_ATV.py:117-143 / model/HybridRNN_AT.py:107-132, and its
+ * BPTT), executed by GROUPS of co-resident thread blocks that keep the chain weights sharded and resident in shared
+ * memory as bf16 hi/lo operand images and run every product on tcgen05 tensor cores (three-term split, fp32 accumulate).
+ * `rows_per_cta` of the descriptor is read as "dialogues per group" (0 = auto, at most 96).
+ * Constraints: map_h = 64, n_att = 4, every dh_m a multiple of 16 in 16..128, sum dh_m <= 256.
+ * ------------------------------------------------------------------------------------------ */
+
+/* bytes of the packed weight area (composite weights + per-rank operand images for forward and backward) */
+size_t lsthm_mab2_pack_bytes(const lsthm_mab_desc *d);
+/* bytes of the exchange workspace a launch needs (group exchange buffers + barrier counters); the library resets
+ * the counters itself (one cudaMemsetAsync on `stream` per launch), the rest needs no initialisation */
+size_t lsthm_mab2_workspace_bytes(const lsthm_mab_desc *d);
+/* compose W1 = Wf1.blockdiag(Wr_m), W2 = Vcat.Wf2 (fp64 accumulation) and split every rank's slices into bf16 hi/lo
+ * images in the canonical K-major UMMA layout (call after every optimizer step, before fwd/bwd) */
+int lsthm_mab2_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *packed, void *stream);
+
+/*
+ * Forward over all T steps (cooperative launch).  gx, drop_mask, hz, u as for lsthm_mab_fwd.
+ * stash (all out, may ALL be NULL for inference):
+ *   sC [T][N][D] cell states        sG [T][N][4D] gates after sigmoid/tanh (layout of gx)
+ *   sE [T][N][4][D] attention logits (att.0 output incl. bias, BEFORE the softmax)
+ *   sMS [T][N][4][2] per head (max logit, 1 / sum exp(e - max)): softmax weights are a = exp(e - max) * inv
+ *   sP [T][N][4][map_h] per head  W1[:, head block] . (a_head * c)   (the softmax backward needs <dup, P_head>)
+ */
+int lsthm_mab2_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx, const float *drop_mask, float *hz, float *u,
+                   float *sC, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream);
+
+/* BPTT (cooperative launch).  dhz, duz, drop_mask, u and the outputs dgx, de, dup, att as for lsthm_mab_bwd. */
+int lsthm_mab2_bwd(const lsthm_mab_desc *d, const void *packed, const float *dhz, const float *duz, const float *drop_mask,
+                   const float *sC, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
+                   float *dgx, float *de, float *dup, float *att, void *workspace, void *stream);
+
+/* Launch geometry on the current device: grid = groups * group size. */
+int lsthm_mab2_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *group,
+                           int32_t *dialogues_per_group, int32_t *smem_fwd, int32_t *smem_bwd);
+/* The sharding plan for a 148-SM device (host only, no device needed): 14 header ints (G, ranges per head, dialogues
+ * per group, padded rows, groups, blocks, combine share, blob_f, blob_b, act_f, act_b, smem_fwd, smem_bwd, ws_group)
+ * followed by (modality, first unit, units, head, first feature, features) per rank. */
+int lsthm_mab2_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out);
 
 /* ------------------------------------------------------------------------------------------
  * lsthm_sps: speaker-state LSTHM cell (one direction of the bidirectional MARN1_sps).

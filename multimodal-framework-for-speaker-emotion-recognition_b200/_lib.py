@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
 SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_MOD = 3
 
 _f32p = C.POINTER(C.c_float)
@@ -94,6 +94,20 @@ def lib() -> C.CDLL:
     L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 13
     L.lsthm_mab_launch_info.restype = C.c_int
     L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 5
+    L.lsthm_mab2_pack_bytes.restype = C.c_size_t
+    L.lsthm_mab2_pack_bytes.argtypes = [C.POINTER(MabDesc)]
+    L.lsthm_mab2_workspace_bytes.restype = C.c_size_t
+    L.lsthm_mab2_workspace_bytes.argtypes = [C.POINTER(MabDesc)]
+    L.lsthm_mab2_pack.restype = C.c_int
+    L.lsthm_mab2_pack.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights), C.c_void_p, C.c_void_p]
+    L.lsthm_mab2_fwd.restype = C.c_int
+    L.lsthm_mab2_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 12
+    L.lsthm_mab2_bwd.restype = C.c_int
+    L.lsthm_mab2_bwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 16
+    L.lsthm_mab2_launch_info.restype = C.c_int
+    L.lsthm_mab2_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 6
+    L.lsthm_mab2_plan_info.restype = C.c_int
+    L.lsthm_mab2_plan_info.argtypes = [C.POINTER(MabDesc), C.POINTER(C.c_int32), C.c_int32]
     L.lsthm_sps_packed_floats.restype = C.c_size_t
     L.lsthm_sps_packed_floats.argtypes = []
     L.lsthm_sps_workspace_floats.restype = C.c_size_t
@@ -215,6 +229,65 @@ def mab_launch_info(d: MabDesc) -> dict:
     v = [C.c_int32() for _ in range(5)]
     _check(lib().lsthm_mab_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab_launch_info")
     return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))
+
+
+# ------------------------------------------------------------------------------------------------
+# AT / ATV recurrence, weight-stationary tensor-core kernels (lsthm_mab2_*)
+# ------------------------------------------------------------------------------------------------
+def _byte_ptr(t: torch.Tensor, name: str) -> int:
+    if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and t.data_ptr() % 128 == 0):
+        raise RuntimeError(f"{name}: expected a contiguous, 128-byte aligned CUDA uint8 buffer")
+    return t.data_ptr()
+
+
+def mab2_pack_bytes(d: MabDesc) -> int:
+    n = lib().lsthm_mab2_pack_bytes(C.byref(d))
+    if n == 0:
+        raise RuntimeError(f"unsupported recurrence dims: {lib().lsthm_last_error().decode()}")
+    return n
+
+
+def mab2_workspace_bytes(d: MabDesc) -> int:
+    n = lib().lsthm_mab2_workspace_bytes(C.byref(d))
+    if n == 0:
+        raise RuntimeError(f"unsupported recurrence dims: {lib().lsthm_last_error().decode()}")
+    return n
+
+
+def mab2_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
+    _check(lib().lsthm_mab2_pack(C.byref(d), C.byref(w), _byte_ptr(packed, "packed"), _stream()), "lsthm_mab2_pack")
+
+
+def mab2_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sG, sE, sMS, sP, workspace) -> None:
+    """Writes the h half of hz[T,N,2D] and u[T,N,map_h]; the caller forms z = u Wf2^T + bf2 (include/lsthm_b200.h)."""
+    _check(lib().lsthm_mab2_fwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(gx, "gx"), _dev_ptr(drop_mask, "drop_mask"),
+                                _dev_ptr(hz, "hz"), _dev_ptr(u, "u"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
+                                _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _byte_ptr(workspace, "workspace"), _stream()),
+           "lsthm_mab2_fwd")
+
+
+def mab2_bwd(d: MabDesc, packed, dhz, duz, drop_mask, sC, sG, sE, sMS, sP, u, dgx, de, dup, att, workspace) -> None:
+    _check(lib().lsthm_mab2_bwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"), _dev_ptr(duz, "duz"),
+                                _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
+                                _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _dev_ptr(u, "u"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
+                                _dev_ptr(dup, "dup"), _dev_ptr(att, "att"), _byte_ptr(workspace, "workspace"), _stream()),
+           "lsthm_mab2_bwd")
+
+
+def mab2_launch_info(d: MabDesc) -> dict:
+    v = [C.c_int32() for _ in range(6)]
+    _check(lib().lsthm_mab2_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab2_launch_info")
+    return dict(zip(("grid", "block", "group", "dialogues_per_group", "smem_fwd", "smem_bwd"), (x.value for x in v)))
+
+
+def mab2_plan_info(d: MabDesc) -> dict:
+    """The sharding plan for a 148-SM device (host-only query)."""
+    buf = (C.c_int32 * (14 + 6 * 16))()
+    _check(lib().lsthm_mab2_plan_info(C.byref(d), buf, len(buf)), "lsthm_mab2_plan_info")
+    keys = ("G", "nr", "DG", "Mr", "ngroups", "nblocks", "cd", "blob_f", "blob_b", "act_f", "act_b", "smem_fwd", "smem_bwd", "ws_group")
+    out = dict(zip(keys, list(buf[:14])))
+    out["ranks"] = [dict(zip(("m", "u0", "nu", "head", "j0", "nj"), list(buf[14 + 6 * r:20 + 6 * r]))) for r in range(out["G"])]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 namespace lsthm {
 
 constexpr int kMaxMod = 3;
+constexpr int kHeads = 4;
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) — used to stage each timestep's

@@ -23,7 +23,7 @@
 
 namespace lsthm {
 
-constexpr int kHeads = 4;
+
 #ifndef LSTHM_MAXT
 #define LSTHM_MAXT 448
 #endif
