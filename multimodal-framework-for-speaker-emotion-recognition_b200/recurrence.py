@@ -24,6 +24,20 @@ launch_counter = {"pack": 0, "fwd": 0, "bwd": 0}
 kernel_events = None
 
 
+_workspaces = {}
+
+
+def _workspace(desc, device) -> torch.Tensor:
+    """Exchange workspace of the group kernels (per device; forward and backward of a step run back to back on one stream)."""
+    nbytes = _lib.mab2_workspace_bytes(desc)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    w = _workspaces.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(nbytes, device=device, dtype=torch.uint8)
+        _workspaces[key] = w
+    return w
+
+
 def _timed(kind, fn, *args):
     if kernel_events is None:
         return fn(*args)
@@ -62,31 +76,32 @@ class MabRecurrenceFn(torch.autograd.Function):
         Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
         desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
         wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-        packed = torch.empty(_lib.mab_packed_floats(desc), device=gx.device, dtype=torch.float32)
-        _lib.mab_pack(desc, wstruct, packed)
-        launch_counter["pack"] += 1
+        packed = torch.empty(_lib.mab2_pack_bytes(desc), device=gx.device, dtype=torch.uint8)
+        _lib.mab2_pack(desc, wstruct, packed)
+        launch_counter["pack"] += 2
+        work = _workspace(desc, gx.device)
         new = lambda *s: torch.empty(*s, device=gx.device, dtype=torch.float32)
         hz, u = new(T, N, 2 * D), new(T, N, map_h)
         need_grad = any(ctx.needs_input_grad)
         if drop_mask is not None:
             drop_mask = drop_mask.contiguous()
         if need_grad:
-            sC, sG, sA = new(T, N, D), new(T, N, G), new(T, N, G)
+            sC, sG, sE, sMS, sP = new(T, N, D), new(T, N, G), new(T, N, G), new(T, N, 4, 2), new(T, N, 4, map_h)
         else:
-            sC = sG = sA = None
-        _timed("fwd", _lib.mab_fwd, desc, packed, gx, drop_mask, hz, u, sC, sG, sA)
+            sC = sG = sE = sMS = sP = None
+        _timed("fwd", _lib.mab2_fwd, desc, packed, gx, drop_mask, hz, u, sC, sG, sE, sMS, sP, work)
         launch_counter["fwd"] += 1
         # z_t = fc.3(u_t) for all steps at once, written into the z half of hz (HybridRNN_ATV.py:129)
         linear_into(u.view(T * N, map_h), Wf2, bf2, hz.view(T * N, 2 * D)[:, D:])
         if need_grad:
-            ctx.save_for_backward(packed, hz, u, sC, sG, sA, *weights)
+            ctx.save_for_backward(packed, hz, u, sC, sG, sE, sMS, sP, *weights)
             ctx.drop_mask = drop_mask
             ctx.dims = dims
         return hz
 
     @staticmethod
     def backward(ctx, dhz: torch.Tensor):
-        packed, hz, u, sC, sG, sA, *weights = ctx.saved_tensors
+        packed, hz, u, sC, sG, sE, sMS, sP, *weights = ctx.saved_tensors
         dh, rd, map_h, rows_per_cta = ctx.dims
         M = len(dh)
         T, N, _ = hz.shape
@@ -97,15 +112,14 @@ class MabRecurrenceFn(torch.autograd.Function):
         Wr, br = weights[2 * M + 2:3 * M + 2], weights[3 * M + 2:4 * M + 2]
         Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
         desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
-        wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
         new = lambda *s: torch.empty(*s, device=hz.device, dtype=torch.float32)
         dhz = dhz.contiguous()
         dz_head = dhz.view(TN, 2 * D)[:, D:]
         duz = mm_nn(dz_head, Wf2)                              # the head's dL/dz pulled through fc.3: [TN, map_h]
         dgx, de, dup = new(T, N, G), new(T, N, G), new(T, N, map_h)
         att = new(T, N, G)     # attended = a * cs (HybridRNN_ATV.py:125), regrouped per modality head-major (lines 126-128) by the kernel
-        _timed("bwd", _lib.mab_bwd, desc, wstruct, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sC, sG, sA, u,
-               dgx, de, dup, att)
+        _timed("bwd", _lib.mab2_bwd, desc, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sC, sG, sE, sMS, sP, u,
+               dgx, de, dup, att, _workspace(desc, hz.device))
         launch_counter["bwd"] += 1
 
         # ---- time-parallel weight-gradient products (fp32-accurate; allow_tf32 stays off) ----

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE — import shim for the *live* reference (container only).
+"""TEST INFRASTRUCTURE — import shim for the *live* reference.
 
 The reference at /root/reference is pure Python/PyTorch but its import paths are
 broken as shipped: code says ``models.*`` / ``attention.*`` while the
@@ -6,19 +6,30 @@ directories are ``model/`` and ``attention:/``; several files ``import imp`` (go
 Python 3.12).  This shim repairs those three things *in sys.modules only* — nothing
 is copied out of /root/reference and nothing is written into it.
 
-/root/reference does not exist on the GPU box: only ``oracle/make_golden.py`` and the
-``-m "not gpu"`` tests that are explicitly skipped when the directory is absent may
-call :func:`load_reference`.
+/root/reference does not exist on the GPU box.  ``make -C oracle ref`` (run by ``__graft_entry__.build()`` in the build
+container) stages byte-for-byte copies of the hot-path files into the git-ignored ``oracle/_ref/`` — with a SHA256SUMS
+manifest — which does travel to the GPU box; the shim uses /root/reference when present and the staged tree otherwise.
+Users: ``oracle/make_golden.py``, the tests, and ``bench.py``'s reference arm / ``cpu_baseline`` (the unmodified
+reference, timed; never the product path).
 """
 import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REF_ROOT = os.environ.get("LSTHM_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "model")) and os.path.isdir(os.path.join(_STAGED, "model")):
+    REF_ROOT = _STAGED
+REF_KIND = "staged" if REF_ROOT == _STAGED else "tree"
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "model"))
+
+
+def _attention_dir() -> str:
+    a = os.path.join(REF_ROOT, "attention:")
+    return a if os.path.isdir(a) else os.path.join(REF_ROOT, "attention_")
 
 
 def _alias_package(name: str, path: str) -> None:
@@ -35,18 +46,23 @@ def load_reference():
     if "models" not in sys.modules:
         _alias_package("models", os.path.join(REF_ROOT, "model"))
     if "attention" not in sys.modules:
-        _alias_package("attention", os.path.join(REF_ROOT, "attention:"))
-    if REF_ROOT not in sys.path:
-        sys.path.append(REF_ROOT)  # for loss.py
+        _alias_package("attention", _attention_dir())
     ns = types.SimpleNamespace()
     from models.HybridRNN_ATV import MARN as MARN_ATV  # model/HybridRNN_ATV.py:40
     from models.HybridRNN_AT import MARN as MARN_AT    # model/HybridRNN_AT.py:40
     from models.lsthm_sps import MARN1_sps              # model/lsthm_sps.py:298
     from models.lsthm_onlysp import MARN1_onlysp        # model/lsthm_onlysp.py:213 (train.py default model)
+    from models.lsthm_nsps import MARN1_nsps            # model/lsthm_nsps.py:283
     from models.encoder import EncoderLayer             # model/encoder.py:116
-    import loss as ref_loss                             # loss.py:6
+    from models.DialogueRNN import BiModel              # model/DialogueRNN.py:201 (config 4 baseline)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_lsthm_ref_loss", os.path.join(REF_ROOT, "loss.py"))
+    ref_loss = importlib.util.module_from_spec(spec)    # loss.py:6 (loaded by path: our package also has a loss.py)
+    spec.loader.exec_module(ref_loss)
     ns.MARN_ATV, ns.MARN_AT, ns.MARN1_sps, ns.MARN1_onlysp = MARN_ATV, MARN_AT, MARN1_sps, MARN1_onlysp
+    ns.MARN1_nsps, ns.BiModel = MARN1_nsps, BiModel
     ns.EncoderLayer, ns.MaskedLoss = EncoderLayer, ref_loss.MaskedLoss
+    ns.root, ns.kind = REF_ROOT, REF_KIND
     return ns
 
 

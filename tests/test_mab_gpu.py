@@ -2,7 +2,7 @@
 
 All calls go through the C ABI (ctypes -> liblsthm_b200.so).  Layers of evidence:
   1. kernel boundary vs the fp64 plain-C oracle, every stash tensor and every adjoint, ragged
-     tiles (N not a multiple of rows_per_cta), all tile heights, eval and masked (train) mode;
+     dialogue blocks (N not a multiple of the group's block), several groups and waves, eval and masked (train) mode;
   2. drop-in module vs the reference-generated fixtures in tests/golden/ (north-star bars:
      outputs/loss 1e-4, gradients 1e-3 scale-relative, identical argmax);
   3. drop-in module vs the oracle's torch restatement at the full dialogue length T=110;
@@ -54,30 +54,43 @@ def _run_kernels(c, T, N):
     Wf1, bf1, Wf2, bf2 = w[4 * M + 2:4 * M + 6]
     d = lib.make_desc(T, N, dh, rd, MH, 4, c["rows"])
     ws = lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-    packed = torch.empty(lib.mab_packed_floats(d), device=dev)
-    lib.mab_pack(d, ws, packed)
+    packed = torch.empty(lib.mab2_pack_bytes(d), device=dev, dtype=torch.uint8)
+    lib.mab2_pack(d, ws, packed)
+    work = torch.empty(lib.mab2_workspace_bytes(d), device=dev, dtype=torch.uint8)
     new = lambda *s: torch.full(s, float("nan"), device=dev)
-    out = dict(hz=new(T, N, 2 * D), C=new(T, N, D), G=new(T, N, 4 * D), A=new(T, N, 4 * D), UH=new(T, N, MH))
+    out = dict(hz=new(T, N, 2 * D), C=new(T, N, D), G=new(T, N, 4 * D), UH=new(T, N, MH))
+    sE, sMS, sP = new(T, N, 4 * D), new(T, N, 4, 2), new(T, N, 4, MH)
     gx = c["gx"].to(dev)
     mask = None if c["mask"] is None else c["mask"].to(dev)
-    lib.mab_fwd(d, packed, gx, mask, out["hz"], out["UH"], out["C"], out["G"], out["A"])
-    # the kernel boundary (include/lsthm_b200.h): z_t = fc.3(u_t) is the caller's time-parallel product
+    lib.mab2_fwd(d, packed, gx, mask, out["hz"], out["UH"], out["C"], out["G"], sE, sMS, sP, work)
+    # the kernel boundary (include/lsthm_b200.h): z_t = fc.3(u_t) is the caller's time-parallel product, and the softmax
+    # weights are stashed as (logits, max, 1/sum)
     out["hz"][:, :, D:] = out["UH"] @ Wf2.t() + bf2
+    out["A"] = torch.exp(sE.view(T, N, 4, D) - sMS[..., 0:1]) * sMS[..., 1:2]
     dhz = c["dhz"].to(dev)
     duz = (dhz[:, :, D:] @ Wf2).contiguous()                  # the head's dL/dz pulled through fc.3
     adj = dict(dgx=new(T, N, 4 * D), de=new(T, N, 4 * D), dup=new(T, N, MH))
     att = new(T, N, 4 * D)
-    lib.mab_bwd(d, ws, packed, dhz, duz, mask, out["C"], out["G"], out["A"], out["UH"],
-                adj["dgx"], adj["de"], adj["dup"], att)
+    lib.mab2_bwd(d, packed, dhz, duz, mask, out["C"], out["G"], sE, sMS, sP, out["UH"],
+                 adj["dgx"], adj["de"], adj["dup"], att, work)
     torch.cuda.synchronize()
     # the regrouped attended features the backward also emits: a * c, per modality, head-major (HybridRNN_ATV.py:125-128)
-    a4 = out["A"].view(T, N, 4, D) * out["C"].view(T, N, 1, D)
+    a4 = out["A"] * out["C"].view(T, N, 1, D)
     o = ro = 0
     R_parts = []
     for m, h in enumerate(dh):
-        assert torch.equal(att[:, :, 4 * o:4 * o + 4 * h], a4[:, :, :, o:o + h].reshape(T, N, 4 * h))
+        assert torch.allclose(att[:, :, 4 * o:4 * o + 4 * h], a4[:, :, :, o:o + h].reshape(T, N, 4 * h), rtol=2e-6, atol=1e-8)
         R_parts.append(att[:, :, 4 * o:4 * o + 4 * h] @ Wr[m].t() + br[m])
         o += h
+    # the per-head fused reduce+fc.0 products the softmax backward uses: P_k = W1[:, head k] . (a_k * c)
+    W1 = torch.zeros(MH, 4, D, device=dev, dtype=torch.float64)
+    o = ro = 0
+    for m, h in enumerate(dh):
+        W1[:, :, o:o + h] = torch.einsum("qr,rkj->qkj", Wf1[:, ro:ro + rd[m]].double(), Wr[m].double().view(rd[m], 4, h))
+        o += h
+        ro += rd[m]
+    Pref = torch.einsum("qkj,tnkj->tnkq", W1, a4.double())
+    assert e_inf(sP.cpu().numpy(), Pref.cpu().numpy()) < 2e-5
     # quantities the kernels no longer produce, reconstructed the way recurrence.py does, so that the oracle still
     # checks the whole boundary: reduce outputs, their adjoint, and the total dL/dz_t
     out["R"] = torch.cat(R_parts, dim=-1)
@@ -89,10 +102,12 @@ def _run_kernels(c, T, N):
     return {k: v.cpu().numpy() for k, v in out.items()}, {k: v.cpu().numpy() for k, v in adj.items()}
 
 
+# rows = dialogues per CTA group (0 = auto): blocks smaller than the batch exercise several groups, ragged last blocks
+# and, when there are more blocks than co-resident groups, the multi-wave path
 @pytest.mark.parametrize("kind,T,N,rows,masked", [
-    ("ATV", 5, 11, 4, False), ("ATV", 4, 3, 1, True), ("ATV", 3, 13, 8, True), ("ATV", 3, 15, 7, False),
-    ("ATV", 2, 5, 2, False), ("ATV", 2, 7, 3, True), ("ATV", 2, 11, 5, False), ("ATV", 2, 13, 6, True),
-    ("AT", 5, 11, 4, True), ("AT", 3, 17, 8, False), ("AT", 1, 1, 1, False), ("ATV", 1, 9, 8, False),
+    ("ATV", 5, 11, 0, False), ("ATV", 4, 3, 1, True), ("ATV", 3, 13, 8, True), ("ATV", 3, 15, 7, False),
+    ("ATV", 2, 5, 2, False), ("ATV", 2, 100, 3, True), ("ATV", 2, 211, 16, False), ("ATV", 2, 130, 96, True),
+    ("AT", 5, 11, 4, True), ("AT", 3, 170, 8, False), ("AT", 1, 1, 1, False), ("ATV", 1, 9, 8, False),
 ])
 def test_kernel_boundary_vs_c_oracle(kind, T, N, rows, masked):
     c = _boundary_case(kind, T, N, rows, masked, seed=T * 100 + N)
@@ -168,8 +183,8 @@ def test_properties_at_benchmark_size():
     # (a) run-to-run determinism: bitwise
     p1, dx1, g1 = _fwd_bwd(model, x, labels, T, N)
     assert torch.equal(p0, p1) and torch.equal(dx0, dx1)
-    # (b) tile-height invariance (7 vs 8 dialogues per CTA): same arithmetic per dialogue -> bitwise
-    model.rows_per_cta = 8
+    # (b) block-size invariance (88 vs 48 dialogues per CTA group): same arithmetic per dialogue -> bitwise
+    model.rows_per_cta = 48
     p8, dx8, g8 = _fwd_bwd(model, x, labels, T, N)
     model.rows_per_cta = 0
     assert torch.equal(p0, p8) and torch.equal(dx0, dx8)
