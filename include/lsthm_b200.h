@@ -151,6 +151,9 @@ int lsthm_mab2_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *bloc
  * per group, padded rows, groups, blocks, combine share, blob_f, blob_b, act_f, act_b, smem_fwd, smem_bwd, ws_group)
  * followed by (modality, first unit, units, head, first feature, features) per rank. */
 int lsthm_mab2_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out);
+/* Profiling aid: buf = device buffer of [T][2][16] int64 (or NULL to switch off); block 0 of the forward kernel records
+ * clock64() at the phase boundaries of its control thread (role 0) and of its first epilogue warp (role 1). */
+int lsthm_mab2_set_trace(void *buf);
 
 /* ------------------------------------------------------------------------------------------
  * lsthm_sps: speaker-state LSTHM cell (one direction of the bidirectional MARN1_sps).

@@ -108,6 +108,8 @@ def lib() -> C.CDLL:
     L.lsthm_mab2_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 6
     L.lsthm_mab2_plan_info.restype = C.c_int
     L.lsthm_mab2_plan_info.argtypes = [C.POINTER(MabDesc), C.POINTER(C.c_int32), C.c_int32]
+    L.lsthm_mab2_set_trace.restype = C.c_int
+    L.lsthm_mab2_set_trace.argtypes = [C.c_void_p]
     L.lsthm_sps_packed_floats.restype = C.c_size_t
     L.lsthm_sps_packed_floats.argtypes = []
     L.lsthm_sps_workspace_floats.restype = C.c_size_t
@@ -272,6 +274,10 @@ def mab2_bwd(d: MabDesc, packed, dhz, duz, drop_mask, sC, sG, sE, sMS, sP, u, dg
                                 _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _dev_ptr(u, "u"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
                                 _dev_ptr(dup, "dup"), _dev_ptr(att, "att"), _byte_ptr(workspace, "workspace"), _stream()),
            "lsthm_mab2_bwd")
+
+
+def mab2_set_trace(buf: Optional[torch.Tensor]) -> None:
+    _check(lib().lsthm_mab2_set_trace(None if buf is None else buf.data_ptr()), "lsthm_mab2_set_trace")
 
 
 def mab2_launch_info(d: MabDesc) -> dict:

@@ -196,6 +196,12 @@ int lsthm_mab2_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out) {
     return 0;
 }
 
+int lsthm_mab2_set_trace(void *buf) {
+    long long *p = reinterpret_cast<long long *>(buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_m2_trace, &p, sizeof(p));
+    return e == cudaSuccess ? 0 : set_error("lsthm_mab2_set_trace", e);
+}
+
 int lsthm_mab2_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *packed, void *stream) {
     M2Plan P;
     if (build_plan(d, 0, P)) return 1;

@@ -303,6 +303,14 @@ __device__ __forceinline__ void m2_join8(const uint4 hi, const uint4 lo, float (
     }
 }
 
+// Development trace: when the host has set a buffer (lsthm_mab2_set_trace), the control thread and lane 0 of epilogue
+// warp 0 of CTA 0 record clock64() at their phase boundaries, [step][role][16] — read back by profiles/dev_mab2_check.py.
+__device__ long long *g_m2_trace = nullptr;
+#define M2_TRACE(role, slot)                                                                          \
+    do {                                                                                              \
+        if (trace != nullptr) trace[((size_t)tstep * 2 + (role)) * 16 + (slot)] = clock64();          \
+    } while (0)
+
 // shared-memory control block: mbarriers
 enum { M2B_W = 0, M2B_H, M2B_U, M2B_C, M2B_G, M2B_E, M2B_P, M2B_B, M2E_A, M2E_B, M2E_C, M2E_D, M2B_X0, M2B_X1, M2B_X2, M2B_X3, M2_NBAR };
 constexpr int kM2CtrlBytes = 256;
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
     const M2Rank R = P.r[rank];
     const M2FwdBlob B = m2_fwd_blob(P, rank);
     const int Mr = P.Mr, MH = P.MH, D = P.D, G4 = P.G4, N = P.N, T = P.T, G = P.G;
+    long long *trace = blockIdx.x == 0 ? g_m2_trace : nullptr;
     const int m = R.m, dhm = P.dh[m], u0l = R.u0 - P.off[m], goff = 4 * P.off[m];
     const bool s2 = R.head >= 0;
     const int nch1 = R.nu / 8, nch2 = s2 ? R.nj / 8 : 0;
@@ -395,39 +404,52 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                 for (int t = 0; t < T; ++t) {
                     const uint32_t ph = (uint32_t)((wave * T + t) & 1);
                     const uint32_t ph1 = (uint32_t)((wave * (T - 1) + (t - 1)) & 1);     // barriers used only for t >= 1
+                    const int tstep = t;
+                    M2_TRACE(0, 0);
                     // ---- gates: U_m h_{t-1} as soon as h has arrived, W2 u_{t-1} after exchange C ----
                     if (t > 0) { m2_mbar_wait(&bar[M2B_H], ph1); tc_fence_after(); }
+                    M2_TRACE(0, 1);
                     m2_issue3(accG, act_s, act_s + offH_lo, rowb, wg_hi, wg_lo, wg_lbo, dhm / 16, idG, true);
+                    M2_TRACE(0, 2);
                     if (t > 0) {
                         m2_poll(barC, (base + t) * G);
+                        M2_TRACE(0, 3);
                         proxy_fence_all();
                         mbar_expect_tx(&bar[M2B_U], (uint32_t)(MH * Mr * 4));
                         bulk_g2s(act + offU, xu, (uint32_t)(MH * Mr * 4), &bar[M2B_U]);
                         m2_mbar_wait(&bar[M2B_U], ph1);
                         tc_fence_after();
                     }
+                    M2_TRACE(0, 4);
                     m2_issue3(accG, act_s + offU, act_s + offU_lo, rowb, wg_hi + (dhm / 8) * wg_lbo, wg_lo + (dhm / 8) * wg_lbo, wg_lbo,
                               MH / 16, idG, false);
                     umma_commit(&bar[M2B_G]);
+                    M2_TRACE(0, 5);
                     // ---- exchange A: c_t / h_t slices of all ranks ----
                     m2_mbar_wait(&bar[M2E_A], ph);
+                    M2_TRACE(0, 6);
                     m2_signal(barA);
+                    M2_TRACE(0, 7);
                     m2_poll(barA, (base + t + 1) * G);
+                    M2_TRACE(0, 8);
                     proxy_fence_all();
                     if (s2) {
                         mbar_expect_tx(&bar[M2B_C], (uint32_t)imgC);
                         bulk_g2s(act, xc, (uint32_t)imgC, &bar[M2B_C]);
                         m2_mbar_wait(&bar[M2B_C], ph);
                         tc_fence_after();
+                        M2_TRACE(0, 9);
                         m2_issue3(accE, act_s, act_s + imgC / 2, rowb, wa_hi, wa_lo, wa_lbo, D / 16, idE, true);
                         umma_commit(&bar[M2B_E]);
                         // ---- fused reduce + fc.0 over the own K slice ----
                         m2_mbar_wait(&bar[M2E_B], ph);
                         tc_fence_after();
+                        M2_TRACE(0, 10);
                         m2_issue3(accP, act_s, act_s + offAtt_lo, rowb, w1_hi, w1_lo, w1_lbo, R.nj / 16, idP, true);
                         umma_commit(&bar[M2B_P]);
                         m2_mbar_wait(&bar[M2B_P], ph);
                     }
+                    M2_TRACE(0, 11);
                     // the operand buffer is free: fetch h_t of the own modality for the next step's gates
                     if (t + 1 < T) {
                         const uint8_t *hsrc = xh + (size_t)(t & 1) * imgC + (size_t)(P.off[m] / 8) * rowb;
@@ -437,12 +459,16 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     }
                     // ---- exchange B: partial products + softmax statistics ----
                     if (s2) m2_mbar_wait(&bar[M2E_C], ph);
+                    M2_TRACE(0, 12);
                     m2_signal(barB);
                     m2_poll(barB, (base + t + 1) * G);
+                    M2_TRACE(0, 13);
                     mbar_arrive(&bar[M2B_B]);
                     // ---- exchange C: u_t slices ----
                     m2_mbar_wait(&bar[M2E_D], ph);
+                    M2_TRACE(0, 14);
                     m2_signal(barC);
+                    M2_TRACE(0, 15);
                 }
             }
         } else {
@@ -464,6 +490,10 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)((wave * T + t) & 1);
                 const size_t tn = (size_t)t * N + n0 + row;
                 const float bvon = t > 0 ? 1.f : 0.f;
+                const int tstep = t;
+                long long *trace_ct = trace;
+                if (tid != 0) trace = nullptr;
+                M2_TRACE(1, 0);
                 // ---- gate pre-activations of the hoisted W x (+ biases): the first chunk is fetched before the wait, and the
                 //      lines of the next step are pulled into L2 now ----
                 float gxr[32];
@@ -493,6 +523,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                 // ================= epilogue 1: LSTHM cell update of the own hidden units =================
                 m2_mbar_wait(&bar[M2B_G], ph);
                 tc_fence_after();
+                M2_TRACE(1, 1);
 #pragma unroll
                 for (int ci = 0; ci < 2; ++ci) {
                     const int c = hh + 2 * ci;
@@ -547,16 +578,19 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                         }
                     }
                 }
+                M2_TRACE(1, 2);
                 proxy_fence_all();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar[M2E_A]);
+                M2_TRACE(1, 3);
 
                 if (s2) {
                     // ================= epilogue 2: logits -> local softmax statistics -> attended operand =================
                     m2_mbar_wait(&bar[M2B_C], ph);           // the gathered c image is visible to this thread
                     m2_mbar_wait(&bar[M2B_E], ph);
                     tc_fence_after();
+                    M2_TRACE(1, 4);
                     float e[6][8], cv[6][8];
                     float mx = -INFINITY;
 #pragma unroll
@@ -578,7 +612,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                         }
                     }
                     smax[hh * 128 + row] = mx;
+                    M2_TRACE(1, 5);
                     asm volatile("bar.sync 1, 256;" ::: "memory");      // all c reads done before the attended image overwrites them
+                    M2_TRACE(1, 6);
                     const float mfin = fmaxf(smax[row], smax[128 + row]);
                     float sum = 0.f;
 #pragma unroll
@@ -609,9 +645,11 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[M2E_B]);
+                    M2_TRACE(1, 7);
                     // ================= epilogue 3: partial W1 product + statistics to the group =================
                     m2_mbar_wait(&bar[M2B_P], ph);
                     tc_fence_after();
+                    M2_TRACE(1, 8);
                     {
                         uint32_t v[32];
                         tmem_ld32(accP + lane_base + 32 * hh, v);
@@ -630,10 +668,12 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[M2E_C]);
+                    M2_TRACE(1, 9);
                 }
                 // ================= combine (warps 0-3): u_t of this rank's share of the dialogues =================
                 if (warp < 4) {
                     m2_mbar_wait(&bar[M2B_B], ph);
+                    M2_TRACE(1, 10);
                     if (comb) {
                         const int nr = P.nr;
                         float u8[8];
@@ -681,7 +721,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     proxy_fence_all();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[M2E_D]);
+                    M2_TRACE(1, 11);
                 }
+                trace = trace_ct;
             }
         }
         __syncthreads();
@@ -722,6 +764,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
     const M2Rank R = P.r[rank];
     const M2BwdBlob B = m2_bwd_blob(P, rank);
     const int Mr = P.Mr, MH = P.MH, D = P.D, G4 = P.G4, N = P.N, T = P.T, G = P.G;
+    long long *trace = blockIdx.x == 0 ? g_m2_trace : nullptr;
     const int m = R.m, dhm = P.dh[m], u0l = R.u0 - P.off[m], goff = 4 * P.off[m];
     const bool s2 = R.head >= 0;
     const int nch1 = R.nu / 8, nch2 = s2 ? R.nj / 8 : 0, ng = B.ng, nF = MH + dhm;

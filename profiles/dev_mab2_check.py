@@ -148,6 +148,29 @@ def run_timing():
             torch.cuda.synchronize()
             res[what] = e0.elapsed_time(e1) / 10
         print("TIMING", kind, T, N, lib.mab2_launch_info(d), {k: f"{v:.3f} ms" for k, v in res.items()}, flush=True)
+        # phase trace of block 0 (control thread / first epilogue warp), cycles, median over the steps
+        tr = torch.zeros(T, 2, 16, device=dev, dtype=torch.int64)
+        for what in ("fwd", "bwd"):
+            tr.zero_()
+            lib.mab2_set_trace(tr)
+            if what == "fwd":
+                lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sG, sE, sMS, sP, work)
+            else:
+                lib.mab2_bwd(d, packed, dhz, duz, mask, sC, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)
+            torch.cuda.synchronize()
+            lib.mab2_set_trace(None)
+            tc = tr.cpu()
+            if int(tc.abs().sum()) == 0:
+                continue
+            for role in (0, 1):
+                x = tc[5:T - 5, role, :]                      # steady-state steps
+                nz = [k for k in range(16) if int(x[:, k].abs().sum()) > 0]
+                if not nz:
+                    continue
+                base = x[:, nz[0]]
+                rel = {k: int((x[:, k] - base).median()) for k in nz}
+                step = int((tc[6:T - 4, role, nz[0]] - tc[5:T - 5, role, nz[0]]).median())
+                print(f"TRACE {what} {kind} N={N} role{role} step={step} cyc:", rel, flush=True)
 
 
 if __name__ == "__main__":
