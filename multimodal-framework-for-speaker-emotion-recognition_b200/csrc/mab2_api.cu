@@ -104,7 +104,7 @@ static int build_plan(const lsthm_mab_desc *d, int sms, M2Plan &P) {
     const int gmax = sms / G;
     if (gmax < 1) return fail_msg("device has fewer SMs than one CTA group");
     int DG = d->rows_per_cta > 0 ? std::min(d->rows_per_cta, kM2MaxDG) : std::min(kM2MaxDG, m2_align(cdiv2(P.N, gmax), 8));
-    DG = std::min(DG, 16 * G);
+    DG = std::min(DG, 8 * G);                                   // the combine role covers 8 dialogues per rank
     for (;; DG -= 8) {
         if (DG < 1) return fail_msg("the group plan does not fit in shared memory");
         const int Mr = m2_align(DG, 8);

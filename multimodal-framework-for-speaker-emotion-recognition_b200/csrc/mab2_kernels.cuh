@@ -229,14 +229,25 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 }
 // D[128 x N] (+)= A . B^T over nk16 k-steps of 16; both operands K-major no-swizzle images [chunk][row][8 bf16]:
 // chunk stride = lbo bytes, 8-row groups contiguous (SBO 128).  Three terms per k-step: hi.hi + hi.lo + lo.hi.
-__device__ __forceinline__ void m2_issue3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t b_hi, uint32_t b_lo,
-                                          uint32_t b_lbo, int nk16, uint32_t idesc, bool zero_first) {
+// Called by the WHOLE control warp with warp-uniform arguments (descriptors stay in uniform registers); only the elected
+// lane issues.  A k-step advances a descriptor's 14-bit address field by 2 * lbo / 16.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void m2_issue3(bool leader, uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t a_lbo, uint32_t b_hi,
+                                          uint32_t b_lo, uint32_t b_lbo, int nk16, uint32_t idesc, bool zero_first) {
+    uint64_t ah = umma_desc(a_hi, a_lbo, 128), al = umma_desc(a_lo, a_lbo, 128);
+    uint64_t bh = umma_desc(b_hi, b_lbo, 128), bl = umma_desc(b_lo, b_lbo, 128);
+    const uint64_t da = (uint64_t)((2 * a_lbo) >> 4), db = (uint64_t)((2 * b_lbo) >> 4);
     for (int ks = 0; ks < nk16; ++ks) {
-        const uint64_t ah = umma_desc(a_hi + ks * 2 * a_lbo, a_lbo, 128), al = umma_desc(a_lo + ks * 2 * a_lbo, a_lbo, 128);
-        const uint64_t bh = umma_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128), bl = umma_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
-        umma_f16(tmem_d, ah, bh, idesc, (zero_first && ks == 0) ? 0u : 1u);
-        umma_f16(tmem_d, ah, bl, idesc, 1u);
-        umma_f16(tmem_d, al, bh, idesc, 1u);
+        if (leader) {
+            umma_f16(tmem_d, ah, bh, idesc, (zero_first && ks == 0) ? 0u : 1u);
+            umma_f16(tmem_d, ah, bl, idesc, 1u);
+            umma_f16(tmem_d, al, bh, idesc, 1u);
+        }
+        ah += da; al += da; bh += db; bl += db;
     }
 }
 __device__ __forceinline__ uint32_t m2_idesc(int n) {      // kind::f16, bf16 x bf16 -> f32, K-major both, M = 128
@@ -275,8 +286,8 @@ __device__ __forceinline__ void m2_poll(const unsigned *ctr, unsigned target) {
         if (clock64() - t0 > kM2Timeout) __trap();
     } while ((int)(v - target) < 0);
 }
-__device__ __forceinline__ void m2_signal(unsigned *ctr) {        // after the CTA's writes were collected by an mbarrier wait
-    __threadfence();
+// publish: the CTA's writes were collected by an mbarrier wait (they happen-before this thread); the release is cumulative
+__device__ __forceinline__ void m2_signal(unsigned *ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
@@ -393,14 +404,16 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
         if (wave == 0) m2_mbar_wait(&bar[M2B_W], 0);
 
         if (warp == kM2EpiWarps) {
-            // =============================== control thread ===============================
-            if (lane == 0) {
+            // =============================== control warp (one elected lane issues) ===============================
+            {
+                const bool leader = elect_one();
                 const uint32_t act_s = smem_u32(act), blob_s = smem_u32(blob);
                 const uint32_t wg_hi = blob_s + B.wg, wg_lo = wg_hi + B.kcg * B.ng * 16, wg_lbo = B.ng * 16;
                 const uint32_t wa_hi = blob_s + B.wa, wa_lo = wa_hi + (D / 8) * R.nj * 16, wa_lbo = R.nj * 16;
                 const uint32_t w1_hi = blob_s + B.w1, w1_lo = w1_hi + nch2 * MH * 16, w1_lbo = MH * 16;
                 const uint32_t idG = m2_idesc(B.ng), idE = m2_idesc(R.nj), idP = m2_idesc(MH);
                 const unsigned base = (unsigned)wave * T;        // barrier epochs are monotonic over the whole launch
+                if (lane != 0) trace = nullptr;
                 for (int t = 0; t < T; ++t) {
                     const uint32_t ph = (uint32_t)((wave * T + t) & 1);
                     const uint32_t ph1 = (uint32_t)((wave * (T - 1) + (t - 1)) & 1);     // barriers used only for t >= 1
@@ -409,50 +422,55 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     // ---- gates: U_m h_{t-1} as soon as h has arrived, W2 u_{t-1} after exchange C ----
                     if (t > 0) { m2_mbar_wait(&bar[M2B_H], ph1); tc_fence_after(); }
                     M2_TRACE(0, 1);
-                    m2_issue3(accG, act_s, act_s + offH_lo, rowb, wg_hi, wg_lo, wg_lbo, dhm / 16, idG, true);
+                    m2_issue3(leader, accG, act_s, act_s + offH_lo, rowb, wg_hi, wg_lo, wg_lbo, dhm / 16, idG, true);
                     M2_TRACE(0, 2);
                     if (t > 0) {
                         m2_poll(barC, (base + t) * G);
                         M2_TRACE(0, 3);
-                        proxy_fence_all();
-                        mbar_expect_tx(&bar[M2B_U], (uint32_t)(MH * Mr * 4));
-                        bulk_g2s(act + offU, xu, (uint32_t)(MH * Mr * 4), &bar[M2B_U]);
+                        if (leader) {
+                            proxy_fence_all();
+                            mbar_expect_tx(&bar[M2B_U], (uint32_t)(MH * Mr * 4));
+                            bulk_g2s(act + offU, xu, (uint32_t)(MH * Mr * 4), &bar[M2B_U]);
+                        }
                         m2_mbar_wait(&bar[M2B_U], ph1);
                         tc_fence_after();
                     }
                     M2_TRACE(0, 4);
-                    m2_issue3(accG, act_s + offU, act_s + offU_lo, rowb, wg_hi + (dhm / 8) * wg_lbo, wg_lo + (dhm / 8) * wg_lbo, wg_lbo,
-                              MH / 16, idG, false);
-                    umma_commit(&bar[M2B_G]);
+                    m2_issue3(leader, accG, act_s + offU, act_s + offU_lo, rowb, wg_hi + (dhm / 8) * wg_lbo, wg_lo + (dhm / 8) * wg_lbo,
+                              wg_lbo, MH / 16, idG, false);
+                    if (leader) umma_commit(&bar[M2B_G]);
                     M2_TRACE(0, 5);
                     // ---- exchange A: c_t / h_t slices of all ranks ----
                     m2_mbar_wait(&bar[M2E_A], ph);
                     M2_TRACE(0, 6);
-                    m2_signal(barA);
+                    if (leader) m2_signal(barA);
                     M2_TRACE(0, 7);
                     m2_poll(barA, (base + t + 1) * G);
                     M2_TRACE(0, 8);
-                    proxy_fence_all();
                     if (s2) {
-                        mbar_expect_tx(&bar[M2B_C], (uint32_t)imgC);
-                        bulk_g2s(act, xc, (uint32_t)imgC, &bar[M2B_C]);
+                        if (leader) {
+                            proxy_fence_all();
+                            mbar_expect_tx(&bar[M2B_C], (uint32_t)imgC);
+                            bulk_g2s(act, xc, (uint32_t)imgC, &bar[M2B_C]);
+                        }
                         m2_mbar_wait(&bar[M2B_C], ph);
                         tc_fence_after();
                         M2_TRACE(0, 9);
-                        m2_issue3(accE, act_s, act_s + imgC / 2, rowb, wa_hi, wa_lo, wa_lbo, D / 16, idE, true);
-                        umma_commit(&bar[M2B_E]);
+                        m2_issue3(leader, accE, act_s, act_s + imgC / 2, rowb, wa_hi, wa_lo, wa_lbo, D / 16, idE, true);
+                        if (leader) umma_commit(&bar[M2B_E]);
                         // ---- fused reduce + fc.0 over the own K slice ----
                         m2_mbar_wait(&bar[M2E_B], ph);
                         tc_fence_after();
                         M2_TRACE(0, 10);
-                        m2_issue3(accP, act_s, act_s + offAtt_lo, rowb, w1_hi, w1_lo, w1_lbo, R.nj / 16, idP, true);
-                        umma_commit(&bar[M2B_P]);
+                        m2_issue3(leader, accP, act_s, act_s + offAtt_lo, rowb, w1_hi, w1_lo, w1_lbo, R.nj / 16, idP, true);
+                        if (leader) umma_commit(&bar[M2B_P]);
                         m2_mbar_wait(&bar[M2B_P], ph);
                     }
                     M2_TRACE(0, 11);
                     // the operand buffer is free: fetch h_t of the own modality for the next step's gates
-                    if (t + 1 < T) {
+                    if (t + 1 < T && leader) {
                         const uint8_t *hsrc = xh + (size_t)(t & 1) * imgC + (size_t)(P.off[m] / 8) * rowb;
+                        proxy_fence_all();
                         mbar_expect_tx(&bar[M2B_H], 2u * (uint32_t)offH_lo);
                         bulk_g2s(act, hsrc, (uint32_t)offH_lo, &bar[M2B_H]);
                         bulk_g2s(act + offH_lo, hsrc + imgC / 2, (uint32_t)offH_lo, &bar[M2B_H]);
@@ -460,14 +478,14 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     // ---- exchange B: partial products + softmax statistics ----
                     if (s2) m2_mbar_wait(&bar[M2E_C], ph);
                     M2_TRACE(0, 12);
-                    m2_signal(barB);
+                    if (leader) m2_signal(barB);
                     m2_poll(barB, (base + t + 1) * G);
                     M2_TRACE(0, 13);
-                    mbar_arrive(&bar[M2B_B]);
+                    if (leader) mbar_arrive(&bar[M2B_B]);
                     // ---- exchange C: u_t slices ----
                     m2_mbar_wait(&bar[M2E_D], ph);
                     M2_TRACE(0, 14);
-                    m2_signal(barC);
+                    if (leader) m2_signal(barC);
                     M2_TRACE(0, 15);
                 }
             }
@@ -482,8 +500,8 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cprev[ci][i] = 0.f;
             const bool stash = a.sC != nullptr;
-            // combine role (warps 0-3): dialogue dd of this rank's share, chunk qc of the MH outputs
-            const int cdd = tid >> 3, cqc = tid & 7, cdia = rank * P.cd + cdd;
+            // combine role (warps 0-3): dialogue dd of this rank's share, piece pc (4 of the MH outputs)
+            const int cdd = tid >> 4, cpc = tid & 15, cdia = rank * P.cd + cdd;
             const bool comb = tid < 128 && cdd < P.cd && cdia < rows;
 
             for (int t = 0; t < T; ++t) {
@@ -514,12 +532,8 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
 #pragma unroll
                             for (int gate = 0; gate < 4; ++gate) prefetch_l2(a.gx + (tn + N) * G4 + goff + u0l + 8 * c + gate * dhm);
                 }
-                float4 mk0 = make_float4(1.f, 1.f, 1.f, 1.f), mk1 = mk0;
-                if (comb && a.mask != nullptr) {
-                    const float *mp = a.mask + ((size_t)t * N + n0 + cdia) * MH + 8 * cqc;
-                    mk0 = __ldg(reinterpret_cast<const float4 *>(mp));
-                    mk1 = __ldg(reinterpret_cast<const float4 *>(mp) + 1);
-                }
+                float4 mk0 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (comb && a.mask != nullptr) mk0 = __ldg(reinterpret_cast<const float4 *>(a.mask + ((size_t)t * N + n0 + cdia) * MH + 4 * cpc));
                 // ================= epilogue 1: LSTHM cell update of the own hidden units =================
                 m2_mbar_wait(&bar[M2B_G], ph);
                 tc_fence_after();
@@ -655,11 +669,12 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                         tmem_ld32(accP + lane_base + 32 * hh, v);
                         tmem_ld_wait();
                         if (rv) {
-                            float4 *pp = reinterpret_cast<float4 *>(xp + ((size_t)rank * Mr + row) * MH + 32 * hh);
+                            // piece-major [rank][MH/4][Mr][4]: a warp's store of one piece is 512 contiguous bytes
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                pp[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                                    __uint_as_float(v[4 * i + 3]));
+                                *reinterpret_cast<float4 *>(xp + (((size_t)rank * (MH / 4) + 8 * hh + i) * Mr + row) * 4) =
+                                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                __uint_as_float(v[4 * i + 3]));
                             if (hh == 0)
                                 *reinterpret_cast<float2 *>(xst + ((size_t)rank * Mr + row) * 2) =
                                     make_float2(fmaxf(smax[row], smax[128 + row]), ssum[row] + ssum[128 + row]);
@@ -671,52 +686,66 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     M2_TRACE(1, 9);
                 }
                 // ================= combine (warps 0-3): u_t of this rank's share of the dialogues =================
+                // thread = (dialogue, piece of 4 outputs); every load of the reduction is in flight before the first use
                 if (warp < 4) {
                     m2_mbar_wait(&bar[M2B_B], ph);
                     M2_TRACE(1, 10);
+                    float u4[4] = {0.f, 0.f, 0.f, 0.f};
                     if (comb) {
                         const int nr = P.nr;
-                        float u8[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) u8[i] = s_b1[8 * cqc + i];
                         const size_t tnc = (size_t)t * N + n0 + cdia;
+                        float2 ms[kHeads][4];
+                        float4 pp[kHeads][4];
+#pragma unroll
+                        for (int k = 0; k < kHeads; ++k)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (i < nr) {
+                                    const int r = k * nr + i;
+                                    ms[k][i] = __ldcg(reinterpret_cast<const float2 *>(xst + ((size_t)r * Mr + cdia) * 2));
+                                    pp[k][i] = ldcg4(xp + (((size_t)r * (MH / 4) + cpc) * Mr + cdia) * 4);
+                                }
+                        const float4 b1v = *reinterpret_cast<const float4 *>(s_b1 + 4 * cpc);
+                        u4[0] = b1v.x; u4[1] = b1v.y; u4[2] = b1v.z; u4[3] = b1v.w;
 #pragma unroll
                         for (int k = 0; k < kHeads; ++k) {
                             float Mk = -INFINITY;
-                            for (int r = k * nr; r < (k + 1) * nr; ++r) Mk = fmaxf(Mk, __ldcg(xst + ((size_t)r * Mr + cdia) * 2));
-                            float S = 0.f, acc[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                            for (int r = k * nr; r < (k + 1) * nr; ++r) {
-                                const float2 ms = __ldcg(reinterpret_cast<const float2 *>(xst + ((size_t)r * Mr + cdia) * 2));
-                                const float w = __expf(ms.x - Mk);
-                                S += ms.y * w;
-                                const float *pr = xp + ((size_t)r * Mr + cdia) * MH + 8 * cqc;
-                                const float4 p0 = ldcg4(pr), p1 = ldcg4(pr + 4);
-                                acc[0] += w * p0.x; acc[1] += w * p0.y; acc[2] += w * p0.z; acc[3] += w * p0.w;
-                                acc[4] += w * p1.x; acc[5] += w * p1.y; acc[6] += w * p1.z; acc[7] += w * p1.w;
-                            }
+                            for (int i = 0; i < 4; ++i)
+                                if (i < nr) Mk = fmaxf(Mk, ms[k][i].x);
+                            float S = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                if (i < nr) {
+                                    const float w = __expf(ms[k][i].x - Mk);
+                                    S += ms[k][i].y * w;
+                                    acc[0] += w * pp[k][i].x; acc[1] += w * pp[k][i].y; acc[2] += w * pp[k][i].z; acc[3] += w * pp[k][i].w;
+                                }
                             const float inv = 1.0f / S;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) { acc[i] *= inv; u8[i] += acc[i]; }
+                            for (int i = 0; i < 4; ++i) { acc[i] *= inv; u4[i] += acc[i]; }
                             if (stash) {
-                                float4 *sp = reinterpret_cast<float4 *>(a.sP + (tnc * kHeads + k) * MH + 8 * cqc);
-                                sp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                                sp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                                if (cqc == 0) *reinterpret_cast<float2 *>(a.sMS + (tnc * kHeads + k) * 2) = make_float2(Mk, inv);
+                                *reinterpret_cast<float4 *>(a.sP + (tnc * kHeads + k) * MH + 4 * cpc) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                                if (cpc == 0) *reinterpret_cast<float2 *>(a.sMS + (tnc * kHeads + k) * 2) = make_float2(Mk, inv);
                             }
                         }
-                        const float mk[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) u8[i] = fmaxf(u8[i], 0.f) * mk[i];
-                        float4 *up = reinterpret_cast<float4 *>(a.sU + tnc * MH + 8 * cqc);
-                        up[0] = make_float4(u8[0], u8[1], u8[2], u8[3]);
-                        up[1] = make_float4(u8[4], u8[5], u8[6], u8[7]);
-                        uint4 hi, lo;
-                        m2_split8(u8, hi, lo);
-                        const size_t uo = ((size_t)cqc * Mr + cdia) * 16;
-                        *reinterpret_cast<uint4 *>(xu + uo) = hi;
-                        *reinterpret_cast<uint4 *>(xu + (size_t)(MH / 8) * Mr * 16 + uo) = lo;
+                        u4[0] = fmaxf(u4[0], 0.f) * mk0.x; u4[1] = fmaxf(u4[1], 0.f) * mk0.y;
+                        u4[2] = fmaxf(u4[2], 0.f) * mk0.z; u4[3] = fmaxf(u4[3], 0.f) * mk0.w;
+                        *reinterpret_cast<float4 *>(a.sU + tnc * MH + 4 * cpc) = make_float4(u4[0], u4[1], u4[2], u4[3]);
+                    }
+                    // operand image: the even / odd piece of a chunk sit in adjacent lanes; the even lane stores the hi chunk,
+                    // the odd lane the lo chunk
+                    {
+                        const uint32_t h0 = pack_bf16(u4[0], u4[1]), h1 = pack_bf16(u4[2], u4[3]);
+                        const uint32_t l0 = pack_bf16(u4[0] - __uint_as_float(h0 << 16), u4[1] - __uint_as_float(h0 & 0xffff0000u));
+                        const uint32_t l1 = pack_bf16(u4[2] - __uint_as_float(h1 << 16), u4[3] - __uint_as_float(h1 & 0xffff0000u));
+                        const uint32_t oh0 = __shfl_xor_sync(0xffffffffu, h0, 1), oh1 = __shfl_xor_sync(0xffffffffu, h1, 1);
+                        const uint32_t ol0 = __shfl_xor_sync(0xffffffffu, l0, 1), ol1 = __shfl_xor_sync(0xffffffffu, l1, 1);
+                        if (comb) {
+                            const size_t uo = ((size_t)(cpc >> 1) * Mr + cdia) * 16;
+                            if ((cpc & 1) == 0) *reinterpret_cast<uint4 *>(xu + uo) = make_uint4(h0, h1, oh0, oh1);
+                            else *reinterpret_cast<uint4 *>(xu + (size_t)(MH / 8) * Mr * 16 + uo) = make_uint4(ol0, ol1, l0, l1);
+                        }
                     }
                     proxy_fence_all();
                     __syncwarp();
@@ -784,7 +813,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
 
     uint8_t *wsg = a.ws + (size_t)grp * P.ws_group;
     float *xdc = reinterpret_cast<float *>(wsg + P.ws_xdc);       // [rank][D/8][Mr][8]  dc partials; then [4][D/8][Mr][8] direct terms
-    float *xdir = xdc + (size_t)G * D * Mr;
+    float *xdir = xdc + (size_t)G * D * Mr;                     // pseudo-ranks G .. G+3 of the same piece-major layout
     float *xdu = reinterpret_cast<float *>(wsg + P.ws_xdu);       // [rank][Mr][MH]
     float *xdh = reinterpret_cast<float *>(wsg + P.ws_xdh);       // [rank][16][Mr][8]
     uint8_t *xdup = wsg + P.ws_xdup;                              // dup image (hi|lo) then dots [Mr][4]
@@ -822,49 +851,67 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
         if (wave == 0) m2_mbar_wait(&bar[B2_W], 0);
 
         if (warp == kM2EpiWarps) {
-            // =============================== control thread ===============================
-            if (lane == 0) {
+            // =============================== control warp (one elected lane issues) ===============================
+            {
+                const bool leader = elect_one();
                 const uint32_t act_s = smem_u32(act), blob_s = smem_u32(blob);
                 const uint32_t w1t_hi = blob_s + B.w1t, w1t_lo = w1t_hi + (MH / 8) * R.nj * 16, w1t_lbo = R.nj * 16;
                 const uint32_t wat_hi = blob_s + B.wat, wat_lo = wat_hi + nch2 * D * 16, wat_lbo = D * 16;
                 const uint32_t wf_hi = blob_s + B.wf, wf_lo = wf_hi + (ng / 8) * nF * 16, wf_lbo = nF * 16;
                 const uint32_t idV = m2_idesc(R.nj), idC = m2_idesc(D), idF = m2_idesc(nF);
                 const unsigned baseS = (unsigned)wave * T, baseF = (unsigned)wave * (T - 1);
+                if (lane != 0) trace = nullptr;
                 // the pre-step combine publishes dup_{T-1}
                 m2_mbar_wait(&bar[E2_CMB], (uint32_t)((wave * T) & 1));
-                m2_signal(barX1b);
+                if (leader) m2_signal(barX1b);
                 for (int t = T - 1, s = 0; t >= 0; --t, ++s) {         // s = steps done in this wave
                     const uint32_t ph = (uint32_t)((wave * T + s) & 1);
                     const uint32_t phF = (uint32_t)((wave * (T - 1) + s) & 1);      // barriers skipped at t == 0
+                    const int tstep = s;
+                    M2_TRACE(0, 0);
                     if (s2) {
                         m2_poll(barX1b, (baseS + s + 1) * G);
-                        proxy_fence_all();
-                        mbar_expect_tx(&bar[B2_DUP], (uint32_t)imgU);
-                        bulk_g2s(act, xdup, (uint32_t)imgU, &bar[B2_DUP]);
+                        M2_TRACE(0, 1);
+                        if (leader) {
+                            proxy_fence_all();
+                            mbar_expect_tx(&bar[B2_DUP], (uint32_t)imgU);
+                            bulk_g2s(act, xdup, (uint32_t)imgU, &bar[B2_DUP]);
+                        }
                         m2_mbar_wait(&bar[B2_DUP], ph);
                         tc_fence_after();
-                        m2_issue3(accDV, act_s, act_s + imgU / 2, rowb, w1t_hi, w1t_lo, w1t_lbo, MH / 16, idV, true);
-                        umma_commit(&bar[B2_DV]);
+                        M2_TRACE(0, 2);
+                        m2_issue3(leader, accDV, act_s, act_s + imgU / 2, rowb, w1t_hi, w1t_lo, w1t_lbo, MH / 16, idV, true);
+                        if (leader) umma_commit(&bar[B2_DV]);
+                        M2_TRACE(0, 3);
                         m2_mbar_wait(&bar[E2_B], ph);
                         tc_fence_after();
-                        m2_issue3(accDC, act_s + offDE, act_s + offDE + nch2 * Mr * 16, rowb, wat_hi, wat_lo, wat_lbo, R.nj / 16, idC, true);
-                        umma_commit(&bar[B2_DC]);
+                        M2_TRACE(0, 4);
+                        m2_issue3(leader, accDC, act_s + offDE, act_s + offDE + nch2 * Mr * 16, rowb, wat_hi, wat_lo, wat_lbo, R.nj / 16, idC, true);
+                        if (leader) umma_commit(&bar[B2_DC]);
+                        M2_TRACE(0, 5);
                         m2_mbar_wait(&bar[E2_D], ph);
                     }
-                    m2_signal(barX2);
+                    M2_TRACE(0, 6);
+                    if (leader) m2_signal(barX2);
                     m2_poll(barX2, (baseS + s + 1) * G);
-                    mbar_arrive(&bar[B2_X2]);
+                    M2_TRACE(0, 7);
+                    if (leader) mbar_arrive(&bar[B2_X2]);
                     m2_mbar_wait(&bar[E2_S], ph);
+                    M2_TRACE(0, 8);
                     if (t > 0) {
                         tc_fence_after();
-                        m2_issue3(accF, act_s + offDS, act_s + offDS + (ng / 8) * Mr * 16, rowb, wf_hi, wf_lo, wf_lbo, ng / 16, idF, true);
-                        umma_commit(&bar[B2_F]);
+                        m2_issue3(leader, accF, act_s + offDS, act_s + offDS + (ng / 8) * Mr * 16, rowb, wf_hi, wf_lo, wf_lbo, ng / 16, idF, true);
+                        if (leader) umma_commit(&bar[B2_F]);
+                        M2_TRACE(0, 9);
                         m2_mbar_wait(&bar[E2_F], phF);
-                        m2_signal(barX1a);
+                        M2_TRACE(0, 10);
+                        if (leader) m2_signal(barX1a);
                         m2_poll(barX1a, (baseF + s + 1) * G);
-                        mbar_arrive(&bar[B2_X1A]);
+                        M2_TRACE(0, 11);
+                        if (leader) mbar_arrive(&bar[B2_X1A]);
                         m2_mbar_wait(&bar[E2_CMB], (uint32_t)((wave * T + s + 1) & 1));
-                        m2_signal(barX1b);
+                        M2_TRACE(0, 12);
+                        if (leader) m2_signal(barX1b);
                     }
                 }
             }
@@ -878,57 +925,62 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
             for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dhc[ci][i] = dcc[ci][i] = 0.f;
-            const int cdd = tid >> 3, cqc = tid & 7, cdia = rank * P.cd + cdd;
+            const int cdd = tid >> 4, cpc = tid & 15, cdia = rank * P.cd + cdd;
             const bool comb = tid < 128 && cdd < P.cd && cdia < rows;
 
             // combine: du (sum of the ranks' partials, fixed order) -> dup_tt, its operand image and the dots <dup_tt, P_k>
             auto combine = [&](int tt, bool first) {
-                float s8[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s8[i] = 0.f;
+                // thread = (dialogue, piece of 4 outputs); all partial loads in flight before the first add (fixed rank order)
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
                 float dots[kHeads] = {0.f, 0.f, 0.f, 0.f};
                 if (comb) {
                     const size_t tnc = (size_t)tt * N + n0 + cdia;
+                    float4 pr[kM2MaxRanks];
                     if (!first) {
-                        for (int r = 0; r < G; ++r) {
-                            const float *pr = xdu + ((size_t)r * Mr + cdia) * MH + 8 * cqc;
-                            const float4 p0 = ldcg4(pr), p1 = ldcg4(pr + 4);
-                            s8[0] += p0.x; s8[1] += p0.y; s8[2] += p0.z; s8[3] += p0.w;
-                            s8[4] += p1.x; s8[5] += p1.y; s8[6] += p1.z; s8[7] += p1.w;
-                        }
-                    }
-                    const float4 z0 = __ldg(reinterpret_cast<const float4 *>(a.duz + tnc * MH + 8 * cqc)), z1 = __ldg(reinterpret_cast<const float4 *>(a.duz + tnc * MH + 8 * cqc) + 1);
-                    const float4 u0 = __ldg(reinterpret_cast<const float4 *>(a.sU + tnc * MH + 8 * cqc)), u1 = __ldg(reinterpret_cast<const float4 *>(a.sU + tnc * MH + 8 * cqc) + 1);
-                    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w}, uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-                    float mk[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
-                    if (a.mask != nullptr) {
-                        const float4 k0 = __ldg(reinterpret_cast<const float4 *>(a.mask + tnc * MH + 8 * cqc)), k1 = __ldg(reinterpret_cast<const float4 *>(a.mask + tnc * MH + 8 * cqc) + 1);
-                        mk[0] = k0.x; mk[1] = k0.y; mk[2] = k0.z; mk[3] = k0.w; mk[4] = k1.x; mk[5] = k1.y; mk[6] = k1.z; mk[7] = k1.w;
-                    }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) s8[i] = (uu[i] != 0.f ? s8[i] + zz[i] : 0.f) * mk[i];
-                    float4 *dp = reinterpret_cast<float4 *>(a.dup + tnc * MH + 8 * cqc);
-                    dp[0] = make_float4(s8[0], s8[1], s8[2], s8[3]);
-                    dp[1] = make_float4(s8[4], s8[5], s8[6], s8[7]);
-                    uint4 hi, lo;
-                    m2_split8(s8, hi, lo);
-                    const size_t uo = ((size_t)cqc * Mr + cdia) * 16;
-                    *reinterpret_cast<uint4 *>(xdup + uo) = hi;
-                    *reinterpret_cast<uint4 *>(xdup + imgU / 2 + uo) = lo;
+                        for (int r = 0; r < kM2MaxRanks; ++r)
+                            if (r < G) pr[r] = ldcg4(xdu + (((size_t)r * (MH / 4) + cpc) * Mr + cdia) * 4);
+                    }
+                    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.duz + tnc * MH + 4 * cpc));
+                    const float4 u = __ldg(reinterpret_cast<const float4 *>(a.sU + tnc * MH + 4 * cpc));
+                    float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (a.mask != nullptr) mk = __ldg(reinterpret_cast<const float4 *>(a.mask + tnc * MH + 4 * cpc));
+                    float4 pk[kHeads];
 #pragma unroll
-                    for (int k = 0; k < kHeads; ++k) {
-                        const float *pp = a.sP + (tnc * kHeads + k) * MH + 8 * cqc;
-                        const float4 p0 = __ldg(reinterpret_cast<const float4 *>(pp)), p1 = __ldg(reinterpret_cast<const float4 *>(pp) + 1);
-                        dots[k] = s8[0] * p0.x + s8[1] * p0.y + s8[2] * p0.z + s8[3] * p0.w + s8[4] * p1.x + s8[5] * p1.y + s8[6] * p1.z + s8[7] * p1.w;
+                    for (int k = 0; k < kHeads; ++k) pk[k] = __ldg(reinterpret_cast<const float4 *>(a.sP + (tnc * kHeads + k) * MH + 4 * cpc));
+                    if (!first) {
+#pragma unroll
+                        for (int r = 0; r < kM2MaxRanks; ++r)
+                            if (r < G) { s4[0] += pr[r].x; s4[1] += pr[r].y; s4[2] += pr[r].z; s4[3] += pr[r].w; }
+                    }
+                    s4[0] = (u.x != 0.f ? s4[0] + z.x : 0.f) * mk.x;
+                    s4[1] = (u.y != 0.f ? s4[1] + z.y : 0.f) * mk.y;
+                    s4[2] = (u.z != 0.f ? s4[2] + z.z : 0.f) * mk.z;
+                    s4[3] = (u.w != 0.f ? s4[3] + z.w : 0.f) * mk.w;
+                    *reinterpret_cast<float4 *>(a.dup + tnc * MH + 4 * cpc) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+#pragma unroll
+                    for (int k = 0; k < kHeads; ++k) dots[k] = s4[0] * pk[k].x + s4[1] * pk[k].y + s4[2] * pk[k].z + s4[3] * pk[k].w;
+                }
+                {
+                    const uint32_t h0 = pack_bf16(s4[0], s4[1]), h1 = pack_bf16(s4[2], s4[3]);
+                    const uint32_t l0 = pack_bf16(s4[0] - __uint_as_float(h0 << 16), s4[1] - __uint_as_float(h0 & 0xffff0000u));
+                    const uint32_t l1 = pack_bf16(s4[2] - __uint_as_float(h1 << 16), s4[3] - __uint_as_float(h1 & 0xffff0000u));
+                    const uint32_t oh0 = __shfl_xor_sync(0xffffffffu, h0, 1), oh1 = __shfl_xor_sync(0xffffffffu, h1, 1);
+                    const uint32_t ol0 = __shfl_xor_sync(0xffffffffu, l0, 1), ol1 = __shfl_xor_sync(0xffffffffu, l1, 1);
+                    if (comb) {
+                        const size_t uo = ((size_t)(cpc >> 1) * Mr + cdia) * 16;
+                        if ((cpc & 1) == 0) *reinterpret_cast<uint4 *>(xdup + uo) = make_uint4(h0, h1, oh0, oh1);
+                        else *reinterpret_cast<uint4 *>(xdup + imgU / 2 + uo) = make_uint4(ol0, ol1, l0, l1);
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < kHeads; ++k) {                    // the 8 chunk-threads of a dialogue are 8 adjacent lanes
+                for (int k = 0; k < kHeads; ++k) {                    // the 16 piece-threads of a dialogue are 16 adjacent lanes
                     dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 1);
                     dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 2);
                     dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 4);
+                    dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 8);
                 }
-                if (comb && cqc == 0) *reinterpret_cast<float4 *>(xdot + (size_t)cdia * 4) = make_float4(dots[0], dots[1], dots[2], dots[3]);
+                if (comb && cpc == 0) *reinterpret_cast<float4 *>(xdot + (size_t)cdia * 4) = make_float4(dots[0], dots[1], dots[2], dots[3]);
                 proxy_fence_all();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar[E2_CMB]);
@@ -940,12 +992,17 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)((wave * T + s) & 1);
                 const uint32_t phF = (uint32_t)((wave * (T - 1) + s) & 1);
                 const size_t tn = (size_t)t * N + n0 + row;
+                const int tstep = s;
+                long long *trace_ct = trace;
+                if (tid != 0) trace = nullptr;
+                M2_TRACE(1, 0);
                 if (s2) {
                     // ================= softmax backward of the own (head, range) slice =================
                     float2 ms = make_float2(0.f, 0.f);
                     if (rv) ms = __ldg(reinterpret_cast<const float2 *>(a.sMS + (tn * kHeads + R.head) * 2));
                     m2_mbar_wait(&bar[B2_DV], ph);
                     tc_fence_after();
+                    M2_TRACE(1, 1);
                     const float dot = rv ? __ldcg(xdot + (size_t)row * 4 + R.head) : 0.f;
 #pragma unroll
                     for (int ci = 0; ci < 6; ++ci) {
@@ -978,9 +1035,8 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                                     ap[0] = make_float4(atc[0], atc[1], atc[2], atc[3]);
                                     ap[1] = make_float4(atc[4], atc[5], atc[6], atc[7]);
                                 }
-                                float4 *xp4 = reinterpret_cast<float4 *>(xdir + (((size_t)R.head * (D / 8) + j / 8) * Mr + row) * 8);
-                                xp4[0] = make_float4(dir[0], dir[1], dir[2], dir[3]);
-                                xp4[1] = make_float4(dir[4], dir[5], dir[6], dir[7]);
+                                *reinterpret_cast<float4 *>(xdir + (((size_t)R.head * (D / 4) + j / 4) * Mr + row) * 4) = make_float4(dir[0], dir[1], dir[2], dir[3]);
+                                *reinterpret_cast<float4 *>(xdir + (((size_t)R.head * (D / 4) + j / 4 + 1) * Mr + row) * 4) = make_float4(dir[4], dir[5], dir[6], dir[7]);
                                 uint4 hi, lo;
                                 m2_split8(dev, hi, lo);
                                 const size_t ao = ((size_t)c2 * Mr + row) * 16;
@@ -993,22 +1049,26 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[E2_B]);
+                    M2_TRACE(1, 2);
                     // ================= dc partial of the own slice -> group =================
                     m2_mbar_wait(&bar[B2_DC], ph);
                     tc_fence_after();
+                    M2_TRACE(1, 3);
                     for (int kc = hh; kc < D / 8; kc += 2) {
                         uint32_t v[8];
                         tmem_ld8(accDC + lane_base + 8 * kc, v);
                         tmem_ld_wait();
                         if (rv) {
-                            float4 *pp = reinterpret_cast<float4 *>(xdc + (((size_t)rank * (D / 8) + kc) * Mr + row) * 8);
-                            pp[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                            pp[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                            *reinterpret_cast<float4 *>(xdc + (((size_t)rank * (D / 4) + 2 * kc) * Mr + row) * 4) =
+                                make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                            *reinterpret_cast<float4 *>(xdc + (((size_t)rank * (D / 4) + 2 * kc + 1) * Mr + row) * 4) =
+                                make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[E2_D]);
+                    M2_TRACE(1, 4);
                 }
                 // ================= cell backward of the own hidden units =================
                 float gf[8], gi[8], go[8], gg[8], cc[8], cp[8], gh[8];
@@ -1038,7 +1098,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                             prefetch_l2(a.dhz + (tn - N) * 2 * D + R.u0 + 8 * c);
                         }
                 }
+                M2_TRACE(1, 5);
                 m2_mbar_wait(&bar[B2_X2], ph);
+                M2_TRACE(1, 6);
 #pragma unroll
                 for (int ci = 0; ci < 2; ++ci) {
                     const int c = hh + 2 * ci;
@@ -1048,16 +1110,27 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                         float gc[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) gc[i] = dcc[ci][i];
-                        for (int r = 0; r < ns2; ++r) {
-                            const float *pr = xdc + (((size_t)r * (D / 8) + ug / 8) * Mr + row) * 8;
-                            const float4 p0 = ldcg4(pr), p1 = ldcg4(pr + 4);
-                            gc[0] += p0.x; gc[1] += p0.y; gc[2] += p0.z; gc[3] += p0.w; gc[4] += p1.x; gc[5] += p1.y; gc[6] += p1.z; gc[7] += p1.w;
-                        }
+                        // sources 0 .. ns2-1: the ranks' dc partials; then the four heads' direct terms (they follow xdc in memory
+                        // as pseudo-ranks G .. G+3).  Batches of 8 sources: all loads of a batch in flight, adds in fixed order.
 #pragma unroll
-                        for (int k = 0; k < kHeads; ++k) {
-                            const float *pr = xdir + (((size_t)k * (D / 8) + ug / 8) * Mr + row) * 8;
-                            const float4 p0 = ldcg4(pr), p1 = ldcg4(pr + 4);
-                            gc[0] += p0.x; gc[1] += p0.y; gc[2] += p0.z; gc[3] += p0.w; gc[4] += p1.x; gc[5] += p1.y; gc[6] += p1.z; gc[7] += p1.w;
+                        for (int b0 = 0; b0 < kM2MaxRanks + kHeads; b0 += 8) {
+                            float4 p0[8], p1[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int sidx = b0 + i;
+                                if (sidx < ns2 + kHeads) {
+                                    const int src = sidx < ns2 ? sidx : G + (sidx - ns2);
+                                    const float *pr = xdc + (((size_t)src * (D / 4) + ug / 4) * Mr + row) * 4;
+                                    p0[i] = ldcg4(pr);
+                                    p1[i] = ldcg4(pr + (size_t)Mr * 4);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (b0 + i < ns2 + kHeads) {
+                                    gc[0] += p0[i].x; gc[1] += p0[i].y; gc[2] += p0[i].z; gc[3] += p0[i].w;
+                                    gc[4] += p1[i].x; gc[5] += p1[i].y; gc[6] += p1[i].z; gc[7] += p1[i].w;
+                                }
                         }
                         float ds[4][8];
 #pragma unroll
@@ -1095,20 +1168,22 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar[E2_S]);
+                M2_TRACE(1, 7);
                 if (t > 0) {
                     // ================= [du | dh_m] partials -> group =================
                     m2_mbar_wait(&bar[B2_F], phF);
                     tc_fence_after();
+                    M2_TRACE(1, 8);
                     {
                         uint32_t v[32];
                         tmem_ld32(accF + lane_base + 32 * hh, v);
                         tmem_ld_wait();
                         if (rv) {
-                            float4 *pp = reinterpret_cast<float4 *>(xdu + ((size_t)rank * Mr + row) * MH + 32 * hh);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
-                                pp[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                                    __uint_as_float(v[4 * i + 3]));
+                                *reinterpret_cast<float4 *>(xdu + (((size_t)rank * (MH / 4) + 8 * hh + i) * Mr + row) * 4) =
+                                    make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                __uint_as_float(v[4 * i + 3]));
                         }
                     }
                     for (int kc = hh; kc < dhm / 8; kc += 2) {
@@ -1116,15 +1191,18 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                         tmem_ld8(accF + lane_base + MH + 8 * kc, v);
                         tmem_ld_wait();
                         if (rv) {
-                            float4 *pp = reinterpret_cast<float4 *>(xdh + (((size_t)rank * 16 + kc) * Mr + row) * 8);
-                            pp[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                            pp[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                            *reinterpret_cast<float4 *>(xdh + (((size_t)rank * 32 + 2 * kc) * Mr + row) * 4) =
+                                make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                            *reinterpret_cast<float4 *>(xdh + (((size_t)rank * 32 + 2 * kc + 1) * Mr + row) * 4) =
+                                make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
                         }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[E2_F]);
+                    M2_TRACE(1, 9);
                     m2_mbar_wait(&bar[B2_X1A], phF);
+                    M2_TRACE(1, 10);
                     // dh carry of the own units: sum over the ranks of the own modality (fixed order)
 #pragma unroll
                     for (int ci = 0; ci < 2; ++ci) {
@@ -1132,17 +1210,29 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                         if (c < nch1 && rv) {
                             const int kc = (u0l + 8 * c) / 8;
                             float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            for (int r = mr0; r < mr1; ++r) {
-                                const float *pr = xdh + (((size_t)r * 16 + kc) * Mr + row) * 8;
-                                const float4 p0 = ldcg4(pr), p1 = ldcg4(pr + 4);
-                                s8[0] += p0.x; s8[1] += p0.y; s8[2] += p0.z; s8[3] += p0.w; s8[4] += p1.x; s8[5] += p1.y; s8[6] += p1.z; s8[7] += p1.w;
-                            }
+                            float4 p0[kM2MaxRanks], p1[kM2MaxRanks];   // loads of all ranks of the modality in flight, adds in fixed order
+#pragma unroll
+                            for (int i = 0; i < kM2MaxRanks; ++i)
+                                if (mr0 + i < mr1) {
+                                    const float *pr = xdh + (((size_t)(mr0 + i) * 32 + 2 * kc) * Mr + row) * 4;
+                                    p0[i] = ldcg4(pr);
+                                    p1[i] = ldcg4(pr + (size_t)Mr * 4);
+                                }
+#pragma unroll
+                            for (int i = 0; i < kM2MaxRanks; ++i)
+                                if (mr0 + i < mr1) {
+                                    s8[0] += p0[i].x; s8[1] += p0[i].y; s8[2] += p0[i].z; s8[3] += p0[i].w;
+                                    s8[4] += p1[i].x; s8[5] += p1[i].y; s8[6] += p1[i].z; s8[7] += p1[i].w;
+                                }
 #pragma unroll
                             for (int i = 0; i < 8; ++i) dhc[ci][i] = s8[i];
                         }
                     }
+                    M2_TRACE(1, 11);
                     if (warp < 4) combine(t - 1, false);
+                    M2_TRACE(1, 12);
                 }
+                trace = trace_ct;
             }
         }
         __syncthreads();
