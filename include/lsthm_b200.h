@@ -131,22 +131,27 @@ int lsthm_mab2_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *p
 /*
  * Forward over all T steps (cooperative launch).  gx, drop_mask, hz, u as for lsthm_mab_fwd.
  * stash (all out, may ALL be NULL for inference):
- *   sC [T][N][D] cell states        sG [T][N][4D] gates after sigmoid/tanh (layout of gx)
- *   sE [T][N][4][D] attention logits (att.0 output incl. bias, BEFORE the softmax)
- *   sMS [T][N][4][2] per head (max logit, 1 / sum exp(e - max)): softmax weights are a = exp(e - max) * inv
- *   sP [T][N][4][map_h] per head  W1[:, head block] . (a_head * c)   (the softmax backward needs <dup, P_head>)
+ *   sC [T][N][D] cell states, row-major (the caller's weight-gradient products read it)
+ * and the PRIVATE stash of the kernel pair, piece-major inside a dialogue block so that every warp access is one contiguous
+ * run:  [T][block][column / 4][row][4]  with `padded_rows / blocks` rows per block (lsthm_mab2_launch_info):
+ *   sCp (width D) cell states        sG (width 4D) gates after sigmoid/tanh, column order of gx
+ *   sE (width 4D) attention logits (att.0 output incl. bias, BEFORE the softmax), column = head * D + feature
+ *   sMS [T][block][4][row][2] per head (max logit, 1 / sum exp(e - max)): softmax weights are a = exp(e - max) * inv
+ *   sP (width 4 * map_h) per head  W1[:, head block] . (a_head * c), column = head * map_h + q
+ *      (the softmax backward needs <dup, P_head>)
+ * each private tensor holds T * padded_rows * width floats (sMS: T * padded_rows * 8).
  */
 int lsthm_mab2_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx, const float *drop_mask, float *hz, float *u,
-                   float *sC, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream);
+                   float *sC, float *sCp, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream);
 
 /* BPTT (cooperative launch).  dhz, duz, drop_mask, u and the outputs dgx, de, dup, att as for lsthm_mab_bwd. */
 int lsthm_mab2_bwd(const lsthm_mab_desc *d, const void *packed, const float *dhz, const float *duz, const float *drop_mask,
-                   const float *sC, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
+                   const float *sCp, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
                    float *dgx, float *de, float *dup, float *att, void *workspace, void *stream);
 
-/* Launch geometry on the current device: grid = groups * group size. */
+/* Launch geometry on the current device: grid = groups * group size; padded_rows = blocks * rows per block (multiple of 8). */
 int lsthm_mab2_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *group,
-                           int32_t *dialogues_per_group, int32_t *smem_fwd, int32_t *smem_bwd);
+                           int32_t *dialogues_per_group, int32_t *smem_fwd, int32_t *smem_bwd, int32_t *padded_rows);
 /* The sharding plan for a 148-SM device (host only, no device needed): 14 header ints (G, ranges per head, dialogues
  * per group, padded rows, groups, blocks, combine share, blob_f, blob_b, act_f, act_b, smem_fwd, smem_bwd, ws_group)
  * followed by (modality, first unit, units, head, first feature, features) per rank. */

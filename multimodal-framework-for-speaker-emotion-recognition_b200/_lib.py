@@ -101,11 +101,11 @@ def lib() -> C.CDLL:
     L.lsthm_mab2_pack.restype = C.c_int
     L.lsthm_mab2_pack.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights), C.c_void_p, C.c_void_p]
     L.lsthm_mab2_fwd.restype = C.c_int
-    L.lsthm_mab2_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 12
+    L.lsthm_mab2_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 13
     L.lsthm_mab2_bwd.restype = C.c_int
     L.lsthm_mab2_bwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 16
     L.lsthm_mab2_launch_info.restype = C.c_int
-    L.lsthm_mab2_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 6
+    L.lsthm_mab2_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 7
     L.lsthm_mab2_plan_info.restype = C.c_int
     L.lsthm_mab2_plan_info.argtypes = [C.POINTER(MabDesc), C.POINTER(C.c_int32), C.c_int32]
     L.lsthm_mab2_set_trace.restype = C.c_int
@@ -260,17 +260,17 @@ def mab2_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
     _check(lib().lsthm_mab2_pack(C.byref(d), C.byref(w), _byte_ptr(packed, "packed"), _stream()), "lsthm_mab2_pack")
 
 
-def mab2_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sG, sE, sMS, sP, workspace) -> None:
+def mab2_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, workspace) -> None:
     """Writes the h half of hz[T,N,2D] and u[T,N,map_h]; the caller forms z = u Wf2^T + bf2 (include/lsthm_b200.h)."""
     _check(lib().lsthm_mab2_fwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(gx, "gx"), _dev_ptr(drop_mask, "drop_mask"),
-                                _dev_ptr(hz, "hz"), _dev_ptr(u, "u"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
+                                _dev_ptr(hz, "hz"), _dev_ptr(u, "u"), _dev_ptr(sC, "sC"), _dev_ptr(sCp, "sCp"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
                                 _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _byte_ptr(workspace, "workspace"), _stream()),
            "lsthm_mab2_fwd")
 
 
-def mab2_bwd(d: MabDesc, packed, dhz, duz, drop_mask, sC, sG, sE, sMS, sP, u, dgx, de, dup, att, workspace) -> None:
+def mab2_bwd(d: MabDesc, packed, dhz, duz, drop_mask, sCp, sG, sE, sMS, sP, u, dgx, de, dup, att, workspace) -> None:
     _check(lib().lsthm_mab2_bwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"), _dev_ptr(duz, "duz"),
-                                _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
+                                _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sCp, "sCp"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
                                 _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _dev_ptr(u, "u"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
                                 _dev_ptr(dup, "dup"), _dev_ptr(att, "att"), _byte_ptr(workspace, "workspace"), _stream()),
            "lsthm_mab2_bwd")
@@ -281,9 +281,31 @@ def mab2_set_trace(buf: Optional[torch.Tensor]) -> None:
 
 
 def mab2_launch_info(d: MabDesc) -> dict:
-    v = [C.c_int32() for _ in range(6)]
+    v = [C.c_int32() for _ in range(7)]
     _check(lib().lsthm_mab2_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab2_launch_info")
-    return dict(zip(("grid", "block", "group", "dialogues_per_group", "smem_fwd", "smem_bwd"), (x.value for x in v)))
+    return dict(zip(("grid", "block", "group", "dialogues_per_group", "smem_fwd", "smem_bwd", "padded_rows"), (x.value for x in v)))
+
+
+def mab2_alloc_stash(d: MabDesc, device) -> dict:
+    """The private (piece-major) stash tensors of a forward/backward pair, sized for the current device's plan."""
+    info = mab2_launch_info(d)
+    D = sum(d.dh[i] for i in range(d.n_mod))
+    rows = d.T * info["padded_rows"]
+    new = lambda w: torch.empty(rows * w, device=device, dtype=torch.float32)
+    return dict(sCp=new(D), sG=new(4 * D), sE=new(4 * D), sMS=new(8), sP=new(4 * d.map_h))
+
+
+def mab2_unblock(x: torch.Tensor, d: MabDesc, width: int) -> torch.Tensor:
+    """Private piece-major stash tensor -> row-major [T, N, width] (tests and debugging only)."""
+    info = mab2_launch_info(d)
+    DG = info["dialogues_per_group"]
+    Mr = (DG + 7) // 8 * 8
+    nb = info["padded_rows"] // Mr
+    if width == 8:          # sMS: [T][block][4 heads][row][2]
+        y = x.view(d.T, nb, 4, Mr, 2).permute(0, 1, 3, 2, 4).reshape(d.T, nb, Mr, width)[:, :, :DG]
+    else:
+        y = x.view(d.T, nb, width // 4, Mr, 4).permute(0, 1, 3, 2, 4).reshape(d.T, nb, Mr, width)[:, :, :DG]
+    return y.reshape(d.T, nb * DG, width)[:, :d.N].contiguous()
 
 
 def mab2_plan_info(d: MabDesc) -> dict:

@@ -57,16 +57,14 @@ static int build_plan(const lsthm_mab_desc *d, int sms, M2Plan &P) {
     P.nr = cdiv2(k16, 5);
     const int ns2 = 4 * P.nr;
     if (ns2 > kM2MaxRanks) return fail_msg("too many attention slices for one CTA group");
-    // stage 1: group size = the stage-2 job count, plus up to two ranks while that cuts the gate cost by a quarter
-    int G = std::max(ns2, P.nm), ranks[kMaxMod];
-    int cmax = stage1_alloc(P, G, ranks);
-    for (int extra = 0; extra < 2 && G < kM2MaxRanks; ++extra) {
-        int r2[kMaxMod];
-        const int c2 = stage1_alloc(P, G + 1, r2);
-        if (4 * c2 > 3 * cmax) break;
-        ++G; cmax = c2;
-    }
-    stage1_alloc(P, G, ranks);
+    // stage 1: every rank owns at most 16 hidden units of one modality (one 8-unit chunk per epilogue warp of a lane quarter);
+    // the group has as many ranks as the larger of the two stages needs
+    int ranks[kMaxMod], n1 = 0;
+    for (int m = 0; m < P.nm; ++m) { ranks[m] = cdiv2(P.dh[m] / 8, 2); n1 += ranks[m]; }
+    const int G = std::max(ns2, n1);
+    if (G > kM2MaxRanks) return fail_msg("cells too large for one CTA group");
+    for (int m = 0; n1 < G; m = (m + 1) % P.nm)                     // spare ranks: spread the widest modality thinner
+        if (ranks[m] < P.dh[m] / 8) { ++ranks[m]; ++n1; }
     P.G = G;
     int rank = 0;
     for (int m = 0; m < P.nm; ++m) {
@@ -74,7 +72,10 @@ static int build_plan(const lsthm_mab_desc *d, int sms, M2Plan &P) {
         int c0 = 0;
         for (int i = 0; i < ranks[m]; ++i, ++rank) {
             const int nc = base + (i < rem ? 1 : 0);
+            if (ranks[m] > 8) return fail_msg("more than 8 ranks per modality");
             P.r[rank].m = m; P.r[rank].u0 = P.off[m] + 8 * c0; P.r[rank].nu = 8 * nc;
+            P.r[rank].dhm = P.dh[m]; P.r[rank].offm = P.off[m];
+            P.r[rank].mr0 = rank - i; P.r[rank].mr1 = rank - i + ranks[m];
             if (8 * nc > kM2MaxNU) return fail_msg("cell too large for the group plan");
             c0 += nc;
         }
@@ -96,8 +97,8 @@ static int build_plan(const lsthm_mab_desc *d, int sms, M2Plan &P) {
     }
     // blobs
     for (int r = 0; r < G; ++r) {
-        P.blob_f = std::max(P.blob_f, m2_fwd_blob(P, r).total);
-        P.blob_b = std::max(P.blob_b, m2_bwd_blob(P, r).total);
+        P.blob_f = std::max(P.blob_f, m2_fwd_blob(P, P.r[r]).total);
+        P.blob_b = std::max(P.blob_b, m2_bwd_blob(P, P.r[r]).total);
     }
     // dialogues per group
     if (sms <= 0) sms = 148;
@@ -137,7 +138,10 @@ static int build_plan(const lsthm_mab_desc *d, int sms, M2Plan &P) {
     return 0;
 }
 
+// packed area: [composite weights fp32][rank table][forward blobs][backward blobs]
 static size_t comp_floats(const M2Plan &P) { return (size_t)2 * P.MH * P.G4 + P.MH + P.G4; }
+static size_t ranktab_off(const M2Plan &P) { return (size_t)m2_align((int)(comp_floats(P) * 4), 128); }
+static size_t blobs_off(const M2Plan &P) { return ranktab_off(P) + (size_t)m2_align((int)(kM2MaxRanks * sizeof(M2Rank)), 128); }
 static size_t bars_bytes(const M2Plan &P) { return (size_t)std::max(1, 148 / P.G + 1) * 512; }
 
 static int device_sms() {
@@ -165,7 +169,7 @@ extern "C" {
 size_t lsthm_mab2_pack_bytes(const lsthm_mab_desc *d) {
     M2Plan P;
     if (build_plan(d, 0, P)) return 0;
-    return comp_floats(P) * 4 + (size_t)P.G * (P.blob_f + P.blob_b) + 256;
+    return blobs_off(P) + (size_t)P.G * (P.blob_f + P.blob_b) + 256;
 }
 
 size_t lsthm_mab2_workspace_bytes(const lsthm_mab_desc *d) {
@@ -226,7 +230,8 @@ int lsthm_mab2_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *p
     ia.P = P;
     for (int m = 0; m < kMaxMod; ++m) ia.U[m] = w->U[m];
     ia.Watt = w->Watt; ia.batt = w->batt; ia.W1 = c.W1; ia.W2 = c.W2; ia.b1 = c.b1; ia.bv = c.bv;
-    uint8_t *base = reinterpret_cast<uint8_t *>(packed) + m2_align((int)(comp_floats(P) * 4), 128);
+    uint8_t *base = reinterpret_cast<uint8_t *>(packed) + blobs_off(P);
+    ia.ranktab = reinterpret_cast<M2Rank *>(reinterpret_cast<uint8_t *>(packed) + ranktab_off(P));
     ia.blob_f = base;
     ia.blob_b = base + (size_t)P.G * P.blob_f;
     mab2_image_kernel<<<dim3(12, P.G), 256, 0, (cudaStream_t)stream>>>(ia);
@@ -235,7 +240,7 @@ int lsthm_mab2_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *p
 }
 
 int lsthm_mab2_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *group, int32_t *dialogues_per_group,
-                           int32_t *smem_fwd, int32_t *smem_bwd) {
+                           int32_t *smem_fwd, int32_t *smem_bwd, int32_t *padded_rows) {
     M2Plan P;
     if (build_plan(d, device_sms(), P)) return 1;
     if (grid) *grid = P.ngroups * P.G;
@@ -244,22 +249,24 @@ int lsthm_mab2_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *bloc
     if (dialogues_per_group) *dialogues_per_group = P.DG;
     if (smem_fwd) *smem_fwd = kM2CtrlBytes + P.blob_f + P.act_f + 3072;
     if (smem_bwd) *smem_bwd = kM2CtrlBytes + P.blob_b + P.act_b + 3072;
+    if (padded_rows) *padded_rows = P.nblocks * P.Mr;
     return 0;
 }
 
 int lsthm_mab2_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx, const float *drop_mask, float *hz, float *u,
-                   float *sC, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream) {
+                   float *sC, float *sCp, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream) {
     M2FwdArgs a;
     const int sms = device_sms();
     if (sms <= 0) return fail_msg("no CUDA device (there is no CPU path)");
     if (build_plan(d, sms, a.P)) return 1;
     if (!packed || !gx || !hz || !u || !workspace) return fail_msg("null packed/gx/hz/u/workspace pointer");
-    const bool any = sC || sG || sE || sMS || sP, all = sC && sG && sE && sMS && sP;
+    const bool any = sC || sCp || sG || sE || sMS || sP, all = sC && sCp && sG && sE && sMS && sP;
     if (any && !all) return fail_msg("stash pointers must be all set or all NULL");
     const M2Plan &P = a.P;
-    a.blob = reinterpret_cast<const uint8_t *>(packed) + m2_align((int)(comp_floats(P) * 4), 128);
+    a.blob = reinterpret_cast<const uint8_t *>(packed) + blobs_off(P);
+    a.ranktab = reinterpret_cast<const M2Rank *>(reinterpret_cast<const uint8_t *>(packed) + ranktab_off(P));
     a.gx = gx; a.mask = drop_mask; a.hz = hz; a.sU = u;
-    a.sC = sC; a.sG = sG; a.sE = sE; a.sMS = sMS; a.sP = sP;
+    a.sC = sC; a.sCp = sCp; a.sG = sG; a.sE = sE; a.sMS = sMS; a.sP = sP;
     a.bars = reinterpret_cast<unsigned *>(workspace);
     a.ws = reinterpret_cast<uint8_t *>(workspace) + bars_bytes(P);
     cudaError_t e = cudaMemsetAsync(workspace, 0, bars_bytes(P), (cudaStream_t)stream);
@@ -269,17 +276,18 @@ int lsthm_mab2_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx,
 }
 
 int lsthm_mab2_bwd(const lsthm_mab_desc *d, const void *packed, const float *dhz, const float *duz, const float *drop_mask,
-                   const float *sC, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
+                   const float *sCp, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
                    float *dgx, float *de, float *dup, float *att, void *workspace, void *stream) {
     M2BwdArgs a;
     const int sms = device_sms();
     if (sms <= 0) return fail_msg("no CUDA device (there is no CPU path)");
     if (build_plan(d, sms, a.P)) return 1;
-    if (!packed || !dhz || !duz || !sC || !sG || !sE || !sMS || !sP || !u || !dgx || !de || !dup || !workspace)
+    if (!packed || !dhz || !duz || !sCp || !sG || !sE || !sMS || !sP || !u || !dgx || !de || !dup || !workspace)
         return fail_msg("null pointer argument");
     const M2Plan &P = a.P;
-    a.blob = reinterpret_cast<const uint8_t *>(packed) + m2_align((int)(comp_floats(P) * 4), 128) + (size_t)P.G * P.blob_f;
-    a.dhz = dhz; a.duz = duz; a.mask = drop_mask; a.sC = sC; a.sG = sG; a.sE = sE; a.sMS = sMS; a.sP = sP; a.sU = u;
+    a.blob = reinterpret_cast<const uint8_t *>(packed) + blobs_off(P) + (size_t)P.G * P.blob_f;
+    a.ranktab = reinterpret_cast<const M2Rank *>(reinterpret_cast<const uint8_t *>(packed) + ranktab_off(P));
+    a.dhz = dhz; a.duz = duz; a.mask = drop_mask; a.sCp = sCp; a.sG = sG; a.sE = sE; a.sMS = sMS; a.sP = sP; a.sU = u;
     a.dgx = dgx; a.de = de; a.dup = dup; a.att = att;
     a.bars = reinterpret_cast<unsigned *>(workspace);
     a.ws = reinterpret_cast<uint8_t *>(workspace) + bars_bytes(P);

@@ -28,15 +28,26 @@ namespace lsthm {
 
 constexpr int kM2MaxRanks = 16;
 constexpr int kM2EpiWarps = 8;
-constexpr int kM2Threads = (kM2EpiWarps + 1) * 32;      // 8 epilogue warps + 1 control warp (MMA issue, copies, barriers)
+// 8 epilogue warps (two warpgroups) + one control warpgroup whose first warp issues MMAs, copies and barriers.  The control
+// warpgroup hands most of its registers to the epilogue warps (setmaxnreg): with shared memory at ~215 KB the L1 is only a
+// few KB, so a spilled register costs an L2 round trip — the epilogues must not spill.
+constexpr int kM2Threads = (kM2EpiWarps + 4) * 32;
+constexpr int kM2RegsEpi = 224, kM2RegsCtl = 56;
+// the pool setmaxnreg draws from is the CTA's own allocation (launch registers x threads, 168 x 384 under these launch bounds),
+// not the whole register file: an increase that the control warpgroup's release cannot cover blocks forever
+static_assert(kM2EpiWarps * 32 * kM2RegsEpi + 4 * 32 * kM2RegsCtl <= kM2Threads * 168, "setmaxnreg budget exceeds the CTA's register pool");
 constexpr int kM2MaxDG = 96;                            // dialogues per group (operand buffer budget)
 constexpr int kM2MaxNJ = 96;                            // stage-2 feature range per rank
-constexpr int kM2MaxNU = 32;                            // stage-1 hidden units per rank
+constexpr int kM2MaxNU = 16;                            // stage-1 hidden units per rank: one 8-unit chunk per epilogue warp of a lane quarter
+constexpr int kM2CPH = 1;                               // chunks per epilogue half (kM2MaxNU / 16)
 constexpr long long kM2Timeout = 1LL << 31;             // cycles (~1 s): a stuck exchange traps instead of hanging the GPU
 
 struct M2Rank {
     int m, u0, nu;        // stage 1: modality, first hidden unit (global index, multiple of 8), units (multiple of 8)
     int head, j0, nj;     // stage 2/3: head (-1 = none), feature range [j0, j0 + nj), nj multiple of 16
+    int dhm, offm;        // cell size and first unit of the own modality
+    int mr0, mr1;         // ranks of the own modality: [mr0, mr1)
+    int pad0, pad1;       // 48 bytes: the kernels read their rank's record from global memory with three 16-byte loads
 };
 
 struct M2Plan {
@@ -57,11 +68,10 @@ struct M2BwdBlob { int w1t, wat, wf, total, ng, nf; };
 
 __host__ __device__ inline int m2_align(int x, int a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline M2FwdBlob m2_fwd_blob(const M2Plan &P, int rank) {
-    const M2Rank &R = P.r[rank];
+__host__ __device__ inline M2FwdBlob m2_fwd_blob(const M2Plan &P, const M2Rank &R) {
     M2FwdBlob b;
     b.ng = 4 * R.nu;
-    b.kcg = (P.dh[R.m] + P.MH) / 8;
+    b.kcg = (R.dhm + P.MH) / 8;
     int o = 0;
     b.wg = o; o += 2 * b.kcg * b.ng * 16;                            // [hi|lo][kc][n = ul*4+gate][8]  K = [h_m | u]
     b.wa = o; o += R.head >= 0 ? 2 * (P.D / 8) * R.nj * 16 : 0;      // [hi|lo][kc][n = j - j0][8]     K = c (D)
@@ -73,11 +83,10 @@ __host__ __device__ inline M2FwdBlob m2_fwd_blob(const M2Plan &P, int rank) {
     return b;
 }
 
-__host__ __device__ inline M2BwdBlob m2_bwd_blob(const M2Plan &P, int rank) {
-    const M2Rank &R = P.r[rank];
+__host__ __device__ inline M2BwdBlob m2_bwd_blob(const M2Plan &P, const M2Rank &R) {
     M2BwdBlob b;
     b.ng = 4 * R.nu;
-    b.nf = P.MH + P.dh[R.m];
+    b.nf = P.MH + R.dhm;
     int o = 0;
     b.w1t = o; o += R.head >= 0 ? 2 * (P.MH / 8) * R.nj * 16 : 0;    // [N = nj][K = MH]          d attended = dup . W1
     b.wat = o; o += R.head >= 0 ? 2 * (R.nj / 8) * P.D * 16 : 0;     // [N = D][K = nj]           dc partial = de . Watt
@@ -145,6 +154,7 @@ struct M2ImgArgs {
     M2Plan P;
     const float *U[kMaxMod], *Watt, *batt, *W1, *W2, *b1, *bv;
     uint8_t *blob_f, *blob_b;
+    M2Rank *ranktab;
 };
 
 // value (n, k) of image `img` of rank R;  forward: 0 WG, 1 WA, 2 W1;  backward: 3 W1T, 4 WAT, 5 WF = [W2T ; UT] stacked along N
@@ -171,10 +181,11 @@ __global__ void __launch_bounds__(256) mab2_image_kernel(const __grid_constant__
     const M2Plan &P = a.P;
     const int rank = blockIdx.y;
     const M2Rank R = P.r[rank];
-    const M2FwdBlob F = m2_fwd_blob(P, rank);
-    const M2BwdBlob B = m2_bwd_blob(P, rank);
+    const M2FwdBlob F = m2_fwd_blob(P, R);
+    const M2BwdBlob B = m2_bwd_blob(P, R);
     const bool s2 = R.head >= 0;
-    const int dh = P.dh[R.m];
+    const int dh = R.dhm;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.ranktab[rank] = R;          // the kernels' per-rank record
     // images: N rows, K/8 chunks, byte offset of the hi image
     const int iN[6] = {F.ng, R.nj, P.MH, R.nj, P.D, B.nf};
     const int iKc[6] = {F.kcg, P.D / 8, R.nj / 8, P.MH / 8, R.nj / 8, B.ng / 8};
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(256) mab2_image_kernel(const __grid_constant__
         }
     }
     // fp32 vectors of the forward blob
-    const int goff = 4 * P.off[R.m], u0l = R.u0 - P.off[R.m];
+    const int goff = 4 * R.offm, u0l = R.u0 - R.offm;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kM2MaxNJ + P.MH + 4 * kM2MaxNU; i += gridDim.x * blockDim.x) {
         if (i < kM2MaxNJ) {
             reinterpret_cast<float *>(bf + F.batt)[i] = (s2 && i < R.nj) ? __ldg(a.batt + R.head * P.D + R.j0 + i) : 0.f;
@@ -276,15 +287,20 @@ __device__ __forceinline__ void m2_mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity))
         if (clock64() - t0 > kM2Timeout) __trap();
 }
+// Spin on the group counter with RELAXED gpu-scope loads (they are served by L2 and leave the SM's L1 alone) and issue ONE
+// acquire fence after the counter has arrived: an acquire load per spin would invalidate the L1 on every iteration, which
+// evicts the epilogue warps' cached lines (including their spill slots) for as long as the control warp waits.
 __device__ __forceinline__ void m2_poll(const unsigned *ctr, unsigned target) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    if ((int)(v - target) >= 0) return;
-    const long long t0 = clock64();
-    do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (clock64() - t0 > kM2Timeout) __trap();
-    } while ((int)(v - target) < 0);
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    if ((int)(v - target) < 0) {
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            if (clock64() - t0 > kM2Timeout) __trap();
+        } while ((int)(v - target) < 0);
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 // publish: the CTA's writes were collected by an mbarrier wait (they happen-before this thread); the release is cumulative
 __device__ __forceinline__ void m2_signal(unsigned *ctr) {
@@ -332,9 +348,13 @@ constexpr int kM2CtrlBytes = 256;
 struct M2FwdArgs {
     M2Plan P;
     const uint8_t *blob;          // [G][blob_f]
+    const M2Rank *ranktab;        // [G]
     const float *gx, *mask;       // [T][N][4D], [T][N][MH] or null
     float *hz, *sU;               // [T][N][2D] (h half), [T][N][MH]
-    float *sC, *sG, *sE, *sMS, *sP;   // stash (all or none): c [D], gates [4D], logits [4D], (max, 1/sum) [4][2], per-head W1 product [4][MH]
+    float *sC;                    // [T][N][D] cell states, row-major (the host's weight-gradient products read it)
+    // private stash of the kernel pair (all or none), PIECE-MAJOR inside a dialogue block so that a warp's access is one
+    // contiguous run:  [t][block][column / 4][row][4]  with Mr padded rows per block
+    float *sCp, *sG, *sE, *sMS, *sP;  // c [D], gates [4D], logits [4D], (max, 1/sum) [4][2], per-head W1 product [4*MH]
     uint8_t *ws;                  // exchange workspace [ngroups][ws_group]
     unsigned *bars;               // [ngroups][4][32] zero-initialised counters
 };
@@ -344,11 +364,17 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
     const M2Plan &P = a.P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = blockIdx.x % P.G, grp = blockIdx.x / P.G;
-    const M2Rank R = P.r[rank];
-    const M2FwdBlob B = m2_fwd_blob(P, rank);
+    M2Rank R;                     // from global memory: indexing the parameter struct by rank would put a copy of it on the stack
+    {
+        const int4 *rp = reinterpret_cast<const int4 *>(a.ranktab + rank);
+        const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+        R.m = r0.x; R.u0 = r0.y; R.nu = r0.z; R.head = r0.w; R.j0 = r1.x; R.nj = r1.y; R.dhm = r1.z; R.offm = r1.w;
+        R.mr0 = r2.x; R.mr1 = r2.y; R.pad0 = R.pad1 = 0;
+    }
+    const M2FwdBlob B = m2_fwd_blob(P, R);
     const int Mr = P.Mr, MH = P.MH, D = P.D, G4 = P.G4, N = P.N, T = P.T, G = P.G;
     long long *trace = blockIdx.x == 0 ? g_m2_trace : nullptr;
-    const int m = R.m, dhm = P.dh[m], u0l = R.u0 - P.off[m], goff = 4 * P.off[m];
+    const int dhm = R.dhm, u0l = R.u0 - R.offm, goff = 4 * R.offm;
     const bool s2 = R.head >= 0;
     const int nch1 = R.nu / 8, nch2 = s2 ? R.nj / 8 : 0;
 
@@ -364,7 +390,6 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
     // operand buffer views (byte offsets inside `act`)
     const int imgC = D * Mr * 4;                           // c image: hi then lo, D/8 chunks of Mr rows each
     const int offH_lo = (dhm / 8) * Mr * 16, offU = 2 * offH_lo, offU_lo = offU + (MH / 8) * Mr * 16;
-    const int offAtt_lo = nch2 * Mr * 16;
     const uint32_t rowb = (uint32_t)Mr * 16;               // chunk stride of every activation image
 
     uint8_t *wsg = a.ws + (size_t)grp * P.ws_group;
@@ -395,6 +420,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
         for (int o = 0; o < B.total; o += 32768) bulk_g2s(blob + o, src + o, (uint32_t)min(32768, B.total - o), &bar[M2B_W]);
     }
 
+    // role split OUTSIDE the block loop: the control warpgroup shrinks its register budget once, the epilogue warpgroups grow theirs
+    if (warp >= kM2EpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kM2RegsCtl));
     for (int blk = grp, wave = 0; blk < P.nblocks; blk += P.ngroups, ++wave) {
         const int n0 = blk * P.DG, rows = min(P.DG, N - n0);
         // zero operand buffer (h_{-1} = u_{-1} = 0)
@@ -462,14 +490,15 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                         m2_mbar_wait(&bar[M2E_B], ph);
                         tc_fence_after();
                         M2_TRACE(0, 10);
-                        m2_issue3(leader, accP, act_s, act_s + offAtt_lo, rowb, w1_hi, w1_lo, w1_lbo, R.nj / 16, idP, true);
+                        m2_issue3(leader, accP, act_s + (R.j0 / 8) * rowb, act_s + imgC / 2 + (R.j0 / 8) * rowb, rowb, w1_hi, w1_lo, w1_lbo,
+                                  R.nj / 16, idP, true);
                         if (leader) umma_commit(&bar[M2B_P]);
                         m2_mbar_wait(&bar[M2B_P], ph);
                     }
                     M2_TRACE(0, 11);
                     // the operand buffer is free: fetch h_t of the own modality for the next step's gates
                     if (t + 1 < T && leader) {
-                        const uint8_t *hsrc = xh + (size_t)(t & 1) * imgC + (size_t)(P.off[m] / 8) * rowb;
+                        const uint8_t *hsrc = xh + (size_t)(t & 1) * imgC + (size_t)(R.offm / 8) * rowb;
                         proxy_fence_all();
                         mbar_expect_tx(&bar[M2B_H], 2u * (uint32_t)offH_lo);
                         bulk_g2s(act, hsrc, (uint32_t)offH_lo, &bar[M2B_H]);
@@ -489,19 +518,35 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     M2_TRACE(0, 15);
                 }
             }
-        } else {
+        }
+        __syncthreads();
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kM2RegsEpi));
+    for (int blk = grp, wave = 0; blk < P.nblocks; blk += P.ngroups, ++wave) {
+        const int n0 = blk * P.DG, rows = min(P.DG, N - n0);
+        // zero operand buffer (h_{-1} = u_{-1} = 0)
+        for (int i = tid; i < P.act_f / 16; i += kM2Threads) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
+        proxy_fence_smem();
+        __syncthreads();
+        if (wave == 0) m2_mbar_wait(&bar[M2B_W], 0);
+
+        {
             // =============================== epilogue warps ===============================
             const int q = warp & 3, hh = warp >> 2, row = 32 * q + lane;
             const bool rv = row < rows;
             const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-            float cprev[2][8];
+            float cprev[kM2CPH][8];
 #pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
+            for (int ci = 0; ci < kM2CPH; ++ci)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cprev[ci][i] = 0.f;
             const bool stash = a.sC != nullptr;
-            // combine role (warps 0-3): dialogue dd of this rank's share, piece pc (4 of the MH outputs)
-            const int cdd = tid >> 4, cpc = tid & 15, cdia = rank * P.cd + cdd;
+            // private stash addressing (floats): piece-major inside the block
+            const size_t pvb = (size_t)P.nblocks * Mr;                  // padded rows per step
+            auto priv = [&](int width, int tt, int col) { return ((size_t)tt * pvb * width) + ((size_t)blk * (width / 4) + col / 4) * Mr * 4; };
+            // combine role (warps 0-3): dialogue dd of this rank's share (fastest over lanes), piece pc (4 of the MH outputs)
+            const int cdd = tid & 7, cpc = (tid >> 3) & 15, cdia = rank * P.cd + cdd;
             const bool comb = tid < 128 && cdd < P.cd && cdia < rows;
 
             for (int t = 0; t < T; ++t) {
@@ -539,7 +584,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                 tc_fence_after();
                 M2_TRACE(1, 1);
 #pragma unroll
-                for (int ci = 0; ci < 2; ++ci) {
+                for (int ci = 0; ci < kM2CPH; ++ci) {
                     const int c = hh + 2 * ci;
                     if (c < nch1) {                                   // warp-uniform
                         uint32_t v[32];
@@ -569,15 +614,19 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                                 float4 *cp = reinterpret_cast<float4 *>(a.sC + tn * D + ug);
                                 cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
                                 cp[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                                float *gp = a.sG + tn * G4 + goff + u0l + 8 * c;
-                                reinterpret_cast<float4 *>(gp)[0] = make_float4(gf[0], gf[1], gf[2], gf[3]);
-                                reinterpret_cast<float4 *>(gp)[1] = make_float4(gf[4], gf[5], gf[6], gf[7]);
-                                reinterpret_cast<float4 *>(gp + dhm)[0] = make_float4(gi[0], gi[1], gi[2], gi[3]);
-                                reinterpret_cast<float4 *>(gp + dhm)[1] = make_float4(gi[4], gi[5], gi[6], gi[7]);
-                                reinterpret_cast<float4 *>(gp + 2 * dhm)[0] = make_float4(go[0], go[1], go[2], go[3]);
-                                reinterpret_cast<float4 *>(gp + 2 * dhm)[1] = make_float4(go[4], go[5], go[6], go[7]);
-                                reinterpret_cast<float4 *>(gp + 3 * dhm)[0] = make_float4(gg[0], gg[1], gg[2], gg[3]);
-                                reinterpret_cast<float4 *>(gp + 3 * dhm)[1] = make_float4(gg[4], gg[5], gg[6], gg[7]);
+                                float *cq = a.sCp + priv(D, t, ug) + row * 4;
+                                *reinterpret_cast<float4 *>(cq) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                                *reinterpret_cast<float4 *>(cq + Mr * 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                                float *gp = a.sG + priv(G4, t, goff + u0l + 8 * c) + row * 4;
+                                const size_t gst = (size_t)(dhm / 4) * Mr * 4;       // one gate further = dhm columns
+                                *reinterpret_cast<float4 *>(gp) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                                *reinterpret_cast<float4 *>(gp + Mr * 4) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+                                *reinterpret_cast<float4 *>(gp + gst) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                                *reinterpret_cast<float4 *>(gp + gst + Mr * 4) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+                                *reinterpret_cast<float4 *>(gp + 2 * gst) = make_float4(go[0], go[1], go[2], go[3]);
+                                *reinterpret_cast<float4 *>(gp + 2 * gst + Mr * 4) = make_float4(go[4], go[5], go[6], go[7]);
+                                *reinterpret_cast<float4 *>(gp + 3 * gst) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+                                *reinterpret_cast<float4 *>(gp + 3 * gst + Mr * 4) = make_float4(gg[4], gg[5], gg[6], gg[7]);
                             }
                             // exchange A: the producer splits once, every consumer bulk-copies the operand image
                             uint4 hi, lo;
@@ -605,52 +654,49 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     m2_mbar_wait(&bar[M2B_E], ph);
                     tc_fence_after();
                     M2_TRACE(1, 4);
-                    float e[6][8], cv[6][8];
+                    // pass 1: the row's maximum over the own chunks.  Pass 2 re-reads the logits from TMEM (nothing is kept in
+                    // registers across the exchange of the maxima) and writes the attended operand IN PLACE over the c chunks it
+                    // was computed from: thread (row, chunk) is the only reader of that hi/lo pair, so no other thread's input is
+                    // overwritten and the W1 product's A operand is simply the own-slice window of the c image.
                     float mx = -INFINITY;
+#pragma unroll 1
+                    for (int c2 = hh; c2 < nch2; c2 += 2) {               // warp-uniform
+                        uint32_t v[8];
+                        tmem_ld8(accE + lane_base + 8 * c2, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int ci = 0; ci < 6; ++ci) {
-                        const int c2 = hh + 2 * ci;
-                        if (c2 < nch2) {                              // warp-uniform
-                            uint32_t v[8];
-                            tmem_ld8(accE + lane_base + 8 * c2, v);
-                            tmem_ld_wait();
-                            if (rv) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    e[ci][i] = __uint_as_float(v[i]) + s_batt[8 * c2 + i];
-                                    mx = fmaxf(mx, e[ci][i]);
-                                }
-                                const size_t co = ((size_t)(R.j0 / 8 + c2) * Mr + row) * 16;
-                                m2_join8(*reinterpret_cast<const uint4 *>(act + co), *reinterpret_cast<const uint4 *>(act + imgC / 2 + co), cv[ci]);
-                            }
-                        }
+                        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) + s_batt[8 * c2 + i]);
                     }
-                    smax[hh * 128 + row] = mx;
+                    smax[hh * 128 + row] = rv ? mx : -INFINITY;
                     M2_TRACE(1, 5);
-                    asm volatile("bar.sync 1, 256;" ::: "memory");      // all c reads done before the attended image overwrites them
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     M2_TRACE(1, 6);
                     const float mfin = fmaxf(smax[row], smax[128 + row]);
                     float sum = 0.f;
-#pragma unroll
-                    for (int ci = 0; ci < 6; ++ci) {
-                        const int c2 = hh + 2 * ci;
-                        if (c2 < nch2 && rv) {
-                            float at[8];
+#pragma unroll 1
+                    for (int c2 = hh; c2 < nch2; c2 += 2) {               // warp-uniform
+                        uint32_t v[8];
+                        tmem_ld8(accE + lane_base + 8 * c2, v);
+                        tmem_ld_wait();
+                        if (rv) {
+                            const size_t co = ((size_t)(R.j0 / 8 + c2) * Mr + row) * 16;
+                            float cv[8], ev[8], at[8];
+                            m2_join8(*reinterpret_cast<const uint4 *>(act + co), *reinterpret_cast<const uint4 *>(act + imgC / 2 + co), cv);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float p = __expf(e[ci][i] - mfin);
+                                ev[i] = __uint_as_float(v[i]) + s_batt[8 * c2 + i];
+                                const float p = __expf(ev[i] - mfin);
                                 sum += p;
-                                at[i] = p * cv[ci][i];
+                                at[i] = p * cv[i];
                             }
                             uint4 hi, lo;
                             m2_split8(at, hi, lo);
-                            const size_t ao = ((size_t)c2 * Mr + row) * 16;
-                            *reinterpret_cast<uint4 *>(act + ao) = hi;
-                            *reinterpret_cast<uint4 *>(act + offAtt_lo + ao) = lo;
+                            *reinterpret_cast<uint4 *>(act + co) = hi;
+                            *reinterpret_cast<uint4 *>(act + imgC / 2 + co) = lo;
                             if (stash) {
-                                float4 *ep = reinterpret_cast<float4 *>(a.sE + tn * G4 + R.head * D + R.j0 + 8 * c2);
-                                ep[0] = make_float4(e[ci][0], e[ci][1], e[ci][2], e[ci][3]);
-                                ep[1] = make_float4(e[ci][4], e[ci][5], e[ci][6], e[ci][7]);
+                                float *ep = a.sE + priv(G4, t, R.head * D + R.j0 + 8 * c2) + row * 4;
+                                *reinterpret_cast<float4 *>(ep) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+                                *reinterpret_cast<float4 *>(ep + Mr * 4) = make_float4(ev[4], ev[5], ev[6], ev[7]);
                             }
                         }
                     }
@@ -705,6 +751,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                                     ms[k][i] = __ldcg(reinterpret_cast<const float2 *>(xst + ((size_t)r * Mr + cdia) * 2));
                                     pp[k][i] = ldcg4(xp + (((size_t)r * (MH / 4) + cpc) * Mr + cdia) * 4);
                                 }
+                        M2_TRACE(1, 12);
                         const float4 b1v = *reinterpret_cast<const float4 *>(s_b1 + 4 * cpc);
                         u4[0] = b1v.x; u4[1] = b1v.y; u4[2] = b1v.z; u4[3] = b1v.w;
 #pragma unroll
@@ -725,29 +772,32 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
 #pragma unroll
                             for (int i = 0; i < 4; ++i) { acc[i] *= inv; u4[i] += acc[i]; }
                             if (stash) {
-                                *reinterpret_cast<float4 *>(a.sP + (tnc * kHeads + k) * MH + 4 * cpc) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                                if (cpc == 0) *reinterpret_cast<float2 *>(a.sMS + (tnc * kHeads + k) * 2) = make_float2(Mk, inv);
+                                *reinterpret_cast<float4 *>(a.sP + priv(kHeads * MH, t, k * MH + 4 * cpc) + cdia * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                                if (cpc == 0) *reinterpret_cast<float2 *>(a.sMS + (((size_t)t * P.nblocks + blk) * kHeads + k) * Mr * 2 + cdia * 2) = make_float2(Mk, inv);
                             }
                         }
+                        M2_TRACE(1, 13);
                         u4[0] = fmaxf(u4[0], 0.f) * mk0.x; u4[1] = fmaxf(u4[1], 0.f) * mk0.y;
                         u4[2] = fmaxf(u4[2], 0.f) * mk0.z; u4[3] = fmaxf(u4[3], 0.f) * mk0.w;
                         *reinterpret_cast<float4 *>(a.sU + tnc * MH + 4 * cpc) = make_float4(u4[0], u4[1], u4[2], u4[3]);
                     }
-                    // operand image: the even / odd piece of a chunk sit in adjacent lanes; the even lane stores the hi chunk,
-                    // the odd lane the lo chunk
+                    // operand image: the even / odd piece of a chunk sit 8 lanes apart; the even piece's lane stores the hi chunk,
+                    // the odd one the lo chunk
                     {
                         const uint32_t h0 = pack_bf16(u4[0], u4[1]), h1 = pack_bf16(u4[2], u4[3]);
                         const uint32_t l0 = pack_bf16(u4[0] - __uint_as_float(h0 << 16), u4[1] - __uint_as_float(h0 & 0xffff0000u));
                         const uint32_t l1 = pack_bf16(u4[2] - __uint_as_float(h1 << 16), u4[3] - __uint_as_float(h1 & 0xffff0000u));
-                        const uint32_t oh0 = __shfl_xor_sync(0xffffffffu, h0, 1), oh1 = __shfl_xor_sync(0xffffffffu, h1, 1);
-                        const uint32_t ol0 = __shfl_xor_sync(0xffffffffu, l0, 1), ol1 = __shfl_xor_sync(0xffffffffu, l1, 1);
+                        const uint32_t oh0 = __shfl_xor_sync(0xffffffffu, h0, 8), oh1 = __shfl_xor_sync(0xffffffffu, h1, 8);
+                        const uint32_t ol0 = __shfl_xor_sync(0xffffffffu, l0, 8), ol1 = __shfl_xor_sync(0xffffffffu, l1, 8);
                         if (comb) {
                             const size_t uo = ((size_t)(cpc >> 1) * Mr + cdia) * 16;
                             if ((cpc & 1) == 0) *reinterpret_cast<uint4 *>(xu + uo) = make_uint4(h0, h1, oh0, oh1);
                             else *reinterpret_cast<uint4 *>(xu + (size_t)(MH / 8) * Mr * 16 + uo) = make_uint4(ol0, ol1, l0, l1);
                         }
                     }
+                    M2_TRACE(1, 14);
                     proxy_fence_all();
+                    M2_TRACE(1, 15);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[M2E_D]);
                     M2_TRACE(1, 11);
@@ -756,6 +806,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
             }
         }
         __syncthreads();
+    }
     }
     if (warp == kM2EpiWarps) {
         tc_fence_after();
@@ -777,7 +828,8 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
 struct M2BwdArgs {
     M2Plan P;
     const uint8_t *blob;          // [G][blob_b]
-    const float *dhz, *duz, *mask, *sC, *sG, *sE, *sMS, *sP, *sU;
+    const M2Rank *ranktab;        // [G]
+    const float *dhz, *duz, *mask, *sCp, *sG, *sE, *sMS, *sP, *sU;
     float *dgx, *de, *dup, *att;
     uint8_t *ws;
     unsigned *bars;
@@ -790,18 +842,21 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
     const M2Plan &P = a.P;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = blockIdx.x % P.G, grp = blockIdx.x / P.G;
-    const M2Rank R = P.r[rank];
-    const M2BwdBlob B = m2_bwd_blob(P, rank);
+    M2Rank R;                     // from global memory: indexing the parameter struct by rank would put a copy of it on the stack
+    {
+        const int4 *rp = reinterpret_cast<const int4 *>(a.ranktab + rank);
+        const int4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+        R.m = r0.x; R.u0 = r0.y; R.nu = r0.z; R.head = r0.w; R.j0 = r1.x; R.nj = r1.y; R.dhm = r1.z; R.offm = r1.w;
+        R.mr0 = r2.x; R.mr1 = r2.y; R.pad0 = R.pad1 = 0;
+    }
+    const M2BwdBlob B = m2_bwd_blob(P, R);
     const int Mr = P.Mr, MH = P.MH, D = P.D, G4 = P.G4, N = P.N, T = P.T, G = P.G;
     long long *trace = blockIdx.x == 0 ? g_m2_trace : nullptr;
-    const int m = R.m, dhm = P.dh[m], u0l = R.u0 - P.off[m], goff = 4 * P.off[m];
+    const int dhm = R.dhm, u0l = R.u0 - R.offm, goff = 4 * R.offm;
     const bool s2 = R.head >= 0;
     const int nch1 = R.nu / 8, nch2 = s2 ? R.nj / 8 : 0, ng = B.ng, nF = MH + dhm;
     const int ns2 = 4 * P.nr;                                   // ranks holding a stage-2 slice (0 .. ns2-1)
-    int mr0 = 0;                                                // ranks of the own modality are contiguous: [mr0, mr1)
-    while (P.r[mr0].m != m) ++mr0;
-    int mr1 = mr0;
-    while (mr1 < G && P.r[mr1].m == m) ++mr1;
+    const int mr0 = R.mr0, mr1 = R.mr1;                         // ranks of the own modality (contiguous)
 
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 192);
@@ -843,6 +898,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
         for (int o = 0; o < B.total; o += 32768) bulk_g2s(blob + o, src + o, (uint32_t)min(32768, B.total - o), &bar[B2_W]);
     }
 
+    // role split OUTSIDE the block loop: the control warpgroup shrinks its register budget once, the epilogue warpgroups grow theirs
+    if (warp >= kM2EpiWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kM2RegsCtl));
     for (int blk = grp, wave = 0; blk < P.nblocks; blk += P.ngroups, ++wave) {
         const int n0 = blk * P.DG, rows = min(P.DG, N - n0);
         for (int i = tid; i < P.act_b / 16; i += kM2Threads) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
@@ -915,18 +973,33 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     }
                 }
             }
-        } else {
+        }
+        __syncthreads();
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kM2RegsEpi));
+    for (int blk = grp, wave = 0; blk < P.nblocks; blk += P.ngroups, ++wave) {
+        const int n0 = blk * P.DG, rows = min(P.DG, N - n0);
+        for (int i = tid; i < P.act_b / 16; i += kM2Threads) reinterpret_cast<uint4 *>(act)[i] = make_uint4(0, 0, 0, 0);
+        proxy_fence_smem();
+        __syncthreads();
+        if (wave == 0) m2_mbar_wait(&bar[B2_W], 0);
+
+        {
             // =============================== epilogue warps ===============================
             const int q = warp & 3, hh = warp >> 2, row = 32 * q + lane;
             const bool rv = row < rows;
             const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-            float dhc[2][8], dcc[2][8];                             // carries of the own hidden units
+            float dhc[kM2CPH][8], dcc[kM2CPH][8];                   // carries of the own hidden units
 #pragma unroll
-            for (int ci = 0; ci < 2; ++ci)
+            for (int ci = 0; ci < kM2CPH; ++ci)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dhc[ci][i] = dcc[ci][i] = 0.f;
-            const int cdd = tid >> 4, cpc = tid & 15, cdia = rank * P.cd + cdd;
+            const size_t pvb = (size_t)P.nblocks * Mr;
+            auto priv = [&](int width, int tt, int col) { return ((size_t)tt * pvb * width) + ((size_t)blk * (width / 4) + col / 4) * Mr * 4; };
+            const int cdd = tid & 7, cpc = (tid >> 3) & 15, cdia = rank * P.cd + cdd;
             const bool comb = tid < 128 && cdd < P.cd && cdia < rows;
+            float *s_dot = reinterpret_cast<float *>(act + P.act_b);    // [4 warps][8 dialogues][4 heads] partial dots
 
             // combine: du (sum of the ranks' partials, fixed order) -> dup_tt, its operand image and the dots <dup_tt, P_k>
             auto combine = [&](int tt, bool first) {
@@ -947,7 +1020,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     if (a.mask != nullptr) mk = __ldg(reinterpret_cast<const float4 *>(a.mask + tnc * MH + 4 * cpc));
                     float4 pk[kHeads];
 #pragma unroll
-                    for (int k = 0; k < kHeads; ++k) pk[k] = __ldg(reinterpret_cast<const float4 *>(a.sP + (tnc * kHeads + k) * MH + 4 * cpc));
+                    for (int k = 0; k < kHeads; ++k) pk[k] = __ldg(reinterpret_cast<const float4 *>(a.sP + priv(kHeads * MH, tt, k * MH + 4 * cpc) + cdia * 4));
                     if (!first) {
 #pragma unroll
                         for (int r = 0; r < kM2MaxRanks; ++r)
@@ -965,22 +1038,33 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     const uint32_t h0 = pack_bf16(s4[0], s4[1]), h1 = pack_bf16(s4[2], s4[3]);
                     const uint32_t l0 = pack_bf16(s4[0] - __uint_as_float(h0 << 16), s4[1] - __uint_as_float(h0 & 0xffff0000u));
                     const uint32_t l1 = pack_bf16(s4[2] - __uint_as_float(h1 << 16), s4[3] - __uint_as_float(h1 & 0xffff0000u));
-                    const uint32_t oh0 = __shfl_xor_sync(0xffffffffu, h0, 1), oh1 = __shfl_xor_sync(0xffffffffu, h1, 1);
-                    const uint32_t ol0 = __shfl_xor_sync(0xffffffffu, l0, 1), ol1 = __shfl_xor_sync(0xffffffffu, l1, 1);
+                    const uint32_t oh0 = __shfl_xor_sync(0xffffffffu, h0, 8), oh1 = __shfl_xor_sync(0xffffffffu, h1, 8);
+                    const uint32_t ol0 = __shfl_xor_sync(0xffffffffu, l0, 8), ol1 = __shfl_xor_sync(0xffffffffu, l1, 8);
                     if (comb) {
                         const size_t uo = ((size_t)(cpc >> 1) * Mr + cdia) * 16;
                         if ((cpc & 1) == 0) *reinterpret_cast<uint4 *>(xdup + uo) = make_uint4(h0, h1, oh0, oh1);
                         else *reinterpret_cast<uint4 *>(xdup + imgU / 2 + uo) = make_uint4(ol0, ol1, l0, l1);
                     }
                 }
+                // <dup, P_k>: a warp holds 4 of the 16 pieces of its 8 dialogues (8 and 16 lanes apart); the four warps' partial
+                // sums meet in shared memory and are added in fixed warp order
 #pragma unroll
-                for (int k = 0; k < kHeads; ++k) {                    // the 16 piece-threads of a dialogue are 16 adjacent lanes
-                    dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 1);
-                    dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 2);
-                    dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 4);
+                for (int k = 0; k < kHeads; ++k) {
                     dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 8);
+                    dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 16);
                 }
-                if (comb && cpc == 0) *reinterpret_cast<float4 *>(xdot + (size_t)cdia * 4) = make_float4(dots[0], dots[1], dots[2], dots[3]);
+                if (lane < 8) *reinterpret_cast<float4 *>(s_dot + (warp * 8 + lane) * 4) = make_float4(dots[0], dots[1], dots[2], dots[3]);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (comb && cpc == 0) {
+                    float4 d = *reinterpret_cast<const float4 *>(s_dot + cdd * 4);
+#pragma unroll
+                    for (int w = 1; w < 4; ++w) {
+                        const float4 o = *reinterpret_cast<const float4 *>(s_dot + (w * 8 + cdd) * 4);
+                        d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w;
+                    }
+                    *reinterpret_cast<float4 *>(xdot + (size_t)cdia * 4) = d;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
                 proxy_fence_all();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar[E2_CMB]);
@@ -999,7 +1083,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                 if (s2) {
                     // ================= softmax backward of the own (head, range) slice =================
                     float2 ms = make_float2(0.f, 0.f);
-                    if (rv) ms = __ldg(reinterpret_cast<const float2 *>(a.sMS + (tn * kHeads + R.head) * 2));
+                    if (rv) ms = __ldg(reinterpret_cast<const float2 *>(a.sMS + (((size_t)t * P.nblocks + blk) * kHeads + R.head) * Mr * 2 + row * 2));
                     m2_mbar_wait(&bar[B2_DV], ph);
                     tc_fence_after();
                     M2_TRACE(1, 1);
@@ -1013,9 +1097,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                             tmem_ld_wait();
                             if (rv) {
                                 const int j = R.j0 + 8 * c2;          // global feature index of the chunk
-                                const float4 e0 = __ldg(reinterpret_cast<const float4 *>(a.sE + tn * G4 + R.head * D + j)),
-                                             e1 = __ldg(reinterpret_cast<const float4 *>(a.sE + tn * G4 + R.head * D + j) + 1);
-                                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(a.sC + tn * D + j)), c1 = __ldg(reinterpret_cast<const float4 *>(a.sC + tn * D + j) + 1);
+                                const float *ep = a.sE + priv(G4, t, R.head * D + j) + row * 4, *cq = a.sCp + priv(D, t, j) + row * 4;
+                                const float4 e0 = __ldg(reinterpret_cast<const float4 *>(ep)), e1 = __ldg(reinterpret_cast<const float4 *>(ep + Mr * 4));
+                                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cq)), c1 = __ldg(reinterpret_cast<const float4 *>(cq + Mr * 4));
                                 const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                                 float dev[8], dir[8], atc[8];
 #pragma unroll
@@ -1029,9 +1113,11 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                                 dp[0] = make_float4(dev[0], dev[1], dev[2], dev[3]);
                                 dp[1] = make_float4(dev[4], dev[5], dev[6], dev[7]);
                                 if (a.att != nullptr) {
-                                    int mj = 0;
-                                    while (mj + 1 < P.nm && j >= P.off[mj + 1]) ++mj;
-                                    float4 *ap = reinterpret_cast<float4 *>(a.att + tn * G4 + 4 * P.off[mj] + R.head * P.dh[mj] + (j - P.off[mj]));
+                                    // modality of feature j (static indexing of the parameter arrays only)
+                                    int offj = 0, dhj = P.dh[0];
+                                    if (P.nm > 1 && j >= P.off[1]) { offj = P.off[1]; dhj = P.dh[1]; }
+                                    if (P.nm > 2 && j >= P.off[2]) { offj = P.off[2]; dhj = P.dh[2]; }
+                                    float4 *ap = reinterpret_cast<float4 *>(a.att + tn * G4 + 4 * offj + R.head * dhj + (j - offj));
                                     ap[0] = make_float4(atc[0], atc[1], atc[2], atc[3]);
                                     ap[1] = make_float4(atc[4], atc[5], atc[6], atc[7]);
                                 }
@@ -1072,37 +1158,33 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                 }
                 // ================= cell backward of the own hidden units =================
                 float gf[8], gi[8], go[8], gg[8], cc[8], cp[8], gh[8];
-                auto ld8 = [](const float *p, float (&x)[8]) {
-                    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p)), v1 = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+                auto ld8 = [](const float *p, size_t second, float (&x)[8]) {      // two pieces of 4 floats, `second` floats apart
+                    const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p)), v1 = __ldg(reinterpret_cast<const float4 *>(p + second));
                     x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
                 };
                 auto load_stash = [&](int c) {
                     const int ug = R.u0 + 8 * c;
-                    const float *gp = a.sG + tn * G4 + goff + u0l + 8 * c;
-                    ld8(gp, gf); ld8(gp + dhm, gi); ld8(gp + 2 * dhm, go); ld8(gp + 3 * dhm, gg);
-                    ld8(a.sC + tn * D + ug, cc);
-                    if (t > 0) ld8(a.sC + (tn - N) * D + ug, cp);
+                    const size_t pst = (size_t)Mr * 4, gst = (size_t)(dhm / 4) * Mr * 4;
+                    const float *gp = a.sG + priv(G4, t, goff + u0l + 8 * c) + row * 4;
+                    ld8(gp, pst, gf); ld8(gp + gst, pst, gi); ld8(gp + 2 * gst, pst, go); ld8(gp + 3 * gst, pst, gg);
+                    ld8(a.sCp + priv(D, t, ug) + row * 4, pst, cc);
+                    if (t > 0) ld8(a.sCp + priv(D, t - 1, ug) + row * 4, pst, cp);
                     else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) cp[i] = 0.f;
                     }
-                    ld8(a.dhz + tn * 2 * D + ug, gh);
+                    ld8(a.dhz + tn * 2 * D + ug, 4, gh);
                 };
                 if (rv) {
                     if (hh < nch1) load_stash(hh);       // in flight across the exchange
                     if (t > 0)
-                        for (int c = hh; c < nch1; c += 2) {
-                            const float *gp = a.sG + (tn - N) * G4 + goff + u0l + 8 * c;
-#pragma unroll
-                            for (int gate = 0; gate < 4; ++gate) prefetch_l2(gp + gate * dhm);
-                            prefetch_l2(a.dhz + (tn - N) * 2 * D + R.u0 + 8 * c);
-                        }
+                        for (int c = hh; c < nch1; c += 2) prefetch_l2(a.dhz + (tn - N) * 2 * D + R.u0 + 8 * c);
                 }
                 M2_TRACE(1, 5);
                 m2_mbar_wait(&bar[B2_X2], ph);
                 M2_TRACE(1, 6);
 #pragma unroll
-                for (int ci = 0; ci < 2; ++ci) {
+                for (int ci = 0; ci < kM2CPH; ++ci) {
                     const int c = hh + 2 * ci;
                     if (c < nch1 && rv) {
                         if (ci > 0) load_stash(c);
@@ -1205,21 +1287,21 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     M2_TRACE(1, 10);
                     // dh carry of the own units: sum over the ranks of the own modality (fixed order)
 #pragma unroll
-                    for (int ci = 0; ci < 2; ++ci) {
+                    for (int ci = 0; ci < kM2CPH; ++ci) {
                         const int c = hh + 2 * ci;
                         if (c < nch1 && rv) {
                             const int kc = (u0l + 8 * c) / 8;
                             float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            float4 p0[kM2MaxRanks], p1[kM2MaxRanks];   // loads of all ranks of the modality in flight, adds in fixed order
+                            float4 p0[8], p1[8];   // at most 8 ranks per modality (planner): all loads in flight, adds in fixed order
 #pragma unroll
-                            for (int i = 0; i < kM2MaxRanks; ++i)
+                            for (int i = 0; i < 8; ++i)
                                 if (mr0 + i < mr1) {
                                     const float *pr = xdh + (((size_t)(mr0 + i) * 32 + 2 * kc) * Mr + row) * 4;
                                     p0[i] = ldcg4(pr);
                                     p1[i] = ldcg4(pr + (size_t)Mr * 4);
                                 }
 #pragma unroll
-                            for (int i = 0; i < kM2MaxRanks; ++i)
+                            for (int i = 0; i < 8; ++i)
                                 if (mr0 + i < mr1) {
                                     s8[0] += p0[i].x; s8[1] += p0[i].y; s8[2] += p0[i].z; s8[3] += p0[i].w;
                                     s8[4] += p1[i].x; s8[5] += p1[i].y; s8[6] += p1[i].z; s8[7] += p1[i].w;
@@ -1236,6 +1318,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
             }
         }
         __syncthreads();
+    }
     }
     if (warp == kM2EpiWarps) {
         tc_fence_after();

@@ -86,22 +86,24 @@ class MabRecurrenceFn(torch.autograd.Function):
         if drop_mask is not None:
             drop_mask = drop_mask.contiguous()
         if need_grad:
-            sC, sG, sE, sMS, sP = new(T, N, D), new(T, N, G), new(T, N, G), new(T, N, 4, 2), new(T, N, 4, map_h)
+            sC = new(T, N, D)
+            st = _lib.mab2_alloc_stash(desc, gx.device)      # private piece-major stash of the kernel pair
+            sCp, sG, sE, sMS, sP = st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"]
         else:
-            sC = sG = sE = sMS = sP = None
-        _timed("fwd", _lib.mab2_fwd, desc, packed, gx, drop_mask, hz, u, sC, sG, sE, sMS, sP, work)
+            sC = sCp = sG = sE = sMS = sP = None
+        _timed("fwd", _lib.mab2_fwd, desc, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, work)
         launch_counter["fwd"] += 1
         # z_t = fc.3(u_t) for all steps at once, written into the z half of hz (HybridRNN_ATV.py:129)
         linear_into(u.view(T * N, map_h), Wf2, bf2, hz.view(T * N, 2 * D)[:, D:])
         if need_grad:
-            ctx.save_for_backward(packed, hz, u, sC, sG, sE, sMS, sP, *weights)
+            ctx.save_for_backward(packed, hz, u, sC, sCp, sG, sE, sMS, sP, *weights)
             ctx.drop_mask = drop_mask
             ctx.dims = dims
         return hz
 
     @staticmethod
     def backward(ctx, dhz: torch.Tensor):
-        packed, hz, u, sC, sG, sE, sMS, sP, *weights = ctx.saved_tensors
+        packed, hz, u, sC, sCp, sG, sE, sMS, sP, *weights = ctx.saved_tensors
         dh, rd, map_h, rows_per_cta = ctx.dims
         M = len(dh)
         T, N, _ = hz.shape
@@ -118,7 +120,7 @@ class MabRecurrenceFn(torch.autograd.Function):
         duz = mm_nn(dz_head, Wf2)                              # the head's dL/dz pulled through fc.3: [TN, map_h]
         dgx, de, dup = new(T, N, G), new(T, N, G), new(T, N, map_h)
         att = new(T, N, G)     # attended = a * cs (HybridRNN_ATV.py:125), regrouped per modality head-major (lines 126-128) by the kernel
-        _timed("bwd", _lib.mab2_bwd, desc, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sC, sG, sE, sMS, sP, u,
+        _timed("bwd", _lib.mab2_bwd, desc, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sCp, sG, sE, sMS, sP, u,
                dgx, de, dup, att, _workspace(desc, hz.device))
         launch_counter["bwd"] += 1
 

@@ -59,11 +59,19 @@ def run_case(name):
     work = torch.empty(lib.mab2_workspace_bytes(d), device=dev, dtype=torch.uint8)
     new = lambda *s: torch.full(s, float("nan"), device=dev)
     hz, UH = new(T, N, 2 * D), new(T, N, MH)
-    sC, sG, sE, sMS, sP = new(T, N, D), new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, 4, 2), new(T, N, 4, MH)
+    sC = new(T, N, D)
+    st = lib.mab2_alloc_stash(d, dev)
+    for v in st.values():
+        v.fill_(float("nan"))
     gxc = gx.to(dev)
     mc = None if mask is None else mask.to(dev)
-    lib.mab2_fwd(d, packed, gxc, mc, hz, UH, sC, sG, sE, sMS, sP, work)
+    lib.mab2_fwd(d, packed, gxc, mc, hz, UH, sC, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], work)
     torch.cuda.synchronize()
+    sG = lib.mab2_unblock(st["sG"], d, 4 * D)
+    sE = lib.mab2_unblock(st["sE"], d, 4 * D)
+    sP = lib.mab2_unblock(st["sP"], d, 4 * MH).view(T, N, 4, MH)
+    sMS = lib.mab2_unblock(st["sMS"], d, 8).view(T, N, 4, 2)
+    assert torch.equal(lib.mab2_unblock(st["sCp"], d, D), sC), "private c copy differs"
     mask64 = None if mask is None else mask.double().numpy()
     ref = ocpu.mab_forward(params, gx.double().numpy(), dh, rd, mask64)
     A = (torch.exp(sE.view(T, N, 4, D) - sMS[..., 0:1]) * sMS[..., 1:2])
@@ -86,7 +94,7 @@ def run_case(name):
     dhzc = dhz.to(dev)
     duz = (dhzc[:, :, D:] @ Wf2).contiguous()
     dgx, de, dup, att = new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, MH), new(T, N, 4 * D)
-    lib.mab2_bwd(d, packed, dhzc, duz, mc, sC, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)
+    lib.mab2_bwd(d, packed, dhzc, duz, mc, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], UH, dgx, de, dup, att, work)
     torch.cuda.synchronize()
     radj, _ = ocpu.mab_backward(params, dhz.double().numpy(), ref, dh, rd, mask64)
     adj = dict(dgx=dgx, de=de, dup=dup)
@@ -109,7 +117,8 @@ def run_timing():
     import lsthm_b200
     from helpers import SPEC, seeded_model
     lib = import_module(lsthm_b200.__name__ + "._lib")
-    for kind, T, N in (("ATV", 110, 1024), ("ATV", 110, 128), ("AT", 110, 1024)):
+    prof = os.environ.get("MAB2_PROFILE") == "1"          # under ncu: one configuration, two launches of each kernel
+    for kind, T, N in ((("ATV", 110, 1024),) if prof else (("ATV", 110, 1024), ("ATV", 110, 128), ("AT", 110, 1024))):
         spec = SPEC[kind]
         dh, rd = spec["dh"], spec["rd"]
         D, MH, M = sum(dh), 64, len(dh)
@@ -128,35 +137,39 @@ def run_timing():
         gx = torch.randn(T, N, 4 * D, device=dev)
         mask = torch.bernoulli(torch.full((T, N, MH), 0.7, device=dev)) / 0.7
         hz, UH = new(T, N, 2 * D), new(T, N, MH)
-        sC, sG, sE, sMS, sP = new(T, N, D), new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, 4, 2), new(T, N, 4, MH)
+        sC = new(T, N, D)
+        st = lib.mab2_alloc_stash(d, dev)
+        sCp, sG, sE, sMS, sP = st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"]
         dhz = torch.randn(T, N, 2 * D, device=dev)
         duz = torch.randn(T, N, MH, device=dev)
         dgx, de, dup, att = new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, MH), new(T, N, 4 * D)
         res = {}
         for what in ("pack", "fwd", "bwd"):
             fn = {"pack": lambda: lib.mab2_pack(d, ws, packed),
-                  "fwd": lambda: lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sG, sE, sMS, sP, work),
-                  "bwd": lambda: lib.mab2_bwd(d, packed, dhz, duz, mask, sC, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)}[what]
-            for _ in range(3):
+                  "fwd": lambda: lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sCp, sG, sE, sMS, sP, work),
+                  "bwd": lambda: lib.mab2_bwd(d, packed, dhz, duz, mask, sCp, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)}[what]
+            for _ in range(1 if prof else 3):
                 fn()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(10):
+            for _ in range(1 if prof else 10):
                 fn()
             e1.record()
             torch.cuda.synchronize()
             res[what] = e0.elapsed_time(e1) / 10
         print("TIMING", kind, T, N, lib.mab2_launch_info(d), {k: f"{v:.3f} ms" for k, v in res.items()}, flush=True)
+        if prof:
+            continue
         # phase trace of block 0 (control thread / first epilogue warp), cycles, median over the steps
         tr = torch.zeros(T, 2, 16, device=dev, dtype=torch.int64)
         for what in ("fwd", "bwd"):
             tr.zero_()
             lib.mab2_set_trace(tr)
             if what == "fwd":
-                lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sG, sE, sMS, sP, work)
+                lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sCp, sG, sE, sMS, sP, work)
             else:
-                lib.mab2_bwd(d, packed, dhz, duz, mask, sC, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)
+                lib.mab2_bwd(d, packed, dhz, duz, mask, sCp, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)
             torch.cuda.synchronize()
             lib.mab2_set_trace(None)
             tc = tr.cpu()

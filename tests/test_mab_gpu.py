@@ -58,11 +58,19 @@ def _run_kernels(c, T, N):
     lib.mab2_pack(d, ws, packed)
     work = torch.empty(lib.mab2_workspace_bytes(d), device=dev, dtype=torch.uint8)
     new = lambda *s: torch.full(s, float("nan"), device=dev)
-    out = dict(hz=new(T, N, 2 * D), C=new(T, N, D), G=new(T, N, 4 * D), UH=new(T, N, MH))
-    sE, sMS, sP = new(T, N, 4 * D), new(T, N, 4, 2), new(T, N, 4, MH)
+    out = dict(hz=new(T, N, 2 * D), C=new(T, N, D), UH=new(T, N, MH))
+    st = lib.mab2_alloc_stash(d, dev)
+    for v in st.values():
+        v.fill_(float("nan"))
     gx = c["gx"].to(dev)
     mask = None if c["mask"] is None else c["mask"].to(dev)
-    lib.mab2_fwd(d, packed, gx, mask, out["hz"], out["UH"], out["C"], out["G"], sE, sMS, sP, work)
+    lib.mab2_fwd(d, packed, gx, mask, out["hz"], out["UH"], out["C"], st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], work)
+    # private piece-major stash -> row-major views for the comparison
+    out["G"] = lib.mab2_unblock(st["sG"], d, 4 * D)
+    sE = lib.mab2_unblock(st["sE"], d, 4 * D)
+    sP = lib.mab2_unblock(st["sP"], d, 4 * MH).view(T, N, 4, MH)
+    sMS = lib.mab2_unblock(st["sMS"], d, 8).view(T, N, 4, 2)
+    assert torch.equal(lib.mab2_unblock(st["sCp"], d, D), out["C"])
     # the kernel boundary (include/lsthm_b200.h): z_t = fc.3(u_t) is the caller's time-parallel product, and the softmax
     # weights are stashed as (logits, max, 1/sum)
     out["hz"][:, :, D:] = out["UH"] @ Wf2.t() + bf2
@@ -71,7 +79,7 @@ def _run_kernels(c, T, N):
     duz = (dhz[:, :, D:] @ Wf2).contiguous()                  # the head's dL/dz pulled through fc.3
     adj = dict(dgx=new(T, N, 4 * D), de=new(T, N, 4 * D), dup=new(T, N, MH))
     att = new(T, N, 4 * D)
-    lib.mab2_bwd(d, packed, dhz, duz, mask, out["C"], out["G"], sE, sMS, sP, out["UH"],
+    lib.mab2_bwd(d, packed, dhz, duz, mask, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], out["UH"],
                  adj["dgx"], adj["de"], adj["dup"], att, work)
     torch.cuda.synchronize()
     # the regrouped attended features the backward also emits: a * c, per modality, head-major (HybridRNN_ATV.py:125-128)
