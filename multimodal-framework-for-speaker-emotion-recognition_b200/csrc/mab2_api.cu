@@ -201,6 +201,9 @@ int lsthm_mab2_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out) {
 }
 
 int lsthm_mab2_set_trace(void *buf) {
+#ifndef LSTHM_M2_TRACE
+    if (buf) return fail_msg("lsthm_mab2_set_trace: the library was built without LSTHM_M2_TRACE (make TRACE=1)");
+#endif
     long long *p = reinterpret_cast<long long *>(buf);
     cudaError_t e = cudaMemcpyToSymbol(g_m2_trace, &p, sizeof(p));
     return e == cudaSuccess ? 0 : set_error("lsthm_mab2_set_trace", e);

@@ -37,7 +37,7 @@ constexpr int kM2RegsEpi = 224, kM2RegsCtl = 56;
 // not the whole register file: an increase that the control warpgroup's release cannot cover blocks forever
 static_assert(kM2EpiWarps * 32 * kM2RegsEpi + 4 * 32 * kM2RegsCtl <= kM2Threads * 168, "setmaxnreg budget exceeds the CTA's register pool");
 constexpr int kM2MaxDG = 96;                            // dialogues per group (operand buffer budget)
-constexpr int kM2MaxNJ = 96;                            // stage-2 feature range per rank
+constexpr int kM2MaxNJ = 80;                            // stage-2 feature range per rank (at most 5 chunks per epilogue warp)
 constexpr int kM2MaxNU = 16;                            // stage-1 hidden units per rank: one 8-unit chunk per epilogue warp of a lane quarter
 constexpr int kM2CPH = 1;                               // chunks per epilogue half (kM2MaxNU / 16)
 constexpr long long kM2Timeout = 1LL << 31;             // cycles (~1 s): a stuck exchange traps instead of hanging the GPU
@@ -307,6 +307,25 @@ __device__ __forceinline__ void m2_signal(unsigned *ctr) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
 }
 __device__ __forceinline__ float4 ldcg4(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+// 256-bit global accesses (sm_100: LDG/STG.256): a thread's 8-float chunk of a row-major row is one instruction, i.e. half the
+// L1 wavefronts of two float4 accesses when the 32 lanes of a warp touch 32 different rows.  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg8(const float *p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg8(float *p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+// one instruction pulls a contiguous range (multiple of 16 bytes) into L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Makes a pointer opaque to the optimiser at this point.  The epilogue loops are fully unrolled over ranks / chunks; without
+// this the compiler hoists every per-rank address (dozens of 64-bit values) out of the time loop and then spills them.
+template <typename T>
+__device__ __forceinline__ void m2_launder(T *&p) { asm volatile("" : "+l"(p)); }
 
 // 8 fp32 -> one bf16 hi chunk + one bf16 lo chunk (registers)
 __device__ __forceinline__ void m2_split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
@@ -333,10 +352,14 @@ __device__ __forceinline__ void m2_join8(const uint4 hi, const uint4 lo, float (
 // Development trace: when the host has set a buffer (lsthm_mab2_set_trace), the control thread and lane 0 of epilogue
 // warp 0 of CTA 0 record clock64() at their phase boundaries, [step][role][16] — read back by profiles/dev_mab2_check.py.
 __device__ long long *g_m2_trace = nullptr;
+#ifdef LSTHM_M2_TRACE
 #define M2_TRACE(role, slot)                                                                          \
     do {                                                                                              \
         if (trace != nullptr) trace[((size_t)tstep * 2 + (role)) * 16 + (slot)] = clock64();          \
     } while (0)
+#else
+#define M2_TRACE(role, slot) do { (void)tstep; } while (0)      // production build: no trace code in the kernels
+#endif
 
 // shared-memory control block: mbarriers
 enum { M2B_W = 0, M2B_H, M2B_U, M2B_C, M2B_G, M2B_E, M2B_P, M2B_B, M2E_A, M2E_B, M2E_C, M2E_D, M2B_X0, M2B_X1, M2B_X2, M2B_X3, M2_NBAR };
@@ -554,6 +577,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                 const size_t tn = (size_t)t * N + n0 + row;
                 const float bvon = t > 0 ? 1.f : 0.f;
                 const int tstep = t;
+                m2_launder(xp); m2_launder(xst); m2_launder(xc); m2_launder(xh); m2_launder(xu);
                 long long *trace_ct = trace;
                 if (tid != 0) trace = nullptr;
                 M2_TRACE(1, 0);
@@ -564,10 +588,10 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     const float *g0 = a.gx + tn * G4 + goff + u0l + 8 * c;
 #pragma unroll
                     for (int gate = 0; gate < 4; ++gate) {
-                        const float4 v0 = __ldg(reinterpret_cast<const float4 *>(g0 + gate * dhm));
-                        const float4 v1 = __ldg(reinterpret_cast<const float4 *>(g0 + gate * dhm) + 1);
-                        gxr[gate * 8 + 0] = v0.x; gxr[gate * 8 + 1] = v0.y; gxr[gate * 8 + 2] = v0.z; gxr[gate * 8 + 3] = v0.w;
-                        gxr[gate * 8 + 4] = v1.x; gxr[gate * 8 + 5] = v1.y; gxr[gate * 8 + 6] = v1.z; gxr[gate * 8 + 7] = v1.w;
+                        float v8[8];
+                        ldg8(g0 + gate * dhm, v8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) gxr[gate * 8 + i] = v8[i];
                     }
                 };
                 if (rv) {
@@ -607,13 +631,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                                 gf[ul] = f; gi[ul] = ig; go[ul] = og; gg[ul] = g;
                             }
                             const int ug = R.u0 + 8 * c;               // global unit index of the chunk
-                            float4 *hp = reinterpret_cast<float4 *>(a.hz + tn * 2 * D + ug);
-                            hp[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                            hp[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                            stg8(a.hz + tn * 2 * D + ug, hn);
                             if (stash) {
-                                float4 *cp = reinterpret_cast<float4 *>(a.sC + tn * D + ug);
-                                cp[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                                cp[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                                stg8(a.sC + tn * D + ug, cn);
                                 float *cq = a.sCp + priv(D, t, ug) + row * 4;
                                 *reinterpret_cast<float4 *>(cq) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                                 *reinterpret_cast<float4 *>(cq + Mr * 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
@@ -642,7 +662,8 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                     }
                 }
                 M2_TRACE(1, 2);
-                proxy_fence_all();
+                // (exchange images are read by the peers' bulk copies: their control thread orders its acquire against the
+                // async proxy with fence.proxy.async before issuing the copy)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar[M2E_A]);
@@ -796,11 +817,11 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_fwd_kernel(const __grid_co
                         }
                     }
                     M2_TRACE(1, 14);
-                    proxy_fence_all();
-                    M2_TRACE(1, 15);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar[M2E_D]);
                     M2_TRACE(1, 11);
+                } else {
+                    m2_mbar_wait(&bar[M2E_D], ph);     // the next step's feature loads stay out of the combine's way
                 }
                 trace = trace_ct;
             }
@@ -868,7 +889,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
 
     uint8_t *wsg = a.ws + (size_t)grp * P.ws_group;
     float *xdc = reinterpret_cast<float *>(wsg + P.ws_xdc);       // [rank][D/8][Mr][8]  dc partials; then [4][D/8][Mr][8] direct terms
-    float *xdir = xdc + (size_t)G * D * Mr;                     // pseudo-ranks G .. G+3 of the same piece-major layout
+    // (the four heads' direct terms follow as pseudo-ranks G .. G+3 of the same piece-major layout)
     float *xdu = reinterpret_cast<float *>(wsg + P.ws_xdu);       // [rank][Mr][MH]
     float *xdh = reinterpret_cast<float *>(wsg + P.ws_xdh);       // [rank][16][Mr][8]
     uint8_t *xdup = wsg + P.ws_xdup;                              // dup image (hi|lo) then dots [Mr][4]
@@ -927,6 +948,30 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     const uint32_t phF = (uint32_t)((wave * (T - 1) + s) & 1);      // barriers skipped at t == 0
                     const int tstep = s;
                     M2_TRACE(0, 0);
+                    if (leader && t > 0) {
+                        // the private stash of step t-1 is contiguous per (column range, block): pull this rank's slices into L2
+                        // one step ahead of their use (they are first touches from HBM otherwise, on the critical path)
+                        const size_t pvb = (size_t)P.nblocks * Mr, tb = (size_t)(t - 1);
+                        const uint32_t piece = (uint32_t)Mr * 16;
+                        const float *g0 = a.sG + tb * pvb * G4 + ((size_t)blk * (G4 / 4) + (goff + u0l) / 4) * Mr * 4;
+#pragma unroll
+                        for (int gate = 0; gate < 4; ++gate) bulk_prefetch_l2(g0 + (size_t)gate * (dhm / 4) * Mr * 4, (R.nu / 4) * piece);
+                        const float *c0 = a.sCp + tb * pvb * D + ((size_t)blk * (D / 4) + R.u0 / 4) * Mr * 4;
+                        bulk_prefetch_l2(c0, (R.nu / 4) * piece);
+                        if (t > 1) bulk_prefetch_l2(c0 - pvb * D, (R.nu / 4) * piece);
+                        if (s2) {
+                            bulk_prefetch_l2(a.sE + tb * pvb * G4 + ((size_t)blk * (G4 / 4) + (R.head * D + R.j0) / 4) * Mr * 4, (R.nj / 4) * piece);
+                            bulk_prefetch_l2(a.sCp + tb * pvb * D + ((size_t)blk * (D / 4) + R.j0 / 4) * Mr * 4, (R.nj / 4) * piece);
+                            bulk_prefetch_l2(a.sMS + ((tb * P.nblocks + blk) * kHeads + R.head) * Mr * 2, (uint32_t)Mr * 8);
+                        }
+                        const int d0 = rank * P.cd, nd = min(P.cd, rows - d0);
+                        if (nd > 0) {
+                            const size_t tnc = tb * N + n0 + d0;
+                            bulk_prefetch_l2(a.duz + tnc * MH, (uint32_t)nd * MH * 4);
+                            bulk_prefetch_l2(a.sU + tnc * MH, (uint32_t)nd * MH * 4);
+                            if (a.mask != nullptr) bulk_prefetch_l2(a.mask + tnc * MH, (uint32_t)nd * MH * 4);
+                        }
+                    }
                     if (s2) {
                         m2_poll(barX1b, (baseS + s + 1) * G);
                         M2_TRACE(0, 1);
@@ -1002,17 +1047,28 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
             float *s_dot = reinterpret_cast<float *>(act + P.act_b);    // [4 warps][8 dialogues][4 heads] partial dots
 
             // combine: du (sum of the ranks' partials, fixed order) -> dup_tt, its operand image and the dots <dup_tt, P_k>
+            int tstep = 0;
             auto combine = [&](int tt, bool first) {
                 // thread = (dialogue, piece of 4 outputs); all partial loads in flight before the first add (fixed rank order)
                 float s4[4] = {0.f, 0.f, 0.f, 0.f};
                 float dots[kHeads] = {0.f, 0.f, 0.f, 0.f};
                 if (comb) {
                     const size_t tnc = (size_t)tt * N + n0 + cdia;
-                    float4 pr[kM2MaxRanks];
+                    M2_TRACE(1, 13);
                     if (!first) {
+                        // two batches of eight partial pieces: a batch is in flight together; more live registers would make the
+                        // compiler put a spill store behind every load, which serialises them
 #pragma unroll
-                        for (int r = 0; r < kM2MaxRanks; ++r)
-                            if (r < G) pr[r] = ldcg4(xdu + (((size_t)r * (MH / 4) + cpc) * Mr + cdia) * 4);
+                        for (int b0 = 0; b0 < kM2MaxRanks; b0 += 8) {
+                            float4 pr[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (b0 + i < G) pr[i] = ldcg4(xdu + (((size_t)(b0 + i) * (MH / 4) + cpc) * Mr + cdia) * 4);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (b0 + i < G) { s4[0] += pr[i].x; s4[1] += pr[i].y; s4[2] += pr[i].z; s4[3] += pr[i].w; }
+                        }
+                        M2_TRACE(1, 14);
                     }
                     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.duz + tnc * MH + 4 * cpc));
                     const float4 u = __ldg(reinterpret_cast<const float4 *>(a.sU + tnc * MH + 4 * cpc));
@@ -1021,11 +1077,6 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     float4 pk[kHeads];
 #pragma unroll
                     for (int k = 0; k < kHeads; ++k) pk[k] = __ldg(reinterpret_cast<const float4 *>(a.sP + priv(kHeads * MH, tt, k * MH + 4 * cpc) + cdia * 4));
-                    if (!first) {
-#pragma unroll
-                        for (int r = 0; r < kM2MaxRanks; ++r)
-                            if (r < G) { s4[0] += pr[r].x; s4[1] += pr[r].y; s4[2] += pr[r].z; s4[3] += pr[r].w; }
-                    }
                     s4[0] = (u.x != 0.f ? s4[0] + z.x : 0.f) * mk.x;
                     s4[1] = (u.y != 0.f ? s4[1] + z.y : 0.f) * mk.y;
                     s4[2] = (u.z != 0.f ? s4[2] + z.z : 0.f) * mk.z;
@@ -1053,6 +1104,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 8);
                     dots[k] += __shfl_xor_sync(0xffffffffu, dots[k], 16);
                 }
+                M2_TRACE(1, 15);
                 if (lane < 8) *reinterpret_cast<float4 *>(s_dot + (warp * 8 + lane) * 4) = make_float4(dots[0], dots[1], dots[2], dots[3]);
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (comb && cpc == 0) {
@@ -1065,7 +1117,6 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     *reinterpret_cast<float4 *>(xdot + (size_t)cdia * 4) = d;
                 }
                 asm volatile("bar.sync 2, 128;" ::: "memory");
-                proxy_fence_all();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar[E2_CMB]);
             };
@@ -1076,7 +1127,12 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                 const uint32_t ph = (uint32_t)((wave * T + s) & 1);
                 const uint32_t phF = (uint32_t)((wave * (T - 1) + s) & 1);
                 const size_t tn = (size_t)t * N + n0 + row;
-                const int tstep = s;
+                tstep = s;
+                m2_launder(xdc); m2_launder(xdu); m2_launder(xdh); m2_launder(xdot); m2_launder(xdup);
+                if (comb && t > 0) {                    // the combine at the end of this step reads P_k of step t-1: first touch from HBM
+#pragma unroll
+                    for (int k = 0; k < kHeads; ++k) prefetch_l2(a.sP + priv(kHeads * MH, t - 1, k * MH + 4 * cpc) + cdia * 4);
+                }
                 long long *trace_ct = trace;
                 if (tid != 0) trace = nullptr;
                 M2_TRACE(1, 0);
@@ -1088,47 +1144,41 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     tc_fence_after();
                     M2_TRACE(1, 1);
                     const float dot = rv ? __ldcg(xdot + (size_t)row * 4 + R.head) : 0.f;
+#pragma unroll 1
+                    for (int c2 = hh; c2 < nch2; c2 += 2) {               // warp-uniform
+                        uint32_t v[8];
+                        tmem_ld8(accDV + lane_base + 8 * c2, v);
+                        tmem_ld_wait();
+                        if (rv) {
+                            const int j = R.j0 + 8 * c2;          // global feature index of the chunk
+                            const float *ep = a.sE + priv(G4, t, R.head * D + j) + row * 4, *cq = a.sCp + priv(D, t, j) + row * 4;
+                            const float4 e0 = __ldg(reinterpret_cast<const float4 *>(ep)), e1 = __ldg(reinterpret_cast<const float4 *>(ep + Mr * 4));
+                            const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cq)), c1 = __ldg(reinterpret_cast<const float4 *>(cq + Mr * 4));
+                            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                            float dev[8], dir[8], atc[8];
 #pragma unroll
-                    for (int ci = 0; ci < 6; ++ci) {
-                        const int c2 = hh + 2 * ci;
-                        if (c2 < nch2) {                              // warp-uniform
-                            uint32_t v[8];
-                            tmem_ld8(accDV + lane_base + 8 * c2, v);
-                            tmem_ld_wait();
-                            if (rv) {
-                                const int j = R.j0 + 8 * c2;          // global feature index of the chunk
-                                const float *ep = a.sE + priv(G4, t, R.head * D + j) + row * 4, *cq = a.sCp + priv(D, t, j) + row * 4;
-                                const float4 e0 = __ldg(reinterpret_cast<const float4 *>(ep)), e1 = __ldg(reinterpret_cast<const float4 *>(ep + Mr * 4));
-                                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cq)), c1 = __ldg(reinterpret_cast<const float4 *>(cq + Mr * 4));
-                                const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w}, cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                                float dev[8], dir[8], atc[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float av = __expf(ev[i] - ms.x) * ms.y, dv = __uint_as_float(v[i]);
-                                    dev[i] = av * (dv * cv[i] - dot);
-                                    dir[i] = dv * av;
-                                    atc[i] = av * cv[i];
-                                }
-                                float4 *dp = reinterpret_cast<float4 *>(a.de + tn * G4 + R.head * D + j);
-                                dp[0] = make_float4(dev[0], dev[1], dev[2], dev[3]);
-                                dp[1] = make_float4(dev[4], dev[5], dev[6], dev[7]);
-                                if (a.att != nullptr) {
-                                    // modality of feature j (static indexing of the parameter arrays only)
-                                    int offj = 0, dhj = P.dh[0];
-                                    if (P.nm > 1 && j >= P.off[1]) { offj = P.off[1]; dhj = P.dh[1]; }
-                                    if (P.nm > 2 && j >= P.off[2]) { offj = P.off[2]; dhj = P.dh[2]; }
-                                    float4 *ap = reinterpret_cast<float4 *>(a.att + tn * G4 + 4 * offj + R.head * dhj + (j - offj));
-                                    ap[0] = make_float4(atc[0], atc[1], atc[2], atc[3]);
-                                    ap[1] = make_float4(atc[4], atc[5], atc[6], atc[7]);
-                                }
-                                *reinterpret_cast<float4 *>(xdir + (((size_t)R.head * (D / 4) + j / 4) * Mr + row) * 4) = make_float4(dir[0], dir[1], dir[2], dir[3]);
-                                *reinterpret_cast<float4 *>(xdir + (((size_t)R.head * (D / 4) + j / 4 + 1) * Mr + row) * 4) = make_float4(dir[4], dir[5], dir[6], dir[7]);
-                                uint4 hi, lo;
-                                m2_split8(dev, hi, lo);
-                                const size_t ao = ((size_t)c2 * Mr + row) * 16;
-                                *reinterpret_cast<uint4 *>(act + offDE + ao) = hi;
-                                *reinterpret_cast<uint4 *>(act + offDE + nch2 * Mr * 16 + ao) = lo;
+                            for (int i = 0; i < 8; ++i) {
+                                const float av = __expf(ev[i] - ms.x) * ms.y, dv = __uint_as_float(v[i]);
+                                dev[i] = av * (dv * cv[i] - dot);
+                                dir[i] = dv * av;
+                                atc[i] = av * cv[i];
                             }
+                            stg8(a.de + tn * G4 + R.head * D + j, dev);
+                            if (a.att != nullptr) {
+                                // modality of feature j (static indexing of the parameter arrays only)
+                                int offj = 0, dhj = P.dh[0];
+                                if (P.nm > 1 && j >= P.off[1]) { offj = P.off[1]; dhj = P.dh[1]; }
+                                if (P.nm > 2 && j >= P.off[2]) { offj = P.off[2]; dhj = P.dh[2]; }
+                                stg8(a.att + tn * G4 + 4 * offj + R.head * dhj + (j - offj), atc);
+                            }
+                            float *xd = xdc + (((size_t)(G + R.head) * (D / 4) + j / 4) * Mr + row) * 4;
+                            *reinterpret_cast<float4 *>(xd) = make_float4(dir[0], dir[1], dir[2], dir[3]);
+                            *reinterpret_cast<float4 *>(xd + (size_t)Mr * 4) = make_float4(dir[4], dir[5], dir[6], dir[7]);
+                            uint4 hi, lo;
+                            m2_split8(dev, hi, lo);
+                            const size_t ao = ((size_t)c2 * Mr + row) * 16;
+                            *reinterpret_cast<uint4 *>(act + offDE + ao) = hi;
+                            *reinterpret_cast<uint4 *>(act + offDE + nch2 * Mr * 16 + ao) = lo;
                         }
                     }
                     proxy_fence_smem();
@@ -1173,13 +1223,10 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
 #pragma unroll
                         for (int i = 0; i < 8; ++i) cp[i] = 0.f;
                     }
-                    ld8(a.dhz + tn * 2 * D + ug, 4, gh);
+                    ldg8(a.dhz + tn * 2 * D + ug, gh);
                 };
-                if (rv) {
-                    if (hh < nch1) load_stash(hh);       // in flight across the exchange
-                    if (t > 0)
-                        for (int c = hh; c < nch1; c += 2) prefetch_l2(a.dhz + (tn - N) * 2 * D + R.u0 + 8 * c);
-                }
+                if (rv && t > 0)
+                    for (int c = hh; c < nch1; c += 2) prefetch_l2(a.dhz + (tn - N) * 2 * D + R.u0 + 8 * c);
                 M2_TRACE(1, 5);
                 m2_mbar_wait(&bar[B2_X2], ph);
                 M2_TRACE(1, 6);
@@ -1187,7 +1234,6 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                 for (int ci = 0; ci < kM2CPH; ++ci) {
                     const int c = hh + 2 * ci;
                     if (c < nch1 && rv) {
-                        if (ci > 0) load_stash(c);
                         const int ug = R.u0 + 8 * c;
                         float gc[8];
 #pragma unroll
@@ -1214,6 +1260,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                                     gc[4] += p1[i].x; gc[5] += p1[i].y; gc[6] += p1[i].z; gc[7] += p1[i].w;
                                 }
                         }
+                        // the stash only now: the partial loads above must not compete with 56 live stash registers (a spill
+                        // store behind every load would serialise them); the slices were bulk-prefetched into L2 a step ahead
+                        load_stash(c);
                         float ds[4][8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -1229,10 +1278,7 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                         }
                         float *dg = a.dgx + tn * G4 + goff + u0l + 8 * c;
 #pragma unroll
-                        for (int gate = 0; gate < 4; ++gate) {
-                            reinterpret_cast<float4 *>(dg + gate * dhm)[0] = make_float4(ds[gate][0], ds[gate][1], ds[gate][2], ds[gate][3]);
-                            reinterpret_cast<float4 *>(dg + gate * dhm)[1] = make_float4(ds[gate][4], ds[gate][5], ds[gate][6], ds[gate][7]);
-                        }
+                        for (int gate = 0; gate < 4; ++gate) stg8(dg + gate * dhm, ds[gate]);
                         // ds operand image, K order = local unit * 4 + gate: K-chunk 4c + i holds units 2i, 2i+1 of the chunk
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -1285,6 +1331,9 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                     M2_TRACE(1, 9);
                     m2_mbar_wait(&bar[B2_X1A], phF);
                     M2_TRACE(1, 10);
+                    if (warp < 4) combine(t - 1, false);            // first: the whole group waits for dup_{t-1}
+                    else m2_mbar_wait(&bar[E2_CMB], (uint32_t)((wave * T + s + 1) & 1));   // keep the load queue free for the combine
+                    M2_TRACE(1, 11);
                     // dh carry of the own units: sum over the ranks of the own modality (fixed order)
 #pragma unroll
                     for (int ci = 0; ci < kM2CPH; ++ci) {
@@ -1292,26 +1341,29 @@ __global__ void __launch_bounds__(kM2Threads, 1) mab2_bwd_kernel(const __grid_co
                         if (c < nch1 && rv) {
                             const int kc = (u0l + 8 * c) / 8;
                             float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            float4 p0[8], p1[8];   // at most 8 ranks per modality (planner): all loads in flight, adds in fixed order
+                            // at most 8 ranks per modality (planner); two batches of four: off the critical path (the group is
+                            // waiting for dup meanwhile), so a second round trip is cheaper than 64 live registers
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (mr0 + i < mr1) {
-                                    const float *pr = xdh + (((size_t)(mr0 + i) * 32 + 2 * kc) * Mr + row) * 4;
-                                    p0[i] = ldcg4(pr);
-                                    p1[i] = ldcg4(pr + (size_t)Mr * 4);
-                                }
+                            for (int b0 = 0; b0 < 8; b0 += 4) {
+                                float4 p0[4], p1[4];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (mr0 + i < mr1) {
-                                    s8[0] += p0[i].x; s8[1] += p0[i].y; s8[2] += p0[i].z; s8[3] += p0[i].w;
-                                    s8[4] += p1[i].x; s8[5] += p1[i].y; s8[6] += p1[i].z; s8[7] += p1[i].w;
-                                }
+                                for (int i = 0; i < 4; ++i)
+                                    if (mr0 + b0 + i < mr1) {
+                                        const float *pr = xdh + (((size_t)(mr0 + b0 + i) * 32 + 2 * kc) * Mr + row) * 4;
+                                        p0[i] = ldcg4(pr);
+                                        p1[i] = ldcg4(pr + (size_t)Mr * 4);
+                                    }
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (mr0 + b0 + i < mr1) {
+                                        s8[0] += p0[i].x; s8[1] += p0[i].y; s8[2] += p0[i].z; s8[3] += p0[i].w;
+                                        s8[4] += p1[i].x; s8[5] += p1[i].y; s8[6] += p1[i].z; s8[7] += p1[i].w;
+                                    }
+                            }
 #pragma unroll
                             for (int i = 0; i < 8; ++i) dhc[ci][i] = s8[i];
                         }
                     }
-                    M2_TRACE(1, 11);
-                    if (warp < 4) combine(t - 1, false);
                     M2_TRACE(1, 12);
                 }
                 trace = trace_ct;
