@@ -37,8 +37,20 @@ const char *lsthm_last_error(void);
  *     model/HybridRNN_ATV.py:117-143   (AT: model/HybridRNN_AT.py:107-132)
  * i.e. LSTHM.forward (model/HybridRNN_ATV.py:21-37) for every modality, the 4-head softmax
  * attention over the concatenated cell states (123-125), the per-modality reduce layers
- * (126-128) and fc = Linear-ReLU-Dropout-Linear (66, 129).  The input projections W_m x_m and
- * the per-step head nn_out (68-73,139-141) are time-parallel and stay on the host side.
+ * (126-128) and fc = Linear-ReLU-Dropout-Linear (66, 129) — and the BPTT autograd runs through it.
+ * The input projections W_m x_m and the per-step head nn_out (68-73,139-141) are time-parallel and
+ * stay on the host side.
+ *
+ * Execution model (sm_100a): GROUPS of co-resident thread blocks (cooperative launch; 13 blocks for ATV,
+ * 9 for AT) each own a block of up to 96 dialogues for all T steps.  The chain weights are sharded over
+ * the ranks of a group and stay RESIDENT in shared memory for the whole launch as bf16 hi/lo operand
+ * images; every product runs on tcgen05 tensor cores (M = the group's dialogues, three-term split,
+ * fp32 accumulation in TMEM); the ranks exchange c_t/h_t, partial products and u_t through L2.
+ * The kernels use composite weights — the chain has no nonlinearity between reduce_dim_nn_m and fc.0
+ * (HybridRNN_ATV.py:126-129), nor between fc.3 and the V term of the next step's gates (:129 -> :25):
+ *     W1 = Wf1 . blockdiag(Wr_m)  [map_h x 4D],  b1 = Wf1 br + bf1      W2 = Vcat . Wf2  [4D x map_h],  bv = Vcat bf2
+ * (composed in fp64 at pack time): three dependent products per step instead of five.
+ * Constraints: map_h = 64, n_att = 4, every dh_m a multiple of 16 in 16..128, sum dh_m <= 256.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t T;                 /* padded dialogue length                                   */
@@ -46,9 +58,9 @@ typedef struct {
     int32_t n_mod;             /* 2 (AT: text, audio) or 3 (ATV: + visual)                 */
     int32_t n_att;             /* attention heads (reference: 4)                           */
     int32_t map_h;             /* fc hidden width (reference: 64)                          */
-    int32_t dh[LSTHM_MAX_MOD]; /* cell sizes   (ATV 128,16,64)  multiples of 4             */
-    int32_t rd[LSTHM_MAX_MOD]; /* reduce sizes (ATV 16,128,100) multiples of 4             */
-    int32_t rows_per_cta;      /* 0 = auto; else 1..8 dialogues per thread block           */
+    int32_t dh[LSTHM_MAX_MOD]; /* cell sizes   (ATV 128,16,64)                             */
+    int32_t rd[LSTHM_MAX_MOD]; /* reduce sizes (ATV 16,128,100)                            */
+    int32_t rows_per_cta;      /* dialogues per block group: 0 = auto, else 1..96          */
 } lsthm_mab_desc;
 
 /* Weights in nn.Linear layout [out][in], exactly the module's parameter storage. */
@@ -62,33 +74,39 @@ typedef struct {
     const float *Wf2, *bf2;           /* fc.3 [D][map_h]                                      */
 } lsthm_mab_weights;
 
-/* Number of floats of the packed weight image the kernels stream (k-major / gate-interleaved copies of U and Watt,
- * and the COMPOSITE weights: the chain has no nonlinearity between reduce_dim_nn_m and fc.0 (HybridRNN_ATV.py:126-129),
- * nor between fc.3 and the V term of the next step's gates (:129 -> :25), so the kernels use
- *     W1 = Wf1 . blockdiag(Wr_m)  [map_h x 4D],  b1 = Wf1 br + bf1      and      W2 = Vcat . Wf2  [4D x map_h],  bv = Vcat bf2
- * (composed in fp64 at pack time): three dependent products per step instead of five, 28 % fewer serial MACs). */
-size_t lsthm_mab_packed_floats(const lsthm_mab_desc *d);
-
-/* Re-layout / compose the weights into `packed` (call after every optimizer step, before fwd/bwd). */
-int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, float *packed, void *stream);
+/* bytes of the packed weight area (composite weights + per-rank operand images for forward and backward) */
+size_t lsthm_mab_pack_bytes(const lsthm_mab_desc *d);
+/* bytes of the exchange workspace a launch needs (group exchange buffers + barrier counters); the library resets
+ * the counters itself (one cudaMemsetAsync on `stream` per launch), the rest needs no initialisation */
+size_t lsthm_mab_workspace_bytes(const lsthm_mab_desc *d);
+/* compose W1, W2 (fp64 accumulation) and split every rank's slices into bf16 hi/lo images in the canonical K-major UMMA
+ * layout (call after every optimizer step, before fwd/bwd) */
+int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *packed, void *stream);
 
 /*
- * Forward recurrence over all T steps.
+ * Forward recurrence over all T steps (cooperative launch).
  *   gx        [T][N][4D]   W_m x_m + bW_m + bU_m + bV_m, cell-major, f|i|o|g inside a cell
  *   drop_mask [T][N][map_h] keep/(1-p) mask of fc's Dropout, or NULL (eval mode)
  *   hz        [T][N][2D]   out: the h_t half of [h_t | z_t] (what nn_out consumes, HybridRNN_ATV.py:139); the z_t half is
  *                          NOT written: z_t = fc.3(u_t) = u_t Wf2^T + bf2 is one time-parallel product over all T*N rows
- *                          that the caller forms from `u` (nothing on the serial path needs z_t any more)
+ *                          that the caller forms from `u` (nothing on the serial path needs z_t)
  *   u         [T][N][map_h] out: fc hidden after ReLU and dropout (HybridRNN_ATV.py:66)
- *   stash (all out, may ALL be NULL for inference):
- *     sC [T][N][D]  cell states      sG [T][N][4D] gates after sigmoid/tanh (layout of gx)      sA [T][N][4][D] softmax weights
+ * stash (all out, may ALL be NULL for inference):
+ *   sC [T][N][D] cell states, row-major (the caller's weight-gradient products read it)
+ * and the PRIVATE stash of the kernel pair, piece-major inside a dialogue block so that every warp access is one contiguous
+ * run:  [T][block][column / 4][row][4]  with `padded_rows / blocks` rows per block (lsthm_mab_launch_info):
+ *   sCp (width D) cell states        sG (width 4D) gates after sigmoid/tanh, column order of gx
+ *   sE (width 4D) attention logits (att.0 output incl. bias, BEFORE the softmax), column = head * D + feature
+ *   sMS [T][block][4][row][2] per head (max logit, 1 / sum exp(e - max)): softmax weights are a = exp(e - max) * inv
+ *   sP (width 4 * map_h) per head  W1[:, head block] . (a_head * c), column = head * map_h + q
+ *      (the softmax backward needs <dup, P_head>)
+ * each private tensor holds T * padded_rows * width floats (sMS: T * padded_rows * 8).
  */
-int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx, const float *drop_mask,
-                  float *hz, float *u, float *sC, float *sG, float *sA, void *stream);
+int lsthm_mab_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx, const float *drop_mask, float *hz, float *u,
+                  float *sC, float *sCp, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream);
 
 /*
- * BPTT.  `w` gives the native-layout weights (the transposed products of U and Watt read them directly),
- * `packed` the image from lsthm_mab_pack (composite weights).
+ * BPTT (cooperative launch).
  *   dhz  [T][N][2D]  dL/d[h_t|z_t] from the head (the kernel reads the h half)
  *   duz  [T][N][map_h]  (dL/dz_t from the head) . Wf2 — the head's gradient pulled through fc.3, one time-parallel
  *                    product formed by the caller
@@ -101,64 +119,21 @@ int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx,
  *                    head-major inside a modality (columns 4*off_m + head*dh_m + j): column block m is the operand
  *                    of d reduce_dim_nn_m and of the recomputed reduce outputs r_m = att_m Wr_m^T + br_m
  */
-int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed,
-                  const float *dhz, const float *duz, const float *drop_mask,
-                  const float *sC, const float *sG, const float *sA, const float *u,
-                  float *dgx, float *de, float *dup, float *att, void *stream);
-
-/* Launch geometry the library would use (for roofline bookkeeping in bench.py). */
-int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows,
-                          int32_t *smem_fwd, int32_t *smem_bwd);
-
-/* ------------------------------------------------------------------------------------------
- * AT / ATV recurrence, weight-stationary tensor-core form (lsthm_mab2_*): the same operator boundary as lsthm_mab_*
- * (the body of the time loop of MARN.forward, model/HybridRNN_ATV.py:117-143 / model/HybridRNN_AT.py:107-132, and its
- * BPTT), executed by GROUPS of co-resident thread blocks that keep the chain weights sharded and resident in shared
- * memory as bf16 hi/lo operand images and run every product on tcgen05 tensor cores (three-term split, fp32 accumulate).
- * `rows_per_cta` of the descriptor is read as "dialogues per group" (0 = auto, at most 96).
- * Constraints: map_h = 64, n_att = 4, every dh_m a multiple of 16 in 16..128, sum dh_m <= 256.
- * ------------------------------------------------------------------------------------------ */
-
-/* bytes of the packed weight area (composite weights + per-rank operand images for forward and backward) */
-size_t lsthm_mab2_pack_bytes(const lsthm_mab_desc *d);
-/* bytes of the exchange workspace a launch needs (group exchange buffers + barrier counters); the library resets
- * the counters itself (one cudaMemsetAsync on `stream` per launch), the rest needs no initialisation */
-size_t lsthm_mab2_workspace_bytes(const lsthm_mab_desc *d);
-/* compose W1 = Wf1.blockdiag(Wr_m), W2 = Vcat.Wf2 (fp64 accumulation) and split every rank's slices into bf16 hi/lo
- * images in the canonical K-major UMMA layout (call after every optimizer step, before fwd/bwd) */
-int lsthm_mab2_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *packed, void *stream);
-
-/*
- * Forward over all T steps (cooperative launch).  gx, drop_mask, hz, u as for lsthm_mab_fwd.
- * stash (all out, may ALL be NULL for inference):
- *   sC [T][N][D] cell states, row-major (the caller's weight-gradient products read it)
- * and the PRIVATE stash of the kernel pair, piece-major inside a dialogue block so that every warp access is one contiguous
- * run:  [T][block][column / 4][row][4]  with `padded_rows / blocks` rows per block (lsthm_mab2_launch_info):
- *   sCp (width D) cell states        sG (width 4D) gates after sigmoid/tanh, column order of gx
- *   sE (width 4D) attention logits (att.0 output incl. bias, BEFORE the softmax), column = head * D + feature
- *   sMS [T][block][4][row][2] per head (max logit, 1 / sum exp(e - max)): softmax weights are a = exp(e - max) * inv
- *   sP (width 4 * map_h) per head  W1[:, head block] . (a_head * c), column = head * map_h + q
- *      (the softmax backward needs <dup, P_head>)
- * each private tensor holds T * padded_rows * width floats (sMS: T * padded_rows * 8).
- */
-int lsthm_mab2_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx, const float *drop_mask, float *hz, float *u,
-                   float *sC, float *sCp, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream);
-
-/* BPTT (cooperative launch).  dhz, duz, drop_mask, u and the outputs dgx, de, dup, att as for lsthm_mab_bwd. */
-int lsthm_mab2_bwd(const lsthm_mab_desc *d, const void *packed, const float *dhz, const float *duz, const float *drop_mask,
-                   const float *sCp, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
-                   float *dgx, float *de, float *dup, float *att, void *workspace, void *stream);
+int lsthm_mab_bwd(const lsthm_mab_desc *d, const void *packed, const float *dhz, const float *duz, const float *drop_mask,
+                  const float *sCp, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
+                  float *dgx, float *de, float *dup, float *att, void *workspace, void *stream);
 
 /* Launch geometry on the current device: grid = groups * group size; padded_rows = blocks * rows per block (multiple of 8). */
-int lsthm_mab2_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *group,
-                           int32_t *dialogues_per_group, int32_t *smem_fwd, int32_t *smem_bwd, int32_t *padded_rows);
+int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *group,
+                          int32_t *dialogues_per_group, int32_t *smem_fwd, int32_t *smem_bwd, int32_t *padded_rows);
 /* The sharding plan for a 148-SM device (host only, no device needed): 14 header ints (G, ranges per head, dialogues
  * per group, padded rows, groups, blocks, combine share, blob_f, blob_b, act_f, act_b, smem_fwd, smem_bwd, ws_group)
  * followed by (modality, first unit, units, head, first feature, features) per rank. */
-int lsthm_mab2_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out);
-/* Profiling aid: buf = device buffer of [T][2][16] int64 (or NULL to switch off); block 0 of the forward kernel records
- * clock64() at the phase boundaries of its control thread (role 0) and of its first epilogue warp (role 1). */
-int lsthm_mab2_set_trace(void *buf);
+int lsthm_mab_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out);
+/* Profiling aid (library built with `make TRACE=1`): buf = device buffer of [T][2][16] int64 (or NULL to switch off);
+ * block 0 of the kernels records clock64() at the phase boundaries of its control warp (role 0) and of its first
+ * epilogue warp (role 1). */
+int lsthm_mab_set_trace(void *buf);
 
 /* ------------------------------------------------------------------------------------------
  * lsthm_sps: speaker-state LSTHM cell (one direction of the bidirectional MARN1_sps).

@@ -84,32 +84,22 @@ def lib() -> C.CDLL:
     L = C.CDLL(SO_PATH)
     L.lsthm_abi_version.restype = C.c_int
     L.lsthm_last_error.restype = C.c_char_p
-    L.lsthm_mab_packed_floats.restype = C.c_size_t
-    L.lsthm_mab_packed_floats.argtypes = [C.POINTER(MabDesc)]
+    L.lsthm_mab_pack_bytes.restype = C.c_size_t
+    L.lsthm_mab_pack_bytes.argtypes = [C.POINTER(MabDesc)]
+    L.lsthm_mab_workspace_bytes.restype = C.c_size_t
+    L.lsthm_mab_workspace_bytes.argtypes = [C.POINTER(MabDesc)]
     L.lsthm_mab_pack.restype = C.c_int
     L.lsthm_mab_pack.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights), C.c_void_p, C.c_void_p]
     L.lsthm_mab_fwd.restype = C.c_int
-    L.lsthm_mab_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 9
+    L.lsthm_mab_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 13
     L.lsthm_mab_bwd.restype = C.c_int
-    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights)] + [C.c_void_p] * 13
+    L.lsthm_mab_bwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 16
     L.lsthm_mab_launch_info.restype = C.c_int
-    L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 5
-    L.lsthm_mab2_pack_bytes.restype = C.c_size_t
-    L.lsthm_mab2_pack_bytes.argtypes = [C.POINTER(MabDesc)]
-    L.lsthm_mab2_workspace_bytes.restype = C.c_size_t
-    L.lsthm_mab2_workspace_bytes.argtypes = [C.POINTER(MabDesc)]
-    L.lsthm_mab2_pack.restype = C.c_int
-    L.lsthm_mab2_pack.argtypes = [C.POINTER(MabDesc), C.POINTER(MabWeights), C.c_void_p, C.c_void_p]
-    L.lsthm_mab2_fwd.restype = C.c_int
-    L.lsthm_mab2_fwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 13
-    L.lsthm_mab2_bwd.restype = C.c_int
-    L.lsthm_mab2_bwd.argtypes = [C.POINTER(MabDesc)] + [C.c_void_p] * 16
-    L.lsthm_mab2_launch_info.restype = C.c_int
-    L.lsthm_mab2_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 7
-    L.lsthm_mab2_plan_info.restype = C.c_int
-    L.lsthm_mab2_plan_info.argtypes = [C.POINTER(MabDesc), C.POINTER(C.c_int32), C.c_int32]
-    L.lsthm_mab2_set_trace.restype = C.c_int
-    L.lsthm_mab2_set_trace.argtypes = [C.c_void_p]
+    L.lsthm_mab_launch_info.argtypes = [C.POINTER(MabDesc)] + [C.POINTER(C.c_int32)] * 7
+    L.lsthm_mab_plan_info.restype = C.c_int
+    L.lsthm_mab_plan_info.argtypes = [C.POINTER(MabDesc), C.POINTER(C.c_int32), C.c_int32]
+    L.lsthm_mab_set_trace.restype = C.c_int
+    L.lsthm_mab_set_trace.argtypes = [C.c_void_p]
     L.lsthm_sps_packed_floats.restype = C.c_size_t
     L.lsthm_sps_packed_floats.argtypes = []
     L.lsthm_sps_workspace_floats.restype = C.c_size_t
@@ -201,40 +191,8 @@ def make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2) -> MabWeights:
     return w
 
 
-def mab_packed_floats(d: MabDesc) -> int:
-    n = lib().lsthm_mab_packed_floats(C.byref(d))
-    if n == 0:
-        raise RuntimeError(f"unsupported recurrence dims: {lib().lsthm_last_error().decode()}")
-    return n
-
-
-def mab_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
-    _check(lib().lsthm_mab_pack(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _stream()), "lsthm_mab_pack")
-
-
-def mab_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sG, sA) -> None:
-    """Writes the h half of hz[T,N,2D] and u[T,N,map_h]; the caller forms z = u Wf2^T + bf2 (include/lsthm_b200.h)."""
-    _check(lib().lsthm_mab_fwd(C.byref(d), _dev_ptr(packed, "packed"), _dev_ptr(gx, "gx"),
-                               _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(hz, "hz"), _dev_ptr(u, "u"), _dev_ptr(sC, "sC"),
-                               _dev_ptr(sG, "sG"), _dev_ptr(sA, "sA"), _stream()), "lsthm_mab_fwd")
-
-
-def mab_bwd(d: MabDesc, w: MabWeights, packed, dhz, duz, drop_mask, sC, sG, sA, u, dgx, de, dup, att=None) -> None:
-    _check(lib().lsthm_mab_bwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"), _dev_ptr(duz, "duz"),
-                               _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sC, "sC"), _dev_ptr(sG, "sG"),
-                               _dev_ptr(sA, "sA"), _dev_ptr(u, "u"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
-                               _dev_ptr(dup, "dup"), _dev_ptr(att, "att"), _stream()),
-           "lsthm_mab_bwd")
-
-
-def mab_launch_info(d: MabDesc) -> dict:
-    v = [C.c_int32() for _ in range(5)]
-    _check(lib().lsthm_mab_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab_launch_info")
-    return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))
-
-
 # ------------------------------------------------------------------------------------------------
-# AT / ATV recurrence, weight-stationary tensor-core kernels (lsthm_mab2_*)
+# AT / ATV recurrence: weight-stationary tensor-core kernels (lsthm_mab_*)
 # ------------------------------------------------------------------------------------------------
 def _byte_ptr(t: torch.Tensor, name: str) -> int:
     if not (t.is_cuda and t.dtype == torch.uint8 and t.is_contiguous() and t.data_ptr() % 128 == 0):
@@ -242,62 +200,62 @@ def _byte_ptr(t: torch.Tensor, name: str) -> int:
     return t.data_ptr()
 
 
-def mab2_pack_bytes(d: MabDesc) -> int:
-    n = lib().lsthm_mab2_pack_bytes(C.byref(d))
+def mab_pack_bytes(d: MabDesc) -> int:
+    n = lib().lsthm_mab_pack_bytes(C.byref(d))
     if n == 0:
         raise RuntimeError(f"unsupported recurrence dims: {lib().lsthm_last_error().decode()}")
     return n
 
 
-def mab2_workspace_bytes(d: MabDesc) -> int:
-    n = lib().lsthm_mab2_workspace_bytes(C.byref(d))
+def mab_workspace_bytes(d: MabDesc) -> int:
+    n = lib().lsthm_mab_workspace_bytes(C.byref(d))
     if n == 0:
         raise RuntimeError(f"unsupported recurrence dims: {lib().lsthm_last_error().decode()}")
     return n
 
 
-def mab2_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
-    _check(lib().lsthm_mab2_pack(C.byref(d), C.byref(w), _byte_ptr(packed, "packed"), _stream()), "lsthm_mab2_pack")
+def mab_pack(d: MabDesc, w: MabWeights, packed: torch.Tensor) -> None:
+    _check(lib().lsthm_mab_pack(C.byref(d), C.byref(w), _byte_ptr(packed, "packed"), _stream()), "lsthm_mab_pack")
 
 
-def mab2_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, workspace) -> None:
+def mab_fwd(d: MabDesc, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, workspace) -> None:
     """Writes the h half of hz[T,N,2D] and u[T,N,map_h]; the caller forms z = u Wf2^T + bf2 (include/lsthm_b200.h)."""
-    _check(lib().lsthm_mab2_fwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(gx, "gx"), _dev_ptr(drop_mask, "drop_mask"),
+    _check(lib().lsthm_mab_fwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(gx, "gx"), _dev_ptr(drop_mask, "drop_mask"),
                                 _dev_ptr(hz, "hz"), _dev_ptr(u, "u"), _dev_ptr(sC, "sC"), _dev_ptr(sCp, "sCp"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
                                 _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _byte_ptr(workspace, "workspace"), _stream()),
-           "lsthm_mab2_fwd")
+           "lsthm_mab_fwd")
 
 
-def mab2_bwd(d: MabDesc, packed, dhz, duz, drop_mask, sCp, sG, sE, sMS, sP, u, dgx, de, dup, att, workspace) -> None:
-    _check(lib().lsthm_mab2_bwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"), _dev_ptr(duz, "duz"),
+def mab_bwd(d: MabDesc, packed, dhz, duz, drop_mask, sCp, sG, sE, sMS, sP, u, dgx, de, dup, att, workspace) -> None:
+    _check(lib().lsthm_mab_bwd(C.byref(d), _byte_ptr(packed, "packed"), _dev_ptr(dhz, "dhz"), _dev_ptr(duz, "duz"),
                                 _dev_ptr(drop_mask, "drop_mask"), _dev_ptr(sCp, "sCp"), _dev_ptr(sG, "sG"), _dev_ptr(sE, "sE"),
                                 _dev_ptr(sMS, "sMS"), _dev_ptr(sP, "sP"), _dev_ptr(u, "u"), _dev_ptr(dgx, "dgx"), _dev_ptr(de, "de"),
                                 _dev_ptr(dup, "dup"), _dev_ptr(att, "att"), _byte_ptr(workspace, "workspace"), _stream()),
-           "lsthm_mab2_bwd")
+           "lsthm_mab_bwd")
 
 
-def mab2_set_trace(buf: Optional[torch.Tensor]) -> None:
-    _check(lib().lsthm_mab2_set_trace(None if buf is None else buf.data_ptr()), "lsthm_mab2_set_trace")
+def mab_set_trace(buf: Optional[torch.Tensor]) -> None:
+    _check(lib().lsthm_mab_set_trace(None if buf is None else buf.data_ptr()), "lsthm_mab_set_trace")
 
 
-def mab2_launch_info(d: MabDesc) -> dict:
+def mab_launch_info(d: MabDesc) -> dict:
     v = [C.c_int32() for _ in range(7)]
-    _check(lib().lsthm_mab2_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab2_launch_info")
+    _check(lib().lsthm_mab_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_mab_launch_info")
     return dict(zip(("grid", "block", "group", "dialogues_per_group", "smem_fwd", "smem_bwd", "padded_rows"), (x.value for x in v)))
 
 
-def mab2_alloc_stash(d: MabDesc, device) -> dict:
+def mab_alloc_stash(d: MabDesc, device) -> dict:
     """The private (piece-major) stash tensors of a forward/backward pair, sized for the current device's plan."""
-    info = mab2_launch_info(d)
+    info = mab_launch_info(d)
     D = sum(d.dh[i] for i in range(d.n_mod))
     rows = d.T * info["padded_rows"]
     new = lambda w: torch.empty(rows * w, device=device, dtype=torch.float32)
     return dict(sCp=new(D), sG=new(4 * D), sE=new(4 * D), sMS=new(8), sP=new(4 * d.map_h))
 
 
-def mab2_unblock(x: torch.Tensor, d: MabDesc, width: int) -> torch.Tensor:
+def mab_unblock(x: torch.Tensor, d: MabDesc, width: int) -> torch.Tensor:
     """Private piece-major stash tensor -> row-major [T, N, width] (tests and debugging only)."""
-    info = mab2_launch_info(d)
+    info = mab_launch_info(d)
     DG = info["dialogues_per_group"]
     Mr = (DG + 7) // 8 * 8
     nb = info["padded_rows"] // Mr
@@ -308,10 +266,10 @@ def mab2_unblock(x: torch.Tensor, d: MabDesc, width: int) -> torch.Tensor:
     return y.reshape(d.T, nb * DG, width)[:, :d.N].contiguous()
 
 
-def mab2_plan_info(d: MabDesc) -> dict:
+def mab_plan_info(d: MabDesc) -> dict:
     """The sharding plan for a 148-SM device (host-only query)."""
     buf = (C.c_int32 * (14 + 6 * 16))()
-    _check(lib().lsthm_mab2_plan_info(C.byref(d), buf, len(buf)), "lsthm_mab2_plan_info")
+    _check(lib().lsthm_mab_plan_info(C.byref(d), buf, len(buf)), "lsthm_mab_plan_info")
     keys = ("G", "nr", "DG", "Mr", "ngroups", "nblocks", "cd", "blob_f", "blob_b", "act_f", "act_b", "smem_fwd", "smem_bwd", "ws_group")
     out = dict(zip(keys, list(buf[:14])))
     out["ranks"] = [dict(zip(("m", "u0", "nu", "head", "j0", "nj"), list(buf[14 + 6 * r:20 + 6 * r]))) for r in range(out["G"])]

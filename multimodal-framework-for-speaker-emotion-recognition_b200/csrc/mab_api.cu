@@ -1,7 +1,6 @@
-// Host side of liblsthm_b200.so: layout planning, weight packing and the extern "C" entry points
-// declared in include/lsthm_b200.h.
+// Host side of the AT/ATV recurrence (include/lsthm_b200.h, lsthm_mab_*): the sharding plan of a
+// CTA group, weight images, cooperative launches.
 #include <algorithm>
-#include <cstdio>
 #include <cstring>
 #include <string>
 
@@ -10,208 +9,156 @@
 
 namespace lsthm {
 
-__global__ void mab_pack_kernel(const __grid_constant__ PackJobs jobs, float *__restrict__ packed) {
-    const PackJob &b = jobs.j[blockIdx.y];
-    const int total = b.J * b.K;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int j = idx / b.K, k = idx - j * b.K;
-        const int col = b.gate_dh ? 4 * (j % b.gate_dh) + j / b.gate_dh : j;
-        packed[b.dst + (size_t)(b.row_off + k) * b.ld + col] = __ldg(b.src + idx);
+int fail_msg(const char *msg);
+int set_error(const char *what, cudaError_t e);
+
+static int cdiv2(int a, int b) { return (a + b - 1) / b; }
+constexpr int kSmemLimit = 227 * 1024;
+
+// stage-1 allocation of `G` ranks to the modalities (whole 8-unit chunks, contiguous ranks per modality); returns the
+// largest per-rank gate cost
+static int stage1_alloc(const M2Plan &P, int G, int ranks[kMaxMod]) {
+    int chunks[kMaxMod], cost[kMaxMod];
+    for (int m = 0; m < P.nm; ++m) { chunks[m] = P.dh[m] / 8; cost[m] = 32 * (P.dh[m] + P.MH); ranks[m] = 1; }
+    for (int used = P.nm; used < G; ++used) {
+        int best = -1, bc = -1;
+        for (int m = 0; m < P.nm; ++m) {
+            if (ranks[m] >= chunks[m]) continue;
+            const int c = cost[m] * cdiv2(chunks[m], ranks[m]);
+            if (c > bc) { bc = c; best = m; }
+        }
+        if (best < 0) break;
+        ++ranks[best];
     }
+    int cmax = 0;
+    for (int m = 0; m < P.nm; ++m) cmax = std::max(cmax, cost[m] * cdiv2(chunks[m], ranks[m]));
+    return cmax;
 }
 
-
-// Composite weights (fp64 accumulation, rounded once to fp32):
-//   W1 = Wf1 . blockdiag(Wr_m)  [MH x 4D]  (columns in the attended order k = head*D + j),   b1 = Wf1 br + bf1
-//   W2 = Vcat . Wf2             [4D x MH]  (rows in the native gate order),                  bv = Vcat bf2
-// written to every image that uses them (see MabLayout).
-__global__ void mab_compose_kernel(const __grid_constant__ ComposeArgs a, float *__restrict__ packed) {
-    const MabLayout &L = a.L;
-    const int D = L.D, G = L.G, MH = L.MH, R = L.R;
-    const int n1 = MH * G, n2 = G * MH, total = n1 + n2 + MH + G;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        if (idx < n1) {                                        // W1[col][k]
-            const int col = idx / G, k = idx - col * G, head = k / D, j = k - head * D;
-            int m = 0;
-            while (m + 1 < L.nm && j >= L.off[m + 1]) ++m;
-            const int jl = j - L.off[m], dh = L.dh[m];
-            double s = 0.0;
-            for (int r = 0; r < L.rd[m]; ++r)
-                s += (double)__ldg(a.Wf1 + (size_t)col * R + L.roff[m] + r) * (double)__ldg(a.Wr[m] + (size_t)r * 4 * dh + head * dh + jl);
-            packed[L.w1 + (size_t)k * MH + col] = (float)s;
-            packed[L.w1n + (size_t)col * G + k] = (float)s;
-        } else if (idx < n1 + n2) {                            // W2[g][q], g = goff_m + gate*dh_m + jl
-            const int i2 = idx - n1, g = i2 / MH, q = i2 - g * MH;
-            int m = 0;
-            while (m + 1 < L.nm && g >= L.goff[m + 1]) ++m;
-            const int lg = g - L.goff[m], dh = L.dh[m], gate = lg / dh, jl = lg - gate * dh;
-            const float *vrow = a.V[m] + (size_t)lg * D;
-            double s = 0.0;
-            for (int j = 0; j < D; ++j) s += (double)__ldg(vrow + j) * (double)__ldg(a.Wf2 + (size_t)j * MH + q);
-            packed[L.w2n + (size_t)g * MH + q] = (float)s;
-            packed[L.wg[m] + (size_t)(dh + q) * 4 * dh + 4 * jl + gate] = (float)s;      // forward image: row dh+q, gate-interleaved column
-        } else if (idx < n1 + n2 + MH) {                       // b1
-            const int col = idx - n1 - n2;
-            double s = (double)__ldg(a.bf1 + col);
-            for (int m = 0; m < L.nm; ++m)
-                for (int r = 0; r < L.rd[m]; ++r) s += (double)__ldg(a.Wf1 + (size_t)col * R + L.roff[m] + r) * (double)__ldg(a.br[m] + r);
-            packed[L.b1 + col] = (float)s;
-        } else {                                               // bv
-            const int g = idx - n1 - n2 - MH;
-            int m = 0;
-            while (m + 1 < L.nm && g >= L.goff[m + 1]) ++m;
-            const float *vrow = a.V[m] + (size_t)(g - L.goff[m]) * D;
-            double s = 0.0;
-            for (int j = 0; j < D; ++j) s += (double)__ldg(vrow + j) * (double)__ldg(a.bf2 + j);
-            packed[L.bvz + g] = (float)s;
+// Builds the sharding plan.  sms <= 0: assume a B200 (148 SMs) — used by the size queries that must work without a device.
+static int build_plan(const lsthm_mab_desc *d, int sms, M2Plan &P) {
+    if (!d) return fail_msg("null descriptor");
+    if (d->n_mod < 1 || d->n_mod > kMaxMod) return fail_msg("n_mod must be 1..3");
+    if (d->n_att != kHeads) return fail_msg("n_att must be 4 (reference: num_atts = 4)");
+    if (d->T < 1 || d->N < 1) return fail_msg("T and N must be positive");
+    if (d->map_h != 64) return fail_msg("map_h must be 64 (reference: map_h = 64)");
+    memset(&P, 0, sizeof(P));
+    P.T = d->T; P.N = d->N; P.nm = d->n_mod; P.MH = d->map_h;
+    int D = 0;
+    for (int m = 0; m < P.nm; ++m) {
+        if (d->dh[m] < 16 || d->dh[m] % 16 || d->dh[m] > 128) return fail_msg("cell sizes must be multiples of 16 in 16..128");
+        if (d->rd[m] < 1) return fail_msg("reduce sizes must be positive");
+        P.dh[m] = d->dh[m]; P.off[m] = D; D += d->dh[m];
+    }
+    if (D > 256) return fail_msg("sum of cell sizes must be <= 256");
+    P.D = D; P.G4 = 4 * D;
+    // stage 2: per head, D split into ranges of whole k16 steps, at most 80 features each
+    const int k16 = D / 16;
+    P.nr = cdiv2(k16, 5);
+    const int ns2 = 4 * P.nr;
+    if (ns2 > kM2MaxRanks) return fail_msg("too many attention slices for one CTA group");
+    // stage 1: every rank owns at most 16 hidden units of one modality (one 8-unit chunk per epilogue warp of a lane quarter);
+    // the group has as many ranks as the larger of the two stages needs
+    int ranks[kMaxMod], n1 = 0;
+    for (int m = 0; m < P.nm; ++m) { ranks[m] = cdiv2(P.dh[m] / 8, 2); n1 += ranks[m]; }
+    const int G = std::max(ns2, n1);
+    if (G > kM2MaxRanks) return fail_msg("cells too large for one CTA group");
+    for (int m = 0; n1 < G; m = (m + 1) % P.nm)                     // spare ranks: spread the widest modality thinner
+        if (ranks[m] < P.dh[m] / 8) { ++ranks[m]; ++n1; }
+    P.G = G;
+    int rank = 0;
+    for (int m = 0; m < P.nm; ++m) {
+        const int chunks = P.dh[m] / 8, base = chunks / ranks[m], rem = chunks % ranks[m];
+        int c0 = 0;
+        for (int i = 0; i < ranks[m]; ++i, ++rank) {
+            const int nc = base + (i < rem ? 1 : 0);
+            if (ranks[m] > 8) return fail_msg("more than 8 ranks per modality");
+            P.r[rank].m = m; P.r[rank].u0 = P.off[m] + 8 * c0; P.r[rank].nu = 8 * nc;
+            P.r[rank].dhm = P.dh[m]; P.r[rank].offm = P.off[m];
+            P.r[rank].mr0 = rank - i; P.r[rank].mr1 = rank - i + ranks[m];
+            if (8 * nc > kM2MaxNU) return fail_msg("cell too large for the group plan");
+            c0 += nc;
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------
-thread_local std::string g_err;
-static int fail(const std::string &m) {
-    g_err = m;
-    return 1;
-}
-
-static int build_layout(const lsthm_mab_desc *d, MabLayout &L) {
-    if (!d) return fail("null descriptor");
-    if (d->n_mod < 1 || d->n_mod > kMaxMod) return fail("n_mod must be 1..3");
-    if (d->n_att != kHeads) return fail("n_att must be 4 (reference: num_atts = 4)");
-    if (d->T < 1 || d->N < 1) return fail("T and N must be positive");
-    if (d->map_h < 4 || d->map_h % 4) return fail("map_h must be a positive multiple of 4");
-    memset(&L, 0, sizeof(L));
-    L.T = d->T; L.N = d->N; L.nm = d->n_mod; L.MH = d->map_h;
-    int D = 0, R = 0;
-    for (int m = 0; m < L.nm; ++m) {
-        if (d->dh[m] < 4 || d->dh[m] % 4 || d->rd[m] < 4 || d->rd[m] % 4)
-            return fail("cell and reduce sizes must be positive multiples of 4");
-        L.dh[m] = d->dh[m]; L.rd[m] = d->rd[m];
-        L.off[m] = D; L.goff[m] = 4 * D; L.roff[m] = R;
-        D += d->dh[m]; R += d->rd[m];
+    for (; rank < G; ++rank) return fail_msg("internal: unassigned rank in the group plan");
+    for (int r = 0; r < G; ++r) { P.r[r].head = -1; P.r[r].j0 = 0; P.r[r].nj = 0; }
+    {
+        const int base = k16 / P.nr, rem = k16 % P.nr;
+        for (int k = 0; k < kHeads; ++k) {
+            int j0 = 0;
+            for (int i = 0; i < P.nr; ++i) {
+                const int nj = 16 * (base + (i >= P.nr - rem ? 1 : 0));
+                M2Rank &R = P.r[k * P.nr + i];
+                R.head = k; R.j0 = j0; R.nj = nj;
+                if (nj > kM2MaxNJ) return fail_msg("attention slice too wide");
+                j0 += nj;
+            }
+        }
     }
-    L.D = D; L.G = 4 * D; L.R = R;
-    L.nt = rup(2 * D, 32);
-    if (L.nt > kMaxThreads) return fail("sum of cell sizes too large for one CTA (2*D > 448)");
-    if (R > L.nt || L.MH > L.nt || L.nt < 64) return fail("unsupported dims (R or map_h exceed the CTA width)");
-    L.nwarp = L.nt / 32;
-    L.ldr = L.G + ((4 - L.G % 32) + 32) % 32;
-    L.ldc = L.D + ((4 - L.D % 32) + 32) % 32;
-    L.smchunk = rup(cdiv(D, L.nwarp), 8);
-    int o = 0;
-    for (int m = 0; m < L.nm; ++m) { L.wg[m] = o; o += (L.dh[m] + L.MH) * 4 * L.dh[m]; }
-    L.watt = o; o += D * L.G;
-    L.w1 = o; o += L.G * L.MH;
-    L.w1n = o; o += L.MH * L.G;
-    L.w2n = o; o += L.G * L.MH;
-    L.batt = o; o += L.G;
-    L.b1 = o; o += L.MH;
-    L.bvz = o; o += L.G;
-    L.total = o;
-    if (D + L.MH > L.nt) return fail("unsupported dims (D + map_h exceeds the CTA width)");
-    // forward split-K plan of the fused reduce+fc.0 product (K = 4D)
-    L.s34chunk = 64; L.s34ns = cdiv(L.G, 64);
-    // backward split-K plans
-    L.b5total = 0;
-    for (int m = 0; m < L.nm; ++m) {
-        L.b5chunk[m] = 64; L.b5ns[m] = cdiv(4 * L.dh[m], 64);
-        L.b5items[m] = (L.dh[m] / 4) * L.b5ns[m];
-        L.b5total += L.b5items[m];
+    // blobs
+    for (int r = 0; r < G; ++r) {
+        P.blob_f = std::max(P.blob_f, m2_fwd_blob(P, P.r[r]).total);
+        P.blob_b = std::max(P.blob_b, m2_bwd_blob(P, P.r[r]).total);
     }
-    L.b4ns = 8; L.b4chunk = cdiv(L.G, 8);
-    L.b5uchunk = 64; L.b5uns = cdiv(L.G, 64);
-    return 0;
-}
-
-static void fwd_smem(const MabLayout &L, int MT, FwdSmem &S) {
-    const int MTP = (MT + 3) & ~3;
-    int o = 8;  // two mbarriers
-    S.h = o; o += L.D * MTP;
-    S.c = o; o += L.D * MTP;
-    S.km = o; o += L.G * MTP;
-    S.row = o; o += MTP * L.ldr;
-    S.u = o; o += L.MH * MTP;
-    S.red = o; o += L.nwarp * kHeads * MTP * 2;
-    S.fin = o; o += kHeads * MTP * 2;
-    int part = std::max(L.G * MTP, MTP * L.ldr);
-    part = std::max(part, L.s34ns * MTP * L.MH);
-    S.part = o; o += part;
-    S.gx = o; o += 2 * MT * L.G;
-    S.mask = o; o += 2 * MT * L.MH;
-    S.batt = o; o += L.G;
-    S.total = o;
-}
-
-static void bwd_smem(const MabLayout &L, int MT, BwdSmem &S) {
-    const int MTP = (MT + 3) & ~3;
-    int o = 8;  // two mbarriers
-    S.dh = o; o += L.D * MTP;
-    S.du = o; o += L.MH * MTP;
-    S.dc = o; o += L.D * MTP;
-    S.gh = o; o += L.D * MTP;
-    S.dup = o; o += L.MH * MTP;
-    S.km = o; o += L.G * MTP;
-    S.C = o; o += MTP * L.ldc;
-    S.A = o; o += MTP * L.ldr;      // A tile, then (with the dvec rows) the B4 dc / B5 du partials
-    S.row = o; o += MTP * L.ldr;
-    int p5 = 0;
-    for (int m = 0; m < L.nm; ++m) { S.b5pb[m] = p5; p5 += L.b5ns[m] * MTP * L.dh[m]; }
-    S.p2 = o; o += p5;
-    S.red = o; o += L.nwarp * kHeads * MTP;
-    S.fin = o; o += kHeads * MTP;
-    S.dhz = o; o += 2 * MT * 2 * L.D;
-    S.duz = o; o += 2 * MT * L.MH;
-    S.uh = o; o += 2 * MT * L.MH;
-    S.mk = o; o += 2 * MT * L.MH;
-    S.total = o;
-}
-
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
-        g_num_sms = p.multiProcessorCount;
-    }
-    return g_num_sms;
-}
-
-static int pick_rows(const lsthm_mab_desc *d, bool need_device) {
-    if (d->rows_per_cta >= 1 && d->rows_per_cta <= 8) return d->rows_per_cta;
-    int sms = need_device ? num_sms() : 148;
+    // dialogues per group
     if (sms <= 0) sms = 148;
-    return std::min(8, std::max(1, cdiv(d->N, sms)));
-}
-
-static int check_cuda(const char *what) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+    const int gmax = sms / G;
+    if (gmax < 1) return fail_msg("device has fewer SMs than one CTA group");
+    int DG = d->rows_per_cta > 0 ? std::min(d->rows_per_cta, kM2MaxDG) : std::min(kM2MaxDG, m2_align(cdiv2(P.N, gmax), 8));
+    DG = std::min(DG, 8 * G);                                   // the combine role covers 8 dialogues per rank
+    for (;; DG -= 8) {
+        if (DG < 1) return fail_msg("the group plan does not fit in shared memory");
+        const int Mr = m2_align(DG, 8);
+        int kf = D, kb = 0;
+        for (int m = 0; m < P.nm; ++m) kf = std::max(kf, P.dh[m] + P.MH);
+        for (int r = 0; r < G; ++r) kb = std::max(kb, P.MH + P.r[r].nj + 4 * P.r[r].nu);
+        P.act_f = kf * Mr * 4;
+        P.act_b = kb * Mr * 4;
+        if (kM2CtrlBytes + P.blob_f + P.act_f + 3072 <= kSmemLimit && kM2CtrlBytes + P.blob_b + P.act_b + 3072 <= kSmemLimit) break;
+        if (DG <= 8) return fail_msg("the group plan does not fit in shared memory");
+    }
+    P.DG = DG; P.Mr = m2_align(DG, 8);
+    P.nblocks = cdiv2(P.N, DG);
+    P.ngroups = std::min(gmax, P.nblocks);
+    P.cd = cdiv2(DG, G);
+    // exchange workspace of one group
+    const int Mr = P.Mr;
+    int o = 0;
+    auto take = [&](int bytes) { const int at = o; o += m2_align(bytes, 128); return at; };
+    P.ws_xc = take(D * Mr * 4);
+    P.ws_xh = take(2 * D * Mr * 4);
+    P.ws_xu = take(P.MH * Mr * 4);
+    P.ws_xp = take(G * Mr * P.MH * 4);
+    P.ws_xst = take(G * Mr * 2 * 4);
+    P.ws_xdc = take((G + 4) * D * Mr * 4);
+    P.ws_xdu = take(G * Mr * P.MH * 4);
+    P.ws_xdh = take(G * 16 * Mr * 32);
+    P.ws_xdup = take(P.MH * Mr * 4 + Mr * 16);
+    P.ws_group = o;
     return 0;
 }
 
-#define LSTHM_DECL_MT(n)                                                                  \
-    int launch_fwd_##n(const FwdArgs &, int, size_t, cudaStream_t);                       \
-    int launch_bwd_##n(const BwdArgs &, int, size_t, cudaStream_t);
-LSTHM_DECL_MT(1) LSTHM_DECL_MT(2) LSTHM_DECL_MT(3) LSTHM_DECL_MT(4)
-LSTHM_DECL_MT(5) LSTHM_DECL_MT(6) LSTHM_DECL_MT(7) LSTHM_DECL_MT(8)
-static const FwdLaunchFn kFwd[8] = {launch_fwd_1, launch_fwd_2, launch_fwd_3, launch_fwd_4,
-                                    launch_fwd_5, launch_fwd_6, launch_fwd_7, launch_fwd_8};
-static const BwdLaunchFn kBwd[8] = {launch_bwd_1, launch_bwd_2, launch_bwd_3, launch_bwd_4,
-                                    launch_bwd_5, launch_bwd_6, launch_bwd_7, launch_bwd_8};
+// packed area: [composite weights fp32][rank table][forward blobs][backward blobs]
+static size_t comp_floats(const M2Plan &P) { return (size_t)2 * P.MH * P.G4 + P.MH + P.G4; }
+static size_t ranktab_off(const M2Plan &P) { return (size_t)m2_align((int)(comp_floats(P) * 4), 128); }
+static size_t blobs_off(const M2Plan &P) { return ranktab_off(P) + (size_t)m2_align((int)(kM2MaxRanks * sizeof(M2Rank)), 128); }
+static size_t bars_bytes(const M2Plan &P) { return (size_t)std::max(1, 148 / P.G + 1) * 512; }
 
-int set_error(const char *what, cudaError_t e) { return fail(std::string(what) + ": " + cudaGetErrorString(e)); }
-int fail_msg(const char *msg) { return fail(msg); }
-int launch_pack(const PackJobs &jobs, float *packed, cudaStream_t st) {
-    mab_pack_kernel<<<dim3(32, jobs.n), 256, 0, st>>>(jobs, packed);
-    return check_cuda("weight pack launch");
+static int device_sms() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms;
 }
 
-constexpr size_t kMaxSmemBytes = 227 * 1024;
+template <typename K, typename A>
+static int coop_launch2(K kernel, const A &args, int grid, size_t smem_bytes, cudaStream_t st, const char *what) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return set_error(what, e);
+    void *params[] = {const_cast<A *>(&args)};
+    e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kM2Threads), params, smem_bytes, st);
+    return e == cudaSuccess ? 0 : set_error(what, e);
+}
 
 }  // namespace lsthm
 
@@ -219,93 +166,138 @@ using namespace lsthm;
 
 extern "C" {
 
-int lsthm_abi_version(void) { return LSTHM_ABI_VERSION; }
-const char *lsthm_last_error(void) { return g_err.c_str(); }
-
-size_t lsthm_mab_packed_floats(const lsthm_mab_desc *d) {
-    MabLayout L;
-    if (build_layout(d, L)) return 0;
-    return (size_t)L.total;
+size_t lsthm_mab_pack_bytes(const lsthm_mab_desc *d) {
+    M2Plan P;
+    if (build_plan(d, 0, P)) return 0;
+    return blobs_off(P) + (size_t)P.G * (P.blob_f + P.blob_b) + 256;
 }
 
-int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *rows, int32_t *smem_fwd,
-                          int32_t *smem_bwd) {
-    MabLayout L;
-    if (build_layout(d, L)) return 1;
-    const int MT = pick_rows(d, false);
-    FwdSmem F; BwdSmem B;
-    fwd_smem(L, MT, F);
-    bwd_smem(L, MT, B);
-    if (grid) *grid = cdiv(L.N, MT);
-    if (block) *block = L.nt;
-    if (rows) *rows = MT;
-    if (smem_fwd) *smem_fwd = F.total * 4;
-    if (smem_bwd) *smem_bwd = B.total * 4;
+size_t lsthm_mab_workspace_bytes(const lsthm_mab_desc *d) {
+    M2Plan P;
+    if (build_plan(d, 0, P)) return 0;
+    // sized for the largest group count / dialogue block any device could pick for these dims
+    M2Plan Q = P;
+    lsthm_mab_desc d2 = *d;
+    d2.rows_per_cta = kM2MaxDG;
+    if (build_plan(&d2, 0, Q)) return 0;
+    const size_t per_group = (size_t)std::max(P.ws_group, Q.ws_group);
+    return bars_bytes(P) + per_group * (size_t)std::max(1, 160 / P.G);
+}
+
+int lsthm_mab_plan_info(const lsthm_mab_desc *d, int32_t *out, int32_t n_out) {
+    // out: G, nr, DG, Mr, ngroups, nblocks, cd, blob_f, blob_b, act_f, act_b, smem_fwd, smem_bwd, ws_group, then per rank
+    // (m, u0, nu, head, j0, nj)
+    M2Plan P;
+    if (build_plan(d, 0, P)) return 1;
+    const int32_t head[14] = {P.G, P.nr, P.DG, P.Mr, P.ngroups, P.nblocks, P.cd, P.blob_f, P.blob_b, P.act_f, P.act_b,
+                              kM2CtrlBytes + P.blob_f + P.act_f + 3072, kM2CtrlBytes + P.blob_b + P.act_b + 3072, P.ws_group};
+    int k = 0;
+    for (int i = 0; i < 14 && k < n_out; ++i) out[k++] = head[i];
+    for (int r = 0; r < P.G; ++r) {
+        const int32_t v[6] = {P.r[r].m, P.r[r].u0, P.r[r].nu, P.r[r].head, P.r[r].j0, P.r[r].nj};
+        for (int i = 0; i < 6 && k < n_out; ++i) out[k++] = v[i];
+    }
     return 0;
 }
 
-int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, float *packed, void *stream) {
-    MabLayout L;
-    if (build_layout(d, L)) return 1;
-    if (!w || !packed) return fail("null weights/packed pointer");
-    PackJobs jobs;
-    int n = 0;
-    auto add = [&](const float *src, int dst, int J, int K, int ld, int row_off, int gate_dh) {
-        jobs.j[n++] = PackJob{src, dst, J, K, ld, row_off, gate_dh};
-    };
-    for (int m = 0; m < L.nm; ++m) {
-        if (!w->U[m] || !w->V[m] || !w->Wr[m] || !w->br[m]) return fail("null weight pointer");
-        const int dh = L.dh[m];
-        add(w->U[m], L.wg[m], 4 * dh, dh, 4 * dh, 0, dh);
+int lsthm_mab_set_trace(void *buf) {
+#ifndef LSTHM_M2_TRACE
+    if (buf) return fail_msg("lsthm_mab_set_trace: the library was built without LSTHM_M2_TRACE (make TRACE=1)");
+#endif
+    long long *p = reinterpret_cast<long long *>(buf);
+    cudaError_t e = cudaMemcpyToSymbol(g_m2_trace, &p, sizeof(p));
+    return e == cudaSuccess ? 0 : set_error("lsthm_mab_set_trace", e);
+}
+
+int lsthm_mab_pack(const lsthm_mab_desc *d, const lsthm_mab_weights *w, void *packed, void *stream) {
+    M2Plan P;
+    if (build_plan(d, 0, P)) return 1;
+    if (!w || !packed) return fail_msg("null weights/packed pointer");
+    if (!w->Watt || !w->batt || !w->Wf1 || !w->bf1 || !w->Wf2 || !w->bf2) return fail_msg("null weight pointer");
+    float *comp = reinterpret_cast<float *>(packed);
+    M2CompArgs c;
+    c.P = P;
+    int R = 0;
+    for (int m = 0; m < kMaxMod; ++m) {
+        if (m < P.nm && (!w->U[m] || !w->V[m] || !w->Wr[m] || !w->br[m])) return fail_msg("null weight pointer");
+        c.V[m] = w->V[m]; c.Wr[m] = w->Wr[m]; c.br[m] = w->br[m];
+        c.rd[m] = m < P.nm ? d->rd[m] : 0; c.roff[m] = R; R += c.rd[m];
     }
-    if (!w->Watt || !w->batt || !w->Wf1 || !w->bf1 || !w->Wf2 || !w->bf2) return fail("null weight pointer");
-    add(w->Watt, L.watt, L.G, L.D, L.G, 0, 0);
-    add(w->batt, L.batt, L.G, 1, L.G, 0, 0);
-    jobs.n = n;
-    mab_pack_kernel<<<dim3(32, n), 256, 0, (cudaStream_t)stream>>>(jobs, packed);
-    if (check_cuda("lsthm_mab_pack launch")) return 1;
-    ComposeArgs c;
-    c.L = L;
-    for (int m = 0; m < kMaxMod; ++m) { c.V[m] = w->V[m]; c.Wr[m] = w->Wr[m]; c.br[m] = w->br[m]; }
+    c.R = R;
     c.Wf1 = w->Wf1; c.bf1 = w->bf1; c.Wf2 = w->Wf2; c.bf2 = w->bf2;
-    mab_compose_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(c, packed);
-    return check_cuda("lsthm_mab_pack compose launch");
+    c.W1 = comp; c.W2 = c.W1 + (size_t)P.MH * P.G4; c.b1 = c.W2 + (size_t)P.G4 * P.MH; c.bv = c.b1 + P.MH;
+    mab_compose_kernel<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(c);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error("lsthm_mab_pack compose launch", e);
+    M2ImgArgs ia;
+    ia.P = P;
+    for (int m = 0; m < kMaxMod; ++m) ia.U[m] = w->U[m];
+    ia.Watt = w->Watt; ia.batt = w->batt; ia.W1 = c.W1; ia.W2 = c.W2; ia.b1 = c.b1; ia.bv = c.bv;
+    uint8_t *base = reinterpret_cast<uint8_t *>(packed) + blobs_off(P);
+    ia.ranktab = reinterpret_cast<M2Rank *>(reinterpret_cast<uint8_t *>(packed) + ranktab_off(P));
+    ia.blob_f = base;
+    ia.blob_b = base + (size_t)P.G * P.blob_f;
+    mab_image_kernel<<<dim3(12, P.G), 256, 0, (cudaStream_t)stream>>>(ia);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_mab_pack image launch", e);
 }
 
-int lsthm_mab_fwd(const lsthm_mab_desc *d, const float *packed, const float *gx, const float *drop_mask, float *hz,
-                  float *u, float *sC, float *sG, float *sA, void *stream) {
-    FwdArgs a;
-    if (build_layout(d, a.L)) return 1;
-    if (!packed || !gx || !hz || !u) return fail("null packed/gx/hz/u pointer");
-    const bool any = sC || sG || sA, all = sC && sG && sA;
-    if (any && !all) return fail("stash pointers must be all set or all NULL");
-    const int MT = pick_rows(d, true);
-    fwd_smem(a.L, MT, a.S);
-    const size_t bytes = (size_t)a.S.total * 4;
-    if (bytes > kMaxSmemBytes) return fail("forward tile does not fit in shared memory");
-    a.packed = packed; a.gx = gx; a.mask = drop_mask;
-    a.hz = hz; a.sC = sC; a.sG = sG; a.sA = sA; a.sU = u;
-    const int grid = cdiv(a.L.N, MT);
-    return kFwd[MT - 1](a, grid, bytes, (cudaStream_t)stream);
+int lsthm_mab_launch_info(const lsthm_mab_desc *d, int32_t *grid, int32_t *block, int32_t *group, int32_t *dialogues_per_group,
+                           int32_t *smem_fwd, int32_t *smem_bwd, int32_t *padded_rows) {
+    M2Plan P;
+    if (build_plan(d, device_sms(), P)) return 1;
+    if (grid) *grid = P.ngroups * P.G;
+    if (block) *block = kM2Threads;
+    if (group) *group = P.G;
+    if (dialogues_per_group) *dialogues_per_group = P.DG;
+    if (smem_fwd) *smem_fwd = kM2CtrlBytes + P.blob_f + P.act_f + 3072;
+    if (smem_bwd) *smem_bwd = kM2CtrlBytes + P.blob_b + P.act_b + 3072;
+    if (padded_rows) *padded_rows = P.nblocks * P.Mr;
+    return 0;
 }
 
-int lsthm_mab_bwd(const lsthm_mab_desc *d, const lsthm_mab_weights *w, const float *packed, const float *dhz,
-                  const float *duz, const float *drop_mask, const float *sC, const float *sG, const float *sA, const float *u,
-                  float *dgx, float *de, float *dup, float *att, void *stream) {
-    BwdArgs a;
-    if (build_layout(d, a.L)) return 1;
-    if (!w || !packed || !dhz || !duz || !sC || !sG || !sA || !u || !dgx || !de || !dup) return fail("null pointer argument");
-    const int MT = pick_rows(d, true);
-    bwd_smem(a.L, MT, a.S);
-    const size_t bytes = (size_t)a.S.total * 4;
-    if (bytes > kMaxSmemBytes) return fail("backward tile does not fit in shared memory");
-    a.packed = packed;
-    for (int m = 0; m < kMaxMod; ++m) a.U[m] = w->U[m];
-    a.Watt = w->Watt;
-    a.dhz = dhz; a.duz = duz; a.mask = drop_mask; a.sC = sC; a.sG = sG; a.sA = sA; a.sU = u;
+int lsthm_mab_fwd(const lsthm_mab_desc *d, const void *packed, const float *gx, const float *drop_mask, float *hz, float *u,
+                   float *sC, float *sCp, float *sG, float *sE, float *sMS, float *sP, void *workspace, void *stream) {
+    M2FwdArgs a;
+    const int sms = device_sms();
+    if (sms <= 0) return fail_msg("no CUDA device (there is no CPU path)");
+    if (build_plan(d, sms, a.P)) return 1;
+    if (!packed || !gx || !hz || !u || !workspace) return fail_msg("null packed/gx/hz/u/workspace pointer");
+    const bool any = sC || sCp || sG || sE || sMS || sP, all = sC && sCp && sG && sE && sMS && sP;
+    if (any && !all) return fail_msg("stash pointers must be all set or all NULL");
+    const M2Plan &P = a.P;
+    a.blob = reinterpret_cast<const uint8_t *>(packed) + blobs_off(P);
+    a.ranktab = reinterpret_cast<const M2Rank *>(reinterpret_cast<const uint8_t *>(packed) + ranktab_off(P));
+    a.gx = gx; a.mask = drop_mask; a.hz = hz; a.sU = u;
+    a.sC = sC; a.sCp = sCp; a.sG = sG; a.sE = sE; a.sMS = sMS; a.sP = sP;
+    a.bars = reinterpret_cast<unsigned *>(workspace);
+    a.ws = reinterpret_cast<uint8_t *>(workspace) + bars_bytes(P);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, bars_bytes(P), (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error("lsthm_mab_fwd counter reset", e);
+    const size_t smem = (size_t)kM2CtrlBytes + P.blob_f + P.act_f + 3072;
+    return coop_launch2(mab_fwd_kernel, a, P.ngroups * P.G, smem, (cudaStream_t)stream, "lsthm_mab_fwd launch");
+}
+
+int lsthm_mab_bwd(const lsthm_mab_desc *d, const void *packed, const float *dhz, const float *duz, const float *drop_mask,
+                   const float *sCp, const float *sG, const float *sE, const float *sMS, const float *sP, const float *u,
+                   float *dgx, float *de, float *dup, float *att, void *workspace, void *stream) {
+    M2BwdArgs a;
+    const int sms = device_sms();
+    if (sms <= 0) return fail_msg("no CUDA device (there is no CPU path)");
+    if (build_plan(d, sms, a.P)) return 1;
+    if (!packed || !dhz || !duz || !sCp || !sG || !sE || !sMS || !sP || !u || !dgx || !de || !dup || !workspace)
+        return fail_msg("null pointer argument");
+    const M2Plan &P = a.P;
+    a.blob = reinterpret_cast<const uint8_t *>(packed) + blobs_off(P) + (size_t)P.G * P.blob_f;
+    a.ranktab = reinterpret_cast<const M2Rank *>(reinterpret_cast<const uint8_t *>(packed) + ranktab_off(P));
+    a.dhz = dhz; a.duz = duz; a.mask = drop_mask; a.sCp = sCp; a.sG = sG; a.sE = sE; a.sMS = sMS; a.sP = sP; a.sU = u;
     a.dgx = dgx; a.de = de; a.dup = dup; a.att = att;
-    const int grid = cdiv(a.L.N, MT);
-    return kBwd[MT - 1](a, grid, bytes, (cudaStream_t)stream);
+    a.bars = reinterpret_cast<unsigned *>(workspace);
+    a.ws = reinterpret_cast<uint8_t *>(workspace) + bars_bytes(P);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, bars_bytes(P), (cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error("lsthm_mab_bwd counter reset", e);
+    const size_t smem = (size_t)kM2CtrlBytes + P.blob_b + P.act_b + 3072;
+    return coop_launch2(mab_bwd_kernel, a, P.ngroups * P.G, smem, (cudaStream_t)stream, "lsthm_mab_bwd launch");
 }
 
 }  // extern "C"

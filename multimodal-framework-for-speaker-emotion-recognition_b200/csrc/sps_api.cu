@@ -3,14 +3,36 @@
 #include <string>
 
 #include "../../include/lsthm_b200.h"
-#include "mab_kernels.cuh"
 #include "sps_kernels.cuh"
 
 namespace lsthm {
 
 int set_error(const char *what, cudaError_t e);
 int fail_msg(const char *msg);
-int launch_pack(const PackJobs &jobs, float *packed, cudaStream_t st);
+
+// weight packing: transposes nn.Linear / nn.LSTMCell matrices into the k-major, gate-interleaved image the FFMA products stream
+struct PackJob {
+    const float *src;
+    int dst, J, K, ld, row_off, gate_dh;
+};
+struct PackJobs {
+    PackJob j[24];
+    int n;
+};
+__global__ void sps_pack_kernel(const __grid_constant__ PackJobs jobs, float *__restrict__ packed) {
+    const PackJob &b = jobs.j[blockIdx.y];
+    const int total = b.J * b.K;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx / b.K, k = idx - j * b.K;
+        const int col = b.gate_dh ? 4 * (j % b.gate_dh) + j / b.gate_dh : j;
+        packed[b.dst + (size_t)(b.row_off + k) * b.ld + col] = __ldg(b.src + idx);
+    }
+}
+static int launch_pack(const PackJobs &jobs, float *packed, cudaStream_t st) {
+    sps_pack_kernel<<<dim3(32, jobs.n), 256, 0, st>>>(jobs, packed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("weight pack launch", e);
+}
 
 #define LSTHM_DECL_SPS(n)                                                              \
     int launch_sps_fwd_##n(const SpsFwdArgs &, int, size_t, cudaStream_t);             \

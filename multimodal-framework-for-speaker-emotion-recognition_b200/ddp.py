@@ -23,9 +23,22 @@ import torch
 import torch.distributed as dist
 
 
+# Registered-but-never-applied parameters of the drop-in modules: the reference constructs them, so they must
+# exist for state_dict / RNG-order compatibility, but no forward path touches them and their grad stays None.
+#   every model:   encoder_*.pos_ffn.fc.*                                   (encoder.py:99 builds it, :111 never calls it)
+#   MARN1_sps:     marn_cell_{f,b}.lstm_s.*, marn_cell_{f,b}.crossatt_a2l.*, marn_cell_{f,b}.crossatt_l2a.Wv
+#                  (lsthm_sps.py:136,153: constructed; :59-72 uses only Wq, Wk of crossatt_l2a)
+_UNUSED_PATTERNS = (r"\.pos_ffn\.fc\.", r"^marn_cell_[fb]\.lstm_s\.", r"^marn_cell_[fb]\.crossatt_a2l\.",
+                    r"^marn_cell_[fb]\.crossatt_l2a\.Wv$")
+
+
 def unused_parameter_names(model: torch.nn.Module) -> List[str]:
-    """Names of registered-but-never-applied parameters of the drop-in modules."""
-    return [n for n, _ in model.named_parameters() if ".pos_ffn.fc." in n]
+    """Names of the parameters no forward path uses (their gradient must stay None, as in the single-process reference
+    step: Adam with weight decay would otherwise move them).  tests/test_host_logic.py pins this list to the
+    ``grad is None`` set of the reference-generated fixtures."""
+    import re
+    pats = [re.compile(p) for p in _UNUSED_PATTERNS]
+    return [n for n, _ in model.named_parameters() if any(p.search(n) for p in pats)]
 
 
 class GradAllReducer:
@@ -42,6 +55,7 @@ class GradAllReducer:
         self.buckets: List[torch.Tensor] = []
         self._members: List[List[torch.nn.Parameter]] = []
         self._bucket_of: Dict[int, int] = {}
+        self._home: Dict[int, tuple] = {}
         cur, cur_bytes = [], 0
         for n, p in named:
             cur.append(p)
@@ -53,6 +67,7 @@ class GradAllReducer:
             self._add_bucket(cur)
         self._pending = [0] * len(self.buckets)
         self._handles: List = []
+        self.skipped = sorted(skip)
         for b, members in enumerate(self._members):
             for p in members:
                 p.register_post_accumulate_grad_hook(self._make_hook(b))
@@ -74,6 +89,7 @@ class GradAllReducer:
         for p, o in zip(params, offs):
             p.grad = flat[o:o + p.numel()].view_as(p)
             self._bucket_of[id(p)] = len(self.buckets)
+            self._home[id(p)] = (len(self.buckets), o)          # where this parameter's gradient must live
         self.buckets.append(flat)
         self._members.append(list(params))
         if self.flatten_params:
@@ -85,9 +101,20 @@ class GradAllReducer:
                 p.data = pflat[o:o + p.numel()].view_as(p)
             self.param_buckets.append(pflat)
 
+    def _expected_ptr(self, p) -> int:
+        b, o = self._home[id(p)]
+        return self.buckets[b].data_ptr() + o * self.buckets[b].element_size()
+
     def _make_hook(self, b):
-        def hook(_param):
+        def hook(param):
+            # a gradient that autograd allocated itself (someone called optimizer.zero_grad() / model.zero_grad(set_to_none=True)
+            # instead of reducer.zero_grad()) lives outside the buckets and would silently never be reduced
+            if param.grad is None or param.grad.data_ptr() != self._expected_ptr(param):
+                raise RuntimeError("GradAllReducer: a gradient is not a view of its bucket — call reducer.zero_grad() (not "
+                                   "optimizer.zero_grad(set_to_none=True)) between steps")
             self._pending[b] -= 1
+            if self._pending[b] < 0:
+                raise RuntimeError("GradAllReducer: a bucket received more gradients than it has members (zero_grad() not called?)")
             if self._pending[b] == 0 and self.world > 1:
                 self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
@@ -100,25 +127,22 @@ class GradAllReducer:
         for b, members in enumerate(self._members):
             self._pending[b] = len(members)
             for p in members:
-                if p.grad is None or p.grad.data_ptr() != self._view_ptr(p):
+                if p.grad is None or p.grad.data_ptr() != self._expected_ptr(p):
                     self._rebind(p)
         self._handles = []
 
-    def _view_ptr(self, p):
-        return p.grad.data_ptr() if p.grad is not None else -1
-
     def _rebind(self, p):
-        b = self._bucket_of[id(p)]
-        offs, _ = self._offsets(self._members[b])
-        for q, o in zip(self._members[b], offs):
-            if q is p:
-                p.grad = self.buckets[b][o:o + p.numel()].view_as(p)
-                return
+        b, o = self._home[id(p)]
+        p.grad = self.buckets[b][o:o + p.numel()].view_as(p)
 
     def finish(self):
         """Block the current stream until every bucket's allreduce is complete."""
+        for members in self._members:
+            for p in members:
+                if p.grad is not None and p.grad.data_ptr() != self._expected_ptr(p):
+                    raise RuntimeError("GradAllReducer.finish: a gradient was re-allocated outside its bucket during the step")
         for b, n in enumerate(self._pending):
-            if n != 0 and self.world > 1:       # a bucket whose hooks did not all fire (should not happen)
+            if n != 0 and self.world > 1:       # a bucket whose hooks did not all fire (a parameter unused in THIS step)
                 self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
         for h in self._handles:
@@ -126,7 +150,7 @@ class GradAllReducer:
         self._handles = []
 
 
-class FusedAdam:
+class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam(lr, betas, eps, weight_decay) semantics (L2-style decay, no amsgrad; what the reference's
     trainer builds at model_trainer.py:82) as ONE fused CUDA launch per gradient bucket of a
     ``GradAllReducer(..., flatten_params=True)``.  Parameters that are not in a bucket (never-used ones whose grad
@@ -135,16 +159,41 @@ class FusedAdam:
     def __init__(self, reducer: GradAllReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
         if not reducer.flatten_params:
             raise RuntimeError("FusedAdam needs GradAllReducer(..., flatten_params=True)")
-        self.reducer, self.lr, self.betas, self.eps, self.weight_decay = reducer, lr, betas, eps, weight_decay
+        self.reducer = reducer
+        # a torch.optim.Optimizer with ONE param_group: lr schedulers (the reference's StepLR, model_trainer.py:83) read and
+        # write param_groups[0]["lr"]; step() takes every hyper-parameter from there
+        super().__init__([p for members in reducer._members for p in members],
+                         dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self.step_count = 0
         self.exp_avg = [torch.zeros_like(b) for b in reducer.param_buckets]
         self.exp_avg_sq = [torch.zeros_like(b) for b in reducer.param_buckets]
 
-    def step(self) -> None:
+    @property
+    def lr(self) -> float:
+        return self.param_groups[0]["lr"]
+
+    def step(self, closure=None) -> None:
         from . import _lib
+        g0 = self.param_groups[0]
         self.step_count += 1
         for p, g, m, v in zip(self.reducer.param_buckets, self.reducer.buckets, self.exp_avg, self.exp_avg_sq):
-            _lib.adam_step(p, g, m, v, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count)
+            _lib.adam_step(p, g, m, v, g0["lr"], g0["betas"][0], g0["betas"][1], g0["eps"], g0["weight_decay"], self.step_count)
 
-    def zero_grad(self) -> None:
-        self.reducer.zero_grad()
+    def state_dict(self) -> dict:
+        """Checkpointable optimizer state (the reference saves weights only, model_trainer.py:170-171; resuming a run needs this)."""
+        g0 = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        return {"step": self.step_count, "param_group": g0, "exp_avg": [t.clone() for t in self.exp_avg],
+                "exp_avg_sq": [t.clone() for t in self.exp_avg_sq]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if len(sd["exp_avg"]) != len(self.exp_avg) or any(a.shape != b.shape for a, b in zip(sd["exp_avg"], self.exp_avg)):
+            raise RuntimeError("FusedAdam.load_state_dict: bucket layout differs from the checkpoint's")
+        self.step_count = int(sd["step"])
+        self.param_groups[0].update(sd["param_group"])
+        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
+            dst.copy_(src)
+        for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
+            dst.copy_(src)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.reducer.zero_grad()          # gradients are views of the flat buckets: they are zeroed, never dropped

@@ -29,7 +29,7 @@ _workspaces = {}
 
 def _workspace(desc, device) -> torch.Tensor:
     """Exchange workspace of the group kernels (per device; forward and backward of a step run back to back on one stream)."""
-    nbytes = _lib.mab2_workspace_bytes(desc)
+    nbytes = _lib.mab_workspace_bytes(desc)
     key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
     w = _workspaces.get(key)
     if w is None or w.numel() < nbytes:
@@ -76,8 +76,8 @@ class MabRecurrenceFn(torch.autograd.Function):
         Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
         desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
         wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-        packed = torch.empty(_lib.mab2_pack_bytes(desc), device=gx.device, dtype=torch.uint8)
-        _lib.mab2_pack(desc, wstruct, packed)
+        packed = torch.empty(_lib.mab_pack_bytes(desc), device=gx.device, dtype=torch.uint8)
+        _lib.mab_pack(desc, wstruct, packed)
         launch_counter["pack"] += 2
         work = _workspace(desc, gx.device)
         new = lambda *s: torch.empty(*s, device=gx.device, dtype=torch.float32)
@@ -87,11 +87,11 @@ class MabRecurrenceFn(torch.autograd.Function):
             drop_mask = drop_mask.contiguous()
         if need_grad:
             sC = new(T, N, D)
-            st = _lib.mab2_alloc_stash(desc, gx.device)      # private piece-major stash of the kernel pair
+            st = _lib.mab_alloc_stash(desc, gx.device)      # private piece-major stash of the kernel pair
             sCp, sG, sE, sMS, sP = st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"]
         else:
             sC = sCp = sG = sE = sMS = sP = None
-        _timed("fwd", _lib.mab2_fwd, desc, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, work)
+        _timed("fwd", _lib.mab_fwd, desc, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, work)
         launch_counter["fwd"] += 1
         # z_t = fc.3(u_t) for all steps at once, written into the z half of hz (HybridRNN_ATV.py:129)
         linear_into(u.view(T * N, map_h), Wf2, bf2, hz.view(T * N, 2 * D)[:, D:])
@@ -120,7 +120,7 @@ class MabRecurrenceFn(torch.autograd.Function):
         duz = mm_nn(dz_head, Wf2)                              # the head's dL/dz pulled through fc.3: [TN, map_h]
         dgx, de, dup = new(T, N, G), new(T, N, G), new(T, N, map_h)
         att = new(T, N, G)     # attended = a * cs (HybridRNN_ATV.py:125), regrouped per modality head-major (lines 126-128) by the kernel
-        _timed("bwd", _lib.mab2_bwd, desc, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sCp, sG, sE, sMS, sP, u,
+        _timed("bwd", _lib.mab_bwd, desc, packed, dhz, duz.view(T, N, map_h), ctx.drop_mask, sCp, sG, sE, sMS, sP, u,
                dgx, de, dup, att, _workspace(desc, hz.device))
         launch_counter["bwd"] += 1
 

@@ -1,6 +1,6 @@
-"""Development harness for the weight-stationary tensor-core recurrence (lsthm_mab2_*): per-tensor errors of the kernel
+"""Development harness for the weight-stationary tensor-core recurrence (lsthm_mab_*): per-tensor errors of the kernel
 boundary against the fp64 plain-C oracle, one case per subprocess (a trapped kernel must not take the other cases down),
-then kernel timings at the benchmark shape.  Usage (GPU box):  python profiles/dev_mab2_check.py [case ...] [--time]"""
+then kernel timings at the benchmark shape.  Usage (GPU box):  python profiles/dev_mab_check.py [case ...] [--time]"""
 import os
 import subprocess
 import sys
@@ -53,25 +53,25 @@ def run_case(name):
     Wf1, bf1, Wf2, bf2 = w[4 * M + 2:4 * M + 6]
     d = lib.make_desc(T, N, dh, rd, MH, 4, rows)
     ws = lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-    print(name, "launch:", lib.mab2_launch_info(d), flush=True)
-    packed = torch.empty(lib.mab2_pack_bytes(d), device=dev, dtype=torch.uint8)
-    lib.mab2_pack(d, ws, packed)
-    work = torch.empty(lib.mab2_workspace_bytes(d), device=dev, dtype=torch.uint8)
+    print(name, "launch:", lib.mab_launch_info(d), flush=True)
+    packed = torch.empty(lib.mab_pack_bytes(d), device=dev, dtype=torch.uint8)
+    lib.mab_pack(d, ws, packed)
+    work = torch.empty(lib.mab_workspace_bytes(d), device=dev, dtype=torch.uint8)
     new = lambda *s: torch.full(s, float("nan"), device=dev)
     hz, UH = new(T, N, 2 * D), new(T, N, MH)
     sC = new(T, N, D)
-    st = lib.mab2_alloc_stash(d, dev)
+    st = lib.mab_alloc_stash(d, dev)
     for v in st.values():
         v.fill_(float("nan"))
     gxc = gx.to(dev)
     mc = None if mask is None else mask.to(dev)
-    lib.mab2_fwd(d, packed, gxc, mc, hz, UH, sC, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], work)
+    lib.mab_fwd(d, packed, gxc, mc, hz, UH, sC, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], work)
     torch.cuda.synchronize()
-    sG = lib.mab2_unblock(st["sG"], d, 4 * D)
-    sE = lib.mab2_unblock(st["sE"], d, 4 * D)
-    sP = lib.mab2_unblock(st["sP"], d, 4 * MH).view(T, N, 4, MH)
-    sMS = lib.mab2_unblock(st["sMS"], d, 8).view(T, N, 4, 2)
-    assert torch.equal(lib.mab2_unblock(st["sCp"], d, D), sC), "private c copy differs"
+    sG = lib.mab_unblock(st["sG"], d, 4 * D)
+    sE = lib.mab_unblock(st["sE"], d, 4 * D)
+    sP = lib.mab_unblock(st["sP"], d, 4 * MH).view(T, N, 4, MH)
+    sMS = lib.mab_unblock(st["sMS"], d, 8).view(T, N, 4, 2)
+    assert torch.equal(lib.mab_unblock(st["sCp"], d, D), sC), "private c copy differs"
     mask64 = None if mask is None else mask.double().numpy()
     ref = ocpu.mab_forward(params, gx.double().numpy(), dh, rd, mask64)
     A = (torch.exp(sE.view(T, N, 4, D) - sMS[..., 0:1]) * sMS[..., 1:2])
@@ -94,7 +94,7 @@ def run_case(name):
     dhzc = dhz.to(dev)
     duz = (dhzc[:, :, D:] @ Wf2).contiguous()
     dgx, de, dup, att = new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, MH), new(T, N, 4 * D)
-    lib.mab2_bwd(d, packed, dhzc, duz, mc, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], UH, dgx, de, dup, att, work)
+    lib.mab_bwd(d, packed, dhzc, duz, mc, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], UH, dgx, de, dup, att, work)
     torch.cuda.synchronize()
     radj, _ = ocpu.mab_backward(params, dhz.double().numpy(), ref, dh, rd, mask64)
     adj = dict(dgx=dgx, de=de, dup=dup)
@@ -131,23 +131,23 @@ def run_timing():
         Wf1, bf1, Wf2, bf2 = w[4 * M + 2:4 * M + 6]
         d = lib.make_desc(T, N, dh, rd, MH, 4, 0)
         ws = lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-        packed = torch.empty(lib.mab2_pack_bytes(d), device=dev, dtype=torch.uint8)
-        work = torch.empty(lib.mab2_workspace_bytes(d), device=dev, dtype=torch.uint8)
+        packed = torch.empty(lib.mab_pack_bytes(d), device=dev, dtype=torch.uint8)
+        work = torch.empty(lib.mab_workspace_bytes(d), device=dev, dtype=torch.uint8)
         new = lambda *s: torch.empty(s, device=dev)
         gx = torch.randn(T, N, 4 * D, device=dev)
         mask = torch.bernoulli(torch.full((T, N, MH), 0.7, device=dev)) / 0.7
         hz, UH = new(T, N, 2 * D), new(T, N, MH)
         sC = new(T, N, D)
-        st = lib.mab2_alloc_stash(d, dev)
+        st = lib.mab_alloc_stash(d, dev)
         sCp, sG, sE, sMS, sP = st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"]
         dhz = torch.randn(T, N, 2 * D, device=dev)
         duz = torch.randn(T, N, MH, device=dev)
         dgx, de, dup, att = new(T, N, 4 * D), new(T, N, 4 * D), new(T, N, MH), new(T, N, 4 * D)
         res = {}
         for what in ("pack", "fwd", "bwd"):
-            fn = {"pack": lambda: lib.mab2_pack(d, ws, packed),
-                  "fwd": lambda: lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sCp, sG, sE, sMS, sP, work),
-                  "bwd": lambda: lib.mab2_bwd(d, packed, dhz, duz, mask, sCp, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)}[what]
+            fn = {"pack": lambda: lib.mab_pack(d, ws, packed),
+                  "fwd": lambda: lib.mab_fwd(d, packed, gx, mask, hz, UH, sC, sCp, sG, sE, sMS, sP, work),
+                  "bwd": lambda: lib.mab_bwd(d, packed, dhz, duz, mask, sCp, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)}[what]
             for _ in range(1 if prof else 3):
                 fn()
             torch.cuda.synchronize()
@@ -158,20 +158,20 @@ def run_timing():
             e1.record()
             torch.cuda.synchronize()
             res[what] = e0.elapsed_time(e1) / 10
-        print("TIMING", kind, T, N, lib.mab2_launch_info(d), {k: f"{v:.3f} ms" for k, v in res.items()}, flush=True)
+        print("TIMING", kind, T, N, lib.mab_launch_info(d), {k: f"{v:.3f} ms" for k, v in res.items()}, flush=True)
         if prof:
             continue
         # phase trace of block 0 (control thread / first epilogue warp), cycles, median over the steps
         tr = torch.zeros(T, 2, 16, device=dev, dtype=torch.int64)
         for what in ("fwd", "bwd"):
             tr.zero_()
-            lib.mab2_set_trace(tr)
+            lib.mab_set_trace(tr)
             if what == "fwd":
-                lib.mab2_fwd(d, packed, gx, mask, hz, UH, sC, sCp, sG, sE, sMS, sP, work)
+                lib.mab_fwd(d, packed, gx, mask, hz, UH, sC, sCp, sG, sE, sMS, sP, work)
             else:
-                lib.mab2_bwd(d, packed, dhz, duz, mask, sCp, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)
+                lib.mab_bwd(d, packed, dhz, duz, mask, sCp, sG, sE, sMS, sP, UH, dgx, de, dup, att, work)
             torch.cuda.synchronize()
-            lib.mab2_set_trace(None)
+            lib.mab_set_trace(None)
             tc = tr.cpu()
             if int(tc.abs().sum()) == 0:
                 continue

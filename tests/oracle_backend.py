@@ -28,8 +28,11 @@ class OracleBackend:
         self.weights = {k: v.detach().double().numpy() for k, v in p.items()}
         return self.weights
 
-    def mab_packed_floats(self, d):
-        return 4
+    def mab_pack_bytes(self, d):
+        return 128
+
+    def mab_workspace_bytes(self, d):
+        return 128
 
     def mab_pack(self, d, w, packed):
         pass
@@ -38,31 +41,41 @@ class OracleBackend:
     def _dims(d):
         return tuple(d.dh[i] for i in range(d.n_mod)), tuple(d.rd[i] for i in range(d.n_mod))
 
-    def mab_fwd(self, d, packed, gx, drop_mask, hz, u, sC, sG, sA):
+    def mab_alloc_stash(self, d, device):
+        """The stash is private to the fwd/bwd pair: this stand-in keeps the oracle's own tensors (c, gates, softmax)."""
+        dh, _ = self._dims(d)
+        D = sum(dh)
+        z = lambda w: torch.zeros(d.T * d.N * w)
+        return dict(sCp=z(D), sG=z(4 * D), sE=z(4 * D), sMS=z(8), sP=z(4 * d.map_h))
+
+    def mab_fwd(self, d, packed, gx, drop_mask, hz, u, sC, sCp, sG, sE, sMS, sP, workspace):
         dh, rd = self._dims(d)
         f = ocpu.mab_forward(self.weights, gx.double().numpy(), dh, rd,
                              None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
         hz.copy_(torch.from_numpy(f["hz"]))            # the library writes only the h half; the host overwrites the z half
         u.copy_(torch.from_numpy(f["UH"]).reshape(u.shape))
         if sC is not None:
-            for t, k in ((sC, "C"), (sG, "G"), (sA, "A")):
-                t.copy_(torch.from_numpy(f[k]).reshape(t.shape))
+            sC.copy_(torch.from_numpy(f["C"]).reshape(sC.shape))
+            sCp.copy_(torch.from_numpy(f["C"]).reshape(-1))
+            sG.copy_(torch.from_numpy(f["G"]).reshape(-1))
+            sE.copy_(torch.from_numpy(f["A"]).reshape(-1))       # (this stand-in stashes the softmax weights themselves)
 
-    def mab_bwd(self, d, w, packed, dhz, duz, drop_mask, sC, sG, sA, u, dgx, de, dup, att=None):
+    def mab_bwd(self, d, packed, dhz, duz, drop_mask, sCp, sG, sE, sMS, sP, u, dgx, de, dup, att, workspace):
         dh, rd = self._dims(d)
         T, N = d.T, d.N
         D = sum(dh)
+        sC, sA = sCp.view(T, N, D), sE.view(T, N, 4, D)
         # hz / R feed only the oracle's own weight-gradient accumulation, which is not used here; the oracle takes the
         # head's dL/dz directly (dhz carries it), so `duz` (= dz_head Wf2, what the CUDA kernel consumes) is not needed
-        f = dict(hz=np.zeros((T, N, 2 * D)), C=sC.double().numpy(), G=sG.double().numpy(),
-                 A=np.ascontiguousarray(sA.double().numpy().reshape(T, N, 4, D)),
+        f = dict(hz=np.zeros((T, N, 2 * D)), C=sC.double().numpy(), G=sG.view(T, N, 4 * D).double().numpy(),
+                 A=np.ascontiguousarray(sA.double().numpy()),
                  R=np.zeros((T, N, sum(rd))), UH=u.double().numpy())
         adj, _ = ocpu.mab_backward(self.weights, dhz.double().numpy(), f, dh, rd,
                                    None if drop_mask is None else drop_mask.double().numpy(), d.map_h)
         for t, k in ((dgx, "dgx"), (de, "de"), (dup, "dup")):
             t.copy_(torch.from_numpy(adj[k]).reshape(t.shape))
         if att is not None:   # attended = a * c regrouped per modality, head-major (include/lsthm_b200.h: lsthm_mab_bwd)
-            a4 = sA.reshape(T, N, 4, D) * sC.reshape(T, N, 1, D)
+            a4 = sA * sC.reshape(T, N, 1, D)
             o = 0
             for h in dh:
                 att[:, :, 4 * o:4 * o + 4 * h] = a4[:, :, :, o:o + h].reshape(T, N, 4 * h)
@@ -75,8 +88,9 @@ def install(monkeypatch):
     rec = import_module(lsthm_b200.__name__ + ".recurrence")
     net = import_module(lsthm_b200.__name__ + ".mab_net")
     be = OracleBackend()
-    for name in ("make_weights", "mab_packed_floats", "mab_pack", "mab_fwd", "mab_bwd"):
+    for name in ("make_weights", "mab_pack_bytes", "mab_workspace_bytes", "mab_pack", "mab_alloc_stash", "mab_fwd", "mab_bwd"):
         monkeypatch.setattr(lib, name, getattr(be, name))
+    monkeypatch.setattr(rec, "_workspace", lambda desc, device: torch.zeros(128, dtype=torch.uint8))
 
     # the public entry point refuses CPU tensors; tests go through the autograd.Function directly
     def cpu_recurrence(gx, mask, dh, rd, map_h, weights, rows=0):

@@ -3,6 +3,8 @@ oracle (tests/oracle_backend.py).  Checks the drop-in modules end to end against
 reference-generated fixtures: module wiring, autograd.Function plumbing and the hoisted
 weight-gradient products of recurrence.py.  Also: the product path refuses to run without CUDA."""
 import pytest
+from importlib import import_module
+import lsthm_b200
 import torch
 
 import oracle_backend
@@ -84,3 +86,74 @@ def test_rows_view_finds_copy_free_row_matrices():
     assert swapped and rows.shape == (21, 8) and rows.stride() == (24, 1)
     assert torch.equal(rows.view(7, 3, 8), x[:, :, 4:12])
     assert mm3.rows_view(x.permute(2, 0, 1)) is None           # no unit inner stride -> caller copies
+
+
+# ------------------------------------------------------------------------------------------------
+# data-parallel hookup: never-used parameters, bucket views, optimizer state
+# ------------------------------------------------------------------------------------------------
+def _ddp():
+    from importlib import import_module
+    return import_module(lsthm_b200.__name__ + ".ddp")
+
+
+@pytest.mark.parametrize("pattern", ["mab_*.npz", "sps_*.npz"])
+def test_unused_parameter_list_equals_the_reference_grad_none_set(pattern):
+    """the reducer must leave exactly the parameters whose grad is None in the REFERENCE step out of its
+    buckets (20 tensors for MARN1_sps).  The fixtures record that set (gnone/*) from the live reference."""
+    from helpers import golden_files, load_golden
+    files = golden_files(pattern)
+    assert files
+    for f in files:
+        fix = load_golden(f)
+        kind = str(fix["kind"]) if "kind" in fix else "sps"
+        model = {"ATV": lambda: lsthm_b200.HybridRNN_ATV.MARN(), "AT": lambda: lsthm_b200.HybridRNN_AT.MARN()}.get(
+            kind, lambda: lsthm_b200.lsthm_sps.MARN1_sps(6))()
+        assert sorted(_ddp().unused_parameter_names(model)) == sorted(k[6:] for k in fix if k.startswith("gnone/")), f
+        if kind not in ("ATV", "AT"):
+            assert len(_ddp().unused_parameter_names(model)) == 20
+            red = _ddp().GradAllReducer(model, 1)
+            for n, p in model.named_parameters():
+                assert (p.grad is None) == (n in red.skipped), n
+
+
+def test_reducer_rejects_gradients_outside_its_buckets():
+    """optimizer.zero_grad(set_to_none=True) between steps makes autograd allocate fresh .grad tensors: the reducer must
+    notice (hook) or repair (its own zero_grad), never reduce stale buckets silently."""
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    red = _ddp().GradAllReducer(model, 1, bucket_bytes=64)
+    x = torch.randn(3, 8)
+    model(x).sum().backward()
+    red.finish()
+    g0 = [p.grad.clone() for p in model.parameters()]
+    assert all(p.grad.data_ptr() == red._expected_ptr(p) for p in model.parameters())
+    torch.optim.SGD(model.parameters(), lr=0.1).zero_grad(set_to_none=True)      # the mistake
+    with pytest.raises(RuntimeError, match="not a view of its bucket"):
+        model(x).sum().backward()
+    red.zero_grad()                                                              # the repair: views are re-bound
+    model(x).sum().backward()
+    red.finish()
+    for p, g in zip(model.parameters(), g0):
+        assert p.grad.data_ptr() == red._expected_ptr(p) and torch.allclose(p.grad, g)
+    with pytest.raises(RuntimeError, match="more gradients than it has members"):
+        model(x).sum().backward()                                                # second backward without zero_grad
+
+
+def test_fused_adam_exposes_param_groups_and_state(monkeypatch):
+    """StepLR (model_trainer.py:83) attaches to FusedAdam and its lr reaches the kernel call; state round-trips."""
+    torch.manual_seed(0)
+    model = torch.nn.Linear(6, 5)
+    ddp = _ddp()
+    red = ddp.GradAllReducer(model, 1, flatten_params=True)
+    calls = []
+    lib = import_module(lsthm_b200.__name__ + "._lib")
+    monkeypatch.setattr(lib, "adam_step", lambda p, g, m, v, lr, b1, b2, eps, wd, step: calls.append((lr, wd, step)))
+    opt = ddp.FusedAdam(red, lr=1e-3, weight_decay=2e-5)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.98)
+    opt.step(); sched.step(); opt.step()
+    assert calls[0][0] == pytest.approx(1e-3) and calls[-1][0] == pytest.approx(0.98e-3) and calls[-1][1] == 2e-5
+    assert calls[-1][2] == 2
+    sd = opt.state_dict()
+    opt2 = ddp.FusedAdam(red, lr=5e-2)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 2 and opt2.lr == pytest.approx(0.98e-3) and opt2.param_groups[0]["weight_decay"] == 2e-5

@@ -54,23 +54,23 @@ def _run_kernels(c, T, N):
     Wf1, bf1, Wf2, bf2 = w[4 * M + 2:4 * M + 6]
     d = lib.make_desc(T, N, dh, rd, MH, 4, c["rows"])
     ws = lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-    packed = torch.empty(lib.mab2_pack_bytes(d), device=dev, dtype=torch.uint8)
-    lib.mab2_pack(d, ws, packed)
-    work = torch.empty(lib.mab2_workspace_bytes(d), device=dev, dtype=torch.uint8)
+    packed = torch.empty(lib.mab_pack_bytes(d), device=dev, dtype=torch.uint8)
+    lib.mab_pack(d, ws, packed)
+    work = torch.empty(lib.mab_workspace_bytes(d), device=dev, dtype=torch.uint8)
     new = lambda *s: torch.full(s, float("nan"), device=dev)
     out = dict(hz=new(T, N, 2 * D), C=new(T, N, D), UH=new(T, N, MH))
-    st = lib.mab2_alloc_stash(d, dev)
+    st = lib.mab_alloc_stash(d, dev)
     for v in st.values():
         v.fill_(float("nan"))
     gx = c["gx"].to(dev)
     mask = None if c["mask"] is None else c["mask"].to(dev)
-    lib.mab2_fwd(d, packed, gx, mask, out["hz"], out["UH"], out["C"], st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], work)
+    lib.mab_fwd(d, packed, gx, mask, out["hz"], out["UH"], out["C"], st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], work)
     # private piece-major stash -> row-major views for the comparison
-    out["G"] = lib.mab2_unblock(st["sG"], d, 4 * D)
-    sE = lib.mab2_unblock(st["sE"], d, 4 * D)
-    sP = lib.mab2_unblock(st["sP"], d, 4 * MH).view(T, N, 4, MH)
-    sMS = lib.mab2_unblock(st["sMS"], d, 8).view(T, N, 4, 2)
-    assert torch.equal(lib.mab2_unblock(st["sCp"], d, D), out["C"])
+    out["G"] = lib.mab_unblock(st["sG"], d, 4 * D)
+    sE = lib.mab_unblock(st["sE"], d, 4 * D)
+    sP = lib.mab_unblock(st["sP"], d, 4 * MH).view(T, N, 4, MH)
+    sMS = lib.mab_unblock(st["sMS"], d, 8).view(T, N, 4, 2)
+    assert torch.equal(lib.mab_unblock(st["sCp"], d, D), out["C"])
     # the kernel boundary (include/lsthm_b200.h): z_t = fc.3(u_t) is the caller's time-parallel product, and the softmax
     # weights are stashed as (logits, max, 1/sum)
     out["hz"][:, :, D:] = out["UH"] @ Wf2.t() + bf2
@@ -79,7 +79,7 @@ def _run_kernels(c, T, N):
     duz = (dhz[:, :, D:] @ Wf2).contiguous()                  # the head's dL/dz pulled through fc.3
     adj = dict(dgx=new(T, N, 4 * D), de=new(T, N, 4 * D), dup=new(T, N, MH))
     att = new(T, N, 4 * D)
-    lib.mab2_bwd(d, packed, dhz, duz, mask, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], out["UH"],
+    lib.mab_bwd(d, packed, dhz, duz, mask, st["sCp"], st["sG"], st["sE"], st["sMS"], st["sP"], out["UH"],
                  adj["dgx"], adj["de"], adj["dup"], att, work)
     torch.cuda.synchronize()
     # the regrouped attended features the backward also emits: a * c, per modality, head-major (HybridRNN_ATV.py:125-128)
