@@ -116,8 +116,13 @@ class GradAllReducer:
             if self._pending[b] < 0:
                 raise RuntimeError("GradAllReducer: a bucket received more gradients than it has members (zero_grad() not called?)")
             if self._pending[b] == 0 and self.world > 1:
+                nvtx = torch.cuda.nvtx if self.buckets[b].is_cuda else None
+                if nvtx is not None:
+                    nvtx.range_push(f"lsthm/K6_allreduce_bucket{b}")
                 self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
+                if nvtx is not None:
+                    nvtx.range_pop()
         return hook
 
     def zero_grad(self):

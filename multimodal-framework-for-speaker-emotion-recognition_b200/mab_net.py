@@ -98,7 +98,9 @@ class MabNet(nn.Module):
         hz = mab_recurrence(gx, self._fc_mask(T, N, x.device), self._dh, self._rd, self._map_h,
                             self.recurrence_weights(), self.rows_per_cta)
         self.last_hz = hz
-        y = linear3(hz.view(T * N, -1), self.nn_out[0].weight, self.nn_out[0].bias)
-        for layer in list(self.nn_out)[1:]:
-            y = layer(y)
-        return y                                      # time-major [T*N, C] probabilities (line 153)
+        # head nn_out = Linear - ReLU - Dropout(0) - Linear - Softmax (HybridRNN_ATV.py:68-73): both products on the own GEMM
+        # (ReLU in the first one's epilogue; the 6/7-class output is padded to 8 columns inside linear3)
+        y = linear3(hz.view(T * N, -1), self.nn_out[0].weight, self.nn_out[0].bias, relu=True)
+        y = self.nn_out[2](y)
+        y = linear3(y, self.nn_out[3].weight, self.nn_out[3].bias)
+        return self.nn_out[4](y)                      # time-major [T*N, C] probabilities (line 153)

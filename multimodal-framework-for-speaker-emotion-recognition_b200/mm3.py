@@ -11,18 +11,19 @@ TMEM): ~2^-16 relative error per term, measured <2e-5 end to end against fp64.
 (An earlier attempt to get the same effect from three library bf16 GEMMs over torch-side split/concat
 copies was SLOWER than the fp32 SIMT SGEMM it replaced — 70.7 vs 52.6 ms/step — and was dropped.)
 
-``LSTHM_GEMM3=0`` switches back to torch's fp32 SGEMM for A/B timing; both are fp32-accurate.
+There is ONE backend: every fp32 CUDA product goes to ``lsthm_gemm3``.  Output widths that are not a multiple of 4 (the
+6/7-class head) are zero-padded to the next multiple and sliced; an inner dimension that is not a multiple of 4 is an
+error.  The plain torch expressions below are reached only for CPU tensors and fp64 (the parity tests' truth runs), where
+no CUDA kernel applies.
 """
 from __future__ import annotations
 
-import os
 
 import torch
 import torch.nn.functional as F
 
 from . import _lib
 
-_ENABLED = os.environ.get("LSTHM_GEMM3", "1") == "1"
 launches = {"gemm3": 0}
 # bench.py sets this to a list to collect (start_event, end_event, 2*M*N*K) per lsthm_gemm3 launch
 events = None
@@ -41,15 +42,6 @@ def _gemm(mode, a, b, bias=None):
     return c
 
 
-def set_enabled(flag: bool) -> None:
-    global _ENABLED
-    _ENABLED = bool(flag)
-
-
-def enabled() -> bool:
-    return _ENABLED
-
-
 def _rows(t: torch.Tensor) -> torch.Tensor:
     """2-D view with unit inner stride and 16-byte aligned rows (copy only if the layout forces it)."""
     if t.stride(1) != 1 or t.stride(0) % 4:
@@ -60,33 +52,46 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 
 
 def _ok(*ts: torch.Tensor) -> bool:
-    return _ENABLED and all(t.is_cuda and t.dtype == torch.float32 for t in ts)
+    """True when the operands are what the CUDA kernel computes on (fp32 on a CUDA device).  CPU tensors and fp64 —
+    the tests' truth runs — take the equivalent torch expression; nothing else does."""
+    return all(t.is_cuda and t.dtype == torch.float32 for t in ts)
 
 
-def _fits(t: torch.Tensor) -> bool:
-    return t.shape[1] % 4 == 0 or t.stride(1) == 1 and t.stride(0) % 4 == 0
+def _need4(name: str, *dims: int) -> None:
+    if any(d % 4 for d in dims):
+        raise RuntimeError(f"{name}: lsthm_gemm3 needs matrix widths that are multiples of 4, got {dims} (pad the operand)")
 
 
 def mm_tn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a[K,M]^T @ b[K,N]  (weight-gradient product: reduction over the T*N rows)."""
-    if not (_ok(a, b) and _fits(a) and _fits(b)):
+    if not _ok(a, b):
         return a.t() @ b
+    _need4("mm_tn", a.shape[1], b.shape[1])
     return _gemm(_lib.GEMM_TN, _rows(a), _rows(b))
 
 
 def mm_nn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a[M,K] @ b[K,N]."""
-    if not (_ok(a, b) and _fits(a) and _fits(b)):
+    if not _ok(a, b):
         return a @ b
+    _need4("mm_nn", a.shape[1], b.shape[1])
     return _gemm(_lib.GEMM_NN, _rows(a), _rows(b))
+
+
+def mm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a[M,K] @ b[N,K]^T."""
+    if not _ok(a, b):
+        return a @ b.t()
+    _need4("mm_nt", a.shape[1], b.shape[0])
+    return _gemm(_lib.GEMM_NT, _rows(a), _rows(b))
 
 
 def colsum(a: torch.Tensor) -> torch.Tensor:
     """a.sum(0) for a 2-D matrix — the bias gradient of a Linear over all T*N rows — on our deterministic kernel."""
-    if (_ENABLED and a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0 and a.shape[1] % 4 == 0
-            and a.stride(1) == 1 and a.stride(0) % 4 == 0 and a.data_ptr() % 16 == 0):
+    if a.is_cuda and a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] > 0:
+        _need4("colsum", a.shape[1])
         launches["gemm3"] += 2
-        return _lib.colsum(a)
+        return _lib.colsum(_rows(a))
     return a.sum(0)
 
 
@@ -115,8 +120,10 @@ class _LinearTC(torch.autograd.Function):
 def linear_into(x: torch.Tensor, weight: torch.Tensor, bias, out: torch.Tensor) -> None:
     """out[:] = x @ weight^T + bias for 2-D operands, written straight into ``out`` (may be a column block of a wider
     matrix); no autograd (used inside custom backward/forward bodies)."""
-    if (_ok(x, weight, out) and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and out.stride(1) == 1 and out.stride(0) % 4 == 0
-            and out.data_ptr() % 16 == 0 and _fits(x)):
+    if _ok(x, weight, out):
+        _need4("linear_into", x.shape[1], weight.shape[0])
+        if out.stride(1) != 1 or out.stride(0) % 4 or out.data_ptr() % 16:
+            raise RuntimeError("linear_into: the output view needs unit inner stride and 16-byte aligned rows")
         launches["gemm3"] += 1
         _lib.gemm3(_lib.GEMM_NT, _rows(x), _rows(weight), None if bias is None else bias.contiguous(), out=out)
     else:
@@ -147,9 +154,16 @@ def linear3(x: torch.Tensor, weight: torch.Tensor, bias=None, relu: bool = False
     3-D inputs that are permuted views of time-major storage are processed in place (no permute copy) and the
     result is returned as the same kind of view."""
     K, N = x.shape[-1], weight.shape[0]
-    if not (_ok(x, weight) and K % 4 == 0 and N % 4 == 0):
+    if not _ok(x, weight):
         y = F.linear(x, weight, bias)
         return F.relu(y) if relu else y
+    _need4("linear3 (inner dimension)", K)
+    if N % 4:
+        # e.g. the 6/7-class head (nn_out.3): zero rows up to the next multiple of 4, sliced away again (autograd slices the
+        # padded weight's gradient back through F.pad)
+        pad = (-N) % 4
+        y = linear3(x, F.pad(weight, (0, 0, 0, pad)), None if bias is None else F.pad(bias, (0, pad)), relu)
+        return y[..., :N]
     if x.dim() == 3 and x.data_ptr() % 16 == 0:
         rv = rows_view(x)
         if rv is not None:

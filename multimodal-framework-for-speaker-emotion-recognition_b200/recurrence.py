@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .mm3 import mm_tn, mm_nn, colsum, linear_into
+from .mm3 import mm_tn, mm_nn, mm_nt, colsum, linear_into
 
 # Counts launches of OUR kernels (pack/fwd/bwd), for bench.py's `gpu_launches`.
 launch_counter = {"pack": 0, "fwd": 0, "bwd": 0}
@@ -38,14 +38,27 @@ def _workspace(desc, device) -> torch.Tensor:
     return w
 
 
+# NVTX range names of the kernel launches (K1/K2 = AT/ATV recurrence fwd / BPTT, K3/K4 = speaker-state cell
+# fwd / BPTT, K5 = time-parallel GEMMs (mm3.py), K6 = gradient allreduce (ddp.py))
+NVTX_NAMES = {"mab_pack": "lsthm/K0_mab_pack", "mab_fwd": "lsthm/K1_mab_fwd", "mab_bwd": "lsthm/K2_mab_bwd",
+              "sps_fwd": "lsthm/K3_sps_fwd", "sps_bwd": "lsthm/K4_sps_bwd"}
+
+
 def _timed(kind, fn, *args):
-    if kernel_events is None:
-        return fn(*args)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    fn(*args)
-    e1.record()
-    kernel_events[kind].append((e0, e1))
+    nvtx = torch.cuda.nvtx if args and any(isinstance(a, torch.Tensor) and a.is_cuda for a in args) else None
+    if nvtx is not None:
+        nvtx.range_push(NVTX_NAMES.get(getattr(fn, "__name__", ""), "lsthm/" + kind))
+    try:
+        if kernel_events is None or kind not in kernel_events:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(*args)
+        e1.record()
+        kernel_events[kind].append((e0, e1))
+    finally:
+        if nvtx is not None:
+            nvtx.range_pop()
 
 
 class MabRecurrenceFn(torch.autograd.Function):
@@ -77,7 +90,7 @@ class MabRecurrenceFn(torch.autograd.Function):
         desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
         wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
         packed = torch.empty(_lib.mab_pack_bytes(desc), device=gx.device, dtype=torch.uint8)
-        _lib.mab_pack(desc, wstruct, packed)
+        _timed("pack", _lib.mab_pack, desc, wstruct, packed)
         launch_counter["pack"] += 2
         work = _workspace(desc, gx.device)
         new = lambda *s: torch.empty(*s, device=gx.device, dtype=torch.float32)
@@ -138,7 +151,7 @@ class MabRecurrenceFn(torch.autograd.Function):
             cs1 = colsum(ds1)                                   # [G]
         else:
             Xh, Xu, cs1 = dgx.new_zeros(G, D), dgx.new_zeros(G, map_h), dgx.new_zeros(G)
-        gVfull = Xu @ Wf2.t() + torch.outer(cs1, bf2)           # [G, D] (tiny products: fp32 SGEMM)
+        gVfull = mm_nt(Xu, Wf2) + torch.outer(cs1, bf2)         # [G, D]
         gU: List[torch.Tensor] = []
         gV: List[torch.Tensor] = []
         o = 0
@@ -146,8 +159,8 @@ class MabRecurrenceFn(torch.autograd.Function):
             gU.append(Xh[4 * o:4 * o + 4 * dh[m], o:o + dh[m]])
             gV.append(gVfull[4 * o:4 * o + 4 * dh[m]])
             o += dh[m]
-        gWf2 = mm_tn(dz_head, u2) + Vcat.t() @ Xu               # [D, map_h]
-        gbf2 = colsum(dz_head) + Vcat.t() @ cs1
+        gWf2 = mm_tn(dz_head, u2) + mm_tn(Vcat, Xu)             # [D, map_h]
+        gbf2 = colsum(dz_head) + (Vcat * cs1[:, None]).sum(0)
         de2, c2 = de.view(TN, G), sC.view(TN, D)
         gWatt, gbatt = mm_tn(de2, c2), colsum(de2)
         # reduce_m / fc.0: with r = attended Wr^T + br and dr = dup Wf1, one product Y = dup^T attended [map_h, G] gives both:
@@ -158,9 +171,9 @@ class MabRecurrenceFn(torch.autograd.Function):
         o = ro = 0
         for m in range(M):
             Ym, Wf1m = Y[:, 4 * o:4 * o + 4 * dh[m]], Wf1[:, ro:ro + rd[m]]
-            gWr.append(Wf1m.t() @ Ym)
-            gbr.append(Wf1m.t() @ cdup)
-            gWf1_parts.append(Ym @ Wr[m].t() + torch.outer(cdup, br[m]))
+            gWr.append(mm_tn(Wf1m, Ym))
+            gbr.append((Wf1m * cdup[:, None]).sum(0))
+            gWf1_parts.append(mm_nt(Ym, Wr[m]) + torch.outer(cdup, br[m]))
             o += dh[m]
             ro += rd[m]
         gWf1, gbf1 = torch.cat(gWf1_parts, dim=1), cdup

@@ -84,16 +84,12 @@ def test_encoder_layer_fast_path_matches_module_path():
         (ya * w).sum().backward()
         ga = {k: v.grad.clone() for k, v in layer.named_parameters() if v.grad is not None}
         layer.zero_grad()
-        old = enc_mod._FUSED_OWN
-        enc_mod._FUSED_OWN = False
-        try:
-            xb = x_tm.clone().double().requires_grad_(True)
-            layer64 = enc_mod.EncoderLayer(d, d_inner, 8, 40, 40).cuda().double().eval()
-            layer64.load_state_dict({k: v.double() for k, v in layer.state_dict().items()})
-            yb, _ = layer64(xb[:, :, 4:4 + d].permute(1, 0, 2))
-            (yb * w.double()).sum().backward()
-        finally:
-            enc_mod._FUSED_OWN = old
+        # fp64 truth: the module-by-module torch expressions (no kernel computes in fp64)
+        xb = x_tm.clone().double().requires_grad_(True)
+        layer64 = enc_mod.EncoderLayer(d, d_inner, 8, 40, 40).cuda().double().eval()
+        layer64.load_state_dict({k: v.double() for k, v in layer.state_dict().items()})
+        yb, _ = layer64(xb[:, :, 4:4 + d].permute(1, 0, 2))
+        (yb * w.double()).sum().backward()
         assert _rel(ya, yb.detach()) < 2e-5
         assert _rel(xa.grad, xb.grad) < 1e-4
         for k, v in layer64.named_parameters():
