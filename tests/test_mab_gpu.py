@@ -210,6 +210,66 @@ def test_properties_at_benchmark_size():
     assert torch.equal(pi, p0)
 
 
+class _FcOnlyTape(tp.DropoutTape):
+    """Mask tape that drops only at fc.2 (the dropout inside the recurrence); every other site is the identity."""
+
+    def __init__(self, fc_masks):
+        super().__init__(0)
+        self._fc, self._i = fc_masks, 0
+
+    def mask(self, site, shape, p, dtype=torch.float32):
+        if site != "fc.2":
+            return torch.ones(tuple(shape), dtype=dtype)
+        m = self._fc[self._i]
+        self._i += 1
+        assert tuple(m.shape) == tuple(shape)
+        return m.to(dtype)
+
+
+@pytest.mark.parametrize("masked", [False, True], ids=["eval", "fc_mask"])
+def test_oracle_at_benchmark_size(masked):
+    """The headline shape itself (T=110, N=1024: 11 groups of 13 blocks, 96 dialogues per group, the last block ragged)
+    against the oracle: dialogues are independent for ATV, so 8 dialogues of the 1024 — chosen at block
+    boundaries, in the ragged last block and in the middle — are re-run through the oracle's restatement on the CPU and
+    their probabilities and input gradients compared; once in eval mode and once with an explicit fc.2 dropout mask."""
+    T, N, kind = 110, 1024, "ATV"
+    model = seeded_model(kind, 111).eval()
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(T, N, 712, generator=g)
+    labels = torch.randint(0, 6, (T, N), generator=g)
+    mask = (torch.bernoulli(torch.full((T, N, 64), 0.7), generator=g) / 0.7) if masked else None
+    # candidates at block boundaries (96 dialogues per group), in the ragged last block and in between.  A dialogue with a
+    # ReLU pre-activation (fc.0 / nn_out.0 / encoder FFN: 24 000 units per dialogue) within 5e-6 (relative) of zero is
+    # skipped: no derivative is defined there at fp32 parity resolution (DESIGN.md §2, "ReLU kinks") — e.g. dialogue 96 of
+    # this batch has a head unit at 4.7e-7, and flipping it moves that dialogue's dx by 19 %.
+    from helpers import relu_kinks
+    p64 = {k: v.detach().double() for k, v in model.state_dict().items()}
+    sample = []
+    for d in (0, 95, 96, 97, 191, 192, 287, 288, 512, 700, 959, 960, 961, 1022, 1023):
+        tape64 = _FcOnlyTape([mask[t][[d]].double() for t in range(T)]) if masked else None
+        with relu_kinks(None) as rk:
+            tp.mab_forward(p64, x[:, [d]].double(), kind, tape64)
+        if min(float(z.abs().min() / z.abs().max()) for z in rk.z) > 5e-6:
+            sample.append(d)
+    assert len(sample) >= 8 and any(d % 96 in (0, 95) for d in sample) and any(d >= 960 for d in sample), sample
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    xs = x[:, sample].clone().requires_grad_(True)
+    tape = _FcOnlyTape([mask[t][sample] for t in range(T)]) if masked else None
+    pr = tp.mab_forward(params, xs, kind, tape)
+    (masked_ce(pr, labels[:, sample].reshape(-1), T, len(sample)) * (len(sample) / N)).backward()   # same 1/(T N) weight
+    cm = model.to("cuda")
+    if masked:
+        cm.fc_mask_override = mask.to("cuda")
+    xc = x.to("cuda").requires_grad_(True)
+    pc = cm(xc)
+    masked_ce(pc, labels.reshape(-1).to("cuda"), T, N).backward()
+    pc_s = pc.detach().view(T, N, -1)[:, sample].cpu()
+    pr_s = pr.detach().view(T, len(sample), -1)
+    assert e_inf(pc_s, pr_s) <= TOL_OUT, e_inf(pc_s, pr_s)
+    assert (pc_s.argmax(-1) == pr_s.argmax(-1)).all()
+    assert e_inf(xc.grad[:, sample].cpu(), xs.grad) <= TOL_GRAD, e_inf(xc.grad[:, sample].cpu(), xs.grad)
+
+
 def test_train_mode_uses_dropout_and_is_seeded():
     T, N = 9, 40
     model = seeded_model("ATV", 3).to("cuda").train()
