@@ -460,8 +460,42 @@ def run_ours(args):
         h2d = sum(t.numel() * t.element_size() for t in host[0]) * world
         d2h = 4 * world
 
-    # ---- extra arms (N = 1 only; everything the timed region above does not include) ----
+    # ---- N > 1: guarded self-check that the sharded step equals the single-process step (the 2-GPU pytest is skipped on the
+    #      driver's 1-GPU test box, so the multi-GPU runs carry the evidence): same seeded small batch on every rank, rank r
+    #      takes its dialogue shard through GradAllReducer, and compares the reduced gradients with the full batch's ----
     extras = {}
+    if world > 1:
+        try:
+            Tc, Nc = 12, 8 * world
+            gc_ = torch.Generator().manual_seed(4)
+            xc_, lc_ = torch.randn(Tc, Nc, D_IN, generator=gc_).to(dev), torch.randint(0, 6, (Tc, Nc), generator=gc_).to(dev)
+            torch.manual_seed(31)
+            mref = lsthm_b200.HybridRNN_ATV.MARN().to(dev).eval()
+            torch.manual_seed(31)
+            mshd = lsthm_b200.HybridRNN_ATV.MARN().to(dev).eval()
+            um = torch.ones(Nc, Tc, device=dev)
+            loss_fn(mref(xc_), lc_.reshape(-1), um).backward()
+            red2 = ddp.GradAllReducer(mshd, world, bucket_bytes=1 << 20)
+            sh = slice(rank * 8, rank * 8 + 8)
+            red2.zero_grad()
+            (loss_fn(mshd(xc_[:, sh].contiguous()), lc_[:, sh].reshape(-1), um[sh]) * (1.0 / world)).backward()
+            red2.finish()
+            worst = 0.0
+            for (n1, p1), (_, p2) in zip(mref.named_parameters(), mshd.named_parameters()):
+                if p1.grad is None:
+                    assert p2.grad is None, n1
+                    continue
+                worst = max(worst, float((p1.grad - p2.grad).abs().max() / p1.grad.abs().max().clamp_min(1e-30)))
+            wt = torch.tensor([worst], device=dev)
+            dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+            extras["ddp_selfcheck"] = {"max_rel_grad_err": float(wt.item()), "ok": bool(wt.item() < 2e-4), "world": world,
+                                       "what": f"ATV x[{Tc},{Nc},712] eval: NCCL-sharded step (8 dialogues per rank, bucketed allreduce) vs the "
+                                               "single-process step on the whole batch, scale-relative max over all parameter gradients"}
+            del mref, mshd, red2
+        except Exception as e:
+            extras["ddp_selfcheck"] = {"ok": False, "error": repr(e)[:300]}
+
+    # ---- extra arms (N = 1 only; everything the timed region above does not include) ----
     if world == 1 and not args.no_extras:
         # (1) optimizer step, timed separately: fused Adam on the flat gradient buckets of a fresh copy
         try:
