@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define LSTHM_ABI_VERSION 6
+#define LSTHM_ABI_VERSION 7
 #define LSTHM_MAX_MOD 3
 
 int lsthm_abi_version(void);
@@ -199,6 +199,69 @@ int lsthm_sps_bwd(const lsthm_sps_desc *d, const lsthm_sps_weights *w, const flo
                   float *dGL, float *dGQ, float *dWqk, void *stream);
 
 int lsthm_sps_launch_info(const lsthm_sps_desc *d, int32_t *grid, int32_t *block, int32_t *rows, int32_t *smem_fwd,
+                          int32_t *smem_bwd);
+
+/* ------------------------------------------------------------------------------------------
+ * lsthm_gsp: GRU speaker-state LSTHM cell — one direction of MARN1_onlysp (listener = 0) and of
+ * MARN1_nsps (listener = 1).  Replaces MARN_cell.forward of model/lsthm_onlysp.py:156-188 and of
+ * model/lsthm_nsps.py:160-198 (the default model of train.py):
+ *   idx = argmax(qmask_t[d]) (an all-zero padded row selects party 0);  qs = q[d][idx]
+ *   hs  = dropout(GRUCell(U_t, qs))     gate order r|z|n;  n = tanh(W_in U + b_in + r (W_hn qs + b_hn))
+ *   listener = 0:  q[d][p] = q[d][p] (1 - m_p) + hs m_p           (lsthm_onlysp.py:180-182)
+ *   listener = 1:  q[d][p] = q[d][1 - idx] (1 - m_p) + hs m_p     (lsthm_nsps.py:184-188)
+ *   (c_l,h_l) = LSTHM1_l(x_l, c_l,h_l,z_l, hs), same for a; z_l = CrossAttention(c_l, c_a) (rank-1 form)
+ *   out = [h_l | h_a | z_l | hs]
+ * Dialogues are independent: ordinary launch, any N, no workspace.  The input-side GRU product W_ih U + b_ih is
+ * time-parallel and supplied by the caller (gxs), like gx.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t T, N;
+    int32_t rows_per_cta;      /* 0 = automatic (ceil(N/148) clamped to 1..8) */
+    int32_t listener;          /* 0 = lsthm_onlysp party update, 1 = lsthm_nsps (listener state copied from the other party) */
+    float att_p;               /* in-kernel dropout on the in-cell attention weights (0 = off) */
+    uint64_t att_seed;
+} lsthm_gsp_desc;
+
+typedef struct {
+    const float *U[2], *V[2], *S[2];   /* marn_cell.lsthm_{l,a}.{U,V,S}.weight [512][128]   lsthm_onlysp.py:17-20 */
+    const float *Whh;                  /* marn_cell.gru_s.weight_hh [384][128]              lsthm_onlysp.py:152  */
+    const float *bhh;                  /* marn_cell.gru_s.bias_hh [384]                                          */
+    const float *Wq, *Wk;              /* marn_cell.crossatt_l2a.{Wq,Wk} [128]              lsthm_onlysp.py:50-51 */
+} lsthm_gsp_weights;
+
+typedef struct {               /* dropout masks already scaled by 1/(1-p); any may be NULL (= no dropout) */
+    const float *ms;           /* on the speaker state hs   [T][N][128]       lsthm_onlysp.py:176 */
+    const float *ml, *ma;      /* on h_l / h_a              [T][N][128]       lsthm_onlysp.py:184,186 */
+    const float *att_mask;     /* on the attention weights  [T][N][128][128]  lsthm_onlysp.py:63 */
+} lsthm_gsp_masks;
+
+size_t lsthm_gsp_packed_floats(void);
+int lsthm_gsp_pack(const lsthm_gsp_weights *w, float *packed, void *stream);
+
+/*
+ *   gx    [T][N][2][512]  W_c x_c + (bW+bU+bV+bS)_c for c = l, a; gate order f|i|o|g
+ *   gxs   [T][N][384]     gru_s.weight_ih U_t + bias_ih; gate order r|z|n
+ *   qmask [T][N][2]       one-hot current speaker (zero rows on padding)
+ *   out   [T][N][512]     [h_l | h_a | z_l | hs]
+ *   stash (all or none): sGS [T][N][4][128] r|z|n|(W_hn qs + b_hn), sQS [T][N][128] qs,
+ *         sGL [T][N][2][512] LSTHM gates f|i|o|g, sCL [T][N][2][128] cell states
+ */
+int lsthm_gsp_fwd(const lsthm_gsp_desc *d, const lsthm_gsp_weights *w, const float *packed, const float *gx,
+                  const float *gxs, const float *qmask, const lsthm_gsp_masks *masks, float *out, float *sGS,
+                  float *sQS, float *sGL, float *sCL, void *stream);
+
+/*
+ *   dout [T][N][512]    dL/d out
+ *   dGL  [T][N][2][512] dL/d(LSTHM gate pre-activations)       -> W,U,V,S grads and dx
+ *   dGi  [T][N][384]    dL/d(W_ih U + b_ih)                    -> weight_ih, bias_ih, dU
+ *   dGh  [T][N][384]    dL/d(W_hh qs + b_hh)                   -> weight_hh (with sQS), bias_hh
+ *   dWqk [grid][2][128] per-CTA partial sums of dL/dWq, dL/dWk (grid from lsthm_gsp_launch_info)
+ */
+int lsthm_gsp_bwd(const lsthm_gsp_desc *d, const lsthm_gsp_weights *w, const float *qmask, const lsthm_gsp_masks *masks,
+                  const float *dout, const float *sGS, const float *sQS, const float *sGL, const float *sCL, float *dGL,
+                  float *dGi, float *dGh, float *dWqk, void *stream);
+
+int lsthm_gsp_launch_info(const lsthm_gsp_desc *d, int32_t *grid, int32_t *block, int32_t *rows, int32_t *smem_fwd,
                           int32_t *smem_bwd);
 
 /* ------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # LSTHM_B200_SO lets profiling scripts load an experimental build of the same ABI (never a different backend)
 SO_PATH = os.environ.get("LSTHM_B200_SO") or os.path.join(_PKG, "liblsthm_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_MOD = 3
 
 _f32p = C.POINTER(C.c_float)
@@ -46,6 +46,20 @@ class SpsWeights(C.Structure):
 
 class SpsMasks(C.Structure):
     _fields_ = [("mq", C.c_void_p * 2), ("ml", C.c_void_p), ("ma", C.c_void_p), ("att_mask", C.c_void_p)]
+
+
+class GspDesc(C.Structure):
+    _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("rows_per_cta", C.c_int32), ("listener", C.c_int32),
+                ("att_p", C.c_float), ("att_seed", C.c_uint64)]
+
+
+class GspWeights(C.Structure):
+    _fields_ = [("U", C.c_void_p * 2), ("V", C.c_void_p * 2), ("S", C.c_void_p * 2), ("Whh", C.c_void_p),
+                ("bhh", C.c_void_p), ("Wq", C.c_void_p), ("Wk", C.c_void_p)]
+
+
+class GspMasks(C.Structure):
+    _fields_ = [("ms", C.c_void_p), ("ml", C.c_void_p), ("ma", C.c_void_p), ("att_mask", C.c_void_p)]
 
 
 class AttnDesc(C.Structure):
@@ -112,6 +126,16 @@ def lib() -> C.CDLL:
     L.lsthm_sps_bwd.argtypes = [C.POINTER(SpsDesc), C.POINTER(SpsWeights)] + [C.c_void_p] * 4 + [C.POINTER(SpsMasks)] + [C.c_void_p] * 10
     L.lsthm_sps_launch_info.restype = C.c_int
     L.lsthm_sps_launch_info.argtypes = [C.POINTER(SpsDesc)] + [C.POINTER(C.c_int32)] * 5
+    L.lsthm_gsp_packed_floats.restype = C.c_size_t
+    L.lsthm_gsp_packed_floats.argtypes = []
+    L.lsthm_gsp_pack.restype = C.c_int
+    L.lsthm_gsp_pack.argtypes = [C.POINTER(GspWeights), C.c_void_p, C.c_void_p]
+    L.lsthm_gsp_fwd.restype = C.c_int
+    L.lsthm_gsp_fwd.argtypes = [C.POINTER(GspDesc), C.POINTER(GspWeights)] + [C.c_void_p] * 4 + [C.POINTER(GspMasks)] + [C.c_void_p] * 6
+    L.lsthm_gsp_bwd.restype = C.c_int
+    L.lsthm_gsp_bwd.argtypes = [C.POINTER(GspDesc), C.POINTER(GspWeights), C.c_void_p, C.POINTER(GspMasks)] + [C.c_void_p] * 10
+    L.lsthm_gsp_launch_info.restype = C.c_int
+    L.lsthm_gsp_launch_info.argtypes = [C.POINTER(GspDesc)] + [C.POINTER(C.c_int32)] * 5
     L.lsthm_gemm3_workspace_floats.restype = C.c_size_t
     L.lsthm_gemm3_workspace_floats.argtypes = [C.c_int32] * 4
     L.lsthm_gemm3.restype = C.c_int
@@ -341,6 +365,57 @@ def sps_bwd(d, w, qmask, pi, pr, n0, masks, dout, sGQ, sCQ, sGL, sCL, workspace,
 def sps_launch_info(d: SpsDesc) -> dict:
     v = [C.c_int32() for _ in range(5)]
     _check(lib().lsthm_sps_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_sps_launch_info")
+    return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))
+
+
+# ------------------------------------------------------------------------------------------------
+# lsthm_onlysp / lsthm_nsps GRU speaker-state cell
+# ------------------------------------------------------------------------------------------------
+def make_gsp_desc(T: int, N: int, listener: int, rows_per_cta: int = 0, att_p: float = 0.0, att_seed: int = 0) -> GspDesc:
+    d = GspDesc()
+    d.T, d.N, d.rows_per_cta, d.listener, d.att_p, d.att_seed = T, N, rows_per_cta, listener, att_p, att_seed
+    return d
+
+
+def make_gsp_weights(U, V, S, Whh, bhh, Wq, Wk) -> GspWeights:
+    w = GspWeights()
+    for c in range(2):
+        w.U[c], w.V[c], w.S[c] = _dev_ptr(U[c], "U"), _dev_ptr(V[c], "V"), _dev_ptr(S[c], "S")
+    w.Whh, w.bhh = _dev_ptr(Whh, "Whh"), _dev_ptr(bhh, "bhh")
+    w.Wq, w.Wk = _dev_ptr(Wq, "Wq"), _dev_ptr(Wk, "Wk")
+    return w
+
+
+def make_gsp_masks(ms=None, ml=None, ma=None, att_mask=None) -> GspMasks:
+    m = GspMasks()
+    m.ms, m.ml, m.ma, m.att_mask = _dev_ptr(ms, "ms"), _dev_ptr(ml, "ml"), _dev_ptr(ma, "ma"), _dev_ptr(att_mask, "att_mask")
+    return m
+
+
+def gsp_packed_floats() -> int:
+    return lib().lsthm_gsp_packed_floats()
+
+
+def gsp_pack(w: GspWeights, packed: torch.Tensor) -> None:
+    _check(lib().lsthm_gsp_pack(C.byref(w), _dev_ptr(packed, "packed"), _stream()), "lsthm_gsp_pack")
+
+
+def gsp_fwd(d, w, packed, gx, gxs, qmask, masks, out, sGS, sQS, sGL, sCL) -> None:
+    _check(lib().lsthm_gsp_fwd(C.byref(d), C.byref(w), _dev_ptr(packed, "packed"), _dev_ptr(gx, "gx"), _dev_ptr(gxs, "gxs"),
+                               _dev_ptr(qmask, "qmask"), C.byref(masks), _dev_ptr(out, "out"), _dev_ptr(sGS, "sGS"),
+                               _dev_ptr(sQS, "sQS"), _dev_ptr(sGL, "sGL"), _dev_ptr(sCL, "sCL"), _stream()), "lsthm_gsp_fwd")
+
+
+def gsp_bwd(d, w, qmask, masks, dout, sGS, sQS, sGL, sCL, dGL, dGi, dGh, dWqk) -> None:
+    _check(lib().lsthm_gsp_bwd(C.byref(d), C.byref(w), _dev_ptr(qmask, "qmask"), C.byref(masks), _dev_ptr(dout, "dout"),
+                               _dev_ptr(sGS, "sGS"), _dev_ptr(sQS, "sQS"), _dev_ptr(sGL, "sGL"), _dev_ptr(sCL, "sCL"),
+                               _dev_ptr(dGL, "dGL"), _dev_ptr(dGi, "dGi"), _dev_ptr(dGh, "dGh"), _dev_ptr(dWqk, "dWqk"),
+                               _stream()), "lsthm_gsp_bwd")
+
+
+def gsp_launch_info(d: GspDesc) -> dict:
+    v = [C.c_int32() for _ in range(5)]
+    _check(lib().lsthm_gsp_launch_info(C.byref(d), *[C.byref(x) for x in v]), "lsthm_gsp_launch_info")
     return dict(zip(("grid", "block", "rows", "smem_fwd", "smem_bwd"), (x.value for x in v)))
 
 

@@ -26,11 +26,27 @@ static int coop_launch(K kernel, const A &args, int grid, size_t smem_bytes, cud
     return e == cudaSuccess ? 0 : set_error(what, e);
 }
 
+// MODE 1 (GRU speaker state): dialogues are independent, so an ordinary launch of any grid size
+template <typename K, typename A>
+static int plain_launch(K kernel, const A &args, int grid, size_t smem_bytes, cudaStream_t st, const char *what) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return set_error(what, e);
+    kernel<<<grid, kSpsThreads, smem_bytes, st>>>(args);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error(what, e);
+}
+
 int LSTHM_CAT(launch_sps_fwd_, LSTHM_MT)(const SpsFwdArgs &a, int grid, size_t smem_bytes, cudaStream_t st) {
-    return coop_launch(sps_fwd_kernel<LSTHM_MT>, a, grid, smem_bytes, st, "lsthm_sps_fwd launch");
+    return coop_launch(sps_fwd_kernel<LSTHM_MT, 0>, a, grid, smem_bytes, st, "lsthm_sps_fwd launch");
 }
 int LSTHM_CAT(launch_sps_bwd_, LSTHM_MT)(const SpsBwdArgs &a, int grid, size_t smem_bytes, cudaStream_t st) {
-    return coop_launch(sps_bwd_kernel<LSTHM_MT>, a, grid, smem_bytes, st, "lsthm_sps_bwd launch");
+    return coop_launch(sps_bwd_kernel<LSTHM_MT, 0>, a, grid, smem_bytes, st, "lsthm_sps_bwd launch");
+}
+int LSTHM_CAT(launch_gsp_fwd_, LSTHM_MT)(const SpsFwdArgs &a, int grid, size_t smem_bytes, cudaStream_t st) {
+    return plain_launch(sps_fwd_kernel<LSTHM_MT, 1>, a, grid, smem_bytes, st, "lsthm_gsp_fwd launch");
+}
+int LSTHM_CAT(launch_gsp_bwd_, LSTHM_MT)(const SpsBwdArgs &a, int grid, size_t smem_bytes, cudaStream_t st) {
+    return plain_launch(sps_bwd_kernel<LSTHM_MT, 1>, a, grid, smem_bytes, st, "lsthm_gsp_bwd launch");
 }
 
 }  // namespace lsthm

@@ -47,6 +47,13 @@ struct SpsFwdArgs {
     // stash (all or none)
     float *sGQ, *sCQ, *sHQ, *sXQ;        // LSTM: gates [T][N][2][512] (i|f|g|o), c, h(post-drop), input  [T][N][2][128]
     float *sGL, *sCL, *sHL;              // LSTHM: gates [T][N][2][512] (f|i|o|g), c, h(post-drop)      [T][N][2][128]
+    // ---- MODE 1 (GRU speaker state of lsthm_onlysp / lsthm_nsps; dialogues independent, no exchange) ----
+    const float *whh_img;                // k-major [128][128 units x (r,z,n,0)] image of gru_s.weight_hh
+    const float *bhh;                    // gru_s.bias_hh [384] (r|z|n)
+    const float *gxs;                    // [T][N][384]  W_ih U + b_ih, r|z|n
+    const float *ms;                     // dropout mask on the speaker state [T][N][128] or NULL
+    int listener;                        // 0: q[p] = q[p](1-m_p) + h_s m_p (onlysp) ; 1: q[p] = q[other](1-m_p) + h_s m_p (nsps)
+    float *sGS, *sQS;                    // stash: GRU r|z|n|(W_hn q + b_hn) [T][N][4][128], selected party state [T][N][128]
 };
 
 struct SpsBwdArgs {
@@ -64,6 +71,12 @@ struct SpsBwdArgs {
     unsigned *bar;
     float *dGL, *dGQ;                    // [T][N][2][512] adjoints of the gate pre-activations
     float *dWqk;                         // [grid][2][128] per-CTA partial sums of dWq, dWk
+    // ---- MODE 1 ----
+    const float *Whh_s;                  // gru_s.weight_hh native [384][128]
+    const float *ms;
+    int listener;
+    const float *sGS, *sQS;
+    float *dGi, *dGh;                    // [T][N][384] adjoints of (W_ih U + b_ih) and of (W_hh q + b_hh)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -93,7 +106,12 @@ __device__ __forceinline__ void grid_wait(unsigned *bar, unsigned target) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int MT>
+// MODE 0: lsthm_sps (two speaker LSTM cells on packed rows, cooperative launch, two grid exchanges per step)
+// MODE 1: lsthm_onlysp / lsthm_nsps (one GRU on the current speaker's party state, per-dialogue independent):
+//   idx = argmax(qmask_t[d]);  qs = q[d][idx];  hs = drop(GRUCell(U_t, qs))         (lsthm_onlysp.py:174-179, lsthm_nsps.py:177-183)
+//   onlysp: q[d][p] = q[d][p](1-m_p) + hs m_p ;  nsps: q[d][p] = q[d][1-idx](1-m_p) + hs m_p      (:181-182 / :185-188)
+//   LSTHM1 cells with speaker input hs, rank-1 attention, out = [hl | ha | zl | hs]  (identical to MODE 0)
+template <int MT, int MODE>
 __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_constant__ SpsFwdArgs a) {
     constexpr int MTP = (MT + 3) & ~3;
     constexpr int VEC = kU * MTP;             // one k-major state vector
@@ -107,14 +125,18 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
     float *s_hl = smem, *s_cl = s_hl + VEC, *s_ha = s_cl + VEC, *s_ca = s_ha + VEC, *s_zl = s_ca + VEC;
     float *s_hq = s_zl + VEC, *s_hq0 = s_hq + VEC, *s_cq0 = s_hq0 + VEC, *s_hq1 = s_cq0 + VEC, *s_cq1 = s_hq1 + VEC;
     float *s_x0 = s_cq1 + VEC, *s_x1 = s_x0 + VEC, *s_h0 = s_x1 + VEC;
-    float *s_part = s_h0 + VEC;               // [MTP][1024] split-K partials (both cells)
-    float *s_car = s_part + MTP * 2 * kG4;    // [MT][LDA] ca in row layout
+    float *s_part = s_h0 + VEC;               // [MTP][1024] split-K partials (both cells); MODE 1: [4][MTP][512]
+    constexpr int PART = (MODE == 0 ? 2 : 4) * MTP * kG4;
+    float *s_car = s_part + PART;             // [MT][LDA] ca in row layout
     float *s_wk = s_car + MTP * LDA, *s_wq = s_wk + kU, *s_sm = s_wq + kU;   // s_sm [MTP]
-    const bool stash = a.sGQ != nullptr;
-    const int total = 13 * VEC + MTP * 2 * kG4 + MTP * LDA + 2 * kU + MTP;
+    float *s_bhh = s_sm + MTP;                // MODE 1: gru_s.bias_hh [384]
+    const bool stash = a.sGL != nullptr;
+    const int total = 13 * VEC + PART + MTP * LDA + 2 * kU + MTP + (MODE == 1 ? 3 * kU : 0);
     for (int i = tid; i < total; i += nt) smem[i] = 0.f;
     __syncthreads();
     for (int i = tid; i < kU; i += nt) { s_wk[i] = __ldg(a.Wk + i); s_wq[i] = __ldg(a.Wq + i); }
+    if constexpr (MODE == 1)
+        for (int i = tid; i < 3 * kU; i += nt) s_bhh[i] = __ldg(a.bhh + i);
     __syncthreads();
     float wkmax = -INFINITY, wkmin = INFINITY;
     for (int j = 0; j < kU; ++j) { wkmax = fmaxf(wkmax, s_wk[j]); wkmin = fminf(wkmin, s_wk[j]); }
@@ -124,8 +146,74 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
     unsigned epoch = 0;                       // completed grid barriers (each worth G arrivals)
 
     for (int t = 0; t < T; ++t) {
-        const int n0 = __ldg(a.n0 + t), n1 = N - n0;
         const size_t tn0 = (size_t)t * N + r0;
+        Acc<MT> acc;
+        if constexpr (MODE == 1) {
+            float *s_q0 = s_hq0, *s_q1 = s_hq1, *s_qs = s_x0;      // party states and the current speaker's selection
+            // ---- A': current speaker's party state (argmax of an all-zero padded row is party 0)
+            for (int idx = tid; idx < MT * kU; idx += nt) {
+                const int m = idx >> 7, k = idx & 127;
+                float qs = 0.f;
+                if (m < rows) {
+                    const float m0 = __ldg(a.qmask + (tn0 + m) * 2), m1 = __ldg(a.qmask + (tn0 + m) * 2 + 1);
+                    qs = m1 > m0 ? s_q1[k * MTP + m] : s_q0[k * MTP + m];
+                }
+                s_qs[k * MTP + m] = qs;
+            }
+            __syncthreads();
+            // ---- B': W_hh qs, K split over the four thread groups
+            {
+                const int ks = tid >> 7;
+                acc.zero();
+                mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.whh_img) + (size_t)(ks * 32) * kU + g_unit, kU,
+                             s_qs + ks * 32 * MTP, 32);
+                store_partial<MT, MTP>(s_part, kG4, ks, 4 * g_unit, acc);
+            }
+            __syncthreads();
+            // ---- C': GRU gates, speaker state, party update
+            for (int idx = tid; idx < MT * kU; idx += nt) {
+                const int m = idx >> 7, u = idx & 127;
+                float h = 0.f;
+                if (m < rows) {
+                    float4 p = *reinterpret_cast<const float4 *>(s_part + (size_t)m * kG4 + 4 * u);
+#pragma unroll
+                    for (int ks = 1; ks < 4; ++ks) {
+                        const float4 q = *reinterpret_cast<const float4 *>(s_part + (size_t)(ks * MTP + m) * kG4 + 4 * u);
+                        p.x += q.x; p.y += q.y; p.z += q.z;
+                    }
+                    const float *gi = a.gxs + (tn0 + m) * 3 * kU + u;
+                    const float r = sigmoidf_(__ldg(gi) + p.x + s_bhh[u]);
+                    const float z = sigmoidf_(__ldg(gi + kU) + p.y + s_bhh[kU + u]);
+                    const float hn = p.z + s_bhh[2 * kU + u];
+                    const float n = tanhf_(__ldg(gi + 2 * kU) + r * hn);
+                    const float qs = s_qs[u * MTP + m];
+                    h = (1.f - z) * n + z * qs;
+                    if (a.ms) h *= __ldg(a.ms + (tn0 + m) * kU + u);
+                    const float m0 = __ldg(a.qmask + (tn0 + m) * 2), m1 = __ldg(a.qmask + (tn0 + m) * 2 + 1);
+                    const float q0 = s_q0[u * MTP + m], q1 = s_q1[u * MTP + m];
+                    const float b0 = a.listener ? (m1 > m0 ? q0 : q1) : q0, b1 = a.listener ? b0 : q1;
+                    s_q0[u * MTP + m] = b0 * (1.f - m0) + h * m0;
+                    s_q1[u * MTP + m] = b1 * (1.f - m1) + h * m1;
+                    a.out[(tn0 + m) * 4 * kU + 3 * kU + u] = h;
+                    if (stash) {
+                        float *gs = a.sGS + (tn0 + m) * 4 * kU + u;
+                        gs[0] = r; gs[kU] = z; gs[2 * kU] = n; gs[3 * kU] = hn;
+                        a.sQS[(tn0 + m) * kU + u] = qs;
+                    }
+                }
+                s_hq[u * MTP + m] = h;
+            }
+            __syncthreads();
+            // ---- D: LSTHM gate products  [h_c | zl | hs] (K = 384, halves of the three blocks per thread group)
+            acc.zero();
+            {
+                const float4 *wp = reinterpret_cast<const float4 *>(a.wl_img[g_cell]) + g_unit;
+                const float *act = g_half == 0 ? (g_cell == 0 ? s_hl : s_ha) : s_zl;
+                mac<MT, MTP>(acc, wp + (size_t)(g_half * kU) * kU, kU, act, kU);
+            }
+        }
+        const int n0 = MODE == 0 ? __ldg(a.n0 + t) : 0, n1 = N - n0;
+        if constexpr (MODE == 0) {
         const int *pit = a.pi + (size_t)t * N;
         const float *Qprev = a.Q + (size_t)((t + 1) & 1) * N * 2 * kU;
         float *Qcur = a.Q + (size_t)(t & 1) * N * 2 * kU;
@@ -143,7 +231,6 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
         }
         __syncthreads();
         // ---- B: the two speaker LSTM cells on packed rows (skipped entirely when no dialogue has that speaker)
-        Acc<MT> acc;
         const bool run_q = g_cell == 0 ? n0 > 0 : n1 > 0;
         if (run_q) {
             acc.zero();
@@ -220,6 +307,7 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
         }
         grid_arrive(a.bar);                    // Q_t is published (waited for at the top of step t+1)
         ++epoch;
+        }   // MODE 0
         // ---- D2: S hq part (same thread -> same accumulators), K halves of 64
         {
             const float4 *wp = reinterpret_cast<const float4 *>(a.wl_img[g_cell]) + g_unit;
@@ -252,7 +340,7 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
                         float *gl = a.sGL + b * kG4 + g_unit;
                         gl[0] = gf; gl[kU] = gi; gl[2 * kU] = go; gl[3 * kU] = gg;
                         a.sCL[b * kU + g_unit] = c;
-                        a.sHL[b * kU + g_unit] = h;
+                        if (MODE == 0) a.sHL[b * kU + g_unit] = h;
                     }
                     if (g_cell == 1) s_car[m * LDA + g_unit] = c;
                 } else {
@@ -324,7 +412,9 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_fwd_kernel(const __grid_co
 // backward (BPTT).  Adjoint carries: Ghl,Gcl,Gha,Gca,Gzl on dialogue rows; Ghq0,Gcq0,Ghq1,Gcq1 on packed
 // rows; the adjoint of Q_t arrives from step t+1 through the GY exchange buffers.
 // ---------------------------------------------------------------------------------------------
-template <int MT>
+// MODE 1 carries the adjoint of the party state q_t (both parties) in shared memory instead of the packed-row LSTM carries;
+// nothing is exchanged between CTAs.
+template <int MT, int MODE>
 __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_constant__ SpsBwdArgs a) {
     constexpr int MTP = (MT + 3) & ~3;
     constexpr int VEC = kU * MTP;
@@ -356,7 +446,7 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_co
     unsigned epoch = 0;
 
     for (int t = T - 1; t >= 0; --t) {
-        const int n0 = __ldg(a.n0 + t), n1 = N - n0;
+        const int n0 = MODE == 0 ? __ldg(a.n0 + t) : 0, n1 = N - n0;
         const size_t tn0 = (size_t)t * N + r0;
         // ---- P1: stage c_l, c_a (stash) and the incoming dL/dz_l for the attention backward (row layout)
         for (int idx = tid; idx < MT * kU; idx += nt) {
@@ -509,6 +599,70 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_co
             store_partial<MT, MTP>(s_part + (cell * 2 + sp) * MTP * 384, 384, 0, which * kU + 4 * quad, acc);
         }
         __syncthreads();
+        if constexpr (MODE == 1) {
+            float *s_Gq0 = s_Ghq0, *s_Gq1 = s_Ghq1, *s_gqs = s_gh0;
+            // ---- P5'/P6': finish the carries; dL/dhs = S parts + dout + party-update adjoint; GRU cell backward (pointwise)
+            for (int idx = tid; idx < MT * kU; idx += nt) {
+                const int m = idx >> 7, k = idx & 127;
+                float ghl = 0.f, gha = 0.f, gzl = 0.f, nq0 = 0.f, nq1 = 0.f, gqs = 0.f, dgr = 0.f, dgz = 0.f, dhn = 0.f;
+                if (m < rows) {
+                    const float *p00 = s_part + (0 * MTP + m) * 384, *p01 = s_part + (1 * MTP + m) * 384;
+                    const float *p10 = s_part + (2 * MTP + m) * 384, *p11 = s_part + (3 * MTP + m) * 384;
+                    ghl = p00[k] + p01[k];
+                    gha = p10[k] + p11[k];
+                    gzl = (p00[kU + k] + p01[kU + k]) + (p10[kU + k] + p11[kU + k]);
+                    float ghs = (p00[2 * kU + k] + p01[2 * kU + k]) + (p10[2 * kU + k] + p11[2 * kU + k]);
+                    ghs += __ldg(a.dout + (tn0 + m) * 4 * kU + 3 * kU + k);
+                    const float m0 = __ldg(a.qmask + (tn0 + m) * 2), m1 = __ldg(a.qmask + (tn0 + m) * 2 + 1);
+                    const float G0 = s_Gq0[k * MTP + m], G1 = s_Gq1[k * MTP + m];
+                    ghs += G0 * m0 + G1 * m1;
+                    if (a.listener) {       // q_t[p] = q_{t-1}[1 - idx](1 - m_p) + hs m_p
+                        const float gql = G0 * (1.f - m0) + G1 * (1.f - m1);
+                        if (m1 > m0) nq0 = gql; else nq1 = gql;
+                    } else {                // q_t[p] = q_{t-1}[p](1 - m_p) + hs m_p
+                        nq0 = G0 * (1.f - m0); nq1 = G1 * (1.f - m1);
+                    }
+                    if (a.ms) ghs *= __ldg(a.ms + (tn0 + m) * kU + k);
+                    const float *gs = a.sGS + (tn0 + m) * 4 * kU + k;
+                    const float r = __ldg(gs), z = __ldg(gs + kU), n = __ldg(gs + 2 * kU), hn = __ldg(gs + 3 * kU);
+                    const float qs = __ldg(a.sQS + (tn0 + m) * kU + k);
+                    const float dnp = ghs * (1.f - z) * (1.f - n * n);
+                    dgr = dnp * hn * r * (1.f - r);
+                    dgz = ghs * (qs - n) * z * (1.f - z);
+                    dhn = dnp * r;
+                    gqs = ghs * z;
+                    float *gi = a.dGi + (tn0 + m) * 3 * kU + k, *gh = a.dGh + (tn0 + m) * 3 * kU + k;
+                    gi[0] = dgr; gi[kU] = dgz; gi[2 * kU] = dnp;
+                    gh[0] = dgr; gh[kU] = dgz; gh[2 * kU] = dhn;
+                }
+                s_Ghl[k * MTP + m] = ghl; s_Gha[k * MTP + m] = gha; s_Gzl[k * MTP + m] = gzl;
+                s_Gq0[k * MTP + m] = nq0; s_Gq1[k * MTP + m] = nq1; s_gqs[k * MTP + m] = gqs;
+                s_ds[(k) * MTP + m] = dgr; s_ds[(kU + k) * MTP + m] = dgz; s_ds[(2 * kU + k) * MTP + m] = dhn;
+            }
+            __syncthreads();
+            // ---- P7': dL/dqs += d(W_hh qs)^T W_hh   (K = 384 in 12 chunks, J = 128)
+            if (tid < 384) {
+                const int quad = tid & 31, sp = tid >> 5;
+                Acc<MT> acc;
+                acc.zero();
+                mac<MT, MTP>(acc, reinterpret_cast<const float4 *>(a.Whh_s) + (size_t)(sp * 32) * 32 + quad, 32,
+                             s_ds + (sp * 32) * MTP, 32);
+                store_partial<MT, MTP>(s_part + sp * MTP * kU, kU, 0, 4 * quad, acc);
+            }
+            __syncthreads();
+            // ---- P8': the selected party receives the adjoint of qs
+            for (int idx = tid; idx < MT * kU; idx += nt) {
+                const int m = idx >> 7, k = idx & 127;
+                if (m < rows) {
+                    float g = s_gqs[k * MTP + m];
+#pragma unroll
+                    for (int sp = 0; sp < 12; ++sp) g += s_part[(sp * MTP + m) * kU + k];
+                    const float m0 = __ldg(a.qmask + (tn0 + m) * 2), m1 = __ldg(a.qmask + (tn0 + m) * 2 + 1);
+                    if (m1 > m0) s_Gq1[k * MTP + m] += g; else s_Gq0[k * MTP + m] += g;
+                }
+            }
+            __syncthreads();
+        } else {
         // ---- P5: finish the carries; total dL/dhq; adjoint of Q_t from step t+1 (second exchange of that step)
         if (t < T - 1) grid_wait(a.bar, epoch * G);
         for (int idx = tid; idx < MT * kU; idx += nt) {
@@ -626,6 +780,7 @@ __global__ void __launch_bounds__(kSpsThreads, 1) sps_bwd_kernel(const __grid_co
         }
         grid_arrive(a.bar);                     // exchange 2 published; waited for in P5 of step t-1
         ++epoch;
+        }   // MODE 0
     }
     __syncthreads();
     if (tid < kU) {

@@ -51,9 +51,9 @@ class CrossAttention(nn.Module):
 class _SeqCrossAttention(nn.Module):
     """Dense, unmasked attention over the utterances of a dialogue (lsthm_sps.py:88-101, 116-129)."""
 
-    def __init__(self, d_q, d_kv, attn_dropout=0.2):
+    def __init__(self, d_q, d_kv, attn_dropout=0.2, dk=128, dv=128):
         super().__init__()
-        self.dh, self.dk, self.dv = 100, 128, 128
+        self.dh, self.dk, self.dv = 100, dk, dv
         self.Wq = nn.Parameter(torch.ones(d_q, self.dk))
         self.Wk = nn.Parameter(torch.ones(d_kv, self.dk))
         self.Wv = nn.Parameter(torch.ones(d_kv, self.dv))

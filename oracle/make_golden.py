@@ -4,7 +4,8 @@ build container (the reference tree does not exist on the GPU box); the fixtures
 committed, and every consumer regenerates the *weights* from the recorded seed (module default
 init under torch.manual_seed, verified identical between the reference classes and ours).
 
-    python oracle/make_golden.py            # rewrites all fixtures
+    python oracle/make_golden.py            # rewrites the AT/ATV and lsthm_sps fixtures
+    python oracle/make_golden.py gru        # rewrites the lsthm_onlysp / lsthm_nsps fixtures
 
 What is pinned per case: output probabilities, the MaskedLoss(CrossEntropy) scalar
 (loss.py:13-21), d loss/d x, and for every parameter its gradient L2 norm plus a strided sample
@@ -89,14 +90,21 @@ def synth_dialogues(seed, L, lens):
     return x, qmask, umask, labels
 
 
-def sps_case(ref, seed, L, lens, train, perturb):
+def _speaker_model(ref, kind):
+    """kind: sps | onlysp | nsps -> constructor of the live reference class (model/lsthm_<kind>.py)."""
+    return {"sps": lambda: ref.MARN1_sps(6), "onlysp": lambda: ref.MARN1_onlysp(6),
+            "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP")}[kind]
+
+
+def sps_case(ref, seed, L, lens, train, perturb, kind="sps"):
+    make = _speaker_model(ref, kind)
     torch.manual_seed(seed)
-    model = ref.MARN1_sps(6)
+    model = make()
     if perturb:
         perturb_ones(model, seed + 3)
     x, qmask, umask, labels = synth_dialogues(seed, L, lens)
     x.requires_grad_(True)
-    fix = dict(kind="sps", seed=seed, T=L, N=len(lens), train=int(train), perturb=int(perturb), x=x.detach().numpy().copy(),
+    fix = dict(kind=kind, seed=seed, T=L, N=len(lens), train=int(train), perturb=int(perturb), x=x.detach().numpy().copy(),
                qmask=qmask.numpy(), umask=umask.numpy(), labels=labels.numpy(), sample_stride=SAMPLE_STRIDE)
     if train:
         tape = DropoutTape(seed + 2)
@@ -117,7 +125,7 @@ def sps_case(ref, seed, L, lens, train, perturb):
     # so the parity bar for this model is  err(ours, fp64) <= max(tol, 3 * err(reference fp32, fp64)).
     torch.set_default_dtype(torch.float64)
     try:
-        m64 = ref.MARN1_sps(6)
+        m64 = make()
         m64.load_state_dict({k: v.double() for k, v in model.state_dict().items()})
         if train:
             attach_tape(m64, tape.rewind())
@@ -161,6 +169,9 @@ def sps_case(ref, seed, L, lens, train, perturb):
         for site, masks in tape.masks.items():
             if site.endswith("crossatt_l2a.dropout") and site.startswith("marn_cell"):
                 fix["tape/" + site] = torch.stack(masks, 0).numpy().astype(np.float16)   # values 0 / 1.25: exact in fp16
+            elif len({tuple(m.shape) for m in masks}) > 1:
+                for i, m in enumerate(masks):                     # lsthm_nsps: dropout_rec sees 128- and 384-wide tensors
+                    fix[f"tapei/{site}/{i:04d}"] = m.numpy().astype(np.float32)
             else:
                 fix["tape/" + site] = torch.stack(masks, 0).numpy().astype(np.float32)
     return fix
@@ -185,5 +196,22 @@ def main():
         print(name, os.path.getsize(os.path.join(OUT, name)) // 1024, "KiB", "loss", float(fix["loss"]))
 
 
+def main_gru_variants():
+    """Fixtures of the GRU speaker-state variants (lsthm_onlysp = train.py's default model, lsthm_nsps)."""
+    ref = load_reference()
+    cases = [("onlysp", 121, 9, [9, 4, 7, 9, 5], False, False), ("onlysp", 122, 8, [8, 3, 6, 8, 5, 2, 7], False, True),
+             ("onlysp", 123, 6, [6, 4, 2, 5], True, True),
+             ("nsps", 131, 9, [9, 4, 7, 9, 5], False, False), ("nsps", 132, 8, [8, 3, 6, 8, 5, 2, 7], False, True),
+             ("nsps", 133, 6, [6, 4, 2, 5], True, True)]
+    for kind, seed, L, lens, train, perturb in cases:
+        fix = sps_case(ref, seed, L, lens, train, perturb, kind)
+        name = f"{kind}_s{seed}_T{L}_N{len(lens)}_{'train' if train else 'eval'}{'_pert' if perturb else ''}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **fix)
+        print(name, os.path.getsize(os.path.join(OUT, name)) // 1024, "KiB", "loss", float(fix["loss"]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "gru":
+        main_gru_variants()
+        sys.exit(0)
     main()

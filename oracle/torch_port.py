@@ -423,6 +423,74 @@ def onlysp_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = Non
 
 
 # --------------------------------------------------------------------------------------
+# lsthm_nsps.py  (speaker + listener party update, softmax(p) fusion weights, residual+LayerNorm cross attention)
+# --------------------------------------------------------------------------------------
+def nsps_cell(p: Params, pre: str, u, x_l, x_a, qmask, tape: Optional[DropoutTape] = None):
+    """MARN_cell.forward of lsthm_nsps (model/lsthm_nsps.py:159-215): the GRU runs on the step's input features ``u``
+    (line 176) and the current speaker's state; BOTH parties are then rewritten — the speaker's with the new state, the
+    other with the *listener's previous* state (q_l, lines 178, 184-188).  Returns [T,N,512] = [h_l|h_a|z_l|h_s]
+    (the reference returns the first 384 columns as ``h`` and h_l, h_a, h_s separately, lines 196-215)."""
+    T, N, _ = x_l.shape
+    z = lambda: x_l.new_zeros(N, 128)
+    h_l, h_a, c_l, c_a, z_l = (z() for _ in range(5))
+    q = x_l.new_zeros(N, 2, 128)
+    site = pre + ".dropout"
+    ar = torch.arange(N)
+    out = []
+    for t in range(T):
+        idx = torch.argmax(qmask[t], 1)
+        qs_0, ql_0 = q[ar, idx], q[ar, 1 - idx]                       # _select_parties, lines 232-239
+        h_s = _drop(gru_cell(p, pre + ".gru_s", u[t], qs_0), 0.5, site, tape)
+        m = qmask[t].unsqueeze(2)
+        q = ql_0.unsqueeze(1) * (1 - m) + h_s.unsqueeze(1) * m
+        c_l, h_l = lsthm1_cell(p, pre + ".lsthm_l", x_l[t], c_l, h_l, z_l, h_s)
+        h_l = _drop(h_l, 0.5, site, tape)
+        c_a, h_a = lsthm1_cell(p, pre + ".lsthm_a", x_a[t], c_a, h_a, z_l, h_s)
+        h_a = _drop(h_a, 0.5, site, tape)
+        z_l = cross_attention_cell(p, pre + ".crossatt_l2a", c_l, c_a, tape, pre + ".crossatt_l2a.dropout")
+        out.append(torch.cat([h_l, h_a, z_l, h_s], 1))
+    return torch.stack(out, 0)
+
+
+def cross_attention_seq_ln(p: Params, pre: str, x1, x2, tape, dk: int = 100):
+    """CrossAttention2.forward of lsthm_nsps (model/lsthm_nsps.py:90-108): the dense unmasked attention followed by
+    ``LayerNorm(out + x1)`` (eps 1e-6)."""
+    out = cross_attention_seq(p, pre, x1, x2, tape, dk) + x1
+    return F.layer_norm(out, (out.shape[-1],), p[pre + ".layer_norm.weight"], p[pre + ".layer_norm.bias"], 1e-6)
+
+
+def nsps_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None):
+    """MARN1_nsps.forward (model/lsthm_nsps.py:300-359)."""
+    xl0 = _lin(p, "linear_in", x[:, :, :1024].permute(1, 0, 2))
+    xa0 = x[:, :, 1024:1124].permute(1, 0, 2)
+    u = torch.cat([xl0, xa0], dim=2).permute(1, 0, 2)
+    xl1 = encoder_layer(p, "encoder_l", xl0, tape)
+    xa1 = encoder_layer(p, "encoder_a", xa0, tape)
+    xl = encoder_layer(p, "encoder_l", xl0 + xl1, tape).permute(1, 0, 2)
+    xa = encoder_layer(p, "encoder_a", xa0 + xa1, tape).permute(1, 0, 2)
+    rec = lambda t: _drop(t, 0.5, "dropout_rec", tape)
+    o_f = nsps_cell(p, "marn_cell_f", u, xl, xa, qmask, tape)
+    hf_l, hf_a, _ = rec(o_f[..., 0:128]), rec(o_f[..., 128:256]), rec(o_f[..., 384:512])
+    o_b = nsps_cell(p, "marn_cell_b", reverse_seq(u, umask), reverse_seq(xl, umask), reverse_seq(xa, umask),
+                    reverse_seq(qmask, umask), tape)
+    o_b = reverse_seq(o_b, umask)
+    rec(o_b[..., 0:384])                                              # h_b: dropped out but never used (lines 328, 335)
+    hb_l, hb_a, _ = rec(o_b[..., 0:128]), rec(o_b[..., 128:256]), rec(o_b[..., 384:512])
+    h_l, h_a = torch.cat([hf_l, hb_l], -1), torch.cat([hf_a, hb_a], -1)
+    a1 = cross_attention_seq_ln(p, "crossatt_l2a", xl, xa, tape)
+    a2 = cross_attention_seq_ln(p, "crossatt_a2l", xa, xl, tape)
+    e = torch.exp(p["p"])
+    w1, w2 = e[0] / e.sum(), e[1] / e.sum()
+    resid_l = _drop(torch.relu(_lin(p, "fc.0", xl)), 0.5, "fc.2", tape)
+    if tape is not None:
+        _drop(torch.relu(_lin(p, "fc2.0", xa)), 0.5, "fc2.2", tape)   # resid_a: computed and discarded (line 352)
+    fused = torch.cat([w1 * torch.cat([h_l, a2], 2), w2 * torch.cat([h_a, a1], 2)], dim=-1) + resid_l
+    y = _drop(torch.relu(_lin(p, "nn_out.0", fused)), 0.5, "nn_out.2", tape)
+    logp = torch.log_softmax(_lin(p, "nn_out.3", y), 2).permute(1, 0, 2)
+    return logp.reshape(-1, logp.shape[-1]), xl, xa
+
+
+# --------------------------------------------------------------------------------------
 # loss.py
 # --------------------------------------------------------------------------------------
 def masked_loss(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, kind: str = "ce"):

@@ -52,6 +52,8 @@ def tape_from_fixture(fix):
     for k, v in fix.items():
         if k.startswith("tape/"):
             tape.masks[k[5:]] = [torch.from_numpy(m) for m in v]
+    for k in sorted(k for k in fix if k.startswith("tapei/")):      # per-call masks of a site whose calls differ in shape
+        tape.masks.setdefault(k[6:].rsplit("/", 1)[0], []).append(torch.from_numpy(fix[k]))
     return tape.rewind()
 
 
@@ -160,9 +162,14 @@ def run_module(fix, device="cpu", rows_per_cta=0):
 # ------------------------------------------------------------------------------------------------
 # lsthm_sps helpers
 # ------------------------------------------------------------------------------------------------
-def sps_seeded_model(seed, perturb, device="cpu"):
+SPEAKER_MODELS = {"sps": lambda: lsthm_b200.lsthm_sps.MARN1_sps(6), "onlysp": lambda: lsthm_b200.lsthm_onlysp.MARN1_onlysp(6),
+                  "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP")}
+SPEAKER_PORTS = {"sps": tp.sps_forward, "onlysp": tp.onlysp_forward, "nsps": tp.nsps_forward}
+
+
+def sps_seeded_model(seed, perturb, device="cpu", kind="sps"):
     torch.manual_seed(int(seed))
-    m = lsthm_b200.lsthm_sps.MARN1_sps(6)
+    m = SPEAKER_MODELS[kind]()
     if perturb:
         tp.perturb_ones(m, int(seed) + 3)
     return m.to(device)
@@ -188,20 +195,32 @@ def sps_cell_masks(tape, pre, qmask_dir, device="cpu"):
     return tuple(x.to(device).contiguous() for x in (mq0, mq1, ml, ma, att))
 
 
+def gsp_cell_masks(tape, pre, T, N, device="cpu"):
+    """GRU-variant cells (lsthm_onlysp.py:176,184,186 / lsthm_nsps.py:183,192,194): ``<pre>.dropout`` is called three times per
+    step — on h_s, h_l, h_a — and ``<pre>.crossatt_l2a.dropout`` once: -> the (ms, ml, ma, att_mask) tensors of the kernel."""
+    calls = tape.masks[pre + ".dropout"]
+    assert len(calls) == 3 * T
+    ms, ml, ma = (torch.stack([calls[3 * t + i] for t in range(T)], 0).float() for i in range(3))
+    att = torch.stack([m.float() for m in tape.masks[pre + ".crossatt_l2a.dropout"]], 0)
+    return tuple(x.to(device).contiguous() for x in (ms, ml, ma, att))
+
+
 def sps_port_run(fix):
-    model = sps_seeded_model(fix["seed"], int(fix["perturb"]))
+    kind = str(fix["kind"]) if "kind" in fix else "sps"
+    model = sps_seeded_model(fix["seed"], int(fix["perturb"]), kind=kind)
     params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     x = torch.from_numpy(fix["x"]).clone().requires_grad_(True)
     qmask, umask = torch.from_numpy(fix["qmask"]), torch.from_numpy(fix["umask"])
     tape = tape_from_fixture(fix) if int(fix["train"]) else None
-    logp, x_l, x_a = tp.sps_forward(params, x, qmask, umask, tape)
+    logp, x_l, x_a = SPEAKER_PORTS[kind](params, x, qmask, umask, tape)
     loss = tp.masked_loss(logp, torch.from_numpy(fix["labels"]).view(-1), umask, "ce")
     loss.backward()
     return logp.detach(), loss.detach(), x.grad, {k: v.grad for k, v in params.items()}
 
 
 def sps_run_module(fix, device="cuda", rows_per_cta=0):
-    model = sps_seeded_model(fix["seed"], int(fix["perturb"]), device)
+    kind = str(fix["kind"]) if "kind" in fix else "sps"
+    model = sps_seeded_model(fix["seed"], int(fix["perturb"]), device, kind=kind)
     model.marn_cell_f.rows_per_cta = model.marn_cell_b.rows_per_cta = rows_per_cta
     x = torch.from_numpy(fix["x"]).to(device).requires_grad_(True)
     qmask, umask = torch.from_numpy(fix["qmask"]).to(device), torch.from_numpy(fix["umask"]).to(device)
@@ -209,8 +228,13 @@ def sps_run_module(fix, device="cuda", rows_per_cta=0):
         model.train()
         tape = tape_from_fixture(fix)
         q_cpu, u_cpu = torch.from_numpy(fix["qmask"]), torch.from_numpy(fix["umask"])
-        model.marn_cell_f.mask_override = sps_cell_masks(tape, "marn_cell_f", q_cpu, device)
-        model.marn_cell_b.mask_override = sps_cell_masks(tape, "marn_cell_b", tp.reverse_seq(q_cpu, u_cpu), device)
+        if kind == "sps":
+            model.marn_cell_f.mask_override = sps_cell_masks(tape, "marn_cell_f", q_cpu, device)
+            model.marn_cell_b.mask_override = sps_cell_masks(tape, "marn_cell_b", tp.reverse_seq(q_cpu, u_cpu), device)
+        else:
+            T_, N_ = q_cpu.shape[0], q_cpu.shape[1]
+            model.marn_cell_f.mask_override = gsp_cell_masks(tape, "marn_cell_f", T_, N_, device)
+            model.marn_cell_b.mask_override = gsp_cell_masks(tape, "marn_cell_b", T_, N_, device)
         attach_tape_to_ours(model, tape, skip_prefixes=("marn_cell",))
     else:
         model.eval()
@@ -253,12 +277,13 @@ def sps_port_run64(fix, force=None):
     """fp64 run of the oracle restatement (eval fixtures only) -> truth dict shaped like the fixture's fp64 fields,
     plus the recorded ReLU pre-activations."""
     assert not int(fix["train"])
-    model = sps_seeded_model(fix["seed"], int(fix["perturb"]))
+    kind = str(fix["kind"]) if "kind" in fix else "sps"
+    model = sps_seeded_model(fix["seed"], int(fix["perturb"]), kind=kind)
     params = {k: v.detach().double().requires_grad_(True) for k, v in model.state_dict().items()}
     x = torch.from_numpy(fix["x"]).double().requires_grad_(True)
     qmask, umask = torch.from_numpy(fix["qmask"]).double(), torch.from_numpy(fix["umask"]).double()
     with relu_kinks(force) as rk:
-        logp, _, _ = tp.sps_forward(params, x, qmask, umask, None)
+        logp, _, _ = SPEAKER_PORTS[kind](params, x, qmask, umask, None)
         loss = tp.masked_loss(logp, torch.from_numpy(fix["labels"]).view(-1), umask, "ce")
         loss.backward()
     stride = int(fix["sample_stride"])

@@ -16,7 +16,8 @@ from oracle import torch_port as tp
 from oracle.ref_shim import attach_tape, load_reference, reference_available
 
 
-@pytest.mark.parametrize("path", golden_files("sps_*.npz"), ids=lambda p: p.split("/")[-1][:-4])
+@pytest.mark.parametrize("path", golden_files("sps_*.npz") + golden_files("onlysp_*.npz") + golden_files("nsps_*.npz"),
+                         ids=lambda p: p.split("/")[-1][:-4])
 def test_sps_torch_port_matches_reference_fixture(path):
     """lsthm_sps: the index-form restatement (vectorised _select_parties, no per-row loop) vs the reference
     fixtures, eval / perturbed ones-parameters / train with the full dropout mask tape."""
@@ -105,15 +106,17 @@ def test_c_oracle_matches_torch_port_and_autograd(kind):
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("variant", ["onlysp", "nsps"])
 @pytest.mark.parametrize("train,perturb", [(False, False), (False, True), (True, True)])
-def test_onlysp_port_matches_live_reference(train, perturb):
-    """lsthm_onlysp (the reference's train.py default model, next variant to get a kernel): the oracle restatement vs the
-    live reference — log-probs, loss and every gradient, eval / perturbed ones-parameters / train with the mask tape,
-    ragged dialogue lengths."""
+def test_gru_variant_port_matches_live_reference(variant, train, perturb):
+    """lsthm_onlysp (the reference's train.py default model) and lsthm_nsps (listener update, softmax(p) fusion): the
+    oracle restatement vs the live reference — log-probs, loss and every gradient, eval / perturbed ones-parameters /
+    train with the mask tape, ragged dialogue lengths."""
     from oracle.make_golden import synth_dialogues
     ref = load_reference()
     torch.manual_seed(31)
-    m = ref.MARN1_onlysp(6)
+    m = ref.MARN1_onlysp(6) if variant == "onlysp" else ref.MARN1_nsps(6, "IEMOCAP")
+    forward = tp.onlysp_forward if variant == "onlysp" else tp.nsps_forward
     if perturb:
         tp.perturb_ones(m, 5)
     x, qmask, umask, labels = synth_dialogues(17, 9, [9, 4, 7, 9, 5])
@@ -130,7 +133,7 @@ def test_onlysp_port_matches_live_reference(train, perturb):
     loss.backward()
     p = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
     x2 = x.detach().clone().requires_grad_(True)
-    logp2, _, _ = tp.onlysp_forward(p, x2, qmask, umask, tape.rewind() if train else None)
+    logp2, _, _ = forward(p, x2, qmask, umask, tape.rewind() if train else None)
     loss2 = tp.masked_loss(logp2, labels.view(-1), umask, "ce")
     loss2.backward()
     e = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
