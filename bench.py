@@ -306,7 +306,8 @@ def run_ours(args):
         torch.manual_seed(111)
         if k == "ATV":
             return lsthm_b200.HybridRNN_ATV.MARN().to(dev).train()
-        m = lsthm_b200.lsthm_sps.MARN1_sps(6)
+        m = {"sps": lambda: lsthm_b200.lsthm_sps.MARN1_sps(6), "onlysp": lambda: lsthm_b200.lsthm_onlysp.MARN1_onlysp(6),
+             "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP")}[k]()
         # the stock init sets every attention projection / fusion scalar to ones (lsthm_sps.py:52-54,82-84,340-346):
         # degenerate softmaxes; perturb them as the parity tests do so the timed arithmetic is representative
         gpert = torch.Generator().manual_seed(114)
@@ -547,6 +548,36 @@ def run_ours(args):
             _lib.set_precision("bf16" if args.dtype == "bf16" else "fp32")
             sps["workload"] = f"MARN1_sps(6) fwd+bwd (train mode), x[{T},{B},1124], qmask[{T},{B},2]; bf16 = bf16 operands in the time-parallel products, recurrence/softmax/LayerNorm fp32"
             extras["config3_sps"] = sps
+            # (2b) the GRU speaker-state members of the family (lsthm_onlysp = train.py's default model, lsthm_nsps), fp32
+            var = {}
+            for vk in ("onlysp", "nsps"):
+                try:
+                    vm = make_model(vk)
+                    sb = synthetic_batch(111, T, B, device=dev, model="sps")
+
+                    def var_step():
+                        vm.zero_grad(set_to_none=True)
+                        loss_fn(forward_of(vm, vk, sb), sb[1].view(T, B).t().reshape(-1), sb[2]).backward()
+                    for _ in range(3):
+                        var_step()
+                    torch.cuda.synchronize()
+                    rec.kernel_events = {"fwd": [], "bwd": []}
+                    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s0.record()
+                    for _ in range(5):
+                        var_step()
+                    s1.record()
+                    torch.cuda.synchronize()
+                    sm = s0.elapsed_time(s1) / 5
+                    kv = {k: sum(a.elapsed_time(b) for a, b in v) / max(len(v), 1) for k, v in rec.kernel_events.items()}
+                    rec.kernel_events = None
+                    var[vk] = {"ms_per_step": sm, "value": T * B / (sm * 1e-3), "unit": UNIT,
+                               "cell_kernel_ms": {k: round(v, 4) for k, v in kv.items()}}
+                    del vm
+                except Exception as e:
+                    var[vk] = {"error": repr(e)[:200]}
+            var["workload"] = f"MARN1_onlysp(6) / MARN1_nsps(6) fwd+bwd (train mode), x[{T},{B},1124], qmask[{T},{B},2], fp32; cell_kernel_ms = per launch (one direction)"
+            extras["gru_variants"] = var
         # (3) the unmodified reference, PyTorch eager on this B200 and configs 1 and 4
         for name, fn in (("reference_eager_gpu", lambda: time_eager_gpu(kind, B, 3, 2, dev)),
                          ("config1_AT_cpu", lambda: time_cpu("AT", 32, 2)),

@@ -157,3 +157,38 @@ def test_fused_adam_exposes_param_groups_and_state(monkeypatch):
     opt2 = ddp.FusedAdam(red, lr=5e-2)
     opt2.load_state_dict(sd)
     assert opt2.step_count == 2 and opt2.lr == pytest.approx(0.98e-3) and opt2.param_groups[0]["weight_decay"] == 2e-5
+
+
+def test_length_bucketed_batching_and_pinned_collate():
+    """bucketing covers every dialogue once, cuts padding on the res.csv-like length distribution, keeps
+    the shards of one step at one padded length (F11); the collate equals the reference's pad_sequence collate_fn."""
+    from importlib import import_module
+    from torch.nn.utils.rnn import pad_sequence
+    pl = import_module(lsthm_b200.__name__ + ".pipeline")
+    g = torch.Generator().manual_seed(0)
+    lens = torch.clamp(torch.round(52.4 + 17.4 * torch.randn(600, generator=g)), 8, 110).int().tolist()
+    bs = pl.LengthBucketBatchSampler(lens, 32, pool_batches=8, seed=1)
+    seen = sorted(i for b in bs for i in b)
+    assert seen == list(range(600)) and len(bs) == 19
+    rnd = pl.LengthBucketBatchSampler(lens, 32, pool_batches=1, seed=1)      # pool of one batch == plain random batches
+    assert bs.padding_fraction() < 0.5 * rnd.padding_fraction() and rnd.padding_fraction() > 0.25
+    bs.set_epoch(1)
+    assert sorted(i for b in bs for i in b) == list(range(600)) and [b for b in bs] != [b for b in rnd]
+    # two ranks: disjoint shards of every global batch, same padded length per step
+    r0 = pl.LengthBucketBatchSampler(lens, 32, seed=3, world=2, rank=0)
+    r1 = pl.LengthBucketBatchSampler(lens, 32, seed=3, world=2, rank=1)
+    for step, (a, b) in enumerate(zip(r0, r1)):
+        assert not set(a) & set(b) and abs(len(a) - len(b)) <= 1
+        assert r0.global_max_len(step) == r1.global_max_len(step) >= max(lens[i] for i in a + b)
+    assert sorted(i for s in (r0, r1) for b in s for i in b) == list(range(600))
+    # collate == dataloader.py:45-47 (pad_sequence time-major for fields < 7, batch-major for umask/label, ids as a list)
+    def sample(n, vid):
+        return (torch.randn(n, 8), torch.randn(n, 8), torch.randn(n, 8), torch.randn(n, 8), torch.randn(n, 5), torch.randn(n, 3),
+                torch.eye(2)[torch.randint(0, 2, (n,))], torch.ones(n), torch.randint(0, 6, (n,)), vid)
+    data = [sample(n, f"d{n}") for n in (5, 9, 2)]
+    got = pl.collate_dialogues(data)
+    for f in range(10):
+        col = [s[f] for s in data]
+        want = pad_sequence(col) if f < 7 else pad_sequence(col, True) if f < 9 else col
+        assert (got[f] == want) if f == 9 else torch.equal(got[f], want), f
+    assert pl.collate_dialogues(data, pad_to=12)[0].shape == (12, 3, 8) and pl.collate_dialogues(data, pad_to=12)[7].shape == (3, 12)
