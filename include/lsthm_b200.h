@@ -279,6 +279,10 @@ int lsthm_gsp_launch_info(const lsthm_gsp_desc *d, int32_t *grid, int32_t *block
 /* OR this into `mode` for the bf16 mode of BASELINE.json (stated separately from fp32 parity): operands are rounded
  * to bf16 while they are staged and each k-step is ONE UMMA (fp32 accumulation) instead of the three split terms. */
 #define LSTHM_GEMM_BF16 0x10
+/* OR this into `mode` (lsthm_gemm3 only) for the SIX-term product: operands split three ways (24 mantissa bits), terms
+ * hi.hi + hi.mid + mid.hi + hi.lo + lo.hi + mid.mid — fp32-grade accuracy even when the sum cancels structurally, as in
+ * the all-ones projections of a LayerNorm output in CrossAttention2/3 (model/lsthm_sps.py:82-84, 91-93). */
+#define LSTHM_GEMM_X6 0x20
 size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K);
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream);
@@ -290,6 +294,29 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
 size_t lsthm_gemm3w_pack_bytes(int32_t N, int32_t K);
 int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *W, int32_t ldw,
                  const float *bias, float *C, int32_t ldc, void *pack, size_t pack_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sequence-level cross-modal attention core (tcgen05, split-bf16, fp32 accuracy): what CrossAttention2.forward and
+ * CrossAttention3.forward do after their three projections — model/lsthm_sps.py:94-99, 122-127 (same code in
+ * lsthm_onlysp.py) and model/lsthm_nsps.py:100-104:
+ *     out = dropout(softmax(q k^T * scale)) v     per dialogue, unmasked over its L <= 128 utterances, one head,
+ * width D (multiple of 4, <= 128), and its autograd backward.  Scores, probabilities and the dropout mask stay on the SM.
+ * Row i of dialogue b of a matrix X with row stride ldx: X + (b*row_stride_b + i*row_stride_i)*ldx (both 0 = batch-major).
+ * dq/dk/dv use the strides of q/k/v; out/dout use ldo.  lse [B][L] is written by fwd and read by bwd.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t B, L, D;
+    int32_t ldq, ldk, ldv, ldo;
+    float scale;               /* 1/sqrt(d_k)                                   lsthm_sps.py:97 */
+    float p_drop;              /* dropout on the attention weights (0 = off)    lsthm_sps.py:98 */
+    uint64_t seed;
+    int64_t row_stride_b, row_stride_i;
+} lsthm_xattn_desc;
+
+int lsthm_xattn_fwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, float *out, float *lse,
+                    void *stream);
+int lsthm_xattn_bwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, const float *out, const float *lse,
+                    const float *dout, float *dq, float *dk, float *dv, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head self-attention of the utterance encoder (tcgen05, split-bf16, fp32 accuracy).

@@ -69,6 +69,12 @@ class AttnDesc(C.Structure):
                 ("precision", C.c_int32), ("reserved", C.c_int32)]
 
 
+class XAttnDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("D", C.c_int32), ("ldq", C.c_int32), ("ldk", C.c_int32),
+                ("ldv", C.c_int32), ("ldo", C.c_int32), ("scale", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint64),
+                ("row_stride_b", C.c_int64), ("row_stride_i", C.c_int64)]
+
+
 class DlnDesc(C.Structure):
     _fields_ = [("R", C.c_int64), ("d", C.c_int32), ("eps", C.c_float), ("p_drop", C.c_float), ("seed", C.c_uint64)]
 
@@ -145,6 +151,10 @@ def lib() -> C.CDLL:
     L.lsthm_attn_fwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 6
     L.lsthm_attn_bwd.restype = C.c_int
     L.lsthm_attn_bwd.argtypes = [C.POINTER(AttnDesc)] + [C.c_void_p] * 10
+    L.lsthm_xattn_fwd.restype = C.c_int
+    L.lsthm_xattn_fwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 6
+    L.lsthm_xattn_bwd.restype = C.c_int
+    L.lsthm_xattn_bwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 10
     L.lsthm_dln_workspace_floats.restype = C.c_size_t
     L.lsthm_dln_workspace_floats.argtypes = [C.c_int32]
     L.lsthm_dln_fwd.restype = C.c_int
@@ -424,6 +434,7 @@ def gsp_launch_info(d: GspDesc) -> dict:
 # ------------------------------------------------------------------------------------------------
 GEMM_NT, GEMM_NN, GEMM_TN, GEMM_NT_RELU = 0, 1, 2, 3
 GEMM_BF16 = 0x10
+GEMM_X6 = 0x20          # six-term split (24-bit operands): products whose sum cancels structurally (sequence cross attention)
 # "fp32": every tensor-core product is the fp32-accurate three-term bf16 split (parity mode, the default).
 # "bf16": operands rounded to bf16, one UMMA per k-step (BASELINE.json's bf16 mode; tolerance stated in tests/test_bf16_gpu.py).
 PRECISION = os.environ.get("LSTHM_PRECISION", "fp32")
@@ -447,9 +458,10 @@ def _mat(t: torch.Tensor, name: str):
 
 
 def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None,
-          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+          out: Optional[torch.Tensor] = None, x6: bool = False) -> torch.Tensor:
     """mode NT: a[M,K] @ b[N,K]^T (+bias);  NN: a[M,K] @ b[K,N];  TN: a[K,M]^T @ b[K,N].
-    ``out`` (optional): a 2-D fp32 CUDA view [M, N] with unit inner stride (e.g. a column block of a wider matrix)."""
+    ``out`` (optional): a 2-D fp32 CUDA view [M, N] with unit inner stride (e.g. a column block of a wider matrix).
+    ``x6``: the six-term split (LSTHM_GEMM_X6) regardless of the precision mode."""
     if mode in (GEMM_NT, GEMM_NT_RELU):
         M, K = a.shape; N = b.shape[0]; assert b.shape[1] == K
     elif mode == GEMM_NN:
@@ -466,9 +478,11 @@ def gemm3(mode: int, a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tens
         c = out
         _, ldc = _mat(out, "out")
     base_mode = mode
-    if PRECISION == "bf16":
+    if x6:
+        mode |= GEMM_X6
+    elif PRECISION == "bf16":
         mode |= GEMM_BF16
-    if base_mode != GEMM_TN and M >= GEMM3W_MIN_ROWS:
+    if base_mode != GEMM_TN and M >= GEMM3W_MIN_ROWS and not x6:
         # B is a layer weight and there are many rows: pre-split weight images + 128 x 256 tiles
         nbytes = lib().lsthm_gemm3w_pack_bytes(N, K)
         pack = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
@@ -509,6 +523,25 @@ def attn_bwd(d: AttnDesc, q, k, v, out, lse, dout, dq, dk, dv) -> None:
     _check(lib().lsthm_attn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
                                 _f32_cuda(lse, "lse"), _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
                                 _stream()), "lsthm_attn_bwd")
+
+
+def make_xattn_desc(B, L, D, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, time_major=True) -> XAttnDesc:
+    d = XAttnDesc()
+    d.B, d.L, d.D, d.ldq, d.ldk, d.ldv, d.ldo = B, L, D, ldq, ldk, ldv, ldo
+    d.scale, d.p_drop, d.seed = scale, p_drop, seed
+    d.row_stride_b, d.row_stride_i = (1, B) if time_major else (L, 1)
+    return d
+
+
+def xattn_fwd(d: XAttnDesc, q, k, v, out, lse) -> None:
+    _check(lib().lsthm_xattn_fwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
+                                 _f32_cuda(lse, "lse"), _stream()), "lsthm_xattn_fwd")
+
+
+def xattn_bwd(d: XAttnDesc, q, k, v, out, lse, dout, dq, dk, dv) -> None:
+    _check(lib().lsthm_xattn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
+                                 _f32_cuda(lse, "lse"), _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
+                                 _stream()), "lsthm_xattn_bwd")
 
 
 def _rows2d(t: torch.Tensor, name: str):

@@ -8,11 +8,12 @@ namespace lsthm {
 int set_error(const char *what, cudaError_t e);
 int fail_msg(const char *msg);
 
-template <int AMN, int BMN, bool BF16>
+template <int AMN, int BMN, int PREC>
 static int launch_gemm(const GemmArgs &g, dim3 grid, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3_kernel<AMN, BMN, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes);
+    constexpr size_t smem = GemmCfg<PREC>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(gemm3_kernel<AMN, BMN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_gemm3 shared-memory opt-in", e);
-    gemm3_kernel<AMN, BMN, BF16><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(g);
+    gemm3_kernel<AMN, BMN, PREC><<<grid, kGemmThreads, smem, st>>>(g);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : set_error("lsthm_gemm3 launch", e);
 }
@@ -38,7 +39,7 @@ using namespace lsthm;
 extern "C" {
 
 size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t K) {
-    mode &= ~LSTHM_GEMM_BF16;
+    mode &= ~(LSTHM_GEMM_BF16 | LSTHM_GEMM_X6);
     if (mode == 3) return 0;
     const long tiles = (long)((M + kGemmBM - 1) / kGemmBM) * ((N + kGemmBN - 1) / kGemmBN);
     if (tiles >= 148 || K < 4 * kGemmBK * 8) return 0;
@@ -48,9 +49,10 @@ size_t lsthm_gemm3_workspace_floats(int32_t mode, int32_t M, int32_t N, int32_t 
 
 int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *B, int32_t ldb,
                 const float *bias, float *C, int32_t ldc, float *workspace, size_t workspace_floats, void *stream) {
-    const bool bf16 = (mode & LSTHM_GEMM_BF16) != 0;
-    mode &= ~LSTHM_GEMM_BF16;
+    const bool bf16 = (mode & LSTHM_GEMM_BF16) != 0, x6 = (mode & LSTHM_GEMM_X6) != 0;
+    mode &= ~(LSTHM_GEMM_BF16 | LSTHM_GEMM_X6);
     if (mode < 0 || mode > 3) return fail_msg("lsthm_gemm3: mode must be 0 (NT), 1 (NN), 2 (TN) or 3 (NT + ReLU)");
+    if (bf16 && x6) return fail_msg("lsthm_gemm3: LSTHM_GEMM_BF16 and LSTHM_GEMM_X6 exclude each other");
     if (M < 1 || N < 1 || K < 1 || !A || !B || !C) return fail_msg("lsthm_gemm3: bad shape or null pointer");
     if ((lda & 3) || (ldb & 3)) return fail_msg("lsthm_gemm3: lda and ldb must be multiples of 4 floats");
     if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
@@ -73,9 +75,9 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
     const dim3 grid(tn, tm, splits);
     int rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 0 || mode == 3) rc = bf16 ? launch_gemm<0, 0, true>(g, grid, st) : launch_gemm<0, 0, false>(g, grid, st);
-    else if (mode == 1) rc = bf16 ? launch_gemm<0, 1, true>(g, grid, st) : launch_gemm<0, 1, false>(g, grid, st);
-    else rc = bf16 ? launch_gemm<1, 1, true>(g, grid, st) : launch_gemm<1, 1, false>(g, grid, st);
+    if (mode == 0 || mode == 3) rc = x6 ? launch_gemm<0, 0, 2>(g, grid, st) : bf16 ? launch_gemm<0, 0, 1>(g, grid, st) : launch_gemm<0, 0, 0>(g, grid, st);
+    else if (mode == 1) rc = x6 ? launch_gemm<0, 1, 2>(g, grid, st) : bf16 ? launch_gemm<0, 1, 1>(g, grid, st) : launch_gemm<0, 1, 0>(g, grid, st);
+    else rc = x6 ? launch_gemm<1, 1, 2>(g, grid, st) : bf16 ? launch_gemm<1, 1, 1>(g, grid, st) : launch_gemm<1, 1, 0>(g, grid, st);
     if (rc) return rc;
     if (splits > 1) {
         const size_t total = (size_t)M * N;

@@ -68,6 +68,24 @@ __device__ __forceinline__ void split_store8(const float (&x)[8], uint8_t *hi, u
     *reinterpret_cast<uint4 *>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// three-way split x = hi + mid + lo (24 mantissa bits: exact for fp32 up to the last rounding) for the six-term product
+//   D += Ah.Bh + Ah.Bm + Am.Bh + Ah.Bl + Al.Bh + Am.Bm      (dropped terms are <= 2^-24 |a||b|)
+// used where a three-term product is not enough: sums that cancel structurally, e.g. a LayerNorm output times the
+// all-ones projections of the reference's sequence-level cross attention (model/lsthm_sps.py:82-84).
+__device__ __forceinline__ void split_store8_3(const float (&x)[8], uint8_t *hi, uint8_t *mid, uint8_t *lo) {
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+        const float r0 = x[2 * i] - __uint_as_float(h[i] << 16), r1 = x[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+        m[i] = pack_bf16(r0, r1);
+        l[i] = pack_bf16(r0 - __uint_as_float(m[i] << 16), r1 - __uint_as_float(m[i] & 0xffff0000u));
+    }
+    *reinterpret_cast<uint4 *>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(mid) = make_uint4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<uint4 *>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // bf16 mode (one UMMA per k-step, operands rounded to bf16): only the hi image is produced
 __device__ __forceinline__ void store8_hi(const float (&x)[8], uint8_t *hi) {
     *reinterpret_cast<uint4 *>(hi) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
@@ -117,7 +135,8 @@ __device__ __forceinline__ void load_tile(const float *__restrict__ src, int ld,
     }
 }
 
-template <int MN, bool BF16 = false>
+// PREC: 0 = three-term split (fp32 parity mode), 1 = bf16 operands (one term), 2 = six-term split (third image at lo + (lo - hi))
+template <int MN, int PREC = 0>
 __device__ __forceinline__ void store_tile(const TileRegs &t, uint8_t *hi, uint8_t *lo, int ptid) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -129,13 +148,23 @@ __device__ __forceinline__ void store_tile(const TileRegs &t, uint8_t *hi, uint8
             const int k = i * 16 + (ptid >> 4), mc = ptid & 15;
             off = mc * kMnSbo + (k >> 3) * kMnLbo + (k & 7) * 16;
         }
-        if (BF16) store8_hi(t.x[i], hi + off);
+        if (PREC == 1) store8_hi(t.x[i], hi + off);
+        else if (PREC == 2) split_store8_3(t.x[i], hi + off, lo + off, lo + (lo - hi) + off);
         else split_store8(t.x[i], hi + off, lo + off);
     }
 }
 
-template <int AMN, int BMN, bool BF16 = false>
+template <int PREC> struct GemmCfg {
+    static constexpr int kParts = PREC == 2 ? 3 : 2;                    // images per operand
+    static constexpr int kStages = PREC == 2 ? 2 : kGemmStages;        // 2 x 6 tiles = 101 KB: still two CTAs per SM
+    static constexpr int kStage = 2 * kParts * kTileBytes;
+    static constexpr size_t kSmem = (size_t)kStages * kStage + 1024;
+};
+
+template <int AMN, int BMN, int PREC = 0>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_constant__ GemmArgs g) {
+    constexpr int kGemmStages = GemmCfg<PREC>::kStages, kStageBytes = GemmCfg<PREC>::kStage, kParts = GemmCfg<PREC>::kParts;
+    constexpr bool BF16 = PREC == 1;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw;
     __shared__ __align__(8) uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], done_bar;
@@ -170,8 +199,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
             const int s = kb % kGemmStages, round = kb / kGemmStages;
             if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1);      // the MMAs that read this stage have retired
             uint8_t *st = smem + (size_t)s * kStageBytes;
-            store_tile<AMN, BF16>(ta, st, st + kTileBytes, tid);
-            store_tile<BMN, BF16>(tb, st + 2 * kTileBytes, st + 3 * kTileBytes, tid);
+            store_tile<AMN, PREC>(ta, st, st + kTileBytes, tid);
+            store_tile<BMN, PREC>(tb, st + kParts * kTileBytes, st + (kParts + 1) * kTileBytes, tid);
             if (kb + 1 < nkb) {                                             // next block's loads fly during the fence/arrive/wait
                 const int k1 = kbeg + (kb + 1) * kGemmBK;
                 load_tile<AMN>(g.A, g.lda, m0, g.M, k1, kend, tid, ta);
@@ -196,8 +225,8 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
             for (int ks = 0; ks < kGemmBK / 16; ++ks) {
                 const uint64_t ah = umma_desc(base + ks * a_step, a_lbo, a_sbo);
                 const uint64_t al = umma_desc(base + kTileBytes + ks * a_step, a_lbo, a_sbo);
-                const uint64_t bh = umma_desc(base + 2 * kTileBytes + ks * b_step, b_lbo, b_sbo);
-                const uint64_t bl = umma_desc(base + 3 * kTileBytes + ks * b_step, b_lbo, b_sbo);
+                const uint64_t bh = umma_desc(base + kParts * kTileBytes + ks * b_step, b_lbo, b_sbo);
+                const uint64_t bl = umma_desc(base + (kParts + 1) * kTileBytes + ks * b_step, b_lbo, b_sbo);
                 const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem), "l"(ah), "l"(bh), "r"(idesc), "r"(acc0) : "memory");
@@ -206,6 +235,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
                                  ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
                     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                                  ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                }
+                if (PREC == 2) {     // here al / bl are the MID images; the LO images follow them
+                    const uint64_t a3 = umma_desc(base + 2 * kTileBytes + ks * a_step, a_lbo, a_sbo);
+                    const uint64_t b3 = umma_desc(base + (kParts + 2) * kTileBytes + ks * b_step, b_lbo, b_sbo);
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(ah), "l"(b3), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(a3), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                                 ::"r"(tmem), "l"(al), "l"(bl), "r"(idesc), "r"(1u) : "memory");
                 }
             }
             // commit: arrives on the barrier when all MMAs issued so far have completed (implies before_thread_sync)
@@ -371,7 +410,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3w_kernel(const __grid_co
                 mbar_expect_tx(&full_bar[s], wbytes);
                 bulk_g2s(st + 2 * kTileBytes, wsrc + (size_t)kb * (2 * (size_t)kWImgBytes), wbytes, &full_bar[s]);
             }
-            store_tile<0, BF16>(ta, st, st + kTileBytes, tid);
+            store_tile<0, BF16 ? 1 : 0>(ta, st, st + kTileBytes, tid);
             if (kb + 1 < nkb) load_tile<0>(g.A, g.lda, m0, g.M, (kb + 1) * kGemmBK, g.K, tid, ta);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();

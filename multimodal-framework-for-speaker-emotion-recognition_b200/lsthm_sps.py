@@ -5,7 +5,7 @@ Same constructor, parameter names / shapes / registration order (including the n
 ``crossatt_*.Wv`` of the in-cell attention, all of ``marn_cell_*.crossatt_a2l`` and ``lstm_s``;
 SURVEY.md F8) and default-init RNG order as the reference (lsthm_sps.py:11-26, 47-57, 75-86, 103-114,
 132-154, 298-346).  ``MARN_cell.forward`` (156-221) runs as one fused CUDA kernel per direction;
-the rest (encoders, sequence-level cross attention, heads) is PyTorch.
+the encoders and the sequence-level cross attention (88-129) run on the fused attention / GEMM kernels.
 """
 from __future__ import annotations
 
@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from .encoder import EncoderLayer
 from .mm3 import linear3
+from .seq_attention import fused_ok, seq_cross_attention
 from .sps_recurrence import sps_cell
 
 
@@ -60,10 +61,13 @@ class _SeqCrossAttention(nn.Module):
         self.dropout = nn.Dropout(attn_dropout)
 
     def forward(self, x_1, x_2):
+        if type(self.dropout) is nn.Dropout and fused_ok(x_1, x_2, self.dk, self.dv):
+            # own kernels: six-term tensor-core projections + fused attention core (seq_attention.py)
+            p = self.dropout.p if self.training else 0.0
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
+            return seq_cross_attention(x_1, x_2, self.Wq, self.Wk, self.Wv, p, seed)
+        # explicit form: CPU / fp64 truth runs of the tests, and train-mode parity runs that drive the dropout from a mask tape
         a, b = x_1.permute(1, 0, 2), x_2.permute(1, 0, 2)
-        # These projections stay plain fp32 SGEMMs on purpose: with the stock all-ones weights they sum
-        # a LayerNorm output, which is zero up to rounding, so the 2^-17 error of the split-bf16 tensor-core product is
-        # amplified without bound (measured on B200 with lsthm_gemm3w here: dx of sps_s111 off by 2.1e-3).
         q, k, v = a @ self.Wq, b @ self.Wk, b @ self.Wv
         w = self.dropout(torch.softmax((q / self.dk ** 0.5) @ k.transpose(1, 2), dim=-1))
         return (w @ v).permute(1, 0, 2)

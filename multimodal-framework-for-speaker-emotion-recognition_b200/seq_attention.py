@@ -1,0 +1,82 @@
+"""Sequence-level cross-modal attention of the speaker-state family on our own kernels:
+``CrossAttention2/3.forward`` of model/lsthm_sps.py:88-101, 116-129 (same code in lsthm_onlysp.py; lsthm_nsps.py:90-106
+adds a residual + LayerNorm outside).
+
+    Q = x1 Wq,  [K | V] = x2 [Wk | Wv]      two time-parallel GEMMs over all L*B rows, SIX-term bf16 split
+    out = dropout(softmax(Q K^T / sqrt(dk))) V     ``lsthm_xattn_fwd/bwd``: per dialogue, scores stay on the SM
+
+Why six terms in the forward projections: the reference initialises Wq/Wk/Wv to ones and feeds them LayerNorm outputs, so
+every projected value is a sum that cancels to rounding noise; the 2^-17 operand error of the three-term split is 400x
+that noise and reaches dx through dS.K (measured: dx of fixture sps_s111 off by 2.1e-3).  With 24-bit operands the
+tensor-core product is as exact as the fp32 SGEMM it replaces.  The backward products (dx = dQ Wq^T, dW = x^T dQ) have
+no such cancellation and use the ordinary three-term GEMM.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .mm3 import _rows, launches, mm_nt, mm_tn
+
+launches_x = {"xattn": 0}
+
+
+class _ProjX6(torch.autograd.Function):
+    """y[M,N] = x[M,K] @ W[K,N] — forward on the six-term tensor-core product, backward on the three-term one."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        launches["gemm3"] += 1
+        return _lib.gemm3(_lib.GEMM_NN, _rows(x), _rows(w), x6=True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _rows(dy)
+        dx = mm_nt(dy, w) if ctx.needs_input_grad[0] else None
+        dw = mm_tn(x, dy) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+class _SeqAttnCore(torch.autograd.Function):
+    """q [L*B, D], kv [L*B, 2D] (rows time-major: row = i*B + b) -> out [L*B, D]."""
+
+    @staticmethod
+    def forward(ctx, q, kv, B, L, scale, p_drop, seed):
+        D = q.shape[1]
+        q, kv = q.contiguous(), kv.contiguous()
+        out = torch.empty(L * B, D, device=q.device, dtype=torch.float32)
+        lse = torch.empty(B, L, device=q.device, dtype=torch.float32)
+        d = _lib.make_xattn_desc(B, L, D, D, 2 * D, 2 * D, D, scale, p_drop, seed, time_major=True)
+        _lib.xattn_fwd(d, q, kv[:, :D], kv[:, D:], out, lse)
+        launches_x["xattn"] += 1
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.cfg = (B, L, scale, p_drop, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv, out, lse = ctx.saved_tensors
+        B, L, scale, p_drop, seed = ctx.cfg
+        D = q.shape[1]
+        dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+        d = _lib.make_xattn_desc(B, L, D, D, 2 * D, 2 * D, D, scale, p_drop, seed, time_major=True)
+        _lib.xattn_bwd(d, q, kv[:, :D], kv[:, D:], out, lse, dout.contiguous(), dq, dkv[:, :D], dkv[:, D:])
+        launches_x["xattn"] += 1
+        return dq, dkv, None, None, None, None, None
+
+
+def fused_ok(x_1: torch.Tensor, x_2: torch.Tensor, dk: int, dv: int) -> bool:
+    return (x_1.is_cuda and x_1.dtype == torch.float32 and x_2.dtype == torch.float32 and x_1.dim() == 3 and x_1.shape[0] <= 128
+            and dk == dv and dk <= 128 and dk % 4 == 0 and x_1.shape[2] % 4 == 0 and x_2.shape[2] % 4 == 0)
+
+
+def seq_cross_attention(x_1, x_2, Wq, Wk, Wv, p_drop: float = 0.0, seed: int = 0) -> torch.Tensor:
+    """x_1 [L,B,d1] (queries), x_2 [L,B,d2] (keys / values), time-major -> [L,B,dv]."""
+    L, B = x_1.shape[0], x_1.shape[1]
+    dk = Wq.shape[1]
+    q = _ProjX6.apply(x_1.reshape(L * B, -1), Wq)
+    kv = _ProjX6.apply(x_2.reshape(L * B, -1), torch.cat([Wk, Wv], dim=1))
+    out = _SeqAttnCore.apply(q, kv, B, L, 1.0 / dk ** 0.5, float(p_drop), int(seed))
+    return out.view(L, B, -1)
