@@ -165,6 +165,11 @@ template <int AMN, int BMN, int PREC = 0>
 __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_constant__ GemmArgs g) {
     constexpr int kGemmStages = GemmCfg<PREC>::kStages, kStageBytes = GemmCfg<PREC>::kStage, kParts = GemmCfg<PREC>::kParts;
     constexpr bool BF16 = PREC == 1;
+    // six-term mode: the hi.hi products accumulate in columns [0,128), the five correction terms (2^-9 and smaller) in
+    // [128,256); the epilogue adds the two in fp32.  The tensor core's accumulation is not round-to-nearest — measured: one
+    // accumulator taking all 42 UMMAs of a K = 100 product is 3-5x less accurate than an fp32 FMA chain — and its error
+    // scales with the number of UMMAs into the LARGE accumulator; this way that number is 7 instead of 42.
+    constexpr int kTmemCols = PREC == 2 ? 2 * kGemmBN : kGemmBN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw;
     __shared__ __align__(8) uint64_t full_bar[kGemmStages], empty_bar[kGemmStages], done_bar;
@@ -180,7 +185,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
         mbar_fence_init();
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(kGemmBN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -231,20 +236,21 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem), "l"(ah), "l"(bh), "r"(idesc), "r"(acc0) : "memory");
                 if (!BF16) {
+                    const uint32_t tc = PREC == 2 ? tmem + kGemmBN : tmem;          // correction accumulator (six-term mode)
                     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                                 ::"r"(tmem), "l"(ah), "l"(bl), "r"(idesc), "r"(1u) : "memory");
+                                 ::"r"(tc), "l"(ah), "l"(bl), "r"(idesc), "r"(PREC == 2 ? acc0 : 1u) : "memory");
                     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                                 ::"r"(tmem), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                                 ::"r"(tc), "l"(al), "l"(bh), "r"(idesc), "r"(1u) : "memory");
                 }
                 if (PREC == 2) {     // here al / bl are the MID images; the LO images follow them
                     const uint64_t a3 = umma_desc(base + 2 * kTileBytes + ks * a_step, a_lbo, a_sbo);
                     const uint64_t b3 = umma_desc(base + (kParts + 2) * kTileBytes + ks * b_step, b_lbo, b_sbo);
                     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                                 ::"r"(tmem), "l"(ah), "l"(b3), "r"(idesc), "r"(1u) : "memory");
+                                 ::"r"(tmem + kGemmBN), "l"(ah), "l"(b3), "r"(idesc), "r"(1u) : "memory");
                     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                                 ::"r"(tmem), "l"(a3), "l"(bh), "r"(idesc), "r"(1u) : "memory");
+                                 ::"r"(tmem + kGemmBN), "l"(a3), "l"(bh), "r"(idesc), "r"(1u) : "memory");
                     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                                 ::"r"(tmem), "l"(al), "l"(bl), "r"(idesc), "r"(1u) : "memory");
+                                 ::"r"(tmem + kGemmBN), "l"(al), "l"(bl), "r"(idesc), "r"(1u) : "memory");
                 }
             }
             // commit: arrives on the barrier when all MMAs issued so far have completed (implies before_thread_sync)
@@ -269,6 +275,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
                            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (PREC == 2) {
+                uint32_t w[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                               "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                             : "r"(taddr + (uint32_t)kGemmBN));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            }
             if (gm < g.M) {
                 if (n0 + c0 + 16 <= g.N && (g.ldc & 3) == 0) {
 #pragma unroll
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm3_kernel(const __grid_con
     __syncthreads();
     if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kGemmBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
     }
 }
 

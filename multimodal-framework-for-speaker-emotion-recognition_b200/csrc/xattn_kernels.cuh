@@ -2,15 +2,21 @@
 // CrossAttention2 / CrossAttention3.forward after their three projections; model/lsthm_nsps.py:90-106):
 //     out = dropout(softmax(Q K^T / sqrt(d_k))) V        per dialogue, UNMASKED over its L <= 128 utterances,
 // single head, width D <= 128 (128 in lsthm_sps / lsthm_onlysp, 100 in lsthm_nsps), forward and backward, on the
-// tcgen05 tensor cores with the fp32-accurate three-term bf16 split.  The L x L scores, probabilities and dropout
+// tcgen05 tensor cores with a split-bf16 product accurate to fp32 (six terms, see below).  The L x L scores, probabilities and dropout
 // masks never leave the SM (the reference materialises all three in HBM: [B,L,L] x 4 attentions, both passes).
 //
 // Same machinery as attn_kernels.cuh (operand tiles stored once, K-major, in the canonical no-swizzle UMMA layout,
 // re-read through the MN-major view for the transposed products; a thread owns a score row out of TMEM), but a
-// 128-wide operand tile is 64 KB (hi + lo), so the operands cannot all be resident: the forward keeps Q, K, V
-// (192 KB, P aliases Q), the backward walks three 64 KB slots through the chain
-//     S = Q K^T | dPd = dO V^T | Pd -> dV = Pd^T dO | dS -> dQ = dS K, dK = dS^T Q
+// 128-wide operand tile is 96 KB (hi + mid + lo images), so only two operands are resident at a time: the forward runs
+// Q, K -> S -> (P, V) -> O, the backward walks two slots through the chain
+//     S = Q K^T | dPd = dO V^T | Pd -> dV = Pd^T dO | dS -> dQ = dS K | dK = dS^T Q
 // re-staging an operand when its slot has been recycled.  One CTA per dialogue.
+//
+// Precision: every product uses the SIX-term split (operands to 24 bits).  With the family's ones-like projection weights
+// the second-stage keys are almost constant along the feature axis, so logits reach |s| ~ 100 and the 2^-17 operand error
+// of three terms is an ABSOLUTE logit error of 1e-3 — ten times the fp32 reference's own (measured on a 64-dialogue shard:
+// log-prob error 3.7e-3 against a bar of 2.2e-3); the saturated softmax makes the gradient products differences of large
+// terms as well (three terms there: dx 1.7e-2 off).
 #pragma once
 #include "attn_kernels.cuh"
 
@@ -62,6 +68,55 @@ __device__ __forceinline__ void xrow_store(const XRow<NCH> &r, int row, float sc
         split_store8(x, hi + (c0 + i) * 2048 + roff, hi + kSqTile + (c0 + i) * 2048 + roff);
     }
 }
+// three-way split into explicit images (hi, mid, lo)
+template <int NCH>
+__device__ __forceinline__ void xrow_store3(const XRow<NCH> &r, int row, float scale, uint8_t *hi, uint8_t *mid, uint8_t *lo, int c0) {
+    const int roff = (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const float4 a = r.v[2 * i], b = r.v[2 * i + 1];
+        const float x[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+        const int o = (c0 + i) * 2048 + roff;
+        split_store8_3(x, hi + o, mid + o, lo + o);
+    }
+}
+// D[128 x N] (+)= A . B over `ksteps` k16 steps, six split terms: hh + hm + mh + hl + lh + mm.  a[3] / b[3] = shared addresses of the images.
+__device__ __forceinline__ void umma6(uint32_t tmem_d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a_step, uint32_t a_lbo, uint32_t a_sbo,
+                                      uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b_step, uint32_t b_lbo, uint32_t b_sbo,
+                                      uint32_t idesc, int ksteps, uint32_t corr = 128u) {
+    for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t ah = umma_desc(a0 + ks * a_step, a_lbo, a_sbo), am = umma_desc(a1 + ks * a_step, a_lbo, a_sbo),
+                       al = umma_desc(a2 + ks * a_step, a_lbo, a_sbo);
+        const uint64_t bh = umma_desc(b0 + ks * b_step, b_lbo, b_sbo), bm = umma_desc(b1 + ks * b_step, b_lbo, b_sbo),
+                       bl = umma_desc(b2 + ks * b_step, b_lbo, b_sbo);
+        // The hi.hi products go to the accumulator at tmem_d, the five correction terms (2^-9 and smaller) to the one `corr` (128 or 256)
+        // columns further; readers add the two in fp32.  The tensor core's fp32 accumulation is not round-to-nearest (measured
+        // with the GEMM: all 42 UMMAs of a K = 100 product into one accumulator is 3-5x less accurate than an FMA chain, 7 + 35
+        // split this way is more accurate than one), and the products here feed saturated softmaxes.
+        umma_f16(tmem_d, ah, bh, idesc, ks > 0 ? 1u : 0u);
+        umma_f16(tmem_d + corr, ah, bm, idesc, ks > 0 ? 1u : 0u);
+        umma_f16(tmem_d + corr, am, bh, idesc, 1u);
+        umma_f16(tmem_d + corr, ah, bl, idesc, 1u);
+        umma_f16(tmem_d + corr, al, bh, idesc, 1u);
+        umma_f16(tmem_d + corr, am, bm, idesc, 1u);
+    }
+}
+// main + correction accumulator (16 columns of this thread's row)
+__device__ __forceinline__ void tmem_ld16_sum(uint32_t taddr, float (&v)[16]) {
+    float w[16];
+    tmem_ld16x2(taddr, taddr + 128, v, w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += w[i];
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n"
+                 "tcgen05.wait::st.sync.aligned;"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward: 256 threads, thread = (query row r = tid % 128, column half g = tid / 128); 192 KB -> one CTA per SM
@@ -72,46 +127,47 @@ __global__ void __launch_bounds__(256, 1) xattn_fwd_kernel(const __grid_constant
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ uint32_t tmem_base;
     __shared__ float ex[512];
-    uint8_t *sQ = smem, *sK = smem + kXSlot, *sV = smem + 2 * kXSlot, *sP = smem;   // P aliases Q once S is done
+    // [0, 96K): Q hi|mid|lo, later P hi|mid|lo      [96K, 192K): K hi|mid|lo, later V hi|mid|lo
+    uint8_t *sQ = smem, *sK = smem + 3 * kSqTile, *sV = sK, *sP = smem;
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int b = blockIdx.x, L = a.L, D = a.D;
     const size_t grow = (size_t)((long long)b * a.sb + (long long)r * a.si);
     const bool rv = r < L;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     {
         XRow<8> rq, rk;
         xrow_load<8>(rv ? a.q + grow * a.ldq : nullptr, D, 8 * g, rq);
         xrow_load<8>(rv ? a.k + grow * a.ldk : nullptr, D, 8 * g, rk);
-        xrow_store<8>(rq, r, a.scale * kLog2e, sQ, 8 * g);
-        xrow_store<8>(rk, r, 1.f, sK, 8 * g);
+        xrow_store3<8>(rq, r, a.scale * kLog2e, sQ, sQ + kSqTile, sQ + 2 * kSqTile, 8 * g);
+        xrow_store3<8>(rk, r, 1.f, sK, sK + kSqTile, sK + 2 * kSqTile, 8 * g);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base;
-    if (tid == 0) {   // S = Qs K^T : M = query, N = key, K = d (128)
-        umma3<false>(tmem, smem_u32(sQ), kSqTile, 4096u, 2048u, 128u, smem_u32(sK), kSqTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 8);
+    const uint32_t uA = smem_u32(smem), uB = smem_u32(sK);
+    if (tid == 0) {   // S = Qs K^T : M = query, N = key, K = d (128), six terms
+        umma6(tmem, uA, uA + kSqTile, uA + 2 * kSqTile, 4096u, 2048u, 128u, uB, uB + kSqTile, uB + 2 * kSqTile, 4096u, 2048u, 128u,
+              att_idesc(128, 0, 0), 8);
         umma_commit(&bar[0]);
     }
-    {   // V is staged while the score product runs
-        XRow<8> rw;
-        xrow_load<8>(rv ? a.v + grow * a.ldv : nullptr, D, 8 * g, rw);
-        xrow_store<8>(rw, r, 1.f, sV, 8 * g);
-    }
+    XRow<8> rw;       // the V rows are fetched while the score product runs and staged into K's slot once it has retired
+    xrow_load<8>(rv ? a.v + grow * a.ldv : nullptr, D, 8 * g, rw);
     mbar_wait(&bar[0], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    xrow_store3<8>(rw, r, 1.f, sV, sV + kSqTile, sV + 2 * kSqTile, 8 * g);
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int cb = 64 * g;
     float mx = -INFINITY, sum = 0.f;
     {
         float v[16];
         for (int c0 = cb; c0 < cb + 64; c0 += 16) {
-            tmem_ld16(trow + c0, v);
+            tmem_ld16_sum(trow + c0, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
                 if (c0 + j < L) mx = fmaxf(mx, v[j]);
@@ -123,7 +179,7 @@ __global__ void __launch_bounds__(256, 1) xattn_fwd_kernel(const __grid_constant
         const int roff = (r >> 3) * 128 + (r & 7) * 16;
         float p8[8];
         for (int c0 = cb; c0 < cb + 64; c0 += 16) {
-            tmem_ld16(trow + c0, v);
+            tmem_ld16_sum(trow + c0, v);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -139,8 +195,8 @@ __global__ void __launch_bounds__(256, 1) xattn_fwd_kernel(const __grid_constant
                     }
                     p8[j] = e0; p8[j + 1] = e1;
                 }
-                const int chunk = (c0 >> 3) + half;
-                split_store8(p8, sP + chunk * 2048 + roff, sP + kSqTile + chunk * 2048 + roff);
+                const int o = ((c0 >> 3) + half) * 2048 + roff;
+                split_store8_3(p8, sP + o, sP + kSqTile + o, sP + 2 * kSqTile + o);
             }
         }
         ex[256 + tid] = sum;
@@ -149,8 +205,9 @@ __global__ void __launch_bounds__(256, 1) xattn_fwd_kernel(const __grid_constant
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {   // O = P V : M = query, N = d (MN-major view of V), K = key (128)
-        umma3<false>(tmem + 128, smem_u32(sP), kSqTile, 4096u, 2048u, 128u, smem_u32(sV), kSqTile, 256u, 128u, 2048u, att_idesc(128, 0, 1), 8);
+    if (tid == 0) {   // O = P V : M = query, N = d (MN-major view of V), K = key (128), six terms
+        umma6(tmem + 256, uA, uA + kSqTile, uA + 2 * kSqTile, 4096u, 2048u, 128u, uB, uB + kSqTile, uB + 2 * kSqTile, 256u, 128u, 2048u,
+              att_idesc(128, 0, 1), 8);
         umma_commit(&bar[1]);
     }
     sum += ex[256 + (tid ^ 128)];
@@ -163,7 +220,7 @@ __global__ void __launch_bounds__(256, 1) xattn_fwd_kernel(const __grid_constant
         float *orow = a.out + grow * a.ldo;
         for (int c0 = cb; c0 < cb + 64; c0 += 16) {
             if (c0 >= D) break;
-            tmem_ld16(trow + 128 + c0, v);
+            tmem_ld16_sum(trow + 256 + c0, v);
             if (rv) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
@@ -177,188 +234,200 @@ __global__ void __launch_bounds__(256, 1) xattn_fwd_kernel(const __grid_constant
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: 512 threads, thread = (row r = tid % 128, column quarter g = tid / 128); three 64 KB slots X, Y, Z
-// TMEM: S [0,128) -> later dK | dPd [128,256) | dV [256,384) | dQ [384,512)
+// backward: 512 threads, thread = (row r = tid % 128, column quarter g = tid / 128).  Every operand is a three-image
+// (hi | mid | lo) 96 KB slot and every product has six terms; two slots A, B:
+//     A <- Qs, B <- K  : S   = Qs K^T            -> TMEM [0,128)
+//     A <- dO, B <- V  : dPd = dO V^T            -> TMEM [128,256)
+//     B <- Pd          : dV  = Pd^T dO  (B, A)   -> TMEM [256,384)
+//     B <- dS, A <- K  : dQs = dS K     (B, A)   -> TMEM [384,512)
+//     A <- Qs          : dK  = dS^T Qs  (B, A)   -> TMEM [0,128)   (S is dead by then)
+// The rows of the next operand are fetched into registers while the current product runs.
+// Six terms everywhere: with near-constant keys the softmax saturates and dS = P (dPd - delta), dQ = dS K are differences of
+// large, almost equal terms — the three-term split left dx of a perturbed-weights fixture 1.7e-2 off.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1) xattn_bwd_kernel(const __grid_constant__ XAttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ __align__(8) uint64_t bar[5];
     __shared__ uint32_t tmem_base;
-    __shared__ float ex[512];
-    uint8_t *sX = smem, *sY = smem + kXSlot, *sZ = smem + 2 * kXSlot;
+    __shared__ float ex[512], ex2[512];
+    constexpr int kImg = kSqTile, kSlot3 = 3 * kSqTile;
+    uint8_t *sA = smem, *sB = smem + kSlot3;
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, g = tid >> 7;
     const int b = blockIdx.x, L = a.L, D = a.D;
     const size_t grow = (size_t)((long long)b * a.sb + (long long)r * a.si);
     const bool rv = r < L;
-    if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); mbar_fence_init(); }
+    if (tid == 0) { for (int i = 0; i < 5; ++i) mbar_init(&bar[i], 1); mbar_fence_init(); }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const float qscale = a.scale * kLog2e;
-    const uint32_t uX = smem_u32(sX), uY = smem_u32(sY), uZ = smem_u32(sZ);
+    const uint32_t uA = smem_u32(sA), uB = smem_u32(sB);
     const int roff = (r >> 3) * 128 + (r & 7) * 16, cb = 32 * g;
-    // ---- X <- Qs, Y <- K
-    {
-        XRow<4> rq, rk;
-        xrow_load<4>(rv ? a.q + grow * a.ldq : nullptr, D, 4 * g, rq);
-        xrow_load<4>(rv ? a.k + grow * a.ldk : nullptr, D, 4 * g, rk);
-        xrow_store<4>(rq, r, qscale, sX, 4 * g);
-        xrow_store<4>(rk, r, 1.f, sY, 4 * g);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    auto stage = [&](const XRow<4> &x, float sc, uint8_t *slot) { xrow_store3<4>(x, r, sc, slot, slot + kImg, slot + 2 * kImg, 4 * g); };
+    auto publish = [&]() {       // generic-proxy stores -> visible to the UMMAs; all threads' tiles complete
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    auto retire = [&](int i) {
+        mbar_wait(&bar[i], 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    // operand descriptors: K-major row tile (k16 step, LBO, SBO) = (4096, 2048, 128); MN-major view of the same bytes = (256, 128, 2048)
+    XRow<4> x0, x1;
+    xrow_load<4>(rv ? a.q + grow * a.ldq : nullptr, D, 4 * g, x0);
+    xrow_load<4>(rv ? a.k + grow * a.ldk : nullptr, D, 4 * g, x1);
+    stage(x0, qscale, sA);
+    stage(x1, 1.f, sB);
+    publish();
     const uint32_t tmem = tmem_base;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    if (tid == 0) {   // S = Qs K^T
-        umma3<false>(tmem, uX, kSqTile, 4096u, 2048u, 128u, uY, kSqTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 8);
+    if (tid == 0) {   // S = Qs K^T: exactly the forward's product (its row log-sum-exp is reused)
+        umma6(tmem, uA, uA + kImg, uA + 2 * kImg, 4096u, 2048u, 128u, uB, uB + kImg, uB + 2 * kImg, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 8);
         umma_commit(&bar[0]);
     }
-    // ---- Z <- dO (while S runs); delta = rowsum(dO * O)
-    float delta = 0.f;
-    {
-        XRow<4> rd, ro;
-        xrow_load<4>(rv ? a.dout + grow * a.ldo : nullptr, D, 4 * g, rd);
-        xrow_load<4>(rv ? a.o + grow * a.ldo : nullptr, D, 4 * g, ro);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            delta += rd.v[i].x * ro.v[i].x + rd.v[i].y * ro.v[i].y + rd.v[i].z * ro.v[i].z + rd.v[i].w * ro.v[i].w;
-        xrow_store<4>(rd, r, 1.f, sZ, 4 * g);
-        ex[tid] = delta;
-    }
-    const float lse = rv ? __ldg(a.lse + (size_t)b * L + r) : 0.f;
-    mbar_wait(&bar[0], 0);                                   // S done: X is free
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- X <- V
-    {
-        XRow<4> rw;
-        xrow_load<4>(rv ? a.v + grow * a.ldv : nullptr, D, 4 * g, rw);
-        xrow_store<4>(rw, r, 1.f, sX, 4 * g);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    xrow_load<4>(rv ? a.dout + grow * a.ldo : nullptr, D, 4 * g, x0);
+    xrow_load<4>(rv ? a.v + grow * a.ldv : nullptr, D, 4 * g, x1);
+    retire(0);
+    stage(x0, 1.f, sA);                                      // A <- dO
+    stage(x1, 1.f, sB);                                      // B <- V
+    publish();
     if (tid == 0) {   // dPd = dO V^T
-        umma3<false>(tmem + 128, uZ, kSqTile, 4096u, 2048u, 128u, uX, kSqTile, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 8);
+        umma6(tmem + 256, uA, uA + kImg, uA + 2 * kImg, 4096u, 2048u, 128u, uB, uB + kImg, uB + 2 * kImg, 4096u, 2048u, 128u, att_idesc(128, 0, 0), 8);
         umma_commit(&bar[1]);
     }
-    delta = (ex[r] + ex[r + 128]) + (ex[r + 256] + ex[r + 384]);
-    mbar_wait(&bar[1], 0);                                   // dPd done: X (V) is free
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const AttDrop drop(a.seed, blockIdx.x, r, a.p_drop);
-    // ---- pass 1: Pd -> X
+    xrow_load<4>(rv ? a.k + grow * a.ldk : nullptr, D, 4 * g, x1);      // K again, for dQ
+    // Row statistics recomputed from S while dPd runs: p_j = 2^(s_j - max) / sum, normalised exactly as a softmax kernel would.
+    // (Using the forward's log-sum-exp instead leaves sum_j p_j = 1 + O(|lse| 2^-24); with delta formed from the same p that
+    // relative error multiplies delta ~ 100 on saturated rows and swamps dS.)
+    float mx = -INFINITY, inv = 0.f;
     {
-        float s[16], p8[8];
+        float s[16];
+#pragma unroll
+        for (int c0 = cb; c0 < cb + 32; c0 += 16) {
+            tmem_ld16_sum(trow + c0, s);
+            tmem_st16(trow + c0, s);                      // S = main + correction, folded in place: columns [128,256) are free again
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < L) mx = fmaxf(mx, s[j]);
+        }
+        ex[tid] = mx;
+        __syncthreads();
+        mx = fmaxf(fmaxf(ex[r], ex[r + 128]), fmaxf(ex[r + 256], ex[r + 384]));
+        float sum = 0.f;
 #pragma unroll
         for (int c0 = cb; c0 < cb + 32; c0 += 16) {
             tmem_ld16(trow + c0, s);
 #pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < L) sum += fast_exp2(s[j] - mx);
+        }
+        ex2[tid] = sum;
+        __syncthreads();
+        sum = (ex2[r] + ex2[r + 128]) + (ex2[r + 256] + ex2[r + 384]);
+        inv = rv ? 1.0f / sum : 0.f;
+    }
+    retire(1);
+    const AttDrop drop(a.seed, blockIdx.x, r, a.p_drop);
+    // delta_i = sum_j Pd_ij dPd_ij from the SAME accumulator values that form dS below (not rowsum(dO * O): on a saturated
+    // row dS = p (dPd - delta) is the difference of two nearly equal numbers, and two differently rounded evaluations of
+    // delta leave 1e-5-sized residues where the true value is 1e-7; measured: dx of fixture onlysp_s122 4.4e-3 off)
+    float delta = 0.f;
+    {   // pass 1: Pd -> B, partial delta
+        float s[16], gg[16], p8[8];
+#pragma unroll
+        for (int c0 = cb; c0 < cb + 32; c0 += 16) {
+            tmem_ld16(trow + c0, s);
+            tmem_ld16_sum(trow + 256 + c0, gg);
+            tmem_st16(trow + 256 + c0, gg);               // dPd folded in place: columns [384,512) are free again
+#pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {
                     const int col = c0 + half * 8 + j, i0 = half * 8 + j;
-                    const float p0 = (rv && col < L) ? fast_exp2(s[i0] - lse) : 0.f;
-                    const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - lse) : 0.f;
+                    const float p0 = (rv && col < L) ? fast_exp2(s[i0] - mx) * inv : 0.f;
+                    const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - mx) * inv : 0.f;
                     float s0 = 1.f, s1 = 1.f;
                     if (drop.on) drop.pair(col >> 1, s0, s1);
                     p8[j] = p0 * s0; p8[j + 1] = p1 * s1;
+                    delta = fmaf(p8[j], gg[i0], delta);
+                    delta = fmaf(p8[j + 1], gg[i0 + 1], delta);
                 }
-                const int chunk = (c0 >> 3) + half;
-                split_store8(p8, sX + chunk * 2048 + roff, sX + kSqTile + chunk * 2048 + roff);
+                const int o = ((c0 >> 3) + half) * 2048 + roff;
+                split_store8_3(p8, sB + o, sB + kImg + o, sB + 2 * kImg + o);
             }
         }
+        ex[tid] = delta;
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    publish();
+    delta = (ex[r] + ex[r + 128]) + (ex[r + 256] + ex[r + 384]);
     if (tid == 0) {   // dV = Pd^T dO : M = key (MN view of Pd), N = d (MN view of dO), K = query
-        umma3<false>(tmem + 256, uX, kSqTile, 256u, 128u, 2048u, uZ, kSqTile, 256u, 128u, 2048u, att_idesc(128, 1, 1), 8);
+        umma6(tmem + 128, uB, uB + kImg, uB + 2 * kImg, 256u, 128u, 2048u, uA, uA + kImg, uA + 2 * kImg, 256u, 128u, 2048u, att_idesc(128, 1, 1), 8, 256u);
         umma_commit(&bar[2]);
     }
-    // the Q rows for the last product are fetched while dV runs
-    XRow<4> rq2;
-    xrow_load<4>(rv ? a.q + grow * a.ldq : nullptr, D, 4 * g, rq2);
-    mbar_wait(&bar[2], 0);                                   // dV done: X (Pd) and Z (dO) are free
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    xrow_store<4>(rq2, r, qscale, sZ, 4 * g);                // Z <- Qs
-    // ---- pass 2: dS -> X
-    {
+    retire(2);                                               // A (dO) and B (Pd) are free
+    stage(x1, 1.f, sA);                                      // A <- K
+    xrow_load<4>(rv ? a.q + grow * a.ldq : nullptr, D, 4 * g, x0);      // Q again, for dK
+    {   // pass 2: dS -> B
         float s[16], gg[16], d8[8];
 #pragma unroll
         for (int c0 = cb; c0 < cb + 32; c0 += 16) {
-            tmem_ld16x2(trow + c0, trow + 128 + c0, s, gg);
+            tmem_ld16x2(trow + c0, trow + 256 + c0, s, gg);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
                 for (int j = 0; j < 8; j += 2) {
                     const int col = c0 + half * 8 + j, i0 = half * 8 + j;
-                    const float p0 = (rv && col < L) ? fast_exp2(s[i0] - lse) : 0.f;
-                    const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - lse) : 0.f;
+                    const float p0 = (rv && col < L) ? fast_exp2(s[i0] - mx) * inv : 0.f;
+                    const float p1 = (rv && col + 1 < L) ? fast_exp2(s[i0 + 1] - mx) * inv : 0.f;
                     float s0 = 1.f, s1 = 1.f;
                     if (drop.on) drop.pair(col >> 1, s0, s1);
                     d8[j] = p0 * (s0 * gg[i0] - delta); d8[j + 1] = p1 * (s1 * gg[i0 + 1] - delta);
                 }
-                const int chunk = (c0 >> 3) + half;
-                split_store8(d8, sX + chunk * 2048 + roff, sX + kSqTile + chunk * 2048 + roff);
+                const int o = ((c0 >> 3) + half) * 2048 + roff;
+                split_store8_3(d8, sB + o, sB + kImg + o, sB + 2 * kImg + o);
             }
         }
     }
-    // drain dV while the other threads finish their pass (it does not touch the slots)
-    {
-        float v[16];
-        float *dst = a.dv + grow * a.lddv;
+    publish();                                               // also: every thread has finished reading S and dPd
+    if (tid == 0) {   // dQs = dS K : M = query, N = d (MN view of K), K = key
+        umma6(tmem, uB, uB + kImg, uB + 2 * kImg, 4096u, 2048u, 128u, uA, uA + kImg, uA + 2 * kImg, 256u, 128u, 2048u, att_idesc(128, 0, 1), 8, 256u);
+        umma_commit(&bar[3]);
+    }
+    auto drain = [&](uint32_t tcol, float *dst, float mul) {      // main at tcol, correction 256 columns further
+        float v[16], w[16];
         for (int c0 = cb; c0 < cb + 32; c0 += 16) {
             if (c0 >= D) break;
-            tmem_ld16(trow + 256 + c0, v);
+            tmem_ld16x2(trow + tcol + c0, trow + tcol + 256 + c0, v, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
             if (rv) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4)
                     if (c0 + 4 * q4 < D)
-                        reinterpret_cast<float4 *>(dst + c0)[q4] = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        reinterpret_cast<float4 *>(dst + c0)[q4] =
+                            make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
             }
         }
+    };
+    drain(128u, a.dv + grow * a.lddv, 1.f);                  // dV leaves while dQ runs
+    retire(3);                                               // A (K) is free
+    stage(x0, qscale, sA);                                   // A <- Qs
+    publish();
+    if (tid == 0) {   // dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
+        umma6(tmem + 128, uB, uB + kImg, uB + 2 * kImg, 256u, 128u, 2048u, uA, uA + kImg, uA + 2 * kImg, 256u, 128u, 2048u, att_idesc(128, 1, 1), 8, 256u);
+        umma_commit(&bar[4]);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                                         // dS and Qs tiles complete; every thread has read S and dPd
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0) {
-        // dQs = dS K : M = query, N = d (MN view of K), K = key ;  dK = dS^T Qs : M = key (MN view of dS), N = d (MN view of Qs), K = query
-        umma3<false>(tmem + 384, uX, kSqTile, 4096u, 2048u, 128u, uY, kSqTile, 256u, 128u, 2048u, att_idesc(128, 0, 1), 8);
-        umma3<false>(tmem, uX, kSqTile, 256u, 128u, 2048u, uZ, kSqTile, 256u, 128u, 2048u, att_idesc(128, 1, 1), 8);
-        umma_commit(&bar[3]);
-    }
-    mbar_wait(&bar[3], 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-        float v[16];
-        for (int which = 0; which < 2; ++which) {
-            // d/dq = scale * (dS K);  the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
-            float *dst = which == 0 ? a.dq + grow * a.lddq : a.dk + grow * a.lddk;
-            const float mul = which == 0 ? a.scale : kLn2;
-            const uint32_t tcol = which == 0 ? 384u : 0u;
-            for (int c0 = cb; c0 < cb + 32; c0 += 16) {
-                if (c0 >= D) break;
-                tmem_ld16(trow + tcol + c0, v);
-                if (rv) {
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4)
-                        if (c0 + 4 * q4 < D)
-                            reinterpret_cast<float4 *>(dst + c0)[q4] =
-                                make_float4(v[4 * q4] * mul, v[4 * q4 + 1] * mul, v[4 * q4 + 2] * mul, v[4 * q4 + 3] * mul);
-                }
-            }
-        }
-    }
+    drain(0u, a.dq + grow * a.lddq, a.scale);              // d/dq = scale * (dS K)
+    retire(4);
+    drain(128u, a.dk + grow * a.lddk, kLn2);                   // the staged q carries an extra log2(e): d/dk = (dS^T Qs) / log2(e)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
