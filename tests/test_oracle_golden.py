@@ -145,3 +145,24 @@ def test_gru_variant_port_matches_live_reference(variant, train, perturb):
             assert p[n].grad is None or float(p[n].grad.abs().max()) == 0.0, n
         elif float(q.grad.norm()) > 1e-6 * gmax:
             assert e(p[n].grad, q.grad) < 1e-3, (n, e(p[n].grad, q.grad))
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("variant", ["sps", "onlysp", "nsps"])
+def test_speaker_family_state_dict_and_init_match_live_reference(variant):
+    """Drop-in boundary: parameter names, shapes, registration order — including the never-used tensors — and
+    the default-init RNG order are those of the reference, so checkpoints load both ways and seed_everything gives equal weights."""
+    import lsthm_b200
+    ref = load_reference()
+    ours = {"sps": lambda: lsthm_b200.lsthm_sps.MARN1_sps(6), "onlysp": lambda: lsthm_b200.lsthm_onlysp.MARN1_onlysp(6),
+            "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP")}[variant]
+    theirs = {"sps": lambda: ref.MARN1_sps(6), "onlysp": lambda: ref.MARN1_onlysp(6), "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP")}[variant]
+    torch.manual_seed(111)
+    a = ours()
+    torch.manual_seed(111)
+    b = theirs()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    assert all(sa[k].shape == sb[k].shape and torch.equal(sa[k], sb[k]) for k in sa)
+    b.load_state_dict(sa)
+    a.load_state_dict(sb)
