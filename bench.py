@@ -40,8 +40,14 @@ FLOP_FWD_PER_UTT = 999_936
 FLOP_BWD_PER_UTT = 999_936
 
 
+SPEAKER_KINDS = ("sps", "onlysp", "nsps")
+# GRU speaker-state cell (lsthm_onlysp / lsthm_nsps), per direction: W_hh product + two LSTHM1 gate products + collapsed attention
+GSP_FLOP_FWD = 98_304 + 786_432 + 82_432
+GSP_FLOP_BWD = 98_304 + 786_432 + 3 * 82_432
+
+
 def model_name(kind):
-    return "HybridRNN_ATV" if kind == "ATV" else "MARN1_sps"
+    return {"ATV": "HybridRNN_ATV", "sps": "MARN1_sps", "onlysp": "MARN1_onlysp", "nsps": "MARN1_nsps"}[kind]
 
 
 def metric_name(kind):
@@ -108,7 +114,7 @@ def synthetic_batch(seed, T, B, device=None, pinned=False, model="ATV"):
     labels = torch.multinomial(p, T * B, replacement=True, generator=g)
     umask = torch.ones(B, T)
     out = [x, labels, umask]
-    if model == "sps":
+    if model in SPEAKER_KINDS:
         spk = torch.randint(0, 2, (B,), generator=g)
         qmask = torch.zeros(T, B, 2)
         for t in range(T):
@@ -153,8 +159,9 @@ def reference_step_fn(kind, B, device="cpu", T=T_LEN, seed=111):
             loss = loss_fn(model(x), labels, umask)       # HybridRNN_AT(V).py: forward(x) -> [T*B, C] probabilities, time-major
             loss.backward()
             return loss
-    elif kind == "sps":
-        model = ns.MARN1_sps(6).to(device).train()
+    elif kind in SPEAKER_KINDS:
+        model = {"sps": lambda: ns.MARN1_sps(6), "onlysp": lambda: ns.MARN1_onlysp(6), "nsps": lambda: ns.MARN1_nsps(6, "IEMOCAP")}[kind]()
+        model = model.to(device).train()
         x, labels, umask, qmask = [t.to(device) for t in synthetic_batch(seed, T, B, model="sps")]
         lab_bm = labels.view(T, B).t().reshape(-1)        # lsthm_sps.py:392-393 returns batch-major rows
 
@@ -234,8 +241,8 @@ def time_eager_gpu(kind, B, steps, warm, dev):
 
 
 def run_cpu_baseline(steps=2, B=32, model_kind="ATV"):
-    if model_kind == "sps":
-        B = 8                                  # the sps reference loops over the batch in Python: ~6x slower per utterance
+    if model_kind in SPEAKER_KINDS:
+        B = 8                                  # these reference models loop over the batch in Python: ~6x slower per utterance
     return time_cpu(model_kind, B, steps)
 
 
@@ -328,7 +335,7 @@ def run_ours(args):
         return forward_of(model, kind, batch)
     reducer = ddp.GradAllReducer(model, world) if world > 1 else None
     # two host batches (pinned) so consecutive steps see different data; device-resident copies for `value`
-    host = [synthetic_batch(111 + 7 * rank + i, T, B, pinned=True, model=kind) for i in range(2)]
+    host = [synthetic_batch(111 + 7 * rank + i, T, B, pinned=True, model="ATV" if kind == "ATV" else "sps") for i in range(2)]
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     utt_per_step = T * B * world
 
@@ -607,6 +614,15 @@ def run_ours(args):
                   "bwd": 4 * (D + MH + MH + MH + 2 * D + D + G + G + 8 + 4 * MH + G + G + MH + G)}
             din = D_IN
             passes = 3                                              # hi.hi + hi.lo + lo.hi per product term
+        elif kind in ("onlysp", "nsps"):
+            flop_utt = GSP_FLOP_BWD if dom == "bwd" else GSP_FLOP_FWD      # per direction = per launch
+            kname = f"sps_{dom}_kernel<7,1>"
+            info = _l.gsp_launch_info(_l.make_gsp_desc(T, B, 1 if kind == "nsps" else 0))
+            # one direction: gx 1024 + gxs 384 + out 512 + stash (1024 gates + 256 states + 512 GRU + 128 qs); bwd: dout + stash reads + adjoints
+            by = {"fwd": 4 * (1024 + 384 + 512 + 1024 + 256 + 512 + 128), "bwd": 4 * (512 + 1024 + 2 * 256 + 512 + 128 + 1024 + 2 * 384)}
+            by_alg = {"fwd": 800 + 3584, "bwd": 2 * (800 + 3584)}
+            din = 1124
+            passes = 1
         else:
             flop_utt = SPS_FLOP_BWD if dom == "bwd" else SPS_FLOP_FWD      # per direction = per launch
             kname = f"sps_{dom}_kernel"
@@ -684,8 +700,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="dialogues per GPU")
     ap.add_argument("--seq", type=int, default=T_LEN)
-    ap.add_argument("--model", default="ATV", choices=["ATV", "sps"],
-                    help="ATV = BASELINE.json configs[1] (headline); sps = configs[2] shapes (speaker-state model, fp32)")
+    ap.add_argument("--model", default="ATV", choices=["ATV", "sps", "onlysp", "nsps"],
+                    help="ATV = BASELINE.json configs[1] (headline); sps = configs[2] shapes (speaker-state model, fp32); "
+                         "onlysp / nsps = the GRU speaker-state variants (train.py's default model and its listener form)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="f32: every tensor-core product is the fp32-accurate split (parity mode, the metric's precision); "
                          "bf16: time-parallel products with bf16 operands (tests/test_bf16_gpu.py states the tolerance)")
