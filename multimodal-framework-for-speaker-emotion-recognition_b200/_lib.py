@@ -198,7 +198,16 @@ def _dev_ptr(t: Optional[torch.Tensor], name: str) -> Optional[int]:
         raise RuntimeError(f"{name}: expected a contiguous tensor")
     if t.data_ptr() % 16:
         raise RuntimeError(f"{name}: storage must be 16-byte aligned")
+    _on_current_device(t, name)
     return t.data_ptr()
+
+
+def _on_current_device(t: torch.Tensor, name: str) -> None:
+    """The library launches on the calling thread's current device and stream: a tensor of another GPU would be
+    dereferenced on the wrong device.  Fail loudly instead (wrap the call in ``torch.cuda.device(t.device)``)."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                           "(call under torch.cuda.device(tensor.device))")
 
 
 def _stream() -> int:
@@ -454,6 +463,7 @@ def _mat(t: torch.Tensor, name: str):
         raise RuntimeError(f"{name}: expected a 2-D float32 CUDA tensor with contiguous rows")
     if t.data_ptr() % 16 or t.stride(0) % 4:
         raise RuntimeError(f"{name}: rows must be 16-byte aligned (leading dimension multiple of 4)")
+    _on_current_device(t, name)
     return t.data_ptr(), t.stride(0)
 
 
@@ -511,6 +521,7 @@ def make_attn_desc(B, L, H, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, d_hea
 def _f32_cuda(t: torch.Tensor, name: str) -> int:
     if not (t.is_cuda and t.dtype == torch.float32 and t.data_ptr() % 16 == 0):
         raise RuntimeError(f"{name}: expected a 16-byte aligned float32 CUDA tensor")
+    _on_current_device(t, name)
     return t.data_ptr()
 
 

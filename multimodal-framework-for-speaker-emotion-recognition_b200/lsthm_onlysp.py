@@ -105,10 +105,10 @@ class MARN1_onlysp(nn.Module):
         h_b = self.marn_cell_b(torch.cat([r_l, r_a], -1), r_l, r_a, reverse_seq(qmask, umask))
         h_b = self.dropout_rec(reverse_seq(h_b, umask))
         h = torch.cat([h_f, h_b], dim=-1)
-        attn1 = self.crossatt_l2a(self.w * x_l, self.v * x_a)
-        attn2 = self.crossatt_a2l(self.v * x_a, self.w * x_l)
-        attn1 = self.crossatt_l2a_1(self.v * x_a, self.v1 * attn1)
-        attn2 = self.crossatt_a2l_1(self.w * x_l, self.v2 * attn2)
+        attn1 = self.crossatt_l2a(x_l, x_a, self.w, self.v)          # CA2(w x_l, v x_a)          lsthm_onlysp.py:287-288
+        attn2 = self.crossatt_a2l(x_a, x_l, self.v, self.w)
+        attn1 = self.crossatt_l2a_1(x_a, attn1, self.v, self.v1)     # CA3(v x_a, v1 attn1)       lsthm_onlysp.py:292-293
+        attn2 = self.crossatt_a2l_1(x_l, attn2, self.w, self.v2)
         y = self.nn_out[2](self.nn_out[1](linear3(torch.cat([h, attn1, attn2], dim=-1), self.nn_out[0].weight, self.nn_out[0].bias)))
         output = F.log_softmax(linear3(y, self.nn_out[3].weight, self.nn_out[3].bias), 2).permute(1, 0, 2)
         return output.reshape(-1, output.size(-1)), x_l, x_a

@@ -36,6 +36,15 @@ class LSTHM1(nn.Module):
         """W x plus the four biases, for all steps at once (time-parallel part of lines 29-34)."""
         return linear3(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias + self.S.bias)
 
+    def forward(self, x, ctm, htm, ztm, speaker_affine):
+        """One step in the reference's signature (lsthm_sps.py:28-44), for callers that drive a cell by hand; plain tensor
+        expressions — the model never calls it (its cells run inside the fused kernels)."""
+        s = self.W(x) + self.U(htm) + self.V(ztm) + self.S(speaker_affine)
+        d = self.cell_size
+        f, i, o = torch.sigmoid(s[:, :d]), torch.sigmoid(s[:, d:2 * d]), torch.sigmoid(s[:, 2 * d:3 * d])
+        c = f * ctm + i * torch.tanh(s[:, 3 * d:])
+        return c, torch.tanh(c) * o
+
 
 class CrossAttention(nn.Module):
     """In-cell rank-1 attention parameters (lsthm_sps.py:47-57); evaluated inside the kernel."""
@@ -47,6 +56,13 @@ class CrossAttention(nn.Module):
         self.Wk = nn.Parameter(torch.ones(self.dh).unsqueeze(0))
         self.Wv = nn.Parameter(torch.ones(self.dh).unsqueeze(0))
         self.dropout = nn.Dropout(attn_dropout)
+
+    def forward(self, x_1, x_2):
+        """One call in the reference's signature (lsthm_sps.py:59-72), in the collapsed rank-1 form the kernels use
+        (a_i = x1_i (Wq.x2)/sqrt(128); out_i = sum_j dropout(softmax_j(a_i Wk_j)) x2_j); never called by the model."""
+        a = x_1 * ((x_2 * self.Wq).sum(-1, keepdim=True) / self.dh ** 0.5)              # [N, D]
+        w = self.dropout(torch.softmax(a.unsqueeze(-1) * self.Wk.view(1, 1, -1), dim=-1))   # [N, D, D]
+        return torch.matmul(w, x_2.unsqueeze(-1)).squeeze(-1)
 
 
 class _SeqCrossAttention(nn.Module):
@@ -60,13 +76,22 @@ class _SeqCrossAttention(nn.Module):
         self.Wv = nn.Parameter(torch.ones(d_kv, self.dv))
         self.dropout = nn.Dropout(attn_dropout)
 
-    def forward(self, x_1, x_2):
+    def forward(self, x_1, x_2, s_1=None, s_2=None):
+        """``s_1`` / ``s_2``: optional learnable scalars multiplying x_1 / x_2 (``self.w * x_l`` etc., lsthm_sps.py:377-383).
+        On the fused path they are folded into the projection weights — (s x) W = x (s W): a [d, 128] product instead of an
+        [L, B, d] one, forward and backward."""
         if type(self.dropout) is nn.Dropout and fused_ok(x_1, x_2, self.dk, self.dv):
             # own kernels: six-term tensor-core projections + fused attention core (seq_attention.py)
             p = self.dropout.p if self.training else 0.0
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
-            return seq_cross_attention(x_1, x_2, self.Wq, self.Wk, self.Wv, p, seed)
+            Wq = self.Wq if s_1 is None else self.Wq * s_1
+            Wk, Wv = (self.Wk, self.Wv) if s_2 is None else (self.Wk * s_2, self.Wv * s_2)
+            return seq_cross_attention(x_1, x_2, Wq, Wk, Wv, p, seed)
         # explicit form: CPU / fp64 truth runs of the tests, and train-mode parity runs that drive the dropout from a mask tape
+        if s_1 is not None:
+            x_1 = s_1 * x_1
+        if s_2 is not None:
+            x_2 = s_2 * x_2
         a, b = x_1.permute(1, 0, 2), x_2.permute(1, 0, 2)
         q, k, v = a @ self.Wq, b @ self.Wk, b @ self.Wv
         w = self.dropout(torch.softmax((q / self.dk ** 0.5) @ k.transpose(1, 2), dim=-1))
@@ -169,10 +194,10 @@ class MARN1_sps(nn.Module):
         h_b = self.marn_cell_b(x, reverse_seq(x_l, umask), reverse_seq(x_a, umask), reverse_seq(qmask, umask))
         h_b = self.dropout_rec(reverse_seq(h_b, umask))
         h = torch.cat([h_f, h_b], dim=-1)
-        attn1 = self.crossatt_l2a(self.w * x_l, self.v * x_a)
-        attn2 = self.crossatt_a2l(self.v * x_a, self.w * x_l)
-        attn1 = self.crossatt_l2a_1(self.v * x_a, self.v1 * attn1)
-        attn2 = self.crossatt_a2l_1(self.w * x_l, self.v2 * attn2)
+        attn1 = self.crossatt_l2a(x_l, x_a, self.w, self.v)          # CA2(w x_l, v x_a)          lsthm_sps.py:377-378
+        attn2 = self.crossatt_a2l(x_a, x_l, self.v, self.w)
+        attn1 = self.crossatt_l2a_1(x_a, attn1, self.v, self.v1)     # CA3(v x_a, v1 attn1)       lsthm_sps.py:382-383
+        attn2 = self.crossatt_a2l_1(x_l, attn2, self.w, self.v2)
         output = self.fc[2](self.fc[1](linear3(torch.cat([h, attn1, attn2], dim=-1), self.fc[0].weight, self.fc[0].bias)))
         output = F.log_softmax(self.nn_out(output + x_l + x_a), 2).permute(1, 0, 2)
         return output.reshape(-1, output.size(-1)), x_l, x_a

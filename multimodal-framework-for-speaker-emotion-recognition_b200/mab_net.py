@@ -22,8 +22,9 @@ _MODS = ("l", "a", "v")
 
 class LSTHM(nn.Module):
     """Parameter container of one LSTHM cell (model/HybridRNN_ATV.py:12-19).  Its arithmetic
-    (lines 21-37) runs inside the fused recurrence kernel; ``forward`` is kept for API parity and
-    evaluates a single step through that same kernel path by delegating to the owner network."""
+    (lines 21-37) runs inside the fused recurrence kernel when the owner network's ``forward`` is called; ``forward`` here
+    is the reference's single-step signature, kept for callers that drive a cell by hand (plain tensor expressions — the
+    network never calls it)."""
 
     def __init__(self, cell_size, in_size, hybrid_in_size):
         super().__init__()
@@ -35,6 +36,14 @@ class LSTHM(nn.Module):
     def gate_input(self, x: torch.Tensor) -> torch.Tensor:
         """W x + bW + bU + bV for all steps at once (the hoisted, time-parallel part of line 23-27)."""
         return linear3(x, self.W.weight, self.W.bias + self.U.bias + self.V.bias)
+
+    def forward(self, x, ctm, htm, ztm):
+        """One step, HybridRNN_ATV.py:21-37: gates f|i|o|g of W x + U h + V z -> (c_t, h_t)."""
+        s = self.W(x) + self.U(htm) + self.V(ztm)
+        d = self.cell_size
+        f, i, o = torch.sigmoid(s[:, :d]), torch.sigmoid(s[:, d:2 * d]), torch.sigmoid(s[:, 2 * d:3 * d])
+        c = f * ctm + i * torch.tanh(s[:, 3 * d:])
+        return c, torch.tanh(c) * o
 
 
 class MabNet(nn.Module):

@@ -192,3 +192,27 @@ def test_length_bucketed_batching_and_pinned_collate():
         want = pad_sequence(col) if f < 7 else pad_sequence(col, True) if f < 9 else col
         assert (got[f] == want) if f == 9 else torch.equal(got[f], want), f
     assert pl.collate_dialogues(data, pad_to=12)[0].shape == (12, 3, 8) and pl.collate_dialogues(data, pad_to=12)[7].shape == (3, 12)
+
+
+def test_single_step_cell_signatures_match_the_oracle():
+    """API parity of the container cells: LSTHM / LSTHM1 / in-cell CrossAttention keep the reference's single-step
+    ``forward`` signatures; values equal the oracle's restatement of the same lines."""
+    from oracle import torch_port as tp
+    torch.manual_seed(3)
+    net = lsthm_b200.HybridRNN_ATV.MARN()
+    p = {k: v.detach() for k, v in net.state_dict().items()}
+    x, c, h, z = torch.randn(5, 100), torch.randn(5, 128), torch.randn(5, 128), torch.randn(5, 208)
+    c1, h1 = net.lsthm_l(x, c, h, z)
+    c2, h2 = tp.lsthm_cell(p, "lsthm_l", x, c, h, z)
+    assert torch.allclose(c1, c2, atol=1e-6) and torch.allclose(h1, h2, atol=1e-6)
+    sps = lsthm_b200.lsthm_sps.MARN1_sps(6).eval()
+    tp.perturb_ones(sps, 4)
+    ps = {k: v.detach() for k, v in sps.state_dict().items()}
+    cell = sps.marn_cell_f
+    zz, s = torch.randn(5, 128), torch.randn(5, 128)
+    c1, h1 = cell.lsthm_l(x, c, h, zz, s)
+    c2, h2 = tp.lsthm1_cell(ps, "marn_cell_f.lsthm_l", x, c, h, zz, s)
+    assert torch.allclose(c1, c2, atol=1e-6) and torch.allclose(h1, h2, atol=1e-6)
+    a1 = cell.crossatt_l2a(c, h)
+    a2 = tp.cross_attention_cell(ps, "marn_cell_f.crossatt_l2a", c, h, None, "")
+    assert torch.allclose(a1, a2, atol=2e-6)
