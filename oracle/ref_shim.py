@@ -66,6 +66,40 @@ def load_reference():
     return ns
 
 
+def load_trainer(overrides=None, name="_lsthm_ref_model_trainer"):
+    """The reference's UNMODIFIED ``model_trainer.py`` (ModelTrainer: model construction by name, Adam + StepLR,
+    train_network / eval_network, model_trainer.py:29-187) as a module object.  ``overrides`` maps ``models.<file>`` module
+    names to replacement modules that are visible while the trainer's own ``from models.<file> import <Class>`` lines run —
+    that is the whole integration of INTEGRATION.md §2a: the trainer then builds and trains the drop-in classes.
+    ``librosa`` / ``soundfile`` (imported, never used by the trainer) are stubbed when absent."""
+    import importlib.util
+    load_reference()
+    for m in ("librosa", "soundfile"):
+        if m not in sys.modules:
+            try:
+                __import__(m)
+            except Exception:
+                sys.modules[m] = types.ModuleType(m)
+    spec = importlib.util.spec_from_file_location("_lsthm_ref_loss", os.path.join(REF_ROOT, "loss.py"))
+    ref_loss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_loss)
+    saved = {k: sys.modules.get(k) for k in list(overrides or {}) + ["loss"]}
+    try:
+        sys.modules["loss"] = ref_loss                        # `from loss import MaskedLoss, InfoNCE` (model_trainer.py:13)
+        for k, v in (overrides or {}).items():
+            sys.modules[k] = v
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, "model_trainer.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
 def attach_tape(model, tape):
     """Replace every nn.Dropout inside a *reference* model by a tape-driven one whose site
     name is the module path (e.g. ``fc.2``), so reference and oracle/CUDA path consume the
