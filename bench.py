@@ -54,6 +54,33 @@ def metric_name(kind):
     return f"utterances/sec fwd+bwd {model_name(kind)}"
 
 
+def workload_config(kind, T, B, world, info=None):
+    """The `config` object of the JSON line — the same for our arm and for the reference arm (which times a bounded sample of
+    this workload on the host cores and says so in `cpu_baseline.sample`)."""
+    din = D_IN if kind == "ATV" else 1124
+    cfg = {"workload": f"{model_name(kind)} fwd+bwd (train mode), x[{T},{B},{din}] fp32 per GPU, uniform L={T}, "
+                       f"MaskedLoss(CrossEntropy); inputs {T * B * din * 4 / 1e6:.0f} MB per step > 126 MB L2, "
+                       f"two alternating batches", "per_gpu_batch": B, "seq_len": T, "parallelism": f"dp{world}"}
+    if info is not None:
+        cfg.update({"grid": info["grid"], "block": info["block"], "rows_per_cta": info["rows"], "group": info.get("group")})
+    return cfg
+
+
+def launch_info(kind, T, B):
+    """Launch geometry of the dominant kernel pair (host-side query of the library; no GPU needed)."""
+    import lsthm_b200
+    from importlib import import_module
+    _l = import_module(lsthm_b200.__name__ + "._lib")
+    if kind == "ATV":
+        info = _l.mab_launch_info(_l.make_desc(T, B, (128, 16, 64), (16, 128, 100)))
+        info["rows"] = info["dialogues_per_group"]
+    elif kind in ("onlysp", "nsps"):
+        info = _l.gsp_launch_info(_l.make_gsp_desc(T, B, 1 if kind == "nsps" else 0))
+    else:
+        info = _l.sps_launch_info(_l.make_sps_desc(T, B))
+    return info
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -264,13 +291,17 @@ def run_reference_arm(args):
     val = utt * args.steps / dt
     from oracle import ref_shim
     src = "oracle/_ref" if ref_shim.REF_KIND == "staged" else ref_shim.REF_ROOT
+    try:
+        cfg = workload_config(args.model, args.seq, args.batch, args.gpus, launch_info(args.model, args.seq, args.batch))
+    except Exception:
+        cfg = workload_config(args.model, args.seq, args.batch, args.gpus)
     sample = (f"the unmodified reference modules ({src}) on the host cores, train mode, {args.model} x[{T_LEN},{B},*] fp32 per step "
               f"(a bounded sample of the {BATCH}-dialogue workload), {n} torch threads (best of sweep {cands}; {ncpu} host cpus)")
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args.model), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{model_name(args.model)} fwd+bwd, T={T_LEN}, sample batch {B} dialogues on host CPU"},
+        "config": cfg,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": n, "kind": "reference", "source": src, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -585,6 +616,51 @@ def run_ours(args):
                     var[vk] = {"error": repr(e)[:200]}
             var["workload"] = f"MARN1_onlysp(6) / MARN1_nsps(6) fwd+bwd (train mode), x[{T},{B},1124], qmask[{T},{B},2], fp32; cell_kernel_ms = per launch (one direction)"
             extras["gru_variants"] = var
+        # (2c) the ragged set of SURVEY.md §8d (len = clip(round(N(52.4, 17.4)), 8, 110)): real utterances per second with the
+        #      reference's random batching (every batch padded to its longest dialogue) vs the length-bucketed batches of
+        #      pipeline.LengthBucketBatchSampler (f-4), on the headline model — 8 steps of B dialogues from one pool
+        if kind == "ATV":
+            try:
+                pl = import_module(lsthm_b200.__name__ + ".pipeline")
+                gl = torch.Generator().manual_seed(111)
+                pool = 8 * B
+                lens = torch.clamp(torch.round(52.4 + 17.4 * torch.randn(pool, generator=gl)), 8, 110).int().tolist()
+                xs_full = torch.randn(T, B, D_IN, device=dev)
+                lab_full = torch.randint(0, N_CLS, (T * B,), device=dev)
+                rag = {}
+                for label, pool_batches in (("random_batches", 1), ("length_bucketed", 8)):
+                    bs = pl.LengthBucketBatchSampler(lens, B, pool_batches=pool_batches, seed=111)
+                    batches = [b for b in bs if len(b) == B]
+                    plans = []
+                    for b in batches:
+                        bl = torch.tensor([lens[i] for i in b])
+                        Lb = int(bl.max())
+                        um = (torch.arange(Lb)[None, :] < bl[:, None]).float().to(dev)          # [B, Lb]
+                        xb = (xs_full[:Lb] * um.t().unsqueeze(-1)).contiguous()                  # zero on padding, as pad_sequence gives
+                        plans.append((xb, lab_full[:Lb * B], um, int(bl.sum())))
+
+                    def rag_epoch():
+                        for xb, lb, um, _ in plans:
+                            model.zero_grad(set_to_none=True)
+                            loss_fn(model(xb), lb, um).backward()
+                    rag_epoch()
+                    torch.cuda.synchronize()
+                    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    r0.record()
+                    rag_epoch()
+                    r1.record()
+                    torch.cuda.synchronize()
+                    ms_ep = r0.elapsed_time(r1)
+                    real = sum(p[3] for p in plans)
+                    padded = sum(p[0].shape[0] * B for p in plans)
+                    rag[label] = {"real_utterances_per_s": real / (ms_ep * 1e-3), "padded_positions_per_s": padded / (ms_ep * 1e-3),
+                                  "padding_fraction": 1.0 - real / padded, "ms_per_step": ms_ep / len(plans), "steps": len(plans)}
+                rag["workload"] = (f"HybridRNN_ATV fwd+bwd, {pool} synthetic dialogues with len = clip(round(N(52.4, 17.4)), 8, 110) in steps of {B}; "
+                                   "each step padded to its longest dialogue (dataloader.py:45-47)")
+                extras["ragged_set"] = rag
+                del xs_full, plans
+            except Exception as e:
+                extras["ragged_set"] = {"error": repr(e)[:200]}
         # (3) the unmodified reference, PyTorch eager on this B200 and configs 1 and 4
         for name, fn in (("reference_eager_gpu", lambda: time_eager_gpu(kind, B, 3, 2, dev)),
                          ("config1_AT_cpu", lambda: time_cpu("AT", 32, 2)),
@@ -669,11 +745,7 @@ def run_ours(args):
             "metric": metric_name(kind), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"{model_name(kind)} fwd+bwd (train mode), x[{T},{B},{din}] fp32 per GPU, uniform L={T}, "
-                                   f"MaskedLoss(CrossEntropy); inputs {T * B * din * 4 / 1e6:.0f} MB per step > 126 MB L2, "
-                                   f"two alternating batches", "per_gpu_batch": B, "seq_len": T,
-                       "parallelism": f"dp{world}", "grid": info["grid"], "block": info["block"], "rows_per_cta": info["rows"],
-                       "group": info.get("group")},
+            "config": workload_config(kind, T, B, world, info),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": (e2e_ms / args.steps) if e2e_ms else None},
             "gpu_launches": launches,
