@@ -10,6 +10,7 @@
 namespace lsthm {
 
 int set_error(const char *what, cudaError_t e);
+int fail_msg(const char *msg);
 
 template <typename K, typename A>
 static int coop_launch(K kernel, const A &args, int grid, size_t smem_bytes, cudaStream_t st, const char *what) {
@@ -20,7 +21,10 @@ static int coop_launch(K kernel, const A &args, int grid, size_t smem_bytes, cud
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSpsThreads, smem_bytes);
     if (e != cudaSuccess) return set_error(what, e);
-    if (grid > per_sm * sms) return set_error(what, cudaErrorCooperativeLaunchTooLarge);
+    if (grid > per_sm * sms)
+        return fail_msg("lsthm_sps: the shard needs more co-resident CTAs than the device has SMs (8 dialogues per CTA: N <= 8 x #SMs = "
+                        "1184 on a B200).  The reference couples the dialogues of a shard through its packed speaker rows "
+                        "(model/lsthm_sps.py:238-259), so a shard cannot be split inside one call: shard the batch across GPUs or steps.");
     void *params[] = {const_cast<A *>(&args)};
     e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kSpsThreads), params, smem_bytes, st);
     return e == cudaSuccess ? 0 : set_error(what, e);

@@ -196,3 +196,14 @@ def test_train_mode_in_kernel_attention_dropout():
     c, _ = _fwd_bwd(model, x, qmask, umask, labels)
     assert torch.equal(a, b) and torch.equal(da, db) and not torch.equal(a, c)
     assert torch.isfinite(da).all()
+
+
+def test_shard_above_the_cooperative_capacity_fails_loudly():
+    """MODE 0 couples the dialogues of a shard (F3) and needs all its CTAs co-resident: above 8 x #SMs dialogues the call must
+    raise with an explanation, never split the shard silently (that would change the function)."""
+    T, N = 2, 148 * 8 + 8
+    model = sps_seeded_model(3, True, "cuda").eval()
+    g = torch.Generator().manual_seed(0)
+    x_l, x_a = torch.randn(T, N, 100, generator=g).cuda(), torch.randn(T, N, 100, generator=g).cuda()
+    with pytest.raises(RuntimeError, match="cannot be split"):
+        model.marn_cell_f(None, x_l, x_a, _dialogues(T, N, g).cuda())
