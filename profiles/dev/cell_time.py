@@ -12,9 +12,10 @@ g = torch.Generator().manual_seed(0)
 q = torch.zeros(T, N, 2); s = torch.randint(0, 2, (N,), generator=g)
 for t in range(T):
     s = torch.where(torch.rand(N, generator=g) < 0.6, 1 - s, s); q[t, torch.arange(N), s] = 1
-for kind in ("onlysp", "nsps", "sps"):
+for kind, rows in (("onlysp", 0), ("onlysp", 7), ("sps", 0), ("sps", 7)):
     model = sps_seeded_model(1, True, "cuda", kind=kind).train()
     cell = model.marn_cell_f
+    cell.rows_per_cta = rows          # 0: planned tile (256 threads, <= 4 dialogues, two CTAs per SM); 7: 512-thread variant
     x_l, x_a, u = (torch.randn(T, N, d, device="cuda", requires_grad=True) for d in (100, 100, 200))
     qm = q.cuda()
     def step():
@@ -27,5 +28,5 @@ for kind in ("onlysp", "nsps", "sps"):
     for _ in range(5):
         step()
     torch.cuda.synchronize()
-    print(kind, {k: round(sum(a.elapsed_time(b) for a, b in v) / len(v), 3) for k, v in rec.kernel_events.items()}, "ms per launch")
+    print(kind, "rows_per_cta", rows, {k: round(sum(a.elapsed_time(b) for a, b in v) / len(v), 3) for k, v in rec.kernel_events.items()}, "ms per launch")
     rec.kernel_events = None
