@@ -302,7 +302,9 @@ int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, 
  *     out = dropout(softmax(q k^T * scale)) v     per dialogue, unmasked over its L <= 128 utterances, one head,
  * width D (multiple of 4, <= 128), and its autograd backward.  Scores, probabilities and the dropout mask stay on the SM.
  * Row i of dialogue b of a matrix X with row stride ldx: X + (b*row_stride_b + i*row_stride_i)*ldx (both 0 = batch-major).
- * dq/dk/dv use the strides of q/k/v; out/dout use ldo.  lse [B][L] is written by fwd and read by bwd.
+ * dq/dk/dv use the strides of q/k/v; out/dout use ldo.  lse [B][L] (optional, may be NULL): each query row's log-sum-exp of the
+ * scaled scores in log2 units, a diagnostic output of the forward.  The backward needs neither `out` nor `lse`: it recomputes
+ * the row statistics from its own score product so that p, delta and dS come from the same rounded values.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t B, L, D;
@@ -315,8 +317,8 @@ typedef struct {
 
 int lsthm_xattn_fwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, float *out, float *lse,
                     void *stream);
-int lsthm_xattn_bwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, const float *out, const float *lse,
-                    const float *dout, float *dq, float *dk, float *dv, void *stream);
+int lsthm_xattn_bwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, const float *dout, float *dq,
+                    float *dk, float *dv, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head self-attention of the utterance encoder (tcgen05, split-bf16, fp32 accuracy).

@@ -154,7 +154,7 @@ def lib() -> C.CDLL:
     L.lsthm_xattn_fwd.restype = C.c_int
     L.lsthm_xattn_fwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 6
     L.lsthm_xattn_bwd.restype = C.c_int
-    L.lsthm_xattn_bwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 10
+    L.lsthm_xattn_bwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 8
     L.lsthm_dln_workspace_floats.restype = C.c_size_t
     L.lsthm_dln_workspace_floats.argtypes = [C.c_int32]
     L.lsthm_dln_fwd.restype = C.c_int
@@ -544,15 +544,14 @@ def make_xattn_desc(B, L, D, ldq, ldk, ldv, ldo, scale, p_drop=0.0, seed=0, time
     return d
 
 
-def xattn_fwd(d: XAttnDesc, q, k, v, out, lse) -> None:
+def xattn_fwd(d: XAttnDesc, q, k, v, out, lse=None) -> None:
     _check(lib().lsthm_xattn_fwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
-                                 _f32_cuda(lse, "lse"), _stream()), "lsthm_xattn_fwd")
+                                 None if lse is None else _f32_cuda(lse, "lse"), _stream()), "lsthm_xattn_fwd")
 
 
-def xattn_bwd(d: XAttnDesc, q, k, v, out, lse, dout, dq, dk, dv) -> None:
-    _check(lib().lsthm_xattn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(out, "out"),
-                                 _f32_cuda(lse, "lse"), _f32_cuda(dout, "dout"), _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"),
-                                 _stream()), "lsthm_xattn_bwd")
+def xattn_bwd(d: XAttnDesc, q, k, v, dout, dq, dk, dv) -> None:
+    _check(lib().lsthm_xattn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(dout, "dout"),
+                                 _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"), _stream()), "lsthm_xattn_bwd")
 
 
 def _rows2d(t: torch.Tensor, name: str):

@@ -46,15 +46,15 @@ int lsthm_xattn_fwd(const lsthm_xattn_desc *d, const float *q, const float *k, c
     return e == cudaSuccess ? 0 : set_error("lsthm_xattn_fwd launch", e);
 }
 
-int lsthm_xattn_bwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, const float *out, const float *lse,
-                    const float *dout, float *dq, float *dk, float *dv, void *stream) {
+int lsthm_xattn_bwd(const lsthm_xattn_desc *d, const float *q, const float *k, const float *v, const float *dout, float *dq,
+                    float *dk, float *dv, void *stream) {
     if (xattn_check(d)) return 1;
-    if (!q || !k || !v || !out || !lse || !dout || !dq || !dk || !dv) return fail_msg("lsthm_xattn_bwd: null pointer");
-    if (misaligned(q) || misaligned(k) || misaligned(v) || misaligned(out) || misaligned(dout) || misaligned(dq) || misaligned(dk) || misaligned(dv))
+    if (!q || !k || !v || !dout || !dq || !dk || !dv) return fail_msg("lsthm_xattn_bwd: null pointer");
+    if (misaligned(q) || misaligned(k) || misaligned(v) || misaligned(dout) || misaligned(dq) || misaligned(dk) || misaligned(dv))
         return fail_msg("lsthm_xattn_bwd: operands must be 16-byte aligned");
     XAttnArgs a{};
     xattn_fill(d, a);
-    a.q = q; a.k = k; a.v = v; a.o = out; a.lse = const_cast<float *>(lse); a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv;
+    a.q = q; a.k = k; a.v = v; a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv;
     const size_t smem = 3 * kXSlot;
     cudaError_t e = cudaFuncSetAttribute(xattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lsthm_xattn_bwd shared-memory opt-in", e);

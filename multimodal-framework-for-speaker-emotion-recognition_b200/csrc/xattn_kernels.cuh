@@ -26,9 +26,9 @@ constexpr int kXD = 128;                    // padded operand width
 constexpr int kXSlot = 2 * kSqTile;         // hi + lo image of a [128 x 128] tile: 64 KB
 
 struct XAttnArgs {
-    const float *q, *k, *v, *o, *dout;      // row i of dialogue b: base + (b*sb + i*si)*ld
+    const float *q, *k, *v, *dout;          // row i of dialogue b: base + (b*sb + i*si)*ld
     float *out, *dq, *dk, *dv;
-    float *lse;                             // [B][L] row log-sum-exp of the scaled scores, log2 units
+    float *lse;                             // [B][L] row log-sum-exp of the scaled scores, log2 units (forward, optional)
     int B, L, D;                            // D = operand width (multiple of 4, <= 128)
     int ldq, ldk, ldv, ldo, lddq, lddk, lddv;
     long long sb, si;

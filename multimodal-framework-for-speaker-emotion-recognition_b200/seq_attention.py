@@ -47,22 +47,21 @@ class _SeqAttnCore(torch.autograd.Function):
         D = q.shape[1]
         q, kv = q.contiguous(), kv.contiguous()
         out = torch.empty(L * B, D, device=q.device, dtype=torch.float32)
-        lse = torch.empty(B, L, device=q.device, dtype=torch.float32)
         d = _lib.make_xattn_desc(B, L, D, D, 2 * D, 2 * D, D, scale, p_drop, seed, time_major=True)
-        _lib.xattn_fwd(d, q, kv[:, :D], kv[:, D:], out, lse)
+        _lib.xattn_fwd(d, q, kv[:, :D], kv[:, D:], out)
         launches_x["xattn"] += 1
-        ctx.save_for_backward(q, kv, out, lse)
+        ctx.save_for_backward(q, kv)      # the backward recomputes the scores and their row statistics: neither out nor lse is kept
         ctx.cfg = (B, L, scale, p_drop, seed)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, kv, out, lse = ctx.saved_tensors
+        q, kv = ctx.saved_tensors
         B, L, scale, p_drop, seed = ctx.cfg
         D = q.shape[1]
         dq, dkv = torch.empty_like(q), torch.empty_like(kv)
         d = _lib.make_xattn_desc(B, L, D, D, 2 * D, 2 * D, D, scale, p_drop, seed, time_major=True)
-        _lib.xattn_bwd(d, q, kv[:, :D], kv[:, D:], out, lse, dout.contiguous(), dq, dkv[:, :D], dkv[:, D:])
+        _lib.xattn_bwd(d, q, kv[:, :D], kv[:, D:], dout.contiguous(), dq, dkv[:, :D], dkv[:, D:])
         launches_x["xattn"] += 1
         return dq, dkv, None, None, None, None, None
 
