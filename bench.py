@@ -319,6 +319,8 @@ def run_ours(args):
     mm3 = import_module(lsthm_b200.__name__ + ".mm3")
     fat = import_module(lsthm_b200.__name__ + ".fused_attention")
     fdl = import_module(lsthm_b200.__name__ + ".fused_dln")
+    lss = import_module(lsthm_b200.__name__ + ".loss")
+    sqa = import_module(lsthm_b200.__name__ + ".seq_attention")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -406,7 +408,7 @@ def run_ours(args):
     if sampler:
         sampler.start(); time.sleep(0.25)
     rec.kernel_events = {"fwd": [], "bwd": []}
-    for cnt in (rec.launch_counter, mm3.launches, fat.launches, fdl.launches):
+    for cnt in (rec.launch_counter, mm3.launches, fat.launches, fdl.launches, lss.launches, sqa.launches_x):
         for k in cnt:
             cnt[k] = 0
     barrier()
@@ -420,7 +422,7 @@ def run_ours(args):
     wall1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = (sum(rec.launch_counter.values()) + sum(mm3.launches.values()) + sum(fat.launches.values())
-                + sum(fdl.launches.values())) * world
+                + sum(fdl.launches.values()) + sum(lss.launches.values()) + sum(sqa.launches_x.values())) * world
     kev, rec.kernel_events = rec.kernel_events, None
     # the ~60 small tensor-core launches of a step are event-timed in two EXTRA steps outside the timed region
     # (an event pair per launch would perturb `value`)

@@ -296,6 +296,19 @@ int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, 
                  const float *bias, float *C, int32_t ldc, void *pack, size_t pack_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MaskedLoss.forward, loss.py:13-21 (weight = None):  loss = sum_r L(pred[r] * mask[r], target[r]) / sum(mask), L = cross
+ * entropy (kind 0: nn.CrossEntropyLoss, the train.py default) or NLL (kind 1), and its autograd backward.  A padded row
+ * contributes the constant log C to the cross entropy exactly as in the reference.  pred [R][C] fp32 contiguous (C <= 32),
+ * target [R] int64, mask [R] fp32.  out2[0] = loss, out2[1] = sum(mask) (kept for the backward); gout = dL/d loss (device
+ * scalar); workspace: lsthm_masked_loss_workspace_floats(R) floats.  Row sums are reduced in a fixed order (deterministic).
+ * ------------------------------------------------------------------------------------------ */
+size_t lsthm_masked_loss_workspace_floats(int64_t R);
+int lsthm_masked_loss_fwd(int64_t R, int32_t C, int32_t kind, const float *pred, const int64_t *target, const float *mask,
+                          float *workspace, float *out2, void *stream);
+int lsthm_masked_loss_bwd(int64_t R, int32_t C, int32_t kind, const float *pred, const int64_t *target, const float *mask,
+                          const float *out2, const float *gout, float *dpred, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Sequence-level cross-modal attention core (tcgen05, split-bf16, fp32 accuracy): what CrossAttention2.forward and
  * CrossAttention3.forward do after their three projections — model/lsthm_sps.py:94-99, 122-127 (same code in
  * lsthm_onlysp.py) and model/lsthm_nsps.py:100-104:

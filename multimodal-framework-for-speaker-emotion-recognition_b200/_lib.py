@@ -155,6 +155,12 @@ def lib() -> C.CDLL:
     L.lsthm_xattn_fwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 6
     L.lsthm_xattn_bwd.restype = C.c_int
     L.lsthm_xattn_bwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 8
+    L.lsthm_masked_loss_workspace_floats.restype = C.c_size_t
+    L.lsthm_masked_loss_workspace_floats.argtypes = [C.c_int64]
+    L.lsthm_masked_loss_fwd.restype = C.c_int
+    L.lsthm_masked_loss_fwd.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    L.lsthm_masked_loss_bwd.restype = C.c_int
+    L.lsthm_masked_loss_bwd.argtypes = [C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 7
     L.lsthm_dln_workspace_floats.restype = C.c_size_t
     L.lsthm_dln_workspace_floats.argtypes = [C.c_int32]
     L.lsthm_dln_fwd.restype = C.c_int
@@ -552,6 +558,31 @@ def xattn_fwd(d: XAttnDesc, q, k, v, out, lse=None) -> None:
 def xattn_bwd(d: XAttnDesc, q, k, v, dout, dq, dk, dv) -> None:
     _check(lib().lsthm_xattn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(dout, "dout"),
                                  _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"), _stream()), "lsthm_xattn_bwd")
+
+
+def _i64_ptr(t: torch.Tensor, name: str) -> int:
+    if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous()):
+        raise RuntimeError(f"{name}: expected a contiguous CUDA int64 tensor")
+    _on_current_device(t, name)
+    return t.data_ptr()
+
+
+def masked_loss_fwd(kind: int, pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """-> out2 = [loss, sum(mask)] (device)."""
+    R, Cn = pred.shape
+    ws = torch.empty(lib().lsthm_masked_loss_workspace_floats(R), device=pred.device, dtype=torch.float32)
+    out2 = torch.empty(2, device=pred.device, dtype=torch.float32)
+    _check(lib().lsthm_masked_loss_fwd(R, Cn, kind, _dev_ptr(pred, "pred"), _i64_ptr(target, "target"), _dev_ptr(mask, "mask"),
+                                       ws.data_ptr(), out2.data_ptr(), _stream()), "lsthm_masked_loss_fwd")
+    return out2
+
+
+def masked_loss_bwd(kind: int, pred, target, mask, out2, gout) -> torch.Tensor:
+    R, Cn = pred.shape
+    dpred = torch.empty_like(pred)
+    _check(lib().lsthm_masked_loss_bwd(R, Cn, kind, _dev_ptr(pred, "pred"), _i64_ptr(target, "target"), _dev_ptr(mask, "mask"),
+                                       out2.data_ptr(), _dev_ptr(gout, "gout"), dpred.data_ptr(), _stream()), "lsthm_masked_loss_bwd")
+    return dpred
 
 
 def _rows2d(t: torch.Tensor, name: str):
