@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .encoder import EncoderLayer
 from .gsp_recurrence import gsp_cell
 from .lsthm_sps import LSTHM1, CrossAttention, CrossAttention2, CrossAttention3, reverse_seq
-from .mm3 import linear3
+from .mm3 import linear3, linear_cat
 
 
 class MARN_cell(nn.Module):
@@ -50,7 +50,9 @@ class MARN_cell(nn.Module):
     def forward(self, u, x_l, x_a, qmask):
         """u [T,N,200]: the GRU input of every step (onlysp: cat[x_l, x_a], line 173; nsps: the pre-encoder features)."""
         T, N, _ = x_l.shape
-        gx = torch.stack([self.lsthm_l.gate_input(x_l), self.lsthm_a.gate_input(x_a)], dim=2)   # [T,N,2,512]
+        l, a = self.lsthm_l, self.lsthm_a
+        gx = linear_cat([x_l, x_a], [l.W.weight, a.W.weight],
+                        [l.W.bias + l.U.bias + l.V.bias + l.S.bias, a.W.bias + a.U.bias + a.V.bias + a.S.bias]).view(T, N, 2, 512)
         gxs = linear3(u, self.gru_s.weight_ih, self.gru_s.bias_ih)                               # [T,N,384]
         att_p, seed = 0.0, 0
         if self.mask_override is not None:

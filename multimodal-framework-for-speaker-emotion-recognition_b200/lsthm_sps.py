@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .encoder import EncoderLayer
-from .mm3 import linear3
+from .mm3 import linear3, linear_cat
 from .seq_attention import fused_ok, seq_cross_attention
 from .sps_recurrence import sps_cell
 
@@ -131,7 +131,9 @@ class MARN_cell(nn.Module):
 
     def forward(self, x, x_l, x_a, qmask):
         T, N, _ = x_l.shape
-        gx = torch.stack([self.lsthm_l.gate_input(x_l), self.lsthm_a.gate_input(x_a)], dim=2)   # [T,N,2,512]
+        l, a = self.lsthm_l, self.lsthm_a
+        gx = linear_cat([x_l, x_a], [l.W.weight, a.W.weight],
+                        [l.W.bias + l.U.bias + l.V.bias + l.S.bias, a.W.bias + a.U.bias + a.V.bias + a.S.bias]).view(T, N, 2, 512)
         att_p, seed = 0.0, 0
         if self.mask_override is not None:
             masks = self.mask_override

@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .encoder import EncoderLayer
-from .mm3 import linear3
+from .mm3 import linear3, linear_cat
 from .recurrence import mab_recurrence
 
 _MODS = ("l", "a", "v")
@@ -90,7 +90,9 @@ class MabNet(nn.Module):
         return xs
 
     def gate_inputs(self, xs) -> torch.Tensor:
-        return torch.cat([getattr(self, f"lsthm_{m}").gate_input(xm) for m, xm in zip(self._mods, xs)], dim=-1)
+        """[W_m x_m + bW_m + bU_m + bV_m]_m for all steps, written into the column blocks of one [T,N,4D] tensor."""
+        cells = [getattr(self, f"lsthm_{m}") for m in self._mods]
+        return linear_cat(list(xs), [c.W.weight for c in cells], [c.W.bias + c.U.bias + c.V.bias for c in cells])
 
     def _fc_mask(self, T, N, device):
         if self.fc_mask_override is not None:

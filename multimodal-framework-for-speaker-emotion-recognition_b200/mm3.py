@@ -130,6 +130,51 @@ def linear_into(x: torch.Tensor, weight: torch.Tensor, bias, out: torch.Tensor) 
         out.copy_(F.linear(x, weight, bias))
 
 
+class _LinearCat(torch.autograd.Function):
+    """[x_1 W_1^T + b_1 | x_2 W_2^T + b_2 | ...] written straight into the column blocks of ONE output matrix (no torch.cat /
+    torch.stack copy of the T*N-row results).  Inputs: n row matrices, then n weights, then n biases."""
+
+    @staticmethod
+    def forward(ctx, n, *args):
+        xs, ws, bs = args[:n], args[n:2 * n], args[2 * n:3 * n]
+        widths = [w.shape[0] for w in ws]
+        out = torch.empty(xs[0].shape[0], sum(widths), device=xs[0].device, dtype=torch.float32)
+        o = 0
+        for x, w, b, wd in zip(xs, ws, bs, widths):
+            launches["gemm3"] += 1
+            _lib.gemm3(_lib.GEMM_NT, _rows(x), _rows(w), b.contiguous(), out=out[:, o:o + wd])
+            o += wd
+        ctx.n, ctx.widths = n, widths
+        ctx.save_for_backward(*xs, *ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        n = ctx.n
+        xs, ws = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        dy = _rows(dy)
+        gx, gw, gb, o = [], [], [], 0
+        for i, (x, w, wd) in enumerate(zip(xs, ws, ctx.widths)):
+            blk = dy[:, o:o + wd]
+            gx.append(mm_nn(blk, w) if ctx.needs_input_grad[1 + i] else None)
+            gw.append(mm_tn(blk, x) if ctx.needs_input_grad[1 + n + i] else None)
+            gb.append(colsum(blk) if ctx.needs_input_grad[1 + 2 * n + i] else None)
+            o += wd
+        return (None, *gx, *gw, *gb)
+
+
+def linear_cat(xs, weights, biases) -> torch.Tensor:
+    """cat([F.linear(x_i, W_i, b_i)], dim=-1) for inputs that share their leading dimensions ([..., K_i] each)."""
+    lead = xs[0].shape[:-1]
+    if not all(_ok(x, w) for x, w in zip(xs, weights)):
+        return torch.cat([F.linear(x, w, b) for x, w, b in zip(xs, weights, biases)], dim=-1)
+    for x, w in zip(xs, weights):
+        _need4("linear_cat", x.shape[-1], w.shape[0])
+    rows = [x.reshape(-1, x.shape[-1]) for x in xs]
+    y = _LinearCat.apply(len(xs), *rows, *weights, *biases)
+    return y.view(*lead, y.shape[-1])
+
+
 def rows_view(x: torch.Tensor):
     """A 3-D activation [A, B, K] as a 2-D row matrix WITHOUT a copy when its storage allows it.
 
