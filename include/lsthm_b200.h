@@ -295,6 +295,11 @@ size_t lsthm_gemm3w_pack_bytes(int32_t N, int32_t K);
 int lsthm_gemm3w(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, int32_t lda, const float *W, int32_t ldw,
                  const float *bias, float *C, int32_t ldc, void *pack, size_t pack_bytes, void *stream);
 
+/* MARN1_sps._reverse_seq, model/lsthm_sps.py:396-410 (same in lsthm_onlysp.py / lsthm_nsps.py): per-dialogue flip over its own
+ * length with zero padding, X [L][B][w] -> out [L][B][w], len [B] int32 (= sum of umask rows); w even.  Self-adjoint: the
+ * backward is the same call on the gradient. */
+int lsthm_reverse_seq(int32_t L, int32_t B, int32_t w, const float *X, const int32_t *len, float *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * MaskedLoss.forward, loss.py:13-21 (weight = None):  loss = sum_r L(pred[r] * mask[r], target[r]) / sum(mask), L = cross
  * entropy (kind 0: nn.CrossEntropyLoss, the train.py default) or NLL (kind 1), and its autograd backward.  A padded row

@@ -155,6 +155,8 @@ def lib() -> C.CDLL:
     L.lsthm_xattn_fwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 6
     L.lsthm_xattn_bwd.restype = C.c_int
     L.lsthm_xattn_bwd.argtypes = [C.POINTER(XAttnDesc)] + [C.c_void_p] * 8
+    L.lsthm_reverse_seq.restype = C.c_int
+    L.lsthm_reverse_seq.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 4
     L.lsthm_masked_loss_workspace_floats.restype = C.c_size_t
     L.lsthm_masked_loss_workspace_floats.argtypes = [C.c_int64]
     L.lsthm_masked_loss_fwd.restype = C.c_int
@@ -558,6 +560,14 @@ def xattn_fwd(d: XAttnDesc, q, k, v, out, lse=None) -> None:
 def xattn_bwd(d: XAttnDesc, q, k, v, dout, dq, dk, dv) -> None:
     _check(lib().lsthm_xattn_bwd(C.byref(d), _f32_cuda(q, "q"), _f32_cuda(k, "k"), _f32_cuda(v, "v"), _f32_cuda(dout, "dout"),
                                  _f32_cuda(dq, "dq"), _f32_cuda(dk, "dk"), _f32_cuda(dv, "dv"), _stream()), "lsthm_xattn_bwd")
+
+
+def reverse_seq(X: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+    """X [L,B,w] fp32 contiguous, lens [B] int32 -> per-dialogue flipped copy (lsthm_sps.py:396-410)."""
+    L_, B, w = X.shape
+    out = torch.empty_like(X)
+    _check(lib().lsthm_reverse_seq(L_, B, w, _dev_ptr(X, "X"), _int_ptr(lens, "lens"), out.data_ptr(), _stream()), "lsthm_reverse_seq")
+    return out
 
 
 def _i64_ptr(t: torch.Tensor, name: str) -> int:

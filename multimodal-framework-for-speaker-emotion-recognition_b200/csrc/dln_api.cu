@@ -112,4 +112,16 @@ int lsthm_assemble_input(int64_t R, int32_t d_text, int32_t d_audio, const float
     return e == cudaSuccess ? 0 : set_error("lsthm_assemble_input launch", e);
 }
 
+
+int lsthm_reverse_seq(int32_t L, int32_t B, int32_t w, const float *X, const int32_t *len, float *out, void *stream) {
+    if (L < 1 || B < 1 || w < 2 || (w & 1)) return fail_msg("lsthm_reverse_seq: need L, B >= 1 and an even row width");
+    if (!X || !len || !out) return fail_msg("lsthm_reverse_seq: null pointer");
+    if ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(out)) & 7) return fail_msg("lsthm_reverse_seq: operands must be 8-byte aligned");
+    const long long total = (long long)L * B * (w / 2);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    reverse_seq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(X), len, reinterpret_cast<float2 *>(out), L, B, w / 2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : set_error("lsthm_reverse_seq launch", e);
+}
+
 }  // extern "C"

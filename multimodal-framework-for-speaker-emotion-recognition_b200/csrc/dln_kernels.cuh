@@ -311,4 +311,20 @@ __global__ void __launch_bounds__(256) assemble_input_kernel(const float4 *__res
         x[i] = o;
     }
 }
+
+// MARN1_sps._reverse_seq (model/lsthm_sps.py:396-410; same code in every member of the family): each dialogue flipped over
+// its own length, zero padded:  out[t][b][:] = t < len[b] ? X[len[b] - 1 - t][b][:] : 0.   One pass (the reference loops
+// over the batch in Python; a gather + mask product + their autograd scatter is what a tensor-op version costs).  The map is
+// its own adjoint, so the backward is the same kernel on the gradient.  Rows of w floats (w % 2 == 0: float2 lanes so that
+// qmask, w = 2, qualifies).
+__global__ void __launch_bounds__(256) reverse_seq_kernel(const float2 *__restrict__ X, const int *__restrict__ len, float2 *__restrict__ out,
+                                                          int L, int B, int w2) {
+    const long long total = (long long)L * B * w2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / w2;
+        const int c = (int)(i - row * w2), t = (int)(row / B), b = (int)(row - (long long)t * B);
+        const int n = __ldg(len + b);
+        out[i] = t < n ? __ldg(X + ((long long)(n - 1 - t) * B + b) * w2 + c) : make_float2(0.f, 0.f);
+    }
+}
 }  // namespace lsthm

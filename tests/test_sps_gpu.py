@@ -207,3 +207,23 @@ def test_shard_above_the_cooperative_capacity_fails_loudly():
     x_l, x_a = torch.randn(T, N, 100, generator=g).cuda(), torch.randn(T, N, 100, generator=g).cuda()
     with pytest.raises(RuntimeError, match="cannot be split"):
         model.marn_cell_f(None, x_l, x_a, _dialogues(T, N, g).cuda())
+
+
+@pytest.mark.parametrize("w", [2, 100, 512])
+def test_fused_reverse_seq_matches_reference_semantics(w):
+    """lsthm_reverse_seq (one kernel each way) vs the oracle's restatement of MARN1_sps._reverse_seq (lsthm_sps.py:396-410),
+    values and gradient (the map is its own adjoint), ragged lengths incl. length 1 and full length."""
+    L, lens = 11, [11, 1, 4, 7, 11, 2, 10]
+    um = torch.zeros(len(lens), L)
+    for b, n in enumerate(lens):
+        um[b, :n] = 1
+    g = torch.Generator().manual_seed(w)
+    X = torch.randn(L, len(lens), w, generator=g)
+    Xr = X.clone().requires_grad_(True)
+    ref = tp.reverse_seq(Xr, um)
+    gout = torch.randn(ref.shape, generator=g)
+    (ref * gout).sum().backward()
+    Xc = X.cuda().requires_grad_(True)
+    out = lsthm_b200.lsthm_sps.reverse_seq(Xc, um.cuda())
+    (out * gout.cuda()).sum().backward()
+    assert torch.equal(out.detach().cpu(), ref.detach()) and torch.equal(Xc.grad.cpu(), Xr.grad)
