@@ -81,8 +81,12 @@ int lsthm_gemm3(int32_t mode, int32_t M, int32_t N, int32_t K, const float *A, i
     if (rc) return rc;
     if (splits > 1) {
         const size_t total = (size_t)M * N;
-        const int blocks = (int)std::min<size_t>((total + 255) / 256, 1184);
-        gemm3_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(workspace, bias, C, M, N, ldc, splits);
+        if (splits >= 32 && total <= 65536) {
+            gemm3_reduce_wide_kernel<<<(int)((total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(workspace, bias, C, M, N, ldc, splits);
+        } else {
+            const int blocks = (int)std::min<size_t>((total + 255) / 256, 1184);
+            gemm3_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(workspace, bias, C, M, N, ldc, splits);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_error("lsthm_gemm3 reduce launch", e);
     }

@@ -329,6 +329,35 @@ static __global__ void gemm3_reduce_kernel(const float *__restrict__ ws, const f
     }
 }
 
+// The same for MANY partials of a SMALL output (K = T*N weight-gradient products of narrow layers: up to 294 splits of a few
+// thousand outputs): with one thread per output the 294 dependent-address loads of a thread ran at L2 latency (38 us per
+// launch).  Here a block owns 32 consecutive outputs, warp w sums the splits w, w + 8, ... (coalesced 128-byte rows, four
+// independent accumulators), and the eight partial sums are combined in fixed order: deterministic, ~6 us.
+static __global__ void __launch_bounds__(256) gemm3_reduce_wide_kernel(const float *__restrict__ ws, const float *__restrict__ bias,
+                                                                      float *__restrict__ C, int M, int N, int ldc, int splits) {
+    __shared__ float part[8][32];
+    const size_t total = (size_t)M * N, i = (size_t)blockIdx.x * 32 + (threadIdx.x & 31);
+    const int w = threadIdx.x >> 5;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < total) {
+        int k = w;
+        for (; k + 24 < splits; k += 32) {
+            s0 += __ldg(ws + (size_t)k * total + i);
+            s1 += __ldg(ws + (size_t)(k + 8) * total + i);
+            s2 += __ldg(ws + (size_t)(k + 16) * total + i);
+            s3 += __ldg(ws + (size_t)(k + 24) * total + i);
+        }
+        for (; k < splits; k += 8) s0 += __ldg(ws + (size_t)k * total + i);
+    }
+    part[w][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && i < total) {
+        float s = bias ? __ldg(bias + (int)(i % N)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x];
+        C[(i / N) * (size_t)ldc + (i % N)] = s;
+    }
+}
 
 // =============================================================================================
 // gemm3w: the same split-bf16 product for the case "B is a WEIGHT" (y = x W^T: NT; dx = dy W: NN), where M = T*N rows

@@ -41,17 +41,41 @@ def unused_parameter_names(model: torch.nn.Module) -> List[str]:
     return [n for n, _ in model.named_parameters() if any(p.search(n) for p in pats)]
 
 
+def observe_grad_order(model: torch.nn.Module, step_fn) -> List[str]:
+    """Run ``step_fn()`` (one forward + backward of ``model``) and return the parameter names in the order autograd
+    finished their gradients.  Pass the result as ``GradAllReducer(..., order=...)``: buckets laid out in THAT order fill
+    front to back during the backward, so every allreduce but the last overlaps the remaining backward kernels (registration
+    order is a poor guess: the drop-in MARN registers its encoders last, but their gradients are also the last to finish).
+    The gradients this dry run leaves behind are dropped."""
+    names = {id(p): n for n, p in model.named_parameters()}
+    seen: List[str] = []
+    handles = [p.register_post_accumulate_grad_hook(lambda q: seen.append(names[id(q)]))
+               for p in model.parameters() if p.requires_grad]
+    try:
+        step_fn()
+    finally:
+        for h in handles:
+            h.remove()
+    model.zero_grad(set_to_none=True)
+    return seen
+
+
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, world_size: int, bucket_bytes: int = 4 << 20,
-                 group: Optional[dist.ProcessGroup] = None, flatten_params: bool = False):
+                 group: Optional[dist.ProcessGroup] = None, flatten_params: bool = False,
+                 order: Optional[List[str]] = None):
         self.world, self.group = world_size, group
         self.flatten_params = flatten_params
         self.param_buckets: List[torch.Tensor] = []   # flat parameter storage per bucket (FusedAdam steps on these)
         skip = set(unused_parameter_names(model))
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n not in skip]
-        # autograd finishes gradients roughly in reverse registration order of use: walk the
-        # parameters backwards so bucket 0 fills first.
+        # without an observed order: autograd finishes gradients roughly in reverse registration order of use, walk the
+        # parameters backwards so bucket 0 fills first.  With ``order`` (observe_grad_order): exactly that order; parameters it
+        # does not name (no gradient in the observed step) go last.  Every rank must pass the same order.
         named = named[::-1]
+        if order is not None:
+            pos = {n: i for i, n in enumerate(order)}
+            named.sort(key=lambda np_: pos.get(np_[0], len(pos)))     # stable: unnamed ones keep their relative order
         self.buckets: List[torch.Tensor] = []
         self._members: List[List[torch.nn.Parameter]] = []
         self._bucket_of: Dict[int, int] = {}
@@ -67,6 +91,7 @@ class GradAllReducer:
             self._add_bucket(cur)
         self._pending = [0] * len(self.buckets)
         self._handles: List = []
+        self.fire_order: List[int] = []
         self.skipped = sorted(skip)
         for b, members in enumerate(self._members):
             for p in members:
@@ -115,6 +140,8 @@ class GradAllReducer:
             self._pending[b] -= 1
             if self._pending[b] < 0:
                 raise RuntimeError("GradAllReducer: a bucket received more gradients than it has members (zero_grad() not called?)")
+            if self._pending[b] == 0:
+                self.fire_order.append(b)
             if self._pending[b] == 0 and self.world > 1:
                 nvtx = torch.cuda.nvtx if self.buckets[b].is_cuda else None
                 if nvtx is not None:
@@ -135,6 +162,7 @@ class GradAllReducer:
                 if p.grad is None or p.grad.data_ptr() != self._expected_ptr(p):
                     self._rebind(p)
         self._handles = []
+        self.fire_order = []                # bucket indices in the order they completed during this step's backward
 
     def _rebind(self, p):
         b, o = self._home[id(p)]

@@ -32,9 +32,13 @@ def _worker(rank, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     try:
         model = seeded_model("AT", 21).eval()
-        reducer = ddp.GradAllReducer(model, WORLD, bucket_bytes=256 << 10)
         x, lab = _full_batch()
         sh = slice(rank * N // WORLD, (rank + 1) * N // WORLD)
+        # buckets in the order autograd finishes the gradients (observed on a dry step), so they fill front to back
+        order = ddp.observe_grad_order(
+            model, lambda: masked_ce(model(x[:, sh].contiguous()), lab[:, sh].reshape(-1), T, N // WORLD).backward())
+        assert all(p.grad is None for p in model.parameters()) and len(order) == len(set(order)) > 10
+        reducer = ddp.GradAllReducer(model, WORLD, bucket_bytes=256 << 10, order=order)
         for _ in range(2):                       # twice: zero_grad must re-arm the buckets
             reducer.zero_grad()
             probs = model(x[:, sh].contiguous())
@@ -45,6 +49,10 @@ def _worker(rank, port, out):
         if rank == 0:
             torch.save({n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}, out)
             assert len(reducer.buckets) >= 2
+            # every bucket completed during the backward, in index order, and the last-finished gradient sits in the last bucket
+            assert reducer.fire_order == list(range(len(reducer.buckets))), reducer.fire_order
+            last = dict(model.named_parameters())[order[-1]]
+            assert any(q is last for q in reducer._members[-1])
     finally:
         dist.destroy_process_group()
 

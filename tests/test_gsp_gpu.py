@@ -152,3 +152,40 @@ def test_train_mode_in_kernel_attention_dropout(kind):
     c, _ = _fwd_bwd(model, x, qmask, umask, labels)
     assert torch.equal(a, b) and torch.equal(da, db) and not torch.equal(a, c)
     assert torch.isfinite(da).all()
+
+
+@pytest.mark.parametrize("kind", ["onlysp", "sps"])
+def test_in_kernel_attention_dropout_is_the_same_mask_forward_and_backward(kind):
+    """Production train mode draws the in-cell attention dropout from a counter hash inside the kernels (no mask tensor):
+    forward and backward must evaluate the same mask.  With the seed fixed the cell is a deterministic function, so the
+    directional derivative of sum(out * w) along a random direction must equal <grad, direction>; a mismatch between the two
+    kernels' masks would show up as an O(1) error."""
+    from importlib import import_module
+    import lsthm_b200
+    T, N = 3, 6
+    model = sps_seeded_model(21, True, "cuda", kind=kind).eval()       # recurrent-state dropouts off; attention dropout via opts below
+    cell = model.marn_cell_f
+    g = torch.Generator().manual_seed(2)
+    gx = (0.5 * torch.randn(T, N, 2, 512, generator=g)).cuda()
+    qmask = _dialogues(T, N, g).cuda()
+    w = torch.randn(T, N, 512, generator=g).cuda()
+    dirn = torch.randn(gx.shape, generator=g).cuda()
+    if kind == "onlysp":
+        rec = import_module(lsthm_b200.__name__ + ".gsp_recurrence")
+        gxs = (0.5 * torch.randn(T, N, 384, generator=g)).cuda()
+        f = lambda a: rec.gsp_cell(a, gxs, qmask, (None,) * 4, cell.cell_weights(), 0, 0, 0.2, 12345)
+    else:
+        rec = import_module(lsthm_b200.__name__ + ".sps_recurrence")
+        f = lambda a: rec.sps_cell(a, qmask, (None,) * 5, cell.cell_weights(), 0, 0.2, 12345)
+    a0 = gx.clone().requires_grad_(True)
+    out = f(a0)
+    (out * w).sum().backward()
+    assert torch.equal(out.detach(), f(gx).detach())                                  # seeded
+    assert not torch.equal(out.detach()[..., 256:384], model.eval() and
+                           (rec.gsp_cell(gx, gxs, qmask, (None,) * 4, cell.cell_weights(), 0, 0, 0.0, 0) if kind == "onlysp"
+                            else rec.sps_cell(gx, qmask, (None,) * 5, cell.cell_weights(), 0, 0.0, 0))[..., 256:384])   # dropout is active
+    eps = 2e-3
+    with torch.no_grad():
+        num = ((f(gx + eps * dirn) * w).double().sum() - (f(gx - eps * dirn) * w).double().sum()) / (2 * eps)
+    ana = (a0.grad * dirn).double().sum()
+    assert abs(float(num - ana)) <= 5e-3 * max(abs(float(ana)), 1.0), (float(num), float(ana))
