@@ -40,14 +40,14 @@ FLOP_FWD_PER_UTT = 999_936
 FLOP_BWD_PER_UTT = 999_936
 
 
-SPEAKER_KINDS = ("sps", "onlysp", "nsps")
+SPEAKER_KINDS = ("sps", "onlysp", "nsps", "no_en")
 # GRU speaker-state cell (lsthm_onlysp / lsthm_nsps), per direction: W_hh product + two LSTHM1 gate products + collapsed attention
 GSP_FLOP_FWD = 98_304 + 786_432 + 82_432
 GSP_FLOP_BWD = 98_304 + 786_432 + 3 * 82_432
 
 
 def model_name(kind):
-    return {"ATV": "HybridRNN_ATV", "sps": "MARN1_sps", "onlysp": "MARN1_onlysp", "nsps": "MARN1_nsps"}[kind]
+    return {"ATV": "HybridRNN_ATV", "sps": "MARN1_sps", "onlysp": "MARN1_onlysp", "nsps": "MARN1_nsps", "no_en": "MARN1_no_en"}[kind]
 
 
 def metric_name(kind):
@@ -74,8 +74,8 @@ def launch_info(kind, T, B):
     if kind == "ATV":
         info = _l.mab_launch_info(_l.make_desc(T, B, (128, 16, 64), (16, 128, 100)))
         info["rows"] = info["dialogues_per_group"]
-    elif kind in ("onlysp", "nsps"):
-        info = _l.gsp_launch_info(_l.make_gsp_desc(T, B, 1 if kind == "nsps" else 0))
+    elif kind in ("onlysp", "nsps", "no_en"):
+        info = _l.gsp_launch_info(_l.make_gsp_desc(T, B, 0 if kind == "onlysp" else 1))
     else:
         info = _l.sps_launch_info(_l.make_sps_desc(T, B))
     return info
@@ -187,7 +187,8 @@ def reference_step_fn(kind, B, device="cpu", T=T_LEN, seed=111):
             loss.backward()
             return loss
     elif kind in SPEAKER_KINDS:
-        model = {"sps": lambda: ns.MARN1_sps(6), "onlysp": lambda: ns.MARN1_onlysp(6), "nsps": lambda: ns.MARN1_nsps(6, "IEMOCAP")}[kind]()
+        model = {"sps": lambda: ns.MARN1_sps(6), "onlysp": lambda: ns.MARN1_onlysp(6), "nsps": lambda: ns.MARN1_nsps(6, "IEMOCAP"),
+                 "no_en": lambda: ns.MARN1_no_en(6, "IEMOCAP")}[kind]()
         model = model.to(device).train()
         x, labels, umask, qmask = [t.to(device) for t in synthetic_batch(seed, T, B, model="sps")]
         lab_bm = labels.view(T, B).t().reshape(-1)        # lsthm_sps.py:392-393 returns batch-major rows
@@ -347,7 +348,8 @@ def run_ours(args):
         if k == "ATV":
             return lsthm_b200.HybridRNN_ATV.MARN().to(dev).train()
         m = {"sps": lambda: lsthm_b200.lsthm_sps.MARN1_sps(6), "onlysp": lambda: lsthm_b200.lsthm_onlysp.MARN1_onlysp(6),
-             "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP")}[k]()
+             "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP"),
+             "no_en": lambda: lsthm_b200.lsthm_no_en.MARN1_no_en(6, "IEMOCAP")}[k]()
         # the stock init sets every attention projection / fusion scalar to ones (lsthm_sps.py:52-54,82-84,340-346):
         # degenerate softmaxes; perturb them as the parity tests do so the timed arithmetic is representative
         gpert = torch.Generator().manual_seed(114)
@@ -612,7 +614,7 @@ def run_ours(args):
             extras["config3_sps"] = sps
             # (2b) the GRU speaker-state members of the family (lsthm_onlysp = train.py's default model, lsthm_nsps), fp32
             var = {}
-            for vk in ("onlysp", "nsps"):
+            for vk in ("onlysp", "nsps", "no_en"):
                 try:
                     vm = make_model(vk)
                     sb = synthetic_batch(111, T, B, device=dev, model="sps")
@@ -638,7 +640,7 @@ def run_ours(args):
                     del vm
                 except Exception as e:
                     var[vk] = {"error": repr(e)[:200]}
-            var["workload"] = f"MARN1_onlysp(6) / MARN1_nsps(6) fwd+bwd (train mode), x[{T},{B},1124], qmask[{T},{B},2], fp32; cell_kernel_ms = per launch (one direction)"
+            var["workload"] = f"MARN1_onlysp(6) / MARN1_nsps(6) / MARN1_no_en(6) fwd+bwd (train mode), x[{T},{B},1124], qmask[{T},{B},2], fp32; cell_kernel_ms = per launch (one direction)"
             extras["gru_variants"] = var
         # (2c) the ragged set of SURVEY.md §8d (len = clip(round(N(52.4, 17.4)), 8, 110)): real utterances per second with the
         #      reference's random batching (every batch padded to its longest dialogue) vs the length-bucketed batches of
@@ -714,10 +716,10 @@ def run_ours(args):
                   "bwd": 4 * (D + MH + MH + MH + 2 * D + D + G + G + 8 + 4 * MH + G + G + MH + G)}
             din = D_IN
             passes = 3                                              # hi.hi + hi.lo + lo.hi per product term
-        elif kind in ("onlysp", "nsps"):
+        elif kind in ("onlysp", "nsps", "no_en"):
             flop_utt = GSP_FLOP_BWD if dom == "bwd" else GSP_FLOP_FWD      # per direction = per launch
             kname = f"sps_{dom}_kernel<7,1>"
-            info = _l.gsp_launch_info(_l.make_gsp_desc(T, B, 1 if kind == "nsps" else 0))
+            info = _l.gsp_launch_info(_l.make_gsp_desc(T, B, 0 if kind == "onlysp" else 1))
             # one direction: gx 1024 + gxs 384 + out 512 + stash (1024 gates + 256 states + 512 GRU + 128 qs); bwd: dout + stash reads + adjoints
             by = {"fwd": 4 * (1024 + 384 + 512 + 1024 + 256 + 512 + 128), "bwd": 4 * (512 + 1024 + 2 * 256 + 512 + 128 + 1024 + 2 * 384)}
             by_alg = {"fwd": 800 + 3584, "bwd": 2 * (800 + 3584)}
@@ -796,9 +798,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="dialogues per GPU")
     ap.add_argument("--seq", type=int, default=T_LEN)
-    ap.add_argument("--model", default="ATV", choices=["ATV", "sps", "onlysp", "nsps"],
+    ap.add_argument("--model", default="ATV", choices=["ATV", "sps", "onlysp", "nsps", "no_en"],
                     help="ATV = BASELINE.json configs[1] (headline); sps = configs[2] shapes (speaker-state model, fp32); "
-                         "onlysp / nsps = the GRU speaker-state variants (train.py's default model and its listener form)")
+                         "onlysp / nsps / no_en = the GRU speaker-state variants (train.py's default model, its listener form, "
+                         "and the listener form without the text encoder)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
                     help="f32: every tensor-core product is the fp32-accurate split (parity mode, the metric's precision); "
                          "bf16: time-parallel products with bf16 operands (tests/test_bf16_gpu.py states the tolerance)")

@@ -4,7 +4,7 @@ module API.  Import by name with importlib (the directory name has hyphens) or t
 ``lsthm_b200`` alias module at the repo root."""
 from . import _lib  # noqa: F401
 from .recurrence import mab_recurrence, launch_counter  # noqa: F401
-from . import HybridRNN_AT, HybridRNN_ATV, lsthm_sps, lsthm_onlysp, lsthm_nsps  # noqa: F401
+from . import HybridRNN_AT, HybridRNN_ATV, lsthm_sps, lsthm_onlysp, lsthm_nsps, lsthm_no_en  # noqa: F401
 from .loss import MaskedLoss  # noqa: F401
 
-__all__ = ["HybridRNN_AT", "HybridRNN_ATV", "lsthm_sps", "lsthm_onlysp", "lsthm_nsps", "MaskedLoss", "mab_recurrence", "launch_counter"]
+__all__ = ["HybridRNN_AT", "HybridRNN_ATV", "lsthm_sps", "lsthm_onlysp", "lsthm_nsps", "lsthm_no_en", "MaskedLoss", "mab_recurrence", "launch_counter"]

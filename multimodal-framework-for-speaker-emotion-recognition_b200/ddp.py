@@ -32,12 +32,22 @@ _UNUSED_PATTERNS = (r"\.pos_ffn\.fc\.", r"^marn_cell_[fb]\.lstm_s\.", r"^marn_ce
                     r"^marn_cell_[fb]\.crossatt_l2a\.Wv$")
 
 
+# Per model class (looked up along the MRO, so MARN1_no_en inherits MARN1_nsps's):
+#   MARN1_onlysp:  linear.* (lsthm_onlysp.py: constructed, never called), marn_cell_{f,b}.lstm_q0/q1.* (leftovers of lsthm_sps)
+#   MARN1_nsps:    fc2.* (lsthm_nsps.py:352: resid_a is computed and discarded), marn_cell_{f,b}.gru_l.* (line 156: never called)
+#   MARN1_no_en:   additionally encoder_l.* (lsthm_no_en.py:287 constructs it; :306/:309 — its only calls — are commented out)
+_UNUSED_BY_CLASS = {"MARN1_onlysp": (r"^linear\.", r"^marn_cell_[fb]\.lstm_q[01]\."),
+                    "MARN1_nsps": (r"^fc2\.", r"^marn_cell_[fb]\.gru_l\."),
+                    "MARN1_no_en": (r"^encoder_l\.",)}
+
+
 def unused_parameter_names(model: torch.nn.Module) -> List[str]:
     """Names of the parameters no forward path uses (their gradient must stay None, as in the single-process reference
     step: Adam with weight decay would otherwise move them).  tests/test_host_logic.py pins this list to the
     ``grad is None`` set of the reference-generated fixtures."""
     import re
-    pats = [re.compile(p) for p in _UNUSED_PATTERNS]
+    extra = tuple(p for c in type(model).__mro__ for p in _UNUSED_BY_CLASS.get(c.__name__, ()))
+    pats = [re.compile(p) for p in _UNUSED_PATTERNS + extra]
     return [n for n, _ in model.named_parameters() if any(p.search(n) for p in pats)]
 
 

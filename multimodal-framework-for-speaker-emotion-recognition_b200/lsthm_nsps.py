@@ -40,6 +40,8 @@ class MARN_cell(_GruCell):
 
 
 class MARN1_nsps(nn.Module):
+    text_encoder = True          # False in the MARN1_no_en variant (lsthm_no_en.py)
+
     def __init__(self, n_classes, dataset=None):
         super().__init__()
         self.d_l, self.d_a, self.d_r = 100, 100, 1024
@@ -63,9 +65,10 @@ class MARN1_nsps(nn.Module):
         x_l = linear3(x[:, :, :self.d_r].permute(1, 0, 2), self.linear_in.weight, self.linear_in.bias)
         x_a = x[:, :, self.d_r:self.d_r + self.d_a].permute(1, 0, 2)
         u = torch.cat([x_l, x_a], dim=2).permute(1, 0, 2)        # GRU input: PRE-encoder features (line 306)
-        x_l_1, _ = self.encoder_l(x_l)
+        if self.text_encoder:                                    # lsthm_no_en.py:306,309 comments these two calls out
+            x_l_1, _ = self.encoder_l(x_l)
+            x_l, _ = self.encoder_l(x_l + x_l_1)
         x_a_1, _ = self.encoder_a(x_a)
-        x_l, _ = self.encoder_l(x_l + x_l_1)
         x_a, _ = self.encoder_a(x_a + x_a_1)
         x_l, x_a = x_l.permute(1, 0, 2), x_a.permute(1, 0, 2)
         qmask = qmask.to(x_l.dtype)

@@ -5,7 +5,8 @@ committed, and every consumer regenerates the *weights* from the recorded seed (
 init under torch.manual_seed, verified identical between the reference classes and ours).
 
     python oracle/make_golden.py            # rewrites the AT/ATV and lsthm_sps fixtures
-    python oracle/make_golden.py gru        # rewrites the lsthm_onlysp / lsthm_nsps fixtures
+    python oracle/make_golden.py gru        # rewrites the lsthm_onlysp / lsthm_nsps / lsthm_no_en fixtures
+    python oracle/make_golden.py gru no_en  # ... of one kind only
 
 What is pinned per case: output probabilities, the MaskedLoss(CrossEntropy) scalar
 (loss.py:13-21), d loss/d x, and for every parameter its gradient L2 norm plus a strided sample
@@ -91,9 +92,9 @@ def synth_dialogues(seed, L, lens):
 
 
 def _speaker_model(ref, kind):
-    """kind: sps | onlysp | nsps -> constructor of the live reference class (model/lsthm_<kind>.py)."""
+    """kind: sps | onlysp | nsps | no_en -> constructor of the live reference class (model/lsthm_<kind>.py)."""
     return {"sps": lambda: ref.MARN1_sps(6), "onlysp": lambda: ref.MARN1_onlysp(6),
-            "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP")}[kind]
+            "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP"), "no_en": lambda: ref.MARN1_no_en(6, "IEMOCAP")}[kind]
 
 
 def sps_case(ref, seed, L, lens, train, perturb, kind="sps"):
@@ -196,14 +197,18 @@ def main():
         print(name, os.path.getsize(os.path.join(OUT, name)) // 1024, "KiB", "loss", float(fix["loss"]))
 
 
-def main_gru_variants():
-    """Fixtures of the GRU speaker-state variants (lsthm_onlysp = train.py's default model, lsthm_nsps)."""
+def main_gru_variants(only=None):
+    """Fixtures of the GRU speaker-state variants (lsthm_onlysp = train.py's default model, lsthm_nsps, lsthm_no_en);
+    ``only``: restrict to one kind."""
     ref = load_reference()
     cases = [("onlysp", 121, 9, [9, 4, 7, 9, 5], False, False), ("onlysp", 122, 8, [8, 3, 6, 8, 5, 2, 7], False, True),
              ("onlysp", 123, 6, [6, 4, 2, 5], True, True),
              ("nsps", 131, 9, [9, 4, 7, 9, 5], False, False), ("nsps", 132, 8, [8, 3, 6, 8, 5, 2, 7], False, True),
-             ("nsps", 133, 6, [6, 4, 2, 5], True, True)]
+             ("nsps", 133, 6, [6, 4, 2, 5], True, True),
+             ("no_en", 142, 8, [8, 3, 6, 8, 5, 2, 7], False, True), ("no_en", 143, 6, [6, 4, 2, 5], True, True)]
     for kind, seed, L, lens, train, perturb in cases:
+        if only is not None and kind != only:
+            continue
         fix = sps_case(ref, seed, L, lens, train, perturb, kind)
         name = f"{kind}_s{seed}_T{L}_N{len(lens)}_{'train' if train else 'eval'}{'_pert' if perturb else ''}.npz"
         np.savez_compressed(os.path.join(OUT, name), **fix)
@@ -212,6 +217,6 @@ def main_gru_variants():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gru":
-        main_gru_variants()
+        main_gru_variants(sys.argv[2] if len(sys.argv) > 2 else None)
         sys.exit(0)
     main()

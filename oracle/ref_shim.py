@@ -53,6 +53,7 @@ def load_reference():
     from models.lsthm_sps import MARN1_sps              # model/lsthm_sps.py:298
     from models.lsthm_onlysp import MARN1_onlysp        # model/lsthm_onlysp.py:213 (train.py default model)
     from models.lsthm_nsps import MARN1_nsps            # model/lsthm_nsps.py:283
+    from models.lsthm_no_en import MARN1_no_en          # model/lsthm_no_en.py:283 (nsps without the text encoder)
     from models.encoder import EncoderLayer             # model/encoder.py:116
     from models.DialogueRNN import BiModel              # model/DialogueRNN.py:201 (config 4 baseline)
     import importlib.util
@@ -60,7 +61,7 @@ def load_reference():
     ref_loss = importlib.util.module_from_spec(spec)    # loss.py:6 (loaded by path: our package also has a loss.py)
     spec.loader.exec_module(ref_loss)
     ns.MARN_ATV, ns.MARN_AT, ns.MARN1_sps, ns.MARN1_onlysp = MARN_ATV, MARN_AT, MARN1_sps, MARN1_onlysp
-    ns.MARN1_nsps, ns.BiModel = MARN1_nsps, BiModel
+    ns.MARN1_nsps, ns.MARN1_no_en, ns.BiModel = MARN1_nsps, MARN1_no_en, BiModel
     ns.EncoderLayer, ns.MaskedLoss = EncoderLayer, ref_loss.MaskedLoss
     ns.root, ns.kind = REF_ROOT, REF_KIND
     return ns

@@ -459,14 +459,17 @@ def cross_attention_seq_ln(p: Params, pre: str, x1, x2, tape, dk: int = 100):
     return F.layer_norm(out, (out.shape[-1],), p[pre + ".layer_norm.weight"], p[pre + ".layer_norm.bias"], 1e-6)
 
 
-def nsps_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None):
-    """MARN1_nsps.forward (model/lsthm_nsps.py:300-359)."""
+def nsps_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None, text_encoder: bool = True):
+    """MARN1_nsps.forward (model/lsthm_nsps.py:300-359).  ``text_encoder=False`` is MARN1_no_en.forward
+    (model/lsthm_no_en.py:300-359): the same function with the two ``encoder_l`` calls commented out (lines 306, 309), i.e. the
+    text stream reaches the cells and the cross attention as ``linear_in``'s output."""
     xl0 = _lin(p, "linear_in", x[:, :, :1024].permute(1, 0, 2))
     xa0 = x[:, :, 1024:1124].permute(1, 0, 2)
     u = torch.cat([xl0, xa0], dim=2).permute(1, 0, 2)
-    xl1 = encoder_layer(p, "encoder_l", xl0, tape)
+    if text_encoder:
+        xl1 = encoder_layer(p, "encoder_l", xl0, tape)
     xa1 = encoder_layer(p, "encoder_a", xa0, tape)
-    xl = encoder_layer(p, "encoder_l", xl0 + xl1, tape).permute(1, 0, 2)
+    xl = (encoder_layer(p, "encoder_l", xl0 + xl1, tape) if text_encoder else xl0).permute(1, 0, 2)
     xa = encoder_layer(p, "encoder_a", xa0 + xa1, tape).permute(1, 0, 2)
     rec = lambda t: _drop(t, 0.5, "dropout_rec", tape)
     o_f = nsps_cell(p, "marn_cell_f", u, xl, xa, qmask, tape)
@@ -488,6 +491,11 @@ def nsps_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None)
     y = _drop(torch.relu(_lin(p, "nn_out.0", fused)), 0.5, "nn_out.2", tape)
     logp = torch.log_softmax(_lin(p, "nn_out.3", y), 2).permute(1, 0, 2)
     return logp.reshape(-1, logp.shape[-1]), xl, xa
+
+
+def no_en_forward(p: Params, x, qmask, umask, tape: Optional[DropoutTape] = None):
+    """MARN1_no_en.forward (model/lsthm_no_en.py:300-359): lsthm_nsps without the text encoder."""
+    return nsps_forward(p, x, qmask, umask, tape, text_encoder=False)
 
 
 # --------------------------------------------------------------------------------------

@@ -163,8 +163,9 @@ def run_module(fix, device="cpu", rows_per_cta=0):
 # lsthm_sps helpers
 # ------------------------------------------------------------------------------------------------
 SPEAKER_MODELS = {"sps": lambda: lsthm_b200.lsthm_sps.MARN1_sps(6), "onlysp": lambda: lsthm_b200.lsthm_onlysp.MARN1_onlysp(6),
-                  "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP")}
-SPEAKER_PORTS = {"sps": tp.sps_forward, "onlysp": tp.onlysp_forward, "nsps": tp.nsps_forward}
+                  "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP"),
+                  "no_en": lambda: lsthm_b200.lsthm_no_en.MARN1_no_en(6, "IEMOCAP")}
+SPEAKER_PORTS = {"sps": tp.sps_forward, "onlysp": tp.onlysp_forward, "nsps": tp.nsps_forward, "no_en": tp.no_en_forward}
 
 
 def sps_seeded_model(seed, perturb, device="cpu", kind="sps"):

@@ -74,7 +74,8 @@ def test_cell_vs_oracle(kind, T, N, rows, masked):
     assert max(errs.values()) <= 2e-4, sorted(errs.items(), key=lambda kv: -kv[1])[:6]
 
 
-@pytest.mark.parametrize("path", golden_files("onlysp_*.npz") + golden_files("nsps_*.npz"), ids=lambda p: p.split("/")[-1][:-4])
+@pytest.mark.parametrize("path", golden_files("onlysp_*.npz") + golden_files("nsps_*.npz") + golden_files("no_en_*.npz"),
+                         ids=lambda p: p.split("/")[-1][:-4])
 def test_module_matches_reference_fixture(path):
     fix = load_golden(path)
     logp, loss, dx, grads = sps_run_module(fix)

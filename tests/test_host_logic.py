@@ -96,21 +96,22 @@ def _ddp():
     return import_module(lsthm_b200.__name__ + ".ddp")
 
 
-@pytest.mark.parametrize("pattern", ["mab_*.npz", "sps_*.npz"])
+@pytest.mark.parametrize("pattern", ["mab_*.npz", "sps_*.npz", "onlysp_*.npz", "nsps_*.npz", "no_en_*.npz"])
 def test_unused_parameter_list_equals_the_reference_grad_none_set(pattern):
     """the reducer must leave exactly the parameters whose grad is None in the REFERENCE step out of its
-    buckets (20 tensors for MARN1_sps).  The fixtures record that set (gnone/*) from the live reference."""
-    from helpers import golden_files, load_golden
+    buckets (20 tensors for MARN1_sps, 38 / 22 / 34 for onlysp / nsps / no_en).  The fixtures record that set (gnone/*) from
+    the live reference."""
+    from helpers import SPEAKER_MODELS, golden_files, load_golden
     files = golden_files(pattern)
     assert files
     for f in files:
         fix = load_golden(f)
         kind = str(fix["kind"]) if "kind" in fix else "sps"
         model = {"ATV": lambda: lsthm_b200.HybridRNN_ATV.MARN(), "AT": lambda: lsthm_b200.HybridRNN_AT.MARN()}.get(
-            kind, lambda: lsthm_b200.lsthm_sps.MARN1_sps(6))()
+            kind, SPEAKER_MODELS.get(kind))()
         assert sorted(_ddp().unused_parameter_names(model)) == sorted(k[6:] for k in fix if k.startswith("gnone/")), f
         if kind not in ("ATV", "AT"):
-            assert len(_ddp().unused_parameter_names(model)) == 20
+            assert len(_ddp().unused_parameter_names(model)) == {"sps": 20, "onlysp": 38, "nsps": 22, "no_en": 34}[kind]
             red = _ddp().GradAllReducer(model, 1)
             for n, p in model.named_parameters():
                 assert (p.grad is None) == (n in red.skipped), n

@@ -16,7 +16,8 @@ from oracle import torch_port as tp
 from oracle.ref_shim import attach_tape, load_reference, reference_available
 
 
-@pytest.mark.parametrize("path", golden_files("sps_*.npz") + golden_files("onlysp_*.npz") + golden_files("nsps_*.npz"),
+@pytest.mark.parametrize("path", golden_files("sps_*.npz") + golden_files("onlysp_*.npz") + golden_files("nsps_*.npz")
+                         + golden_files("no_en_*.npz"),
                          ids=lambda p: p.split("/")[-1][:-4])
 def test_sps_torch_port_matches_reference_fixture(path):
     """lsthm_sps: the index-form restatement (vectorised _select_parties, no per-row loop) vs the reference
@@ -106,7 +107,7 @@ def test_c_oracle_matches_torch_port_and_autograd(kind):
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
-@pytest.mark.parametrize("variant", ["onlysp", "nsps"])
+@pytest.mark.parametrize("variant", ["onlysp", "nsps", "no_en"])
 @pytest.mark.parametrize("train,perturb", [(False, False), (False, True), (True, True)])
 def test_gru_variant_port_matches_live_reference(variant, train, perturb):
     """lsthm_onlysp (the reference's train.py default model) and lsthm_nsps (listener update, softmax(p) fusion): the
@@ -115,8 +116,9 @@ def test_gru_variant_port_matches_live_reference(variant, train, perturb):
     from oracle.make_golden import synth_dialogues
     ref = load_reference()
     torch.manual_seed(31)
-    m = ref.MARN1_onlysp(6) if variant == "onlysp" else ref.MARN1_nsps(6, "IEMOCAP")
-    forward = tp.onlysp_forward if variant == "onlysp" else tp.nsps_forward
+    m = {"onlysp": lambda: ref.MARN1_onlysp(6), "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP"),
+         "no_en": lambda: ref.MARN1_no_en(6, "IEMOCAP")}[variant]()
+    forward = {"onlysp": tp.onlysp_forward, "nsps": tp.nsps_forward, "no_en": tp.no_en_forward}[variant]
     if perturb:
         tp.perturb_ones(m, 5)
     x, qmask, umask, labels = synth_dialogues(17, 9, [9, 4, 7, 9, 5])
@@ -148,15 +150,17 @@ def test_gru_variant_port_matches_live_reference(variant, train, perturb):
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
-@pytest.mark.parametrize("variant", ["sps", "onlysp", "nsps"])
+@pytest.mark.parametrize("variant", ["sps", "onlysp", "nsps", "no_en"])
 def test_speaker_family_state_dict_and_init_match_live_reference(variant):
     """Drop-in boundary: parameter names, shapes, registration order — including the never-used tensors — and
     the default-init RNG order are those of the reference, so checkpoints load both ways and seed_everything gives equal weights."""
     import lsthm_b200
     ref = load_reference()
     ours = {"sps": lambda: lsthm_b200.lsthm_sps.MARN1_sps(6), "onlysp": lambda: lsthm_b200.lsthm_onlysp.MARN1_onlysp(6),
-            "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP")}[variant]
-    theirs = {"sps": lambda: ref.MARN1_sps(6), "onlysp": lambda: ref.MARN1_onlysp(6), "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP")}[variant]
+            "nsps": lambda: lsthm_b200.lsthm_nsps.MARN1_nsps(6, "IEMOCAP"),
+            "no_en": lambda: lsthm_b200.lsthm_no_en.MARN1_no_en(6, "IEMOCAP")}[variant]
+    theirs = {"sps": lambda: ref.MARN1_sps(6), "onlysp": lambda: ref.MARN1_onlysp(6), "nsps": lambda: ref.MARN1_nsps(6, "IEMOCAP"),
+              "no_en": lambda: ref.MARN1_no_en(6, "IEMOCAP")}[variant]
     torch.manual_seed(111)
     a = ours()
     torch.manual_seed(111)

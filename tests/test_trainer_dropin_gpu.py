@@ -52,7 +52,8 @@ def _kink_free_perturbation(name, state, batches, thr=4e-6, tries=24):
     apart while the loss agrees to the last digit).  The comparison below needs data that is decidable at parity resolution."""
     from helpers import relu_kinks
     from oracle import torch_port as tp
-    fwd = {"MARN1_onlysp": tp.onlysp_forward, "MARN1_nsps": tp.nsps_forward, "MARN1_sps": tp.sps_forward}[name]
+    fwd = {"MARN1_onlysp": tp.onlysp_forward, "MARN1_nsps": tp.nsps_forward, "MARN1_no_en": tp.no_en_forward,
+           "MARN1_sps": tp.sps_forward}[name]
     for seed in range(7, 7 + tries):
         p = {k[len("model."):]: v.detach().clone() for k, v in state.items() if k.startswith("model.")}
         tp.perturb_ones(p, seed)
@@ -69,10 +70,10 @@ def _kink_free_perturbation(name, state, batches, thr=4e-6, tries=24):
 
 
 @pytest.mark.skipif(not ref_shim.reference_available(), reason="reference neither at /root/reference nor staged in oracle/_ref")
-@pytest.mark.parametrize("name", ["MARN1_onlysp", "MARN1_nsps", "MARN1_sps"])
+@pytest.mark.parametrize("name", ["MARN1_onlysp", "MARN1_nsps", "MARN1_no_en", "MARN1_sps"])
 def test_reference_trainer_drives_the_dropin(name, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)                                   # eval_network writes res.csv into the cwd (model_trainer.py:158)
-    mod = {"MARN1_onlysp": "lsthm_onlysp", "MARN1_nsps": "lsthm_nsps", "MARN1_sps": "lsthm_sps"}[name]
+    mod = {"MARN1_onlysp": "lsthm_onlysp", "MARN1_nsps": "lsthm_nsps", "MARN1_no_en": "lsthm_no_en", "MARN1_sps": "lsthm_sps"}[name]
     ref_mt = ref_shim.load_trainer(name="_mt_reference")
     our_mt = ref_shim.load_trainer({f"models.{mod}": getattr(lsthm_b200, mod)}, name="_mt_dropin")
     assert getattr(our_mt, name) is getattr(getattr(lsthm_b200, mod), name) and getattr(ref_mt, name) is not getattr(our_mt, name)
