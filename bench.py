@@ -376,7 +376,8 @@ def run_ours(args):
         # gradient buckets in the order autograd finishes them (one dry step): head + recurrence + gate projections, then the
         # encoders back to front; 2 MB buckets -> only the last encoder's ~1 MB allreduce is left behind the backward's end
         order = ddp.observe_grad_order(model, lambda: loss_fn(forward(resident[0]), resident[0][1], resident[0][2]).backward())
-        reducer = ddp.GradAllReducer(model, world, bucket_bytes=2 << 20, order=order)
+        bb = int(os.environ.get("LSTHM_DDP_BUCKET_MB", "2")) << 20        # experiment knobs (profiles/README.md), defaults = product
+        reducer = ddp.GradAllReducer(model, world, bucket_bytes=bb, order=order, overlap=os.environ.get("LSTHM_DDP_OVERLAP", "1") == "1")
     utt_per_step = T * B * world
 
     def step_resident(i):
@@ -569,6 +570,7 @@ def run_ours(args):
             opt = ddp.FusedAdam(red, lr=1e-3, weight_decay=2e-5)
             bt = resident[0]
             loss_fn(forward_of(m2, kind, bt), bt[1], bt[2]).backward()
+            red.finish()
             for _ in range(3):
                 opt.step()
             torch.cuda.synchronize()

@@ -4,11 +4,11 @@ still running.
 
 The reference has no distributed code at all (its ``import torch.distributed`` at train.py:12 is
 dead); this is the hookup the north star asks for.  Design:
-  * gradients live in a few flat fp32 buckets (``p.grad`` are views), ordered by the order in which
-    autograd finishes them: head -> recurrence weights -> input projections -> encoders;
-  * a post-accumulate-grad hook per parameter counts a bucket down; when it reaches zero the
-    bucket's ``all_reduce(SUM)`` is enqueued asynchronously (NCCL stream) so it overlaps the rest of
-    the backward; ``finish()`` waits for all buckets;
+  * gradients are exchanged in a few flat fp32 buckets, ordered by the order in which autograd finishes them
+    (``observe_grad_order``: head -> recurrence weights -> input projections -> encoders);
+  * a post-accumulate-grad hook per parameter counts a bucket down; when it reaches zero the bucket's gradients are
+    packed into the flat buffer by ONE multi-tensor copy (``p.grad`` become views of it) and its ``all_reduce(SUM)`` is
+    enqueued asynchronously (NCCL stream) so it overlaps the rest of the backward; ``finish()`` waits for all buckets;
   * parameters the model never uses (e.g. ``encoder_*.pos_ffn.fc``) are left out, so
     their ``.grad`` stays ``None`` exactly as in the single-process reference step (Adam with weight
     decay would otherwise move them);
@@ -73,8 +73,9 @@ def observe_grad_order(model: torch.nn.Module, step_fn) -> List[str]:
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, world_size: int, bucket_bytes: int = 4 << 20,
                  group: Optional[dist.ProcessGroup] = None, flatten_params: bool = False,
-                 order: Optional[List[str]] = None):
+                 order: Optional[List[str]] = None, overlap: bool = True):
         self.world, self.group = world_size, group
+        self.overlap = overlap                # False: every bucket is reduced in finish(), after the backward (no concurrent NCCL kernels)
         self.flatten_params = flatten_params
         self.param_buckets: List[torch.Tensor] = []   # flat parameter storage per bucket (FusedAdam steps on these)
         skip = set(unused_parameter_names(model))
@@ -90,6 +91,7 @@ class GradAllReducer:
         self._members: List[List[torch.nn.Parameter]] = []
         self._bucket_of: Dict[int, int] = {}
         self._home: Dict[int, tuple] = {}
+        self._view: Dict[int, torch.Tensor] = {}      # the parameter-shaped view of its slot in the flat bucket
         cur, cur_bytes = [], 0
         for n, p in named:
             cur.append(p)
@@ -102,6 +104,7 @@ class GradAllReducer:
         self._pending = [0] * len(self.buckets)
         self._handles: List = []
         self.fire_order: List[int] = []
+        self._fired = [False] * len(self.buckets)
         self.skipped = sorted(skip)
         for b, members in enumerate(self._members):
             for p in members:
@@ -122,9 +125,9 @@ class GradAllReducer:
         offs, total = self._offsets(params)
         flat = torch.zeros(total, device=params[0].device, dtype=params[0].dtype)
         for p, o in zip(params, offs):
-            p.grad = flat[o:o + p.numel()].view_as(p)
             self._bucket_of[id(p)] = len(self.buckets)
             self._home[id(p)] = (len(self.buckets), o)          # where this parameter's gradient must live
+            self._view[id(p)] = flat[o:o + p.numel()].view_as(p)
         self.buckets.append(flat)
         self._members.append(list(params))
         if self.flatten_params:
@@ -137,57 +140,72 @@ class GradAllReducer:
             self.param_buckets.append(pflat)
 
     def _expected_ptr(self, p) -> int:
-        b, o = self._home[id(p)]
-        return self.buckets[b].data_ptr() + o * self.buckets[b].element_size()
+        return self._view[id(p)].data_ptr()
+
+    def _gather(self, b):
+        """Move the gradients autograd produced for bucket ``b`` into their slots of the flat bucket — ONE multi-tensor copy
+        for the whole bucket — and make ``p.grad`` the views.  Members without a gradient in this step get a zero slot (they
+        take part in the sum) and keep ``grad = None``."""
+        src, dst = [], []
+        with torch.no_grad():
+            for p in self._members[b]:
+                v = self._view[id(p)]
+                if p.grad is None:
+                    v.zero_()
+                elif p.grad.data_ptr() != v.data_ptr():
+                    src.append(p.grad)
+                    dst.append(v)
+            if src:
+                torch._foreach_copy_(dst, src)
+        for p in self._members[b]:
+            if p.grad is not None:
+                p.grad = self._view[id(p)]
+
+    def _reduce(self, b):
+        self._fired[b] = True
+        nvtx = torch.cuda.nvtx if self.buckets[b].is_cuda else None
+        if nvtx is not None:
+            nvtx.range_push(f"lsthm/K6_allreduce_bucket{b}")
+        self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if nvtx is not None:
+            nvtx.range_pop()
 
     def _make_hook(self, b):
         def hook(param):
-            # a gradient that autograd allocated itself (someone called optimizer.zero_grad() / model.zero_grad(set_to_none=True)
-            # instead of reducer.zero_grad()) lives outside the buckets and would silently never be reduced
-            if param.grad is None or param.grad.data_ptr() != self._expected_ptr(param):
-                raise RuntimeError("GradAllReducer: a gradient is not a view of its bucket — call reducer.zero_grad() (not "
-                                   "optimizer.zero_grad(set_to_none=True)) between steps")
             self._pending[b] -= 1
             if self._pending[b] < 0:
                 raise RuntimeError("GradAllReducer: a bucket received more gradients than it has members (zero_grad() not called?)")
-            if self._pending[b] == 0:
+            if self._pending[b] == 0:           # the bucket is complete: pack it, and start its allreduce behind the backward
                 self.fire_order.append(b)
-            if self._pending[b] == 0 and self.world > 1:
-                nvtx = torch.cuda.nvtx if self.buckets[b].is_cuda else None
-                if nvtx is not None:
-                    nvtx.range_push(f"lsthm/K6_allreduce_bucket{b}")
-                self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
-                                                     async_op=True))
-                if nvtx is not None:
-                    nvtx.range_pop()
+                self._gather(b)
+                self._gathered[b] = True
+                if self.world > 1 and self.overlap:
+                    self._reduce(b)
         return hook
 
     def zero_grad(self):
-        """Zero the flat buckets (p.grad stay views of them) and re-arm the per-bucket counters."""
-        for flat in self.buckets:
-            flat.zero_()
+        """Drop the gradients (``p.grad = None``: autograd then hands its freshly computed gradient tensors over instead of
+        launching one accumulate-add per parameter into a zeroed buffer — ~100 tiny kernels per step for the MARN models) and
+        re-arm the per-bucket counters.  ``optimizer.zero_grad()`` / ``model.zero_grad()`` with either ``set_to_none`` are
+        equivalent as far as the gradients go, but only this call re-arms the counters."""
         for b, members in enumerate(self._members):
             self._pending[b] = len(members)
             for p in members:
-                if p.grad is None or p.grad.data_ptr() != self._expected_ptr(p):
-                    self._rebind(p)
+                p.grad = None
         self._handles = []
+        self._fired = [False] * len(self.buckets)
+        self._gathered = [False] * len(self.buckets)
         self.fire_order = []                # bucket indices in the order they completed during this step's backward
 
-    def _rebind(self, p):
-        b, o = self._home[id(p)]
-        p.grad = self.buckets[b][o:o + p.numel()].view_as(p)
-
     def finish(self):
-        """Block the current stream until every bucket's allreduce is complete."""
-        for members in self._members:
-            for p in members:
-                if p.grad is not None and p.grad.data_ptr() != self._expected_ptr(p):
-                    raise RuntimeError("GradAllReducer.finish: a gradient was re-allocated outside its bucket during the step")
-        for b, n in enumerate(self._pending):
-            if n != 0 and self.world > 1:       # a bucket whose hooks did not all fire (a parameter unused in THIS step)
-                self._handles.append(dist.all_reduce(self.buckets[b], op=dist.ReduceOp.SUM, group=self.group,
-                                                     async_op=True))
+        """Block the current stream until every bucket's allreduce is complete.  Afterwards ``p.grad`` of every bucketed
+        parameter that received a gradient is a view of its flat bucket holding the SUM over ranks."""
+        for b in range(len(self.buckets)):
+            if not self._gathered[b]:           # a bucket whose hooks did not all fire (a parameter unused in THIS step)
+                self._gather(b)
+                self._gathered[b] = True
+            if self.world > 1 and not self._fired[b]:
+                self._reduce(b)
         for h in self._handles:
             h.wait()
         self._handles = []
@@ -239,4 +257,4 @@ class FusedAdam(torch.optim.Optimizer):
             dst.copy_(src)
 
     def zero_grad(self, set_to_none: bool = False) -> None:
-        self.reducer.zero_grad()          # gradients are views of the flat buckets: they are zeroed, never dropped
+        self.reducer.zero_grad()          # drops the gradients and re-arms the buckets (see GradAllReducer.zero_grad)

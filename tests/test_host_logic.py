@@ -113,31 +113,45 @@ def test_unused_parameter_list_equals_the_reference_grad_none_set(pattern):
         if kind not in ("ATV", "AT"):
             assert len(_ddp().unused_parameter_names(model)) == {"sps": 20, "onlysp": 38, "nsps": 22, "no_en": 34}[kind]
             red = _ddp().GradAllReducer(model, 1)
+            bucketed = {id(p) for members in red._members for p in members}
             for n, p in model.named_parameters():
-                assert (p.grad is None) == (n in red.skipped), n
+                assert (id(p) not in bucketed) == (n in red.skipped), n      # never-used parameters have no bucket slot
 
 
-def test_reducer_rejects_gradients_outside_its_buckets():
-    """optimizer.zero_grad(set_to_none=True) between steps makes autograd allocate fresh .grad tensors: the reducer must
-    notice (hook) or repair (its own zero_grad), never reduce stale buckets silently."""
+def test_reducer_packs_whatever_autograd_produced_and_rejects_a_missing_rearm():
+    """Gradients start as None (autograd hands its tensors over, no accumulate-add launches); when a bucket is complete they
+    are packed into the flat buffer by one multi-tensor copy and ``p.grad`` become views of it.  A gradient that already IS
+    the view (someone zeroed in place instead of dropping) is left where it is; a backward without ``reducer.zero_grad()``
+    in between is an error, never a silent reduction of stale buckets."""
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
     red = _ddp().GradAllReducer(model, 1, bucket_bytes=64)
+    assert all(p.grad is None for p in model.parameters())
     x = torch.randn(3, 8)
     model(x).sum().backward()
     red.finish()
     g0 = [p.grad.clone() for p in model.parameters()]
     assert all(p.grad.data_ptr() == red._expected_ptr(p) for p in model.parameters())
-    torch.optim.SGD(model.parameters(), lr=0.1).zero_grad(set_to_none=True)      # the mistake
-    with pytest.raises(RuntimeError, match="not a view of its bucket"):
-        model(x).sum().backward()
-    red.zero_grad()                                                              # the repair: views are re-bound
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    ref.load_state_dict(model.state_dict())
+    ref(x).sum().backward()
+    assert all(torch.equal(a.grad, b.grad) for a, b in zip(model.parameters(), ref.parameters()))
+    assert sorted(red.fire_order) == list(range(len(red.buckets))) and len(red.buckets) >= 2
+    with pytest.raises(RuntimeError, match="more gradients than it has members"):
+        model(x).sum().backward()                                                # second backward without zero_grad
+    red.zero_grad()
+    for p in model.parameters():                                                 # in-place zeroed views instead of None
+        p.grad = red._view[id(p)].zero_()
     model(x).sum().backward()
     red.finish()
     for p, g in zip(model.parameters(), g0):
         assert p.grad.data_ptr() == red._expected_ptr(p) and torch.allclose(p.grad, g)
-    with pytest.raises(RuntimeError, match="more gradients than it has members"):
-        model(x).sum().backward()                                                # second backward without zero_grad
+    # a parameter without a gradient in this step: zero slot, grad stays None, the others are unaffected
+    red.zero_grad()
+    model[1](x[:, :8]).sum().backward()
+    red.finish()
+    assert model[0].weight.grad is None and float(red._view[id(model[0].weight)].abs().sum()) == 0.0
+    assert torch.allclose(model[1].bias.grad, g0[3])
 
 
 def test_fused_adam_exposes_param_groups_and_state(monkeypatch):
