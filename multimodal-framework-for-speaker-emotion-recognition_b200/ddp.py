@@ -147,6 +147,11 @@ class GradAllReducer:
         for the whole bucket — and make ``p.grad`` the views.  Members without a gradient in this step get a zero slot (they
         take part in the sum) and keep ``grad = None``."""
         src, dst = [], []
+        if self.buckets[b].is_cuda:
+            cs = torch.cuda.current_stream(self.buckets[b].device)
+            for ev in self._xstream[b]:         # gradients finished on other streams (see the hook)
+                cs.wait_event(ev)
+            self._xstream[b] = []
         with torch.no_grad():
             for p in self._members[b]:
                 v = self._view[id(p)]
@@ -160,6 +165,10 @@ class GradAllReducer:
         for p in self._members[b]:
             if p.grad is not None:
                 p.grad = self._view[id(p)]
+        if self.buckets[b].is_cuda and cs != self._home_stream:
+            ev = torch.cuda.Event()             # packed on a side stream: finish() orders the caller's stream behind it
+            ev.record(cs)
+            self._packed_events.append(ev)
 
     def _reduce(self, b):
         self._fired[b] = True
@@ -175,6 +184,15 @@ class GradAllReducer:
             self._pending[b] -= 1
             if self._pending[b] < 0:
                 raise RuntimeError("GradAllReducer: a bucket received more gradients than it has members (zero_grad() not called?)")
+            if param.grad is not None and param.grad.is_cuda:
+                # Branches of the model may run on their own streams (mab_net.MabNet.encode), and autograd replays a branch's
+                # backward on the stream it ran on: this gradient is only ordered with the stream this hook runs on.  Leave an
+                # event behind for whichever stream ends up packing the bucket.
+                cs = torch.cuda.current_stream(param.grad.device)
+                if cs != self._home_stream:
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    self._xstream[b].append(ev)
             if self._pending[b] == 0:           # the bucket is complete: pack it, and start its allreduce behind the backward
                 self.fire_order.append(b)
                 self._gather(b)
@@ -196,6 +214,11 @@ class GradAllReducer:
         self._fired = [False] * len(self.buckets)
         self._gathered = [False] * len(self.buckets)
         self.fire_order = []                # bucket indices in the order they completed during this step's backward
+        # the training loop's stream (the one zero_grad() / finish() are called on); events of gradients finished elsewhere
+        cuda = bool(self.buckets) and self.buckets[0].is_cuda
+        self._home_stream = torch.cuda.current_stream(self.buckets[0].device) if cuda else None
+        self._xstream: List[List] = [[] for _ in self.buckets]
+        self._packed_events: List = []
 
     def finish(self):
         """Block the current stream until every bucket's allreduce is complete.  Afterwards ``p.grad`` of every bucketed
@@ -209,6 +232,11 @@ class GradAllReducer:
         for h in self._handles:
             h.wait()
         self._handles = []
+        if self._packed_events:
+            cs = torch.cuda.current_stream(self.buckets[0].device)
+            for ev in self._packed_events:
+                cs.wait_event(ev)
+            self._packed_events = []
 
 
 class FusedAdam(torch.optim.Optimizer):

@@ -280,3 +280,35 @@ def test_train_mode_uses_dropout_and_is_seeded():
     b = model(x)
     c = model(x)
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_concurrent_encoder_streams_change_nothing_but_the_schedule():
+    """mab_net.MabNet.encode issues the per-modality encoders on their own CUDA streams (forward, and autograd replays each
+    branch's backward on its stream).  Every kernel is deterministic, so the outputs, the input gradient and every parameter
+    gradient must be BITWISE those of the single-stream schedule — a missing fork/join dependency or a buffer reused too early
+    shows up as a difference.  Repeated, at a size where the branches really overlap, also through the DDP reducer (which packs
+    gradients that were finished on different streams) and with the model's first step already taken on the side streams."""
+    from importlib import import_module
+    import lsthm_b200
+    ddp = import_module(lsthm_b200.__name__ + ".ddp")
+    T, N, kind = 110, 256, "ATV"
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(T, N, 712, device="cuda", generator=g)
+    labels = torch.randint(0, 6, (T * N,), device="cuda", generator=g)
+    model = seeded_model(kind, 111).to("cuda").eval()
+    assert model.concurrent_encoders
+    runs = [_fwd_bwd(model, x, labels, T, N) for _ in range(3)]           # first step on the side streams
+    model.concurrent_encoders = False
+    p0, dx0, g0 = _fwd_bwd(model, x, labels, T, N)
+    model.concurrent_encoders = True
+    runs.append(_fwd_bwd(model, x, labels, T, N))
+    for p1, dx1, g1 in runs:
+        assert torch.equal(p0, p1) and torch.equal(dx0, dx1)
+        assert g0.keys() == g1.keys() and all(torch.equal(g0[k], g1[k]) for k in g0)
+    red = ddp.GradAllReducer(model, 1, bucket_bytes=1 << 20)
+    for _ in range(3):
+        red.zero_grad()
+        masked_ce(model(x), labels, T, N).backward()
+        red.finish()
+        assert all(torch.equal(g0[n], q.grad) for n, q in model.named_parameters() if q.grad is not None)
+        assert all(q.grad.data_ptr() == red._expected_ptr(q) for n, q in model.named_parameters() if q.grad is not None)
