@@ -373,11 +373,12 @@ def run_ours(args):
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     reducer = None
     if world > 1:
-        # gradient buckets in the order autograd finishes them (one dry step): head + recurrence + gate projections, then the
-        # encoders back to front; 2 MB buckets -> only the last encoder's ~1 MB allreduce is left behind the backward's end
+        # gradient buckets in the order autograd finishes them (one dry step).  Default = the measured best on 8 x B200
+        # (profiles/r02/scale_ab_n8.log): ONE bucket, reduced after the backward (14.81 ms per step; 2 MB buckets overlapped
+        # with the backward: 15.22 ms; one GPU: 14.65 ms).  The two environment variables are experiment knobs of this script.
         order = ddp.observe_grad_order(model, lambda: loss_fn(forward(resident[0]), resident[0][1], resident[0][2]).backward())
-        bb = int(os.environ.get("LSTHM_DDP_BUCKET_MB", "2")) << 20        # experiment knobs (profiles/README.md), defaults = product
-        reducer = ddp.GradAllReducer(model, world, bucket_bytes=bb, order=order, overlap=os.environ.get("LSTHM_DDP_OVERLAP", "1") == "1")
+        bb = int(os.environ.get("LSTHM_DDP_BUCKET_MB", "64")) << 20
+        reducer = ddp.GradAllReducer(model, world, bucket_bytes=bb, order=order, overlap=os.environ.get("LSTHM_DDP_OVERLAP", "0") == "1")
     utt_per_step = T * B * world
 
     def step_resident(i):

@@ -1,14 +1,14 @@
 """Data-parallel gradient exchange for the drop-in modules: one process per GPU, dialogues sharded
-across ranks, ONE summed gradient allreduce per step issued bucket by bucket while the backward is
-still running.
+across ranks, ONE summed gradient allreduce per step.
 
 The reference has no distributed code at all (its ``import torch.distributed`` at train.py:12 is
 dead); this is the hookup the north star asks for.  Design:
   * gradients are exchanged in a few flat fp32 buckets, ordered by the order in which autograd finishes them
     (``observe_grad_order``: head -> recurrence weights -> input projections -> encoders);
   * a post-accumulate-grad hook per parameter counts a bucket down; when it reaches zero the bucket's gradients are
-    packed into the flat buffer by ONE multi-tensor copy (``p.grad`` become views of it) and its ``all_reduce(SUM)`` is
-    enqueued asynchronously (NCCL stream) so it overlaps the rest of the backward; ``finish()`` waits for all buckets;
+    packed into the flat buffer by ONE multi-tensor copy (``p.grad`` become views of it); its ``all_reduce(SUM)`` is
+    enqueued in ``finish()`` (default) or, with ``overlap=True``, right away on the NCCL stream next to the rest of the
+    backward — on B200 that costs more than it hides (see ``__init__``); ``finish()`` waits for all buckets;
   * parameters the model never uses (e.g. ``encoder_*.pos_ffn.fc``) are left out, so
     their ``.grad`` stays ``None`` exactly as in the single-process reference step (Adam with weight
     decay would otherwise move them);
@@ -73,9 +73,13 @@ def observe_grad_order(model: torch.nn.Module, step_fn) -> List[str]:
 class GradAllReducer:
     def __init__(self, model: torch.nn.Module, world_size: int, bucket_bytes: int = 4 << 20,
                  group: Optional[dist.ProcessGroup] = None, flatten_params: bool = False,
-                 order: Optional[List[str]] = None, overlap: bool = True):
+                 order: Optional[List[str]] = None, overlap: bool = False):
         self.world, self.group = world_size, group
-        self.overlap = overlap                # False: every bucket is reduced in finish(), after the backward (no concurrent NCCL kernels)
+        # overlap=False (default): every bucket is reduced in finish(), after the backward.  True: a bucket's allreduce is
+        # enqueued the moment it is complete.  Measured on 8 x B200 (profiles/r02/scale_ab_n8.log): the 6.8 MB of gradients are
+        # ~0.15 ms of NVLink time at the end of a 14.7 ms step, while NCCL kernels running NEXT TO the backward take SMs from
+        # its persistent / cooperative kernels (one CTA per SM): 15.22 ms per step overlapped vs 14.81 ms not (1 GPU: 14.65).
+        self.overlap = overlap
         self.flatten_params = flatten_params
         self.param_buckets: List[torch.Tensor] = []   # flat parameter storage per bucket (FusedAdam steps on these)
         skip = set(unused_parameter_names(model))
