@@ -15,7 +15,7 @@ import torch.nn.functional as F
 
 from .encoder import EncoderLayer
 from .mm3 import linear3, linear_cat
-from .recurrence import mab_recurrence
+from .recurrence import mab_recurrence, mab_prepack
 
 _MODS = ("l", "a", "v")
 
@@ -174,6 +174,12 @@ class MabNet(nn.Module):
             o += d
         return xs
 
+    def _aux_stream(self, device):
+        key = ("aux", device.index if device.index is not None else torch.cuda.current_device())
+        if key not in self._side_streams:
+            self._side_streams[key] = torch.cuda.Stream(device=device)
+        return self._side_streams[key]
+
     def _streams(self, device):
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in self._side_streams:
@@ -196,9 +202,14 @@ class MabNet(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         T, N, _ = x.shape
+        pre = None
+        if x.is_cuda and self.concurrent_encoders:
+            # the recurrence's packed weights depend on the parameters only: built next to the encoders, off the critical path
+            pre = mab_prepack(T, N, self._dh, self._rd, self._map_h, self.recurrence_weights(), self.rows_per_cta,
+                              self._aux_stream(x.device))
         gx = self.gate_inputs(self.encode(x))
         hz = mab_recurrence(gx, self._fc_mask(T, N, x.device), self._dh, self._rd, self._map_h,
-                            self.recurrence_weights(), self.rows_per_cta)
+                            self.recurrence_weights(), self.rows_per_cta, prepacked=pre)
         self.last_hz = hz
         # head nn_out = Linear - ReLU - Dropout(0) - Linear - Softmax (HybridRNN_ATV.py:68-73): both products on the own GEMM
         # (ReLU in the first one's epilogue; the 6/7-class output is padded to 8 columns inside linear3)

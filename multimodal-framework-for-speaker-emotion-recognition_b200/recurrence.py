@@ -61,6 +61,36 @@ def _timed(kind, fn, *args):
             nvtx.range_pop()
 
 
+def _pack(desc, weights, M, device) -> torch.Tensor:
+    """Composite chain weights + per-rank UMMA images for one launch pair (``lsthm_mab_pack``: two kernels, ~0.09 ms)."""
+    U, V = weights[0:M], weights[M:2 * M]
+    Watt, batt = weights[2 * M], weights[2 * M + 1]
+    Wr, br = weights[2 * M + 2:3 * M + 2], weights[3 * M + 2:4 * M + 2]
+    Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
+    wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
+    packed = torch.empty(_lib.mab_pack_bytes(desc), device=device, dtype=torch.uint8)
+    _timed("pack", _lib.mab_pack, desc, wstruct, packed)
+    launch_counter["pack"] += 2
+    return packed
+
+
+def mab_prepack(T: int, N: int, dh: Sequence[int], rd: Sequence[int], map_h: int, weights: Sequence[torch.Tensor],
+                rows_per_cta: int, stream: "torch.cuda.Stream"):
+    """Build the packed weights of ``mab_recurrence`` on ``stream`` (forked from the current stream) — they depend on the
+    parameters only, so a caller can have them built while the encoders run.  Returns ``(packed, ready_event)`` for
+    ``mab_recurrence(..., prepacked=...)``.  ``packed`` lives in ``stream``'s pool and is next re-used by this function, behind
+    its own ``wait_stream`` — no record_stream needed (see mab_net._EncoderBranches)."""
+    weights = tuple(w.detach().contiguous() for w in weights)
+    dev = weights[0].device
+    desc = _lib.make_desc(T, N, tuple(dh), tuple(rd), int(map_h), 4, int(rows_per_cta))
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        packed = _pack(desc, weights, len(dh), dev)
+        ready = torch.cuda.Event()
+        ready.record(stream)
+    return packed, ready
+
+
 class MabRecurrenceFn(torch.autograd.Function):
     """hz[T,N,2D] = recurrence(gx[T,N,4D]; U_m, V_m, att, reduce_m, fc).
 
@@ -75,7 +105,8 @@ class MabRecurrenceFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, gx: torch.Tensor, drop_mask: Optional[torch.Tensor], dims: Tuple, *weights: torch.Tensor):
-        dh, rd, map_h, rows_per_cta = dims
+        dh, rd, map_h, rows_per_cta = dims[:4]
+        prepacked = dims[4] if len(dims) > 4 else None
         M = len(dh)
         T, N, G = gx.shape
         D, R = sum(dh), sum(rd)
@@ -88,10 +119,11 @@ class MabRecurrenceFn(torch.autograd.Function):
         Wr, br = weights[2 * M + 2:3 * M + 2], weights[3 * M + 2:4 * M + 2]
         Wf1, bf1, Wf2, bf2 = weights[4 * M + 2:4 * M + 6]
         desc = _lib.make_desc(T, N, dh, rd, map_h, 4, rows_per_cta)
-        wstruct = _lib.make_weights(U, V, Watt, batt, Wr, br, Wf1, bf1, Wf2, bf2)
-        packed = torch.empty(_lib.mab_pack_bytes(desc), device=gx.device, dtype=torch.uint8)
-        _timed("pack", _lib.mab_pack, desc, wstruct, packed)
-        launch_counter["pack"] += 2
+        if prepacked is not None:           # mab_prepack: the images were built on a side stream while the encoders ran
+            packed, ready = prepacked
+            torch.cuda.current_stream(gx.device).wait_event(ready)
+        else:
+            packed = _pack(desc, weights, M, gx.device)
         work = _workspace(desc, gx.device)
         new = lambda *s: torch.empty(*s, device=gx.device, dtype=torch.float32)
         hz, u = new(T, N, 2 * D), new(T, N, map_h)
@@ -111,7 +143,7 @@ class MabRecurrenceFn(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(packed, hz, u, sC, sCp, sG, sE, sMS, sP, *weights)
             ctx.drop_mask = drop_mask
-            ctx.dims = dims
+            ctx.dims = dims[:4]
         return hz
 
     @staticmethod
@@ -182,7 +214,7 @@ class MabRecurrenceFn(torch.autograd.Function):
 
 
 def mab_recurrence(gx: torch.Tensor, drop_mask: Optional[torch.Tensor], dh: Sequence[int], rd: Sequence[int],
-                   map_h: int, weights: Sequence[torch.Tensor], rows_per_cta: int = 0) -> torch.Tensor:
+                   map_h: int, weights: Sequence[torch.Tensor], rows_per_cta: int = 0, prepacked=None) -> torch.Tensor:
     if not gx.is_cuda:
         raise RuntimeError("lsthm_b200: the recurrence runs on a CUDA device only (no CPU fallback)")
-    return MabRecurrenceFn.apply(gx, drop_mask, (tuple(dh), tuple(rd), int(map_h), int(rows_per_cta)), *weights)
+    return MabRecurrenceFn.apply(gx, drop_mask, (tuple(dh), tuple(rd), int(map_h), int(rows_per_cta), prepacked), *weights)

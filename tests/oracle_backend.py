@@ -93,7 +93,8 @@ def install(monkeypatch):
     monkeypatch.setattr(rec, "_workspace", lambda desc, device: torch.zeros(128, dtype=torch.uint8))
 
     # the public entry point refuses CPU tensors; tests go through the autograd.Function directly
-    def cpu_recurrence(gx, mask, dh, rd, map_h, weights, rows=0):
+    def cpu_recurrence(gx, mask, dh, rd, map_h, weights, rows=0, prepacked=None):
+        assert prepacked is None                 # side-stream prepacking is a CUDA-only schedule
         return rec.MabRecurrenceFn.apply(gx, mask, (tuple(dh), tuple(rd), int(map_h), int(rows)), *weights)
 
     monkeypatch.setattr(net, "mab_recurrence", cpu_recurrence)
