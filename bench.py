@@ -92,7 +92,7 @@ def peaks():
 
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -119,13 +119,13 @@ class ClockSampler:
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for ts, line in self.rows:
             f = [s.strip() for s in line.split(",")]
-            if len(f) < 7 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+            if len(f) < 6 or not (t0 - 0.05 <= ts <= t1 + 0.15):
                 continue
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,

@@ -153,8 +153,9 @@ class GradAllReducer:
         src, dst = [], []
         if self.buckets[b].is_cuda:
             cs = torch.cuda.current_stream(self.buckets[b].device)
-            for ev in self._xstream[b]:         # gradients finished on other streams (see the hook)
-                cs.wait_event(ev)
+            for st, ev in self._xstream[b]:     # gradients finished on other streams (see the hook)
+                if st != cs:
+                    cs.wait_event(ev)
             self._xstream[b] = []
         with torch.no_grad():
             for p in self._members[b]:
@@ -166,6 +167,12 @@ class GradAllReducer:
                     dst.append(v)
             if src:
                 torch._foreach_copy_(dst, src)
+                # The sources were allocated on whatever stream produced them and are read HERE, possibly on another stream:
+                # dropping them now would hand their memory back to the producing stream's pool, which may overwrite it before
+                # this copy has run (seen as two corrupted recurrence-weight gradients when a bucket completed on a side stream
+                # while the caller's stream was still busy).  Keep them until the next zero_grad(): by then backward() has
+                # joined every stream into the caller's.  (No record_stream: see mab_net._EncoderBranches.)
+                self._keepalive.extend(src)
         for p in self._members[b]:
             if p.grad is not None:
                 p.grad = self._view[id(p)]
@@ -192,11 +199,11 @@ class GradAllReducer:
                 # Branches of the model may run on their own streams (mab_net.MabNet.encode), and autograd replays a branch's
                 # backward on the stream it ran on: this gradient is only ordered with the stream this hook runs on.  Leave an
                 # event behind for whichever stream ends up packing the bucket.
+                # (Also for gradients finished on the training loop's own stream: the bucket may be packed on a side stream.)
                 cs = torch.cuda.current_stream(param.grad.device)
-                if cs != self._home_stream:
-                    ev = torch.cuda.Event()
-                    ev.record(cs)
-                    self._xstream[b].append(ev)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                self._xstream[b].append((cs, ev))
             if self._pending[b] == 0:           # the bucket is complete: pack it, and start its allreduce behind the backward
                 self.fire_order.append(b)
                 self._gather(b)
@@ -222,11 +229,17 @@ class GradAllReducer:
         cuda = bool(self.buckets) and self.buckets[0].is_cuda
         self._home_stream = torch.cuda.current_stream(self.buckets[0].device) if cuda else None
         self._xstream: List[List] = [[] for _ in self.buckets]
+        self._keepalive: List[torch.Tensor] = []
         self._packed_events: List = []
 
     def finish(self):
         """Block the current stream until every bucket's allreduce is complete.  Afterwards ``p.grad`` of every bucketed
         parameter that received a gradient is a view of its flat bucket holding the SUM over ranks."""
+        if self._packed_events:                 # buckets packed on side streams: order this stream (and the allreduce) behind them
+            cs = torch.cuda.current_stream(self.buckets[0].device)
+            for ev in self._packed_events:
+                cs.wait_event(ev)
+            self._packed_events = []
         for b in range(len(self.buckets)):
             if not self._gathered[b]:           # a bucket whose hooks did not all fire (a parameter unused in THIS step)
                 self._gather(b)
@@ -236,11 +249,6 @@ class GradAllReducer:
         for h in self._handles:
             h.wait()
         self._handles = []
-        if self._packed_events:
-            cs = torch.cuda.current_stream(self.buckets[0].device)
-            for ev in self._packed_events:
-                cs.wait_event(ev)
-            self._packed_events = []
 
 
 class FusedAdam(torch.optim.Optimizer):

@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .encoder import EncoderLayer
-from .mm3 import linear3, linear_cat
+from .mm3 import linear3, linear_cat, _LinearBlock, _rows
 from .recurrence import mab_recurrence, mab_prepack
 
 _MODS = ("l", "a", "v")
@@ -47,8 +47,9 @@ class LSTHM(nn.Module):
 
 
 class _EncoderBranches(torch.autograd.Function):
-    """The per-modality encoders of ``MabNet.encode`` as ONE autograd node that forks to side streams and joins again, in
-    the forward and in the backward.
+    """The per-modality branches of ``MabNet.forward`` — encoder layer, then the LSTHM cell's hoisted gate projection
+    ``W_m x + bW + bU + bV`` written into its column block of gx[T,N,4D] — as ONE autograd node that forks to side streams and
+    joins again, in the forward and in the backward.
 
     Each branch builds its own autograd graph under ``enable_grad`` on its stream and is differentiated by a nested
     ``torch.autograd.backward`` on that same stream, which accumulates the encoder's parameter gradients directly (their
@@ -65,8 +66,11 @@ class _EncoderBranches(torch.autograd.Function):
         cur = torch.cuda.current_stream(x.device)
         side = net._streams(x.device)
         M = len(net._mods)
-        inner, outs = [None] * M, [None] * M
+        inner = [None] * M
         offs = [sum(net._d_in[:i]) for i in range(M)]
+        goffs = [4 * sum(net._dh[:i]) for i in range(M)]
+        T, N = x.shape[0], x.shape[1]
+        gx = torch.empty(T * N, 4 * net.total_h_dim, device=x.device, dtype=torch.float32)     # caller's pool, before the fork
         xd = x.detach()
         # widest branch first (the host is only a few ms ahead of the device: the longest branch must not be queued last;
         # measured 14.69 vs 14.89 ms per step); the narrowest, issued last, stays on the caller's stream
@@ -81,37 +85,40 @@ class _EncoderBranches(torch.autograd.Function):
                 if build and x.requires_grad:
                     xm.requires_grad_(True)                       # a leaf of the branch graph: collects dL/dx of this slice
                 y, _ = getattr(net, f"encoder_{m}")(xm)
-                y = y.permute(1, 0, 2)
-            inner[i] = (xm, y, s)
-            outs[i] = y.detach()
+                y = y.permute(1, 0, 2)                            # [T,N,d]: the rows of the time-major storage
+                cell, box = getattr(net, f"lsthm_{m}"), {}
+                h = _LinearBlock.apply(y.reshape(T * N, d), cell.W.weight, cell.W.bias + cell.U.bias + cell.V.bias,
+                                       gx[:, goffs[i]:goffs[i] + 4 * net._dh[i]], box)
+            inner[i] = (xm, h, s, box)
         for s in side:
             cur.wait_stream(s)
-        ctx.order = order
+        ctx.order, ctx.goffs = order, goffs
         ctx.net, ctx.inner, ctx.x_grad = net, (inner if build else None), bool(build and x.requires_grad)
         ctx.x_width = x.shape[2]
-        return tuple(outs)
+        return gx.view(T, N, -1)
 
     @staticmethod
-    def backward(ctx, *dys):
+    def backward(ctx, dgx):
         if ctx.inner is None:
             raise RuntimeError("lsthm_b200: the encoder branches were already differentiated (retain_graph is not supported here)")
         inner, ctx.inner = ctx.inner, None
-        dev = dys[0].device if dys[0] is not None else inner[0][1].device
-        cur = torch.cuda.current_stream(dev)
-        side = ctx.net._streams(dev)
+        cur = torch.cuda.current_stream(dgx.device)
+        side = ctx.net._streams(dgx.device)
+        dg = _rows(dgx.reshape(-1, dgx.shape[-1]))
         for i in ctx.order:                                       # each branch on the stream its forward ran on
-            (xm, y, s), dy = inner[i], dys[i]
-            if dy is None or not y.requires_grad:
+            xm, h, s, box = inner[i]
+            if not h.requires_grad:
                 continue
+            box["dy"] = dg[:, ctx.goffs[i]:ctx.goffs[i] + 4 * ctx.net._dh[i]]
             if s != cur:
                 s.wait_stream(cur)
             with torch.cuda.stream(s):
-                torch.autograd.backward(y, dy)
+                torch.autograd.backward(h, h.new_empty(0))
         for s in side:
             cur.wait_stream(s)
         dx = None
         if ctx.x_grad:
-            parts = [(xm.grad if xm.grad is not None else torch.zeros_like(xm)).permute(1, 0, 2) for xm, _, _ in inner]
+            parts = [(t[0].grad if t[0].grad is not None else torch.zeros_like(t[0])).permute(1, 0, 2) for t in inner]
             used = sum(q.shape[2] for q in parts)
             if used < ctx.x_width:                                # columns of x beyond the modalities' slices are never read
                 parts.append(parts[0].new_zeros(parts[0].shape[0], parts[0].shape[1], ctx.x_width - used))
@@ -156,23 +163,25 @@ class MabNet(nn.Module):
                 + [self.fc[0].weight, self.fc[0].bias, self.fc[3].weight, self.fc[3].bias])
 
     def encode(self, x: torch.Tensor):
-        """Per-modality slices through their EncoderLayer (HybridRNN_ATV.py:86-96); returns [T,N,d_m] each.
-
-        The encoders are independent of each other until the gate projections, so on a CUDA device each one is issued on its
-        own stream, forward and backward (``_EncoderBranches``): the narrow kernels of one branch (d = 100 row kernels, weight
-        packs, split-K reduces, the partial last wave of every GEMM) fill the SMs the other branches leave idle (ATV step
-        15.08 -> 14.65 ms).  The streams fork from and join the caller's stream, so callers see ordinary stream semantics."""
-        if x.is_cuda and self.concurrent_encoders and len(self._mods) > 1:
-            build = torch.is_grad_enabled() and (x.requires_grad or any(
-                p.requires_grad for m in self._mods for p in getattr(self, f"encoder_{m}").parameters()))
-            anchor = torch.empty(0, device=x.device, requires_grad=True) if build else None
-            return list(_EncoderBranches.apply(self, build, x, anchor))
+        """Per-modality slices through their EncoderLayer (HybridRNN_ATV.py:86-96); returns [T,N,d_m] each (single-stream
+        schedule; ``forward`` on a CUDA device runs the branches concurrently, see ``_branches``)."""
         xs, o = [], 0
         for m, d in zip(self._mods, self._d_in):
             y, _ = getattr(self, f"encoder_{m}")(x[:, :, o:o + d].permute(1, 0, 2))
             xs.append(y.permute(1, 0, 2))
             o += d
         return xs
+
+    def _branches(self, x: torch.Tensor) -> torch.Tensor:
+        """gx[T,N,4D] = gate_inputs(encode(x)) with each modality's encoder + gate projection issued on its own stream, forward
+        and backward (``_EncoderBranches``): the narrow kernels of one branch (d = 100 row kernels, weight packs, split-K
+        reduces, the partial last wave of every GEMM) fill the SMs the other branches leave idle.  The streams fork from and
+        join the caller's stream, so callers see ordinary stream semantics."""
+        build = torch.is_grad_enabled() and (x.requires_grad or any(
+            p.requires_grad for m in self._mods for mod in (getattr(self, f"encoder_{m}"), getattr(self, f"lsthm_{m}"))
+            for p in mod.parameters()))
+        anchor = torch.empty(0, device=x.device, requires_grad=True) if build else None
+        return _EncoderBranches.apply(self, build, x, anchor)
 
     def _aux_stream(self, device):
         key = ("aux", device.index if device.index is not None else torch.cuda.current_device())
@@ -207,7 +216,10 @@ class MabNet(nn.Module):
             # the recurrence's packed weights depend on the parameters only: built next to the encoders, off the critical path
             pre = mab_prepack(T, N, self._dh, self._rd, self._map_h, self.recurrence_weights(), self.rows_per_cta,
                               self._aux_stream(x.device))
-        gx = self.gate_inputs(self.encode(x))
+        if x.is_cuda and x.dtype == torch.float32 and self.concurrent_encoders and len(self._mods) > 1:
+            gx = self._branches(x)
+        else:
+            gx = self.gate_inputs(self.encode(x))
         hz = mab_recurrence(gx, self._fc_mask(T, N, x.device), self._dh, self._rd, self._map_h,
                             self.recurrence_weights(), self.rows_per_cta, prepacked=pre)
         self.last_hz = hz

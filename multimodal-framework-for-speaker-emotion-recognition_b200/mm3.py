@@ -163,6 +163,31 @@ class _LinearCat(torch.autograd.Function):
         return (None, *gx, *gw, *gb)
 
 
+class _LinearBlock(torch.autograd.Function):
+    """One column block of ``linear_cat`` as its own autograd node, for callers that build the blocks on different streams
+    (mab_net._EncoderBranches): forward writes ``x W^T + b`` into ``out`` — a column block of a wider matrix the caller owns —
+    and returns a zero-size handle; backward takes the block's gradient (a strided column block of the wide gradient) from
+    ``box["dy"]``, which the caller sets before it differentiates the handle."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out, box):
+        _need4("linear_block", x.shape[1], weight.shape[0])
+        launches["gemm3"] += 1
+        _lib.gemm3(_lib.GEMM_NT, _rows(x), _rows(weight), bias.contiguous(), out=out)
+        ctx.save_for_backward(x, weight)
+        ctx.box = box
+        return x.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, _):
+        x, weight = ctx.saved_tensors
+        blk = ctx.box.pop("dy")
+        dx = mm_nn(blk, weight) if ctx.needs_input_grad[0] else None
+        dw = mm_tn(blk, x) if ctx.needs_input_grad[1] else None
+        db = colsum(blk) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
 def linear_cat(xs, weights, biases) -> torch.Tensor:
     """cat([F.linear(x_i, W_i, b_i)], dim=-1) for inputs that share their leading dimensions ([..., K_i] each)."""
     lead = xs[0].shape[:-1]

@@ -310,5 +310,6 @@ def test_concurrent_encoder_streams_change_nothing_but_the_schedule():
         red.zero_grad()
         masked_ce(model(x), labels, T, N).backward()
         red.finish()
-        assert all(torch.equal(g0[n], q.grad) for n, q in model.named_parameters() if q.grad is not None)
+        bad = [n for n, q in model.named_parameters() if q.grad is not None and not torch.equal(g0[n], q.grad)]
+        assert not bad, bad
         assert all(q.grad.data_ptr() == red._expected_ptr(q) for n, q in model.named_parameters() if q.grad is not None)
