@@ -17,6 +17,7 @@ from .encoder import EncoderLayer
 from .lsthm_onlysp import MARN_cell as _GruCell
 from .lsthm_sps import _SeqCrossAttention, reverse_seq
 from .mm3 import linear3
+from .streams import fork_join
 
 
 class CrossAttention2(_SeqCrossAttention):
@@ -60,16 +61,19 @@ class MARN1_nsps(nn.Module):
         self.crossatt_l2a = CrossAttention2(self.d_l, self.d_l, self.d_l)
         self.crossatt_a2l = CrossAttention2(self.d_a, self.d_a, self.d_a)
         self.p = nn.Parameter(torch.ones(2))
+        self.concurrent_encoders = True           # text / audio encoder chains on two CUDA streams (same results bit for bit)
 
     def forward(self, x, qmask, umask):
         x_l = linear3(x[:, :, :self.d_r].permute(1, 0, 2), self.linear_in.weight, self.linear_in.bias)
         x_a = x[:, :, self.d_r:self.d_r + self.d_a].permute(1, 0, 2)
         u = torch.cat([x_l, x_a], dim=2).permute(1, 0, 2)        # GRU input: PRE-encoder features (line 306)
-        if self.text_encoder:                                    # lsthm_no_en.py:306,309 comments these two calls out
-            x_l_1, _ = self.encoder_l(x_l)
-            x_l, _ = self.encoder_l(x_l + x_l_1)
-        x_a_1, _ = self.encoder_a(x_a)
-        x_a, _ = self.encoder_a(x_a + x_a_1)
+        enc2 = lambda enc: (lambda t: enc(t + enc(t)[0])[0])    # enc(x + enc(x)), lsthm_nsps.py:306-310
+        if not self.text_encoder:                                # lsthm_no_en.py:306,309 comments the two encoder_l calls out
+            x_a = enc2(self.encoder_a)(x_a)
+        elif x.is_cuda and x.dtype == torch.float32 and self.concurrent_encoders:
+            x_l, x_a = fork_join(self, [enc2(self.encoder_l), enc2(self.encoder_a)], [x_l, x_a])   # two streams (streams.py)
+        else:
+            x_l, x_a = enc2(self.encoder_l)(x_l), enc2(self.encoder_a)(x_a)
         x_l, x_a = x_l.permute(1, 0, 2), x_a.permute(1, 0, 2)
         qmask = qmask.to(x_l.dtype)
         drop = self.dropout_rec

@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from .encoder import EncoderLayer
 from .gsp_recurrence import gsp_cell
 from .lsthm_sps import LSTHM1, CrossAttention, CrossAttention2, CrossAttention3, reverse_seq
+from .streams import fork_join
 from .mm3 import linear3, linear_cat
 
 
@@ -92,14 +93,18 @@ class MARN1_onlysp(nn.Module):
         self.v = nn.Parameter(torch.ones(1))
         self.v1 = nn.Parameter(torch.ones(1))
         self.v2 = nn.Parameter(torch.ones(1))
+        self.concurrent_encoders = True           # text / audio encoder chains on two CUDA streams (same results bit for bit)
 
     def forward(self, x, qmask, umask):
         x_l = linear3(x[:, :, :self.d_r].permute(1, 0, 2), self.linear_in.weight, self.linear_in.bias)
         x_a = x[:, :, self.d_r:self.d_r + self.d_a].permute(1, 0, 2)
-        x_l, _ = self.encoder_l(x_l)                      # the encoders are applied twice, without residual (264-268)
-        x_a, _ = self.encoder_a(x_a)
-        x_l, _ = self.encoder_l(x_l)
-        x_a, _ = self.encoder_a(x_a)
+        # the encoders are applied twice, without residual (264-268); text and audio are independent up to the cells: on a CUDA
+        # device the two chains run on two streams, forward and backward (streams.fork_join)
+        enc2 = lambda enc: (lambda t: enc(enc(t)[0])[0])
+        if x.is_cuda and x.dtype == torch.float32 and self.concurrent_encoders:
+            x_l, x_a = fork_join(self, [enc2(self.encoder_l), enc2(self.encoder_a)], [x_l, x_a])
+        else:
+            x_l, x_a = enc2(self.encoder_l)(x_l), enc2(self.encoder_a)(x_a)
         x_l, x_a = x_l.permute(1, 0, 2), x_a.permute(1, 0, 2)
         qmask = qmask.to(x_l.dtype)
         h_f = self.dropout_rec(self.marn_cell_f(torch.cat([x_l, x_a], -1), x_l, x_a, qmask))

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .encoder import EncoderLayer
+from .streams import fork_join
 from .mm3 import linear3, linear_cat
 from .seq_attention import fused_ok, seq_cross_attention
 from .sps_recurrence import sps_cell
@@ -201,14 +202,18 @@ class MARN1_sps(nn.Module):
         self.v = nn.Parameter(torch.ones(1))
         self.v1 = nn.Parameter(torch.ones(1))
         self.v2 = nn.Parameter(torch.ones(1))
+        self.concurrent_encoders = True           # text / audio encoder chains on two CUDA streams (same results bit for bit)
 
     def forward(self, x, qmask, umask):
         x_l = linear3(x[:, :, :self.d_r].permute(1, 0, 2), self.linear_in.weight, self.linear_in.bias)
         x_a = x[:, :, self.d_r:self.d_r + self.d_a].permute(1, 0, 2)
-        x_l_1, _ = self.encoder_l(x_l)
-        x_a_1, _ = self.encoder_a(x_a)
-        x_l, _ = self.encoder_l(x_l + x_l_1)
-        x_a, _ = self.encoder_a(x_a + x_a_1)
+        # enc(x + enc(x)) per modality (lsthm_sps.py:356-361); text and audio are independent up to the cells: on a CUDA device
+        # the two chains run on two streams, forward and backward (streams.fork_join)
+        enc2 = lambda enc: (lambda t: enc(t + enc(t)[0])[0])
+        if x.is_cuda and x.dtype == torch.float32 and self.concurrent_encoders:
+            x_l, x_a = fork_join(self, [enc2(self.encoder_l), enc2(self.encoder_a)], [x_l, x_a])
+        else:
+            x_l, x_a = enc2(self.encoder_l)(x_l), enc2(self.encoder_a)(x_a)
         x_l, x_a = x_l.permute(1, 0, 2), x_a.permute(1, 0, 2)
         qmask = qmask.to(x_l.dtype)
         h_f = self.dropout_rec(self.marn_cell_f(x, x_l, x_a, qmask))

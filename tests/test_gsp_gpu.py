@@ -190,3 +190,25 @@ def test_in_kernel_attention_dropout_is_the_same_mask_forward_and_backward(kind)
         num = ((f(gx + eps * dirn) * w).double().sum() - (f(gx - eps * dirn) * w).double().sum()) / (2 * eps)
     ana = (a0.grad * dirn).double().sum()
     assert abs(float(num - ana)) <= 5e-3 * max(abs(float(ana)), 1.0), (float(num), float(ana))
+
+
+@pytest.mark.parametrize("kind", ["onlysp", "nsps", "sps"])
+def test_two_stream_encoders_change_nothing_but_the_schedule(kind):
+    """The text and audio encoder chains run on two CUDA streams, forward and backward (streams.fork_join).  Every kernel is
+    deterministic, so log-probs, dx and every parameter gradient must be BITWISE those of the single-stream schedule — a missing
+    fork/join dependency or memory reused too early shows up as a difference.  Repeated, at a size where the chains overlap."""
+    T, N = 40, 96
+    model = sps_seeded_model(31, True, "cuda", kind=kind).eval()
+    assert model.concurrent_encoders
+    x, qmask, umask, labels = _batch(T, N, 5)
+
+    def run():
+        logp, dx = _fwd_bwd(model, x, qmask, umask, labels)
+        return logp, dx, {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    runs = [run() for _ in range(3)]
+    model.concurrent_encoders = False
+    l0, dx0, g0 = run()
+    for l1, dx1, g1 in runs:
+        assert torch.equal(l0, l1) and torch.equal(dx0, dx1)
+        bad = [k for k in g0 if not torch.equal(g0[k], g1[k])]
+        assert g0.keys() == g1.keys() and not bad, bad
