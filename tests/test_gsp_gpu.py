@@ -212,3 +212,14 @@ def test_two_stream_encoders_change_nothing_but_the_schedule(kind):
         assert torch.equal(l0, l1) and torch.equal(dx0, dx1)
         bad = [k for k in g0 if not torch.equal(g0[k], g1[k])]
         assert g0.keys() == g1.keys() and not bad, bad
+
+
+@pytest.mark.parametrize("kind", ["onlysp", "no_en", "sps"])
+def test_no_grad_inference_takes_the_same_kernels(kind):
+    T, N = 9, 6
+    model = sps_seeded_model(32, True, "cuda", kind=kind).eval()
+    x, qmask, umask, _ = _batch(T, N, 6)
+    lp_grad = model(x, qmask, umask)[0]
+    with torch.no_grad():
+        lp0 = model(x, qmask, umask)[0]
+    assert lp_grad.requires_grad and not lp0.requires_grad and torch.equal(lp0, lp_grad.detach())

@@ -313,3 +313,18 @@ def test_concurrent_encoder_streams_change_nothing_but_the_schedule():
         bad = [n for n, q in model.named_parameters() if q.grad is not None and not torch.equal(g0[n], q.grad)]
         assert not bad, bad
         assert all(q.grad.data_ptr() == red._expected_ptr(q) for n, q in model.named_parameters() if q.grad is not None)
+
+
+def test_no_grad_inference_takes_the_same_kernels():
+    """Under ``torch.no_grad()`` the branch node builds no graphs; the outputs are bitwise those of the grad-enabled forward, on
+    both schedules, and nothing requires grad."""
+    T, N, kind = 12, 9, "ATV"
+    model = seeded_model(kind, 111).to("cuda").eval()
+    x = torch.randn(T, N, 712, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    p_grad = model(x)
+    with torch.no_grad():
+        p0 = model(x)
+        model.concurrent_encoders = False
+        p1 = model(x)
+    assert p_grad.requires_grad and not p0.requires_grad
+    assert torch.equal(p0, p_grad.detach()) and torch.equal(p0, p1)
