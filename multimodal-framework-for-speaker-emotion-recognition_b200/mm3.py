@@ -32,7 +32,11 @@ events = None
 def _gemm(mode, a, b, bias=None):
     launches["gemm3"] += 1
     if events is None:
-        return _lib.gemm3(mode, a, b, bias)
+        torch.cuda.nvtx.range_push("lsthm/K5_gemm3")         # K5 = the time-parallel GEMMs
+        try:
+            return _lib.gemm3(mode, a, b, bias)
+        finally:
+            torch.cuda.nvtx.range_pop()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     c = _lib.gemm3(mode, a, b, bias)
