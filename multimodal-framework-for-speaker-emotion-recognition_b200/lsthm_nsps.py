@@ -17,7 +17,7 @@ from .encoder import EncoderLayer
 from .lsthm_onlysp import MARN_cell as _GruCell
 from .lsthm_sps import _SeqCrossAttention, reverse_seq
 from .mm3 import linear3
-from .streams import fork_join
+from .streams import fork_join, state_without_streams
 
 
 class CrossAttention2(_SeqCrossAttention):
@@ -41,6 +41,9 @@ class MARN_cell(_GruCell):
 
 
 class MARN1_nsps(nn.Module):
+    def __getstate__(self):
+        return state_without_streams(self)          # cached CUDA streams are not part of the module's state
+
     text_encoder = True          # False in the MARN1_no_en variant (lsthm_no_en.py)
 
     def __init__(self, n_classes, dataset=None):

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .encoder import EncoderLayer
 from .gsp_recurrence import gsp_cell
 from .lsthm_sps import LSTHM1, CrossAttention, CrossAttention2, CrossAttention3, reverse_seq
-from .streams import fork_join
+from .streams import fork_join, state_without_streams
 from .mm3 import linear3, linear_cat
 
 
@@ -70,6 +70,9 @@ class MARN_cell(nn.Module):
 
 
 class MARN1_onlysp(nn.Module):
+    def __getstate__(self):
+        return state_without_streams(self)          # cached CUDA streams are not part of the module's state
+
     def __init__(self, n_classes):
         super().__init__()
         self.d_l, self.d_a, self.d_r = 100, 100, 1024

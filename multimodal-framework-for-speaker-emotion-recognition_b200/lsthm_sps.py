@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .encoder import EncoderLayer
-from .streams import fork_join
+from .streams import fork_join, state_without_streams
 from .mm3 import linear3, linear_cat
 from .seq_attention import fused_ok, seq_cross_attention
 from .sps_recurrence import sps_cell
@@ -180,6 +180,9 @@ def reverse_seq(X: torch.Tensor, umask: torch.Tensor) -> torch.Tensor:
 
 
 class MARN1_sps(nn.Module):
+    def __getstate__(self):
+        return state_without_streams(self)          # cached CUDA streams are not part of the module's state
+
     def __init__(self, n_classes):
         super().__init__()
         self.d_l, self.d_a, self.d_r = 100, 100, 1024

@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from .encoder import EncoderLayer
 from .mm3 import linear3, linear_cat, _LinearBlock, _rows
 from .recurrence import mab_recurrence, mab_prepack
+from .streams import state_without_streams
 
 _MODS = ("l", "a", "v")
 
@@ -127,6 +128,9 @@ class _EncoderBranches(torch.autograd.Function):
 
 
 class MabNet(nn.Module):
+    def __getstate__(self):
+        return state_without_streams(self)          # cached CUDA streams are not part of the module's state
+
     def __init__(self, d_in: Sequence[int], dh: Sequence[int], reduce: Sequence[int], output_dim: int):
         super().__init__()
         self._mods = _MODS[:len(d_in)]

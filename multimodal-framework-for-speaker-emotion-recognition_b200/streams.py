@@ -24,6 +24,16 @@ def side_streams(owner, device: torch.device, n: int) -> List["torch.cuda.Stream
     return cache[key][:n]
 
 
+def state_without_streams(module) -> dict:
+    """``__getstate__`` body for modules that cache CUDA streams on themselves: ``copy.deepcopy`` / ``pickle`` of the module must
+    not try to copy the streams (they are re-created on first use)."""
+    d = module.__dict__.copy()
+    for k in ("_fork_streams", "_side_streams"):
+        if k in d:
+            d[k] = {}
+    return d
+
+
 class _ForkJoin(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fns, streams, build, anchor, *xs):

@@ -231,3 +231,21 @@ def test_single_step_cell_signatures_match_the_oracle():
     a1 = cell.crossatt_l2a(c, h)
     a2 = tp.cross_attention_cell(ps, "marn_cell_f.crossatt_l2a", c, h, None, "")
     assert torch.allclose(a1, a2, atol=2e-6)
+
+
+def test_modules_copy_and_pickle_without_their_cached_streams():
+    """The drop-in modules cache CUDA streams on themselves (mab_net / streams.fork_join); ``copy.deepcopy`` and ``pickle`` of a
+    module (EMA copies, ``torch.save(model)``) must not try to copy them.  A lock stands in for a stream here (neither pickles)."""
+    import copy
+    import pickle
+    import threading
+    m = lsthm_b200.HybridRNN_AT.MARN()
+    m._side_streams[0] = [threading.Lock()]
+    s = lsthm_b200.lsthm_onlysp.MARN1_onlysp(6)
+    s.__dict__["_fork_streams"] = {0: [threading.Lock()]}
+    for mod, attr in ((m, "_side_streams"), (s, "_fork_streams")):
+        for clone in (copy.deepcopy(mod), pickle.loads(pickle.dumps(mod))):
+            assert getattr(clone, attr) == {} and len(getattr(mod, attr)) == 1
+            a, b = mod.state_dict(), clone.state_dict()
+            assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+            assert clone.concurrent_encoders is True
